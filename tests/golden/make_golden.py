@@ -1,0 +1,259 @@
+"""Generate golden input/output vectors by running the UNMODIFIED reference (akvas/grates,
+mounted read-only at /root/reference) on seeded inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, so the resulting small ``*.npz`` fixtures are
+committed.  netCDF4/h5py are absent and unused on this path; they are stubbed so that
+``import grates`` succeeds (grates/__init__.py:48 -> grates/io.py:18-19).
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+_nc = types.ModuleType("netCDF4")
+_nc.Dataset = object
+sys.modules.setdefault("netCDF4", _nc)
+sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+sys.path.insert(0, "/root/reference")
+import grates  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GM, R = 3.9860044150e+14, 6.3781363000e+06
+
+
+def coeffs(nmax, seed):
+    """Kaula-like synthetic coefficients: degree-n entries * 1e-5/n^2, degrees 0-1 zero."""
+    rng = np.random.default_rng(seed)
+    anm = rng.standard_normal((nmax + 1, nmax + 1))
+    for n in range(1, nmax + 1):
+        anm[grates.gravityfield.degree_indices(n)] *= 1e-5 / n ** 2
+    anm[0:2, 0:2] = 0
+    pc = grates.gravityfield.PotentialCoefficients(GM, R)
+    pc.anm = anm
+    return pc
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(name, {k: np.asarray(v).shape for k, v in arrays.items()}, os.path.getsize(path) // 1024, "KiB")
+
+
+def l1_numerics():
+    rng = np.random.default_rng(11)
+    colat = np.sort(rng.uniform(0.01, np.pi - 0.01, 13))
+    colat[0], colat[-1] = 1e-3, np.pi - 2e-3
+    lon = rng.uniform(-np.pi, np.pi, 13)
+    out = dict(colat=colat, lon=lon)
+    for N in (5, 40, 200):
+        c = colat if N < 200 else colat[::4]
+        out["legendre_%d" % N] = grates.utilities.legendre_functions(N, c)
+    for m in (0, 1, 7, 40):
+        out["legendre_order_%d" % m] = grates.utilities.legendre_functions_per_order(40, m, colat)
+    out["legendre_polynomials_40"] = grates.utilities.legendre_polynomials(40, colat)
+    out["trig_12"] = grates.utilities.trigonometric_functions(12, lon)
+    out["ynm_9"] = grates.utilities.spherical_harmonics(9, colat, lon)
+    a3 = rng.standard_normal((3, 7, 7))
+    out["ravel_in"] = a3
+    out["ravel_0_6"] = grates.utilities.ravel_coefficients(a3, 0, 6)
+    out["ravel_2_6"] = grates.utilities.ravel_coefficients(a3, 2, 6)
+    out["ravel_2_4"] = grates.utilities.ravel_coefficients(a3[0], 2, 4)
+    v = rng.standard_normal(49 - 4)
+    out["unravel_in"] = v
+    out["unravel_2_6"] = grates.utilities.unravel_coefficients(v, 2, 6)
+    lat = np.linspace(-np.pi / 2, np.pi / 2, 9)
+    out["lat"] = lat
+    out["geocentric_radius"] = grates.utilities.geocentric_radius(lat)
+    out["colatitude"] = grates.utilities.colatitude(lat)
+    out["colatitude_wgs"] = grates.utilities.colatitude(lat, 6378137.0, 1 / 298.257223563)
+    save("l1_numerics", **out)
+
+
+def kernels():
+    lat = np.linspace(89.5, -89.5, 7) * np.pi / 180
+    colat = grates.utilities.colatitude(lat)
+    r = grates.utilities.geocentric_radius(lat)
+    out = dict(lat=lat, colat=colat, r=r)
+    N = 24
+    for name in ("ewh", "obp", "potential", "geoid", "surface_density", "anomaly", "deformation", "uplift"):
+        k = grates.kernel.get_kernel(name)
+        out["coeff_" + name] = k.coefficients(0, N, r, colat)
+        out["inv_" + name] = k.inverse_coefficients(0, N, r, colat)
+        out["kn_" + name] = k.inverse_coefficients(0, N, r, colat) * \
+            np.power((R / r)[:, np.newaxis], np.arange(N + 1, dtype=int) + 1) * GM / R
+    out["normal_gravity"] = grates.gravityfield.GRS80.normal_gravity(r, colat)
+    # known answers the reference's own tests assert (testing/gravityfield.py:80-86)
+    out["gamma_equator_pole"] = np.array([
+        grates.gravityfield.GRS80.normal_gravity(np.array([grates.gravityfield.GRS80.R]), np.array([np.pi / 2]))[0],
+        grates.gravityfield.GRS80.normal_gravity(
+            np.array([grates.gravityfield.GRS80.R * (1 - grates.gravityfield.GRS80.flattening)]), np.array([0.0]))[0]])
+    k_ce, h_ce, l_ce = grates.data.load_love_numbers(frame="CE")
+    out["love_k_200"] = k_ce[:201]
+    out["love_h_200"] = h_ce[:201]
+    save("kernels", **out)
+
+
+def grids():
+    out = {}
+    g = grates.grid.GeographicGrid(2.0, 4.0)
+    out["geo_meridians"], out["geo_parallels"], out["geo_area"] = g.meridians, g.parallels, g.area
+    gg = grates.grid.GaussGrid(14)
+    out["gauss_meridians"], out["gauss_parallels"], out["gauss_area"] = gg.meridians, gg.parallels, gg.area
+    rng = np.random.default_rng(21)
+    mer = np.sort(rng.uniform(-np.pi, np.pi, 20))
+    par = np.sort(rng.uniform(-1.5, 1.5, 11))[::-1]
+    rg = grates.grid.RegularGrid(mer, par)
+    out["reg_meridians"], out["reg_parallels"], out["reg_area"] = rg.meridians, rg.parallels, rg.area
+    save("grids", **out)
+
+
+def synthesis():
+    out = {}
+    # config 1 of BASELINE.json: degree 60 -> 1 deg x 1 deg, ewh
+    pc = coeffs(60, 1000)
+    g = grates.grid.GeographicGrid(1.0, 1.0)
+    out["c1_anm"] = pc.anm
+    out["c1_ewh"] = pc.to_grid(g, "ewh").value_array
+    # small multi-kernel / multi-epoch cases on a 10 degree grid
+    g10 = grates.grid.GeographicGrid(10.0, 10.0)
+    anm = np.stack([coeffs(20, 1000 + e).anm for e in range(3)])
+    out["s_anm"] = anm
+    for name in ("ewh", "obp", "potential", "geoid", "surface_density", "anomaly", "deformation", "uplift"):
+        vals = []
+        for e in range(3):
+            pc = grates.gravityfield.PotentialCoefficients(GM, R)
+            pc.anm = anm[e]
+            vals.append(pc.to_grid(g10, name).value_array)
+        out["s_" + name] = np.stack(vals)
+    # non-default GM / R
+    pc = grates.gravityfield.PotentialCoefficients(3.986004415e14 * 1.001, 6378137.0)
+    pc.anm = anm[0]
+    out["s_gmr"] = np.array([pc.GM, pc.R])
+    out["s_ewh_gmr"] = pc.to_grid(g10, "ewh").value_array
+    # Gauss grid and a regular grid with random parallels / meridians
+    gg = grates.grid.GaussGrid(24)
+    pc = coeffs(20, 1000)
+    out["gauss_ewh"] = pc.to_grid(gg, "ewh").value_array
+    rng = np.random.default_rng(21)
+    mer = np.sort(rng.uniform(-np.pi, np.pi, 50))
+    par = np.sort(rng.uniform(-1.5, 1.5, 31))[::-1]
+    rg = grates.grid.RegularGrid(mer, par)
+    out["reg_meridians"], out["reg_parallels"] = mer, par
+    out["reg_geoid"] = pc.to_grid(rg, "geoid").value_array
+    # degree 0 / degree 1 only and a high-degree polar-underflow case (N=200 on 4 parallels near the pole)
+    pc0 = grates.gravityfield.PotentialCoefficients(GM, R)
+    pc0.anm = np.array([[1.0]])
+    out["deg0_potential"] = pc0.to_grid(g10, "potential").value_array
+    pch = coeffs(200, 7)
+    par_p = np.array([89.9, 89.0, 0.3, -89.95]) * np.pi / 180
+    mer_p = np.linspace(-np.pi + 0.1, np.pi - 0.1, 16)
+    rp = grates.grid.RegularGrid(mer_p, par_p)
+    out["hi_anm"], out["hi_parallels"], out["hi_meridians"] = pch.anm, par_p, mer_p
+    out["hi_ewh"] = pch.to_grid(rp, "ewh").value_array
+    # irregular branch (gravityfield.py:370-388)
+    lon = rng.uniform(-np.pi, np.pi, 700)
+    lat = rng.uniform(-1.55, 1.55, 700)
+    ig = grates.grid.IrregularGrid(lon, lat)
+    pc = coeffs(15, 1003)
+    out["irr_lon"], out["irr_lat"], out["irr_anm"] = lon, lat, pc.anm
+    out["irr_ewh"] = pc.to_grid(ig, "ewh").values
+    save("synthesis", **out)
+
+
+def analysis():
+    out = {}
+    rng = np.random.default_rng(31)
+    g = grates.grid.GeographicGrid(10.0, 10.0)    # 18 x 36 -> N <= 12
+    N = 12
+    pc = coeffs(N, 1000)
+    for name in ("ewh", "potential"):
+        grid = pc.to_grid(g, name)
+        noise = grid.copy()
+        noise.values = grid.values + rng.standard_normal(grid.values.size) * 1e-3 * np.abs(grid.values).max()
+        out["in_" + name] = noise.value_array
+        out["anm_%s_0_12" % name] = noise.to_potential_coefficients(0, N, name, GM, R).anm
+        out["anm_%s_2_12" % name] = noise.to_potential_coefficients(2, N, name, GM, R).anm
+        out["anm_%s_3_9" % name] = noise.to_potential_coefficients(3, 9, name, GM, R).anm
+    gg = grates.grid.GaussGrid(14)
+    grid = coeffs(10, 1001).to_grid(gg, "ewh")
+    out["gauss_in"] = grid.value_array
+    out["gauss_anm_0_10"] = grid.to_potential_coefficients(0, 10, "ewh", GM, R).anm
+    mer = np.sort(rng.uniform(-np.pi, np.pi, 30))
+    par = np.sort(rng.uniform(-1.5, 1.5, 17))[::-1]
+    rg = grates.grid.RegularGrid(mer, par)
+    grid = coeffs(8, 1002).to_grid(rg, "geoid")
+    out["reg_meridians"], out["reg_parallels"] = mer, par
+    out["reg_in"] = grid.value_array
+    out["reg_anm_0_8"] = grid.to_potential_coefficients(0, 8, "geoid", GM, R).anm
+    # dense operators in degree-wise order (grid.py:412-443, :698-730)
+    g30 = grates.grid.GeographicGrid(30.0, 30.0)
+    out["synthesis_matrix_1_4"] = g30.synthesis_matrix(1, 4, "ewh", GM, R)
+    out["analysis_matrix_0_4"] = g30.analysis_matrix(0, 4, "ewh", GM, R)
+    save("analysis", **out)
+
+
+def covariance():
+    out = {}
+    rng = np.random.default_rng(4)
+    N = 8
+    K = (N + 1) ** 2
+    Lr = rng.standard_normal((K, 16)) * 1e-11
+    sigma = Lr @ Lr.T + np.diag(rng.uniform(0.5, 1.5, K) * 1e-22)
+    out["sigma"] = sigma
+    g = grates.grid.GeographicGrid(15.0, 15.0)
+    out["std_ewh_0_8"] = g.copy().covariance_propagation(sigma, 0, N, "ewh", GM, R)
+    out["std_potential_2_8"] = g.copy().covariance_propagation(sigma[4:, 4:], 2, N, "potential", GM, R)
+    gg = grates.grid.GaussGrid(10)
+    out["std_gauss_geoid"] = gg.covariance_propagation(sigma, 0, N, "geoid", GM, R)
+    lon = rng.uniform(-np.pi, np.pi, 300)
+    lat = rng.uniform(-1.55, 1.55, 300)
+    ig = grates.grid.IrregularGrid(lon, lat)
+    out["irr_lon"], out["irr_lat"] = lon, lat
+    out["std_irr_ewh"] = ig.covariance_propagation(sigma, 0, N, "ewh", GM, R)
+    save("covariance", **out)
+
+
+def filters():
+    out = {}
+    rng = np.random.default_rng(5)
+    nf = 12
+    blocks = []
+    for m in range(nf + 1):
+        k = nf + 1 - m
+        for _ in range(1 if m == 0 else 2):
+            blocks.append(0.5 * np.eye(k) + 0.01 * rng.standard_normal((k, k)))
+    flt = grates.filter.OrderWiseFilter(blocks)
+    for i, b in enumerate(blocks):
+        out["block_%02d" % i] = b
+    pc12, pc9 = coeffs(12, 1000), coeffs(9, 1001)
+    pc12.anm[0:2, 0:2] = rng.standard_normal((2, 2))
+    out["in_12"], out["in_9"] = pc12.anm, pc9.anm
+    out["out_12"] = flt.filter(pc12).anm
+    out["out_9"] = flt.filter(pc9).anm
+    out["matrix_2_9"] = flt.matrix(2, 9)
+    # time series ordering (gravityfield.py:964-980)
+    import datetime
+    data = []
+    for e in range(3):
+        p = coeffs(4, 1000 + e)
+        p.epoch = datetime.datetime(2002, 4, 15) + datetime.timedelta(days=30.4375 * (2 - e))
+        data.append(p)
+    ts = grates.gravityfield.TimeSeries(data)
+    out["ts_anm_sorted"] = np.stack([d.anm for _, d in ts.items()])
+    out["ts_array"] = ts.to_array()
+    save("filters", **out)
+
+
+if __name__ == "__main__":
+    l1_numerics()
+    kernels()
+    grids()
+    synthesis()
+    analysis()
+    covariance()
+    filters()
