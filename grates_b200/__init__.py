@@ -1,0 +1,16 @@
+"""grates_b200 -- B200 (sm_100a) implementation of the spherical-harmonic hot path of
+akvas/grates: synthesis (``PotentialCoefficients.to_grid``), grid-to-coefficient analysis,
+covariance propagation and order-wise filtering, single sets and epoch batches.
+
+Host code is Python (numpy for small tables, torch for device memory / streams /
+torch.distributed); all arithmetic on the path runs in hand-written CUDA kernels behind the
+C ABI of ``include/grates_b200.h``.  There is no CPU fallback.
+"""
+from . import _lib, utilities, kernel, plan, grid, gravityfield, filter  # noqa: F401
+from .gravityfield import PotentialCoefficients, TimeSeries, to_grid_batch, gridded_rms  # noqa: F401
+from .grid import RegularGrid, GeographicGrid, GaussGrid, analysis_batch  # noqa: F401
+from .filter import OrderWiseFilter  # noqa: F401
+from .kernel import get_kernel  # noqa: F401
+from .plan import SHPlan, get_plan, clear_plan_cache, PinnedArray  # noqa: F401
+
+__version__ = "0.1.0"

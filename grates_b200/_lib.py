@@ -1,0 +1,99 @@
+"""ctypes binding of libgrates_b200.so (C ABI declared in include/grates_b200.h).
+
+There is deliberately no fallback: if the shared library is missing (and cannot be built
+because nvcc is absent) or no CUDA device is usable, every compute call raises.
+"""
+import ctypes
+import os
+import threading
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int64_p = ctypes.POINTER(ctypes.c_int64)
+_vp = ctypes.c_void_p
+
+GB_OK, GB_ERR_ARGUMENT, GB_ERR_CUDA, GB_ERR_UNSUPPORTED, GB_ERR_MEMORY = 0, 1, 2, 3, 4
+
+# name -> (restype, argtypes); must list every symbol of include/grates_b200.h
+SIGNATURES = {
+    "gb_version": (ctypes.c_int, []),
+    "gb_last_error": (ctypes.c_char_p, []),
+    "gb_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "gb_plan_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
+                                      _vp, _vp, ctypes.c_int]),
+    "gb_plan_destroy": (ctypes.c_int, [_vp]),
+    "gb_plan_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(ctypes.c_int)] * 4),
+    "gb_synthesis": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    "gb_synthesis_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "gb_legendre_table": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "gb_plan_set_analysis": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),
+    "gb_analysis": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    "gb_analysis_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "gb_covariance_propagation": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                                 ctypes.c_int, _vp]),
+    "gb_orderwise_filter": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp,
+                                           ctypes.c_int, _vp]),
+    "gb_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
+    "gb_host_free": (ctypes.c_int, [_vp]),
+    "gb_probe_fp64_peak": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p]),
+    "gb_launch_count": (ctypes.c_int64, [ctypes.c_int]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgrates_b200.so")
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc exists) and return the CDLL."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path) or os.environ.get("GRATES_B200_REBUILD"):
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(path):
+            raise RuntimeError("libgrates_b200.so is missing (%s); run `python -m grates_b200.build`. "
+                               "grates_b200 has no CPU fallback." % path)
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError here means header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    """Turn a C ABI return code into the Python exception the reference would raise."""
+    if rc == GB_OK:
+        return
+    msg = load().gb_last_error().decode("utf-8", "replace")
+    if rc == GB_ERR_ARGUMENT:
+        raise ValueError(msg)
+    if rc == GB_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == GB_ERR_MEMORY:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    check(load().gb_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def require_device():
+    """Fail loudly when there is nothing to run on (no silent CPU path)."""
+    try:
+        n = device_count()
+    except RuntimeError as exc:
+        raise RuntimeError("grates_b200 needs a CUDA device (B200, sm_100a): %s" % exc) from None
+    if n < 1:
+        raise RuntimeError("grates_b200 needs a CUDA device (B200, sm_100a); none is visible")
+    return n

@@ -1,0 +1,138 @@
+// Shared declarations of the grates_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cuda_runtime.h>
+#include "../../include/grates_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "grates_b200 targets sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// error handling: thread-local message + error code returns (no exceptions cross the C ABI)
+// ---------------------------------------------------------------------------------------------
+int gb_set_error(int code, const char* fmt, ...);
+void gb_count_launch(int n = 1);
+
+#define GB_CUDA(expr)                                                                           \
+    do {                                                                                        \
+        cudaError_t gb_e_ = (expr);                                                             \
+        if (gb_e_ != cudaSuccess)                                                               \
+            return gb_set_error(GB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                    \
+                                cudaGetErrorString(gb_e_), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define GB_REQUIRE(cond, ...)                                                                   \
+    do {                                                                                        \
+        if (!(cond)) return gb_set_error(GB_ERR_ARGUMENT, __VA_ARGS__);                         \
+    } while (0)
+
+#define GB_LAUNCH_CHECK()                                                                       \
+    do {                                                                                        \
+        gb_count_launch();                                                                      \
+        GB_CUDA(cudaGetLastError());                                                            \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct gb_plan {
+    int device = 0;
+    int nmax = 0, L = 0, nlat = 0, nlon = 0;
+    int kpad = 0;   // spectral rows of one grid row: k = 2m + {0: cos, 1: sin}, padded to a multiple of 4
+    int nlp = 0;    // nlon padded to a multiple of 8
+    // tables on the device
+    double* d_ct = nullptr;     // [nlat]      cos(theta_i)
+    double* d_kn = nullptr;     // [nlat][L]   per-latitude degree factors
+    double* d_pmm = nullptr;    // [nlat][L]   sectorial seeds P_mm(theta_i)
+    double* d_ra = nullptr;     // [L][L]      recursion coefficient a_nm (utilities.py:52)
+    double* d_rb = nullptr;     // [L][L]      recursion coefficient b_nm (utilities.py:54)
+    double* d_rc = nullptr;     // [L]         sqrt(2n+1), first off-diagonal (utilities.py:46)
+    double* d_trig = nullptr;   // [kpad][nlp] row 2m: cos(m lon_j), row 2m+1: sin(m lon_j)
+    // synthesis workspace, grown on demand (epochs)
+    int ws_epochs = 0;
+    long long ws_mpad = 0;
+    double* d_x = nullptr;      // order-wise packed coefficients, see gb_synthesis.cu
+    double* d_ab = nullptr;     // [kpad][mpad] spectral intermediate
+    // host-buffer pipeline
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* d_io_in = nullptr;  size_t io_in_bytes = 0;
+    double* d_io_out[2] = {nullptr, nullptr}; size_t io_out_bytes = 0;
+    // analysis
+    int ana_nmin = -1;
+    double* d_lon_ops = nullptr;     // [kpad][nlp]
+    double* d_lat_ops = nullptr;
+    long long* d_lat_off = nullptr;  // [L+1]
+    long long* h_lat_off = nullptr;
+    // device facts
+    int sm_count = 0;
+};
+
+int gb_plan_ensure_workspace(gb_plan* p, int n_epochs);
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers (device)
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace gb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col); FP64 tensor op, SASS DMMA.8x8x4
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS UBLKCP); completes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_cs_v2(double* p, double a, double b) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_cs(double* p, double a) {
+    asm volatile("st.global.cs.f64 [%0], %1;\n" ::"l"(p), "d"(a) : "memory");
+}
+
+}  // namespace gb
+#endif

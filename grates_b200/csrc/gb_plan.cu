@@ -1,0 +1,236 @@
+// Plan management, error reporting and small utilities of the grates_b200 C ABI.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "gb_common.cuh"
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+int gb_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void gb_count_launch(int n) { g_launches += n; }
+
+extern "C" int gb_version(void) { return 100; }
+extern "C" const char* gb_last_error(void) { return g_err; }
+extern "C" int64_t gb_launch_count(int reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+extern "C" int gb_device_count(int* count) {
+    GB_REQUIRE(count != nullptr, "gb_device_count: count is NULL");
+    GB_CUDA(cudaGetDeviceCount(count));
+    return GB_OK;
+}
+
+template <typename T>
+static int upload(T** d, const std::vector<T>& h) {
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(d), h.size() * sizeof(T)));
+    GB_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return GB_OK;
+}
+
+extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, const double* cos_theta,
+                              const double* sin_theta, const double* kn, const double* cos_mlon,
+                              const double* sin_mlon, int device) {
+    GB_REQUIRE(plan != nullptr, "gb_plan_create: plan is NULL");
+    *plan = nullptr;
+    GB_REQUIRE(nmax >= 0 && nmax <= 2047, "gb_plan_create: nmax=%d out of range [0, 2047]", nmax);
+    GB_REQUIRE(nlat >= 1 && nlon >= 1, "gb_plan_create: empty grid (%d x %d)", nlat, nlon);
+    GB_REQUIRE(cos_theta && sin_theta && kn && cos_mlon && sin_mlon, "gb_plan_create: NULL table pointer");
+    int ndev = 0;
+    GB_CUDA(cudaGetDeviceCount(&ndev));
+    GB_REQUIRE(device >= 0 && device < ndev, "gb_plan_create: device %d not available (%d visible)", device, ndev);
+    GB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return gb_set_error(GB_ERR_UNSUPPORTED, "gb_plan_create: device %d is sm_%d%d; this library is built for sm_100a",
+                            device, prop.major, prop.minor);
+
+    gb_plan* p = new gb_plan();
+    p->device = device;
+    p->nmax = nmax;
+    p->L = nmax + 1;
+    p->nlat = nlat;
+    p->nlon = nlon;
+    p->kpad = (2 * p->L + 3) / 4 * 4;
+    p->nlp = (nlon + 7) / 8 * 8;
+    p->sm_count = prop.multiProcessorCount;
+    const int L = p->L;
+
+    // Recursion coefficients, evaluated exactly as utilities.py:46,52,54 (IEEE double, same
+    // operation order), so that the device recursion reproduces the reference table bit for bit.
+    std::vector<double> ra((size_t)L * L, 0.0), rb((size_t)L * L, 0.0), rc(L, 0.0);
+    for (int n = 0; n < L; ++n) rc[n] = std::sqrt((double)(2 * n + 1));
+    for (int n = 2; n < L; ++n)
+        for (int m = 0; m <= n - 2; ++m) {
+            const double dn = n, dm = m;
+            ra[(size_t)n * L + m] = std::sqrt((2.0 * dn - 1.0) / (dn - dm) * (2.0 * dn + 1.0) / (dn + dm));
+            rb[(size_t)n * L + m] =
+                std::sqrt((2.0 * dn + 1.0) / (2.0 * dn - 3.0) * (dn - dm - 1.0) / (dn - dm) * (dn + dm - 1.0) / (dn + dm));
+        }
+    // Sectorial seeds P_mm(theta_i) (utilities.py:37,39,41-43): O(nlat * L) values, the only part
+    // of the Legendre triangle that is tabulated; everything below the diagonal is recomputed on
+    // the fly inside the kernels.
+    std::vector<double> pmm((size_t)nlat * L);
+    for (int i = 0; i < nlat; ++i) {
+        double* row = &pmm[(size_t)i * L];
+        row[0] = 1.0;
+        if (L > 1) row[1] = std::sqrt(3.0) * sin_theta[i];
+        for (int n = 2; n < L; ++n) {
+            const double dn = n;
+            const double f = std::sqrt((2.0 * dn + 1.0) / (2.0 * dn));
+            const double fs = f * sin_theta[i];
+            row[n] = fs * row[n - 1];
+        }
+    }
+    std::vector<double> trig((size_t)p->kpad * p->nlp, 0.0);
+    for (int m = 0; m < L; ++m)
+        for (int j = 0; j < nlon; ++j) {
+            trig[(size_t)(2 * m) * p->nlp + j] = cos_mlon[(size_t)m * nlon + j];
+            if (m > 0) trig[(size_t)(2 * m + 1) * p->nlp + j] = sin_mlon[(size_t)m * nlon + j];
+        }
+    std::vector<double> ct(cos_theta, cos_theta + nlat), knv(kn, kn + (size_t)nlat * L);
+
+    int rc_ = GB_OK;
+    if ((rc_ = upload(&p->d_ct, ct)) || (rc_ = upload(&p->d_kn, knv)) || (rc_ = upload(&p->d_pmm, pmm)) ||
+        (rc_ = upload(&p->d_ra, ra)) || (rc_ = upload(&p->d_rb, rb)) || (rc_ = upload(&p->d_rc, rc)) ||
+        (rc_ = upload(&p->d_trig, trig))) {
+        gb_plan_destroy(p);
+        return rc_;
+    }
+    *plan = p;
+    return GB_OK;
+}
+
+extern "C" int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon, int* device) {
+    GB_REQUIRE(plan != nullptr, "gb_plan_info: plan is NULL");
+    if (nmax) *nmax = plan->nmax;
+    if (nlat) *nlat = plan->nlat;
+    if (nlon) *nlon = plan->nlon;
+    if (device) *device = plan->device;
+    return GB_OK;
+}
+
+extern "C" int gb_plan_destroy(gb_plan* p) {
+    if (!p) return GB_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_ct); cudaFree(p->d_kn); cudaFree(p->d_pmm); cudaFree(p->d_ra); cudaFree(p->d_rb);
+    cudaFree(p->d_rc); cudaFree(p->d_trig); cudaFree(p->d_x); cudaFree(p->d_ab);
+    cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);
+    cudaFree(p->d_lon_ops); cudaFree(p->d_lat_ops); cudaFree(p->d_lat_off);
+    delete[] p->h_lat_off;
+    if (p->s_compute) cudaStreamDestroy(p->s_compute);
+    if (p->s_copy) cudaStreamDestroy(p->s_copy);
+    for (auto& e : p->ev)
+        if (e) cudaEventDestroy(e);
+    delete p;
+    return GB_OK;
+}
+
+// Grow the synthesis / analysis workspace to hold n_epochs (never shrinks).
+int gb_plan_ensure_workspace(gb_plan* p, int n_epochs) {
+    if (n_epochs <= p->ws_epochs) return GB_OK;
+    GB_CUDA(cudaSetDevice(p->device));
+    GB_CUDA(cudaDeviceSynchronize());
+    cudaFree(p->d_x); p->d_x = nullptr;
+    cudaFree(p->d_ab); p->d_ab = nullptr;
+    p->ws_epochs = 0;
+    const long long m = (long long)n_epochs * p->nlat;
+    const long long mpad = (m + 127) / 128 * 128;
+    const size_t x_elems = (size_t)p->L * (p->L + 1) / 2 * 2 * (size_t)n_epochs;
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_x), x_elems * sizeof(double)));
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ab), (size_t)p->kpad * mpad * sizeof(double)));
+    // rows k >= 2L and padded columns must stay finite (they meet zero trig rows / masked stores)
+    GB_CUDA(cudaMemset(p->d_ab, 0, (size_t)p->kpad * mpad * sizeof(double)));
+    GB_CUDA(cudaDeviceSynchronize());
+    p->ws_epochs = n_epochs;
+    p->ws_mpad = mpad;
+    return GB_OK;
+}
+
+extern "C" int gb_host_alloc(void** ptr, uint64_t bytes) {
+    GB_REQUIRE(ptr != nullptr, "gb_host_alloc: ptr is NULL");
+    GB_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return GB_OK;
+}
+extern "C" int gb_host_free(void* ptr) {
+    if (ptr) GB_CUDA(cudaFreeHost(ptr));
+    return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe probes (roofline denominators)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gb_probe_dmma(double* out, int iters, double a, double b) {
+    double acc[8][2];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { acc[c][0] = threadIdx.x * 1e-9; acc[c][1] = c; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gb::dmma_884(acc[c][0], acc[c][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += acc[c][0] + acc[c][1];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) gb_probe_dfma(double* out, int iters, double a, double b) {
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = threadIdx.x * 1e-9 + c;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fma(acc[c], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += acc[c];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int gb_probe_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops) {
+    GB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 4;
+    double* out = nullptr;
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&out), (size_t)grid * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    GB_CUDA(cudaEventCreate(&e0));
+    GB_CUDA(cudaEventCreate(&e1));
+    const int iters = 4000;
+    float ms = 0.f;
+    double best_mma = 0, best_fma = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        GB_CUDA(cudaEventRecord(e0));
+        gb_probe_dmma<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+        GB_CUDA(cudaEventRecord(e1));
+        GB_CUDA(cudaEventSynchronize(e1));
+        GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double t1 = 2.0 * 256 * 8 * (double)iters * 8.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t1 > best_mma) best_mma = t1;
+        GB_CUDA(cudaEventRecord(e0));
+        gb_probe_dfma<<<grid, 256>>>(out, iters * 4, 1.0000001, 1e-9);
+        GB_CUDA(cudaEventRecord(e1));
+        GB_CUDA(cudaEventSynchronize(e1));
+        GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double t2 = 2.0 * 8 * (double)iters * 4 * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t2 > best_fma) best_fma = t2;
+    }
+    GB_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (dmma_tflops) *dmma_tflops = best_mma;
+    if (dfma_tflops) *dfma_tflops = best_fma;
+    return GB_OK;
+}

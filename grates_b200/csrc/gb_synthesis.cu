@@ -1,0 +1,409 @@
+// Spherical-harmonic synthesis on B200 (sm_100a), epoch-batched.
+//
+// Replaces the hot loop of PotentialCoefficients.to_grid (reference gravityfield.py:358-368):
+//
+//   V[e,i,j] = sum_m ( A[e,i,m] cos(m lon_j) + B[e,i,m] sin(m lon_j) )                (stage 2)
+//   A[e,i,m] = sum_n kn[i,n] P_nm(theta_i) C_nm^e ,  B likewise with S_nm^e           (stage 1)
+//
+// HBM layout
+//   anm   [E][L][L]          packed coefficients as the reference stores them
+//   X     order-wise packed  X_m[n-m][2e+cs], block of order m at offset 2E*(m*L - m(m-1)/2)
+//   AB    [kpad][mpad]       spectral intermediate, row k = 2m+cs, column = e*nlat + i
+//   trig  [kpad][nlp]        row 2m = cos(m lon_j), row 2m+1 = sin(m lon_j)
+//   V     [E][nlat][nlon]    output
+//
+// Kernels
+//   gb_pack_orderwise    gathers anm into X (18 MB at N=96, E=240; HBM-bound, negligible)
+//   gb_legendre_stage1   per (latitude tile, order m): runs the Legendre recursion on the fly
+//                        (unfused IEEE ops -> bit-identical to utilities.py:37-54), multiplies
+//                        kn[i,n] in, contracts against all epochs, writes AB
+//   gb_fourier_stage2    persistent FP64 tensor-core GEMM  V = AB^T * trig  (DMMA.8x8x4),
+//                        operands staged by the TMA unit (cp.async.bulk) through a 3-stage
+//                        mbarrier pipeline fed by a dedicated producer warp
+#include "gb_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// pack: anm[E][L][L] -> X
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gb_pack_orderwise(const double* __restrict__ anm, double* __restrict__ X,
+                                                         int L, int E) {
+    const int m = blockIdx.y;
+    const int cols = 2 * E;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nn = (int)(j / cols);
+    const int col = (int)(j % cols);
+    if (nn >= L - m) return;
+    const int n = m + nn;
+    const int e = col >> 1;
+    const int cs = col & 1;
+    const double* a = anm + (size_t)e * L * L;
+    double v;
+    if (cs == 0) v = a[(size_t)n * L + m];
+    else v = (m > 0) ? a[(size_t)(m - 1) * L + n] : 0.0;
+    const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
+    X[xo + (long long)nn * cols + col] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Legendre recursion for one (latitude, order): calls f(n - m, P_nm) for n = m..nmax.
+// Unfused multiplies / subtract reproduce numpy's evaluation order of utilities.py:46,52-54.
+// ---------------------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ void legendre_column(int m, int L, double ct, double pmm, const double* __restrict__ ra,
+                                                const double* __restrict__ rb, const double* __restrict__ rc, F&& f) {
+    double p2 = pmm;  // P_mm
+    f(0, p2);
+    if (m + 1 >= L) return;
+    double p1 = __dmul_rn(__dmul_rn(rc[m + 1], ct), p2);  // P_{m+1,m} = sqrt(2n+1) * cos * P_mm
+    f(1, p1);
+    for (int n = m + 2; n < L; ++n) {
+        const double a = ra[(size_t)n * L + m];
+        const double b = rb[(size_t)n * L + m];
+        const double p = __dsub_rn(__dmul_rn(__dmul_rn(a, ct), p1), __dmul_rn(b, p2));
+        f(n - m, p);
+        p2 = p1;
+        p1 = p;
+    }
+}
+
+constexpr int S1_TI = 32;  // latitudes per CTA
+
+__global__ void __launch_bounds__(256)
+gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const double* __restrict__ ct,
+                   const double* __restrict__ kn, const double* __restrict__ pmm, const double* __restrict__ ra,
+                   const double* __restrict__ rb, const double* __restrict__ rc, int L, int nlat, int E,
+                   long long mpad) {
+    extern __shared__ double s_pk[];  // [Kn][S1_TI]
+    const int m = blockIdx.y;
+    const int i0 = blockIdx.x * S1_TI;
+    const int Kn = L - m;
+    const int tid = threadIdx.x;
+    if (tid < S1_TI) {
+        const int i = i0 + tid;
+        if (i < nlat) {
+            const double* kn_i = kn + (size_t)i * L + m;
+            legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc,
+                            [&](int nn, double p) { s_pk[nn * S1_TI + tid] = __dmul_rn(p, kn_i[nn]); });
+        } else {
+            for (int nn = 0; nn < Kn; ++nn) s_pk[nn * S1_TI + tid] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    const int cols = 2 * E;
+    const int lane = tid & 31;
+    const int ig = tid >> 5;  // 8 groups of 4 latitudes
+    const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
+    const double* Xm = X + xo;
+    for (int col0 = 0; col0 < cols; col0 += 32) {
+        const int col = col0 + lane;
+        if (col >= cols) continue;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const double* xp = Xm + col;
+        const double* pk = s_pk + ig * 4;
+#pragma unroll 4
+        for (int nn = 0; nn < Kn; ++nn) {
+            const double x = __ldg(xp + (size_t)nn * cols);
+            const double2 p01 = *reinterpret_cast<const double2*>(pk + nn * S1_TI);
+            const double2 p23 = *reinterpret_cast<const double2*>(pk + nn * S1_TI + 2);
+            a0 = fma(p01.x, x, a0);
+            a1 = fma(p01.y, x, a1);
+            a2 = fma(p23.x, x, a2);
+            a3 = fma(p23.y, x, a3);
+        }
+        const int e = col >> 1, cs = col & 1;
+        const int i = i0 + ig * 4;
+        double* dst = AB + (size_t)(2 * m + cs) * mpad + (size_t)e * nlat + i;
+        if (i + 0 < nlat) dst[0] = a0;
+        if (i + 1 < nlat) dst[1] = a1;
+        if (i + 2 < nlat) dst[2] = a2;
+        if (i + 3 < nlat) dst[3] = a3;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 2: V[row][j] = sum_k AB[k][row] * trig[k][j]   (M = E*nlat rows, K = kpad, N = nlon)
+// ---------------------------------------------------------------------------------------------
+constexpr int S2_WM = 4, S2_WN = 3;            // consumer warp grid
+constexpr int S2_TM = 32 * S2_WM;              // 128 rows per CTA tile
+constexpr int S2_TN = 40 * S2_WN;              // 120 columns per CTA tile
+constexpr int S2_KC = 28;                      // spectral rows per pipeline stage
+constexpr int S2_STAGES = 3;
+constexpr int S2_LDA = S2_TM + 4;              // 132: k-rows land 4 doubles apart mod 16 -> conflict-free fragments
+constexpr int S2_LDB = S2_TN + 4;              // 124
+constexpr int S2_CONSUMER_WARPS = S2_WM * S2_WN;
+constexpr int S2_THREADS = 32 * (S2_CONSUMER_WARPS + 1);
+constexpr int S2_STAGE_DOUBLES = S2_KC * (S2_LDA + S2_LDB);
+constexpr size_t S2_SMEM = (size_t)S2_STAGES * S2_STAGE_DOUBLES * sizeof(double) + 2 * S2_STAGES * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(S2_THREADS, 1)
+gb_fourier_stage2(const double* __restrict__ AB, long long mpad, const double* __restrict__ trig, int nlp, int kpad,
+                  double* __restrict__ out, long long M, int nlon, int n_mtiles, int n_ntiles) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tiles = reinterpret_cast<double*>(s_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)S2_STAGES * S2_STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + S2_STAGES;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S2_STAGES; ++s) {
+            gb::mbar_init(&full[s], 1);
+            gb::mbar_init(&empty[s], S2_CONSUMER_WARPS);
+        }
+        gb::fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long n_tiles = (long long)n_mtiles * n_ntiles;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (warp == S2_CONSUMER_WARPS) {
+        // ===== producer warp: one bulk copy per spectral row of each operand =====
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long mt = t / n_ntiles;
+            const int nt = (int)(t % n_ntiles);
+            const long long m0 = mt * S2_TM;
+            const int n0 = nt * S2_TN;
+            const int width = min(S2_TN, nlp - n0);
+            for (int k0 = 0; k0 < kpad; k0 += S2_KC) {
+                const int kc = min(S2_KC, kpad - k0);
+                gb::mbar_wait(&empty[stage], phase ^ 1u);
+                double* sA = s_tiles + (size_t)stage * S2_STAGE_DOUBLES;
+                double* sB = sA + S2_KC * S2_LDA;
+                if (lane == 0)
+                    gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(kc * (S2_TM + width) * sizeof(double)));
+                __syncwarp();
+                if (lane < kc) {
+                    gb::bulk_g2s(sA + lane * S2_LDA, AB + (size_t)(k0 + lane) * mpad + m0,
+                                 (uint32_t)(S2_TM * sizeof(double)), &full[stage]);
+                    gb::bulk_g2s(sB + lane * S2_LDB, trig + (size_t)(k0 + lane) * nlp + n0,
+                                 (uint32_t)(width * sizeof(double)), &full[stage]);
+                }
+                if (++stage == S2_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== consumer warps: 32 x 40 register tile each, DMMA.8x8x4 =====
+        const int wm = warp / S2_WN;
+        const int wn = warp % S2_WN;
+        const int g = lane >> 2;   // fragment row / column group
+        const int q = lane & 3;    // k index inside a k4 step
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long mt = t / n_ntiles;
+            const int nt = (int)(t % n_ntiles);
+            double acc[4][5][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+            for (int k0 = 0; k0 < kpad; k0 += S2_KC) {
+                const int kc = min(S2_KC, kpad - k0);
+                gb::mbar_wait(&full[stage], phase);
+                const double* sA = s_tiles + (size_t)stage * S2_STAGE_DOUBLES + wm * 32 + g;
+                const double* sB = s_tiles + (size_t)stage * S2_STAGE_DOUBLES + S2_KC * S2_LDA + wn * 40 + g;
+#pragma unroll 1
+                for (int kk = 0; kk < kc; kk += 4) {
+                    double a[4], b[5];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * S2_LDA + mi * 8];
+#pragma unroll
+                    for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * S2_LDB + ni * 8];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                }
+                __syncwarp();
+                if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                if (++stage == S2_STAGES) { stage = 0; phase ^= 1u; }
+            }
+
+            // epilogue: streaming stores straight from the accumulator fragments
+            const long long row_base = mt * S2_TM + wm * 32 + g;
+            const int col_base = nt * S2_TN + wn * 40 + 2 * q;
+            const bool vec_ok = (nlon & 1) == 0;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const long long row = row_base + mi * 8;
+                if (row >= M) continue;
+                double* orow = out + (size_t)row * nlon;
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni) {
+                    const int col = col_base + ni * 8;
+                    if (vec_ok && col + 1 < nlon) {
+                        gb::st_cs_v2(orow + col, acc[mi][ni][0], acc[mi][ni][1]);
+                    } else {
+                        if (col < nlon) gb::st_cs(orow + col, acc[mi][ni][0]);
+                        if (col + 1 < nlon) gb::st_cs(orow + col + 1, acc[mi][ni][1]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Plain one-thread-per-output stage 2 (debug cross-check of the tensor-core kernel, GB_NAIVE_STAGE2=1).
+__global__ void __launch_bounds__(256)
+gb_fourier_stage2_naive(const double* __restrict__ AB, long long mpad, const double* __restrict__ trig, int nlp,
+                        int kpad, double* __restrict__ out, long long M, int nlon) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * nlon) return;
+    const long long row = idx / nlon;
+    const int j = (int)(idx % nlon);
+    double s = 0.0;
+    for (int k = 0; k < kpad; ++k) s = fma(AB[(size_t)k * mpad + row], trig[(size_t)k * nlp + j], s);
+    out[idx] = s;
+}
+
+// Legendre table in the reference's packed layout (bit-exactness hook).
+__global__ void __launch_bounds__(128)
+gb_legendre_table_kernel(double* __restrict__ out, const double* __restrict__ ct, const double* __restrict__ kn,
+                         const double* __restrict__ pmm, const double* __restrict__ ra, const double* __restrict__ rb,
+                         const double* __restrict__ rc, int L, int nlat, int scaled) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nlat * L) return;
+    const int i = idx / L, m = idx % L;
+    double* o = out + (size_t)i * L * L;
+    const double* kn_i = kn + (size_t)i * L;
+    legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int nn, double p) {
+        const int n = m + nn;
+        const double v = scaled ? __dmul_rn(p, kn_i[n]) : p;
+        o[(size_t)n * L + m] = v;
+        if (m > 0) o[(size_t)(m - 1) * L + n] = v;
+    });
+}
+
+bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
+}  // namespace
+
+static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_out, cudaStream_t st) {
+    const int L = p->L;
+    const long long M = (long long)E * p->nlat;
+    const long long mpad = p->ws_mpad;
+    {
+        dim3 grid((unsigned)(((long long)L * 2 * E + 255) / 256), L);
+        gb_pack_orderwise<<<grid, 256, 0, st>>>(d_anm, p->d_x, L, E);
+        GB_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid((p->nlat + S1_TI - 1) / S1_TI, L);
+        const size_t smem = (size_t)L * S1_TI * sizeof(double);
+        if (smem > 48 * 1024)
+            GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gb_legendre_stage1<<<grid, 256, smem, st>>>(p->d_x, p->d_ab, p->d_ct, p->d_kn, p->d_pmm, p->d_ra, p->d_rb,
+                                                    p->d_rc, L, p->nlat, E, mpad);
+        GB_LAUNCH_CHECK();
+    }
+    if (env_flag("GB_NAIVE_STAGE2")) {
+        const long long total = M * p->nlon;
+        gb_fourier_stage2_naive<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p->d_ab, mpad, p->d_trig, p->nlp,
+                                                                                p->kpad, d_out, M, p->nlon);
+        GB_LAUNCH_CHECK();
+    } else {
+        const int n_mtiles = (int)((M + S2_TM - 1) / S2_TM);
+        const int n_ntiles = (p->nlp + S2_TN - 1) / S2_TN;
+        const long long n_tiles = (long long)n_mtiles * n_ntiles;
+        const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
+        GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
+        gb_fourier_stage2<<<grid, S2_THREADS, S2_SMEM, st>>>(p->d_ab, mpad, p->d_trig, p->nlp, p->kpad, d_out, M,
+                                                             p->nlon, n_mtiles, n_ntiles);
+        GB_LAUNCH_CHECK();
+    }
+    return GB_OK;
+}
+
+extern "C" int gb_synthesis(gb_plan* plan, const double* d_anm, int n_epochs, double* d_out, void* stream) {
+    GB_REQUIRE(plan != nullptr, "gb_synthesis: plan is NULL");
+    GB_REQUIRE(n_epochs >= 0, "gb_synthesis: n_epochs=%d is negative", n_epochs);
+    if (n_epochs == 0) return GB_OK;
+    GB_REQUIRE(d_anm && d_out, "gb_synthesis: NULL device pointer");
+    GB_CUDA(cudaSetDevice(plan->device));
+    int rc = gb_plan_ensure_workspace(plan, n_epochs);
+    if (rc) return rc;
+    return launch_synthesis(plan, d_anm, n_epochs, d_out, static_cast<cudaStream_t>(stream));
+}
+
+static int ensure_pipeline(gb_plan* p) {
+    if (!p->s_compute) GB_CUDA(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
+    if (!p->s_copy) GB_CUDA(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+    for (auto& e : p->ev)
+        if (!e) GB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return GB_OK;
+}
+
+static int ensure_io(gb_plan* p, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > p->io_in_bytes) {
+        GB_CUDA(cudaDeviceSynchronize());
+        cudaFree(p->d_io_in);
+        p->d_io_in = nullptr; p->io_in_bytes = 0;
+        GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_io_in), in_bytes));
+        p->io_in_bytes = in_bytes;
+    }
+    if (out_bytes > p->io_out_bytes) {
+        GB_CUDA(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(p->d_io_out[b]);
+            p->d_io_out[b] = nullptr;
+        }
+        p->io_out_bytes = 0;
+        for (int b = 0; b < 2; ++b) GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_io_out[b]), out_bytes));
+        p->io_out_bytes = out_bytes;
+    }
+    return GB_OK;
+}
+
+extern "C" int gb_synthesis_host(gb_plan* plan, const double* h_anm, int n_epochs, double* h_out) {
+    GB_REQUIRE(plan != nullptr, "gb_synthesis_host: plan is NULL");
+    GB_REQUIRE(n_epochs >= 0, "gb_synthesis_host: n_epochs=%d is negative", n_epochs);
+    if (n_epochs == 0) return GB_OK;
+    GB_REQUIRE(h_anm && h_out, "gb_synthesis_host: NULL host pointer");
+    gb_plan* p = plan;
+    GB_CUDA(cudaSetDevice(p->device));
+    int rc = ensure_pipeline(p);
+    if (rc) return rc;
+    const size_t coef = (size_t)p->L * p->L;
+    const size_t pts = (size_t)p->nlat * p->nlon;
+    // chunk the epochs so that the device->host copy of chunk c overlaps the kernels of chunk c+1
+    int chunk = (n_epochs + 15) / 16;
+    if (chunk < 1) chunk = 1;
+    if ((rc = ensure_io(p, (size_t)n_epochs * coef * sizeof(double), (size_t)chunk * pts * sizeof(double)))) return rc;
+    if ((rc = gb_plan_ensure_workspace(p, chunk))) return rc;
+    GB_CUDA(cudaMemcpyAsync(p->d_io_in, h_anm, (size_t)n_epochs * coef * sizeof(double), cudaMemcpyHostToDevice,
+                            p->s_compute));
+    int c = 0;
+    for (int e0 = 0; e0 < n_epochs; e0 += chunk, ++c) {
+        const int ne = (n_epochs - e0 < chunk) ? (n_epochs - e0) : chunk;
+        const int b = c & 1;
+        if (c >= 2) GB_CUDA(cudaStreamWaitEvent(p->s_compute, p->ev[2 + b], 0));  // buffer b drained
+        if ((rc = launch_synthesis(p, p->d_io_in + (size_t)e0 * coef, ne, p->d_io_out[b], p->s_compute))) return rc;
+        GB_CUDA(cudaEventRecord(p->ev[b], p->s_compute));
+        GB_CUDA(cudaStreamWaitEvent(p->s_copy, p->ev[b], 0));
+        GB_CUDA(cudaMemcpyAsync(h_out + (size_t)e0 * pts, p->d_io_out[b], (size_t)ne * pts * sizeof(double),
+                                cudaMemcpyDeviceToHost, p->s_copy));
+        GB_CUDA(cudaEventRecord(p->ev[2 + b], p->s_copy));
+    }
+    GB_CUDA(cudaStreamSynchronize(p->s_copy));
+    GB_CUDA(cudaStreamSynchronize(p->s_compute));
+    return GB_OK;
+}
+
+extern "C" int gb_legendre_table(gb_plan* plan, double* d_out, int scaled, void* stream) {
+    GB_REQUIRE(plan != nullptr && d_out != nullptr, "gb_legendre_table: NULL argument");
+    GB_CUDA(cudaSetDevice(plan->device));
+    const int total = plan->nlat * plan->L;
+    GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)plan->nlat * plan->L * plan->L * sizeof(double),
+                            static_cast<cudaStream_t>(stream)));
+    gb_legendre_table_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_out, plan->d_ct, plan->d_kn, plan->d_pmm, plan->d_ra, plan->d_rb, plan->d_rc, plan->L, plan->nlat, scaled);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}

@@ -1,0 +1,81 @@
+"""Order-wise block filters (DDK-style) on the GPU, batched over epochs.  Mirrors
+OrderWiseFilter of grates.filter (reference filter.py:133-222)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, plan as _plan
+from .gravityfield import PotentialCoefficients
+
+
+class OrderWiseFilter:
+    """Sparse spherical-harmonic filter that only couples coefficients of the same order and
+    trigonometric function.  ``orderwise_blocks[0]`` acts on C_n0; blocks ``2m-1`` / ``2m`` act on
+    C_nm / S_nm (n = m..nmax), each of shape [(nmax+1-m), (nmax+1-m)]."""
+
+    def __init__(self, orderwise_blocks):
+        self._blocks = [np.ascontiguousarray(b, dtype=float) for b in orderwise_blocks]
+        self._nmax = self._blocks[0].shape[0] - 1
+        if len(self._blocks) != 2 * self._nmax + 1:
+            raise ValueError("expected {0} order-wise blocks for degree {1} (got {2})"
+                             .format(2 * self._nmax + 1, self._nmax, len(self._blocks)))
+        for i, b in enumerate(self._blocks):
+            k = self._nmax + 1 - (i + 1) // 2
+            if b.shape != (k, k):
+                raise ValueError("block {0} must have shape ({1}, {1}) (got {2})".format(i, k, b.shape))
+        sizes = np.array([b.size for b in self._blocks], dtype=np.int64)
+        self._offsets = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+        self._flat = np.concatenate([b.ravel() for b in self._blocks])
+        self._device_blocks = {}
+
+    @property
+    def max_degree(self):
+        return self._nmax
+
+    def _blocks_on(self, device):
+        if device not in self._device_blocks:
+            self._device_blocks[device] = torch.as_tensor(self._flat).to(torch.device("cuda", device))
+        return self._device_blocks[device]
+
+    def filter_batch(self, anm, out=None):
+        """anm: [E, L, L] packed coefficients (numpy or CUDA tensor) -> filtered copy, same type."""
+        L = anm.shape[-1]
+        nmax = L - 1
+        if nmax > self._nmax:
+            raise ValueError('DDK filter only implemented for a maximum degree of {1:d} (max_degree={0:d} supplied).'
+                             .format(nmax, self._nmax))
+        on_host = not isinstance(anm, torch.Tensor)
+        dev = _plan._current_device(None if on_host else anm.device)
+        x = torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", dev)) if on_host else anm.contiguous()
+        if x.dim() != 3 or x.shape[1] != x.shape[2] or x.dtype != torch.float64:
+            raise ValueError("coefficients must be a float64 array of shape [epochs, L, L]")
+        y = torch.empty_like(x) if out is None else out
+        lib = _lib.load()
+        _lib.check(lib.gb_orderwise_filter(ctypes.c_void_p(self._blocks_on(dev).data_ptr()),
+                                           self._offsets.ctypes.data_as(ctypes.c_void_p), self._nmax,
+                                           ctypes.c_void_p(x.data_ptr()), x.shape[0], nmax,
+                                           ctypes.c_void_p(y.data_ptr()), dev, _plan._stream_handle(dev)))
+        return y.cpu().numpy() if on_host else y
+
+    def filter(self, gravityfield):
+        """Filtered copy of a PotentialCoefficients instance (reference filter.py:153-191):
+        TypeError for other types, ValueError if its degree exceeds the filter's."""
+        if not isinstance(gravityfield, PotentialCoefficients):
+            raise TypeError("Filter operation only implemented for instances of 'PotentialCoefficients'")
+        result = gravityfield.copy()
+        result.anm = self.filter_batch(np.ascontiguousarray(gravityfield.anm, dtype=float)[None])[0]
+        return result
+
+    def matrix(self, min_degree, max_degree):
+        """Dense filter matrix in degree-wise order (reference filter.py:193-222); host side,
+        it is the F of F Sigma F' and only index bookkeeping."""
+        K = (max_degree + 1) ** 2
+        F = np.zeros((K, K))
+        idx = np.arange(max_degree + 1, dtype=int) ** 2
+        F[np.ix_(idx, idx)] = self._blocks[0][0:max_degree + 1, 0:max_degree + 1]
+        for m in range(1, max_degree + 1):
+            k = max_degree + 1 - m
+            F[np.ix_(idx[m:] + 2 * m - 1, idx[m:] + 2 * m - 1)] = self._blocks[2 * m - 1][0:k, 0:k]
+            F[np.ix_(idx[m:] + 2 * m, idx[m:] + 2 * m)] = self._blocks[2 * m][0:k, 0:k]
+        return F[min_degree * min_degree:, min_degree * min_degree:]

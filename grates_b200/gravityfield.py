@@ -1,0 +1,229 @@
+"""Potential-coefficient containers with GPU synthesis.  Mirrors PotentialCoefficients and
+TimeSeries of grates.gravityfield (reference gravityfield.py:76-421, :815-1052) for the hot
+path: same packed ``anm`` layout, same ``to_grid(grid, kernel)`` signature and return type;
+plus the batched entry points the reference lacks (its users loop over epochs,
+gravityfield.py:1143-1172).
+"""
+import numpy as np
+import torch
+
+from . import plan as _plan, utilities
+from .grid import GeographicGrid
+
+GM_DEFAULT = 3.9860044150e+14
+R_DEFAULT = 6.3781363000e+06
+
+
+def degree_indices(n, max_order=None):
+    """Packed-array indices of all coefficients of degree n: cosines by increasing order, then
+    sines (reference gravityfield.py:15-40)."""
+    count = n if max_order is None else min(n, max_order)
+    rows = np.concatenate((np.full(count + 1, n, dtype=int), np.arange(count, dtype=int)))
+    cols = np.concatenate((np.arange(count + 1, dtype=int), np.full(count, n, dtype=int)))
+    return rows, cols
+
+
+def order_indices(max_degree, m):
+    """Packed-array indices of all coefficients of order m (reference gravityfield.py:43-73)."""
+    rows = np.arange(m, max_degree + 1, dtype=int)
+    cols = np.full(rows.size, m)
+    if m > 0:
+        rows = np.concatenate((rows, np.full(max_degree + 1 - m, m - 1)))
+        cols = np.concatenate((cols, np.arange(m, max_degree + 1, dtype=int)))
+    return rows, cols
+
+
+class PotentialCoefficients:
+    """A set of potential coefficients: C_nm = anm[n, m], S_nm = anm[m-1, n]."""
+
+    def __init__(self, GM=GM_DEFAULT, R=R_DEFAULT, max_degree=None):
+        self.GM = GM
+        self.R = R
+        count = 0 if max_degree is None else max_degree + 1
+        self.anm = np.zeros((count, count))
+        self.epoch = None
+
+    def copy(self):
+        gf = PotentialCoefficients(self.GM, self.R)
+        gf.anm = self.anm.copy()
+        gf.epoch = self.epoch
+        return gf
+
+    @property
+    def max_degree(self):
+        return self.anm.shape[0] - 1
+
+    def truncate(self, max_degree):
+        if max_degree < self.max_degree:
+            self.anm = self.anm[0:max_degree + 1, 0:max_degree + 1]
+
+    def _degree_array(self):
+        idx = np.arange(self.max_degree + 1)
+        return np.maximum(idx[:, None], idx[None, :]) * (idx[None, :] > idx[:, None]) + \
+            idx[:, None] * (idx[None, :] <= idx[:, None])
+
+    def __add__(self, other):
+        if not isinstance(other, PotentialCoefficients):
+            raise TypeError("unsupported operand type(s) for +: '" + str(type(self)) + "' and '" + str(type(other)) + "'")
+        factor = (other.R / self.R) ** other._degree_array() * (other.GM / self.GM)
+        if self.max_degree >= other.max_degree:
+            result = self.copy()
+            result.anm[0:other.anm.shape[0], 0:other.anm.shape[1]] += other.anm * factor
+        else:
+            result = PotentialCoefficients(self.GM, self.R)
+            result.anm = other.anm * factor
+            result.anm[0:self.anm.shape[0], 0:self.anm.shape[1]] += self.anm
+            result.epoch = self.epoch
+        return result
+
+    def __mul__(self, other):
+        if not isinstance(other, (int, float)):
+            raise TypeError("unsupported operand type(s) for *: '" + str(type(self)) + "' and '" + str(type(other)) + "'")
+        result = self.copy()
+        result.anm *= other
+        return result
+
+    def __sub__(self, other):
+        if not isinstance(other, PotentialCoefficients):
+            raise TypeError("unsupported operand type(s) for -: '" + str(type(self)) + "' and '" + str(type(other)) + "'")
+        return self + (other * -1)
+
+    def __truediv__(self, other):
+        if not isinstance(other, (int, float)):
+            raise TypeError("unsupported operand type(s) for /: '" + str(type(self)) + "' and '" + str(type(other)) + "'")
+        return self * (1.0 / other)
+
+    @property
+    def values(self):
+        """Degree-wise ravelled coefficient vector (reference gravityfield.py:392-402)."""
+        return utilities.ravel_coefficients(self.anm)
+
+    @values.setter
+    def values(self, val):
+        if isinstance(val, np.ndarray):
+            if val.ndim > 1:
+                raise ValueError("unable to assign values of dimension {0:d} to gravity field".format(val.ndim))
+            self.anm = utilities.unravel_coefficients(val)
+        else:
+            raise ValueError("grid values must be either None or " + str(np.ndarray))
+
+    def to_grid(self, grid=None, kernel='ewh'):
+        """Gridded values of the coefficient set on a regular grid, computed on the GPU.
+
+        Parameters and return value as reference gravityfield.py:331-390: returns a deep copy
+        of ``grid`` (same class) whose ``value_array`` holds the synthesis; the input grid is
+        left untouched.  Irregular grids raise NotImplementedError (no CPU fallback).
+        """
+        grid = GeographicGrid() if grid is None else grid
+        p = _plan.get_plan(grid, self.max_degree, kernel, self.GM, self.R)
+        output_grid = grid.copy()
+        result = p.synthesis_host(np.ascontiguousarray(self.anm, dtype=float)[None])
+        output_grid.values = result.reshape(-1)
+        return output_grid
+
+
+class TimeSeries:
+    """Epoch-sorted list of gravity fields (reference gravityfield.py:815-1052)."""
+
+    def __init__(self, data):
+        self._data = list(data)
+        self._dtype = type(self._data[0])
+        for d in self._data:
+            if not isinstance(d, self._dtype):
+                raise ValueError("Found inconsistent data types (" + str(self._dtype) + " and " + str(type(d)) + ")")
+            if d.epoch is None:
+                raise ValueError("At least one data point has no valid time stamp")
+        self.sort()
+
+    def __len__(self):
+        return len(self._data)
+
+    def __getitem__(self, index):
+        return self._data[index]
+
+    def sort(self):
+        self._data.sort(key=lambda d: d.epoch)
+
+    def items(self):
+        for d in self._data:
+            yield d.epoch, d
+
+    def epochs(self):
+        return [d.epoch for d in self._data]
+
+    def copy(self):
+        return TimeSeries([d.copy() for d in self._data])
+
+    def interpolate_to(self, epoch):
+        """Piecewise linear interpolation to an epoch inside the series (reference
+        gravityfield.py:915-946); extrapolation raises ValueError."""
+        t = np.array([d.epoch for d in self._data])
+        if t.size < 2:
+            raise ValueError("at least two data points are required for interpolation")
+        if epoch < t[0] or epoch > t[-1]:
+            raise ValueError("extrapolation is not supported (trying to extrapolate to " + str(epoch) +
+                             " from the interval " + str(t[0]) + ", " + str(t[-1]) + ")")
+        idx = max(int(np.searchsorted(t, epoch)), 1)
+        weight = (epoch - t[idx - 1]).total_seconds() / (t[idx] - t[idx - 1]).total_seconds()
+        output = self._data[idx - 1] * (1 - weight) + self._data[idx] * weight
+        output.epoch = epoch
+        return output
+
+    def evaluate_at(self, epoch):
+        return self.interpolate_to(epoch)
+
+    def to_array(self):
+        """[epochs, (N+1)^2] matrix in degree-wise order (reference gravityfield.py:964-980)."""
+        width = self._data[0].values.size
+        return np.stack([d.values[0:width] for d in self._data])
+
+    def to_packed(self):
+        """[epochs, L, L] packed coefficient array (zero-padded to the largest degree)."""
+        L = max(d.anm.shape[0] for d in self._data)
+        out = np.zeros((len(self._data), L, L))
+        for k, d in enumerate(self._data):
+            out[k, :d.anm.shape[0], :d.anm.shape[1]] = d.anm
+        return out
+
+    def to_grid(self, grid=None, kernel='ewh', device_output=False, out=None):
+        """Synthesis of the whole series in one batched GPU call -> [epochs, nlat, nlon]
+        (numpy, or a CUDA tensor with ``device_output=True``)."""
+        first = self._data[0]
+        for d in self._data:
+            if d.GM != first.GM or d.R != first.R:
+                raise ValueError("all epochs of a batched synthesis must share GM and R")
+        return to_grid_batch(self.to_packed(), grid, kernel, first.GM, first.R, device_output=device_output, out=out)
+
+
+def to_grid_batch(anm, grid=None, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT, device_output=False, out=None):
+    """Batched synthesis.  anm: [E, L, L] packed coefficients (numpy array or CUDA float64
+    tensor).  Returns [E, nlat, nlon]; with a CUDA tensor input (or device_output=True) the
+    result stays on the device, otherwise it is copied to the host inside the call."""
+    grid = GeographicGrid() if grid is None else grid
+    L = anm.shape[-1]
+    p = _plan.get_plan(grid, L - 1, kernel, GM, R)
+    if isinstance(anm, torch.Tensor):
+        return p.synthesis(anm, out=out)
+    if device_output:
+        dev = torch.device("cuda", p.device)
+        return p.synthesis(torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(dev), out=out)
+    return p.synthesis_host(anm, out=out)
+
+
+def gridded_rms(temporal_gravityfield, epochs, kernel='ewh', base_grid=None):
+    """Temporal RMS of gridded values over ``epochs`` (reference gravityfield.py:1143-1172).
+    The reference synthesises epoch by epoch; here all epochs go through one batched GPU
+    synthesis and the sum of squares is reduced on the device."""
+    base_grid = GeographicGrid() if base_grid is None else base_grid
+    fields = [temporal_gravityfield.evaluate_at(t) for t in epochs]
+    if not fields:
+        raise ValueError("no epochs selected")
+    L = max(f.anm.shape[0] for f in fields)
+    packed = np.zeros((len(fields), L, L))
+    for k, f in enumerate(fields):
+        packed[k, :f.anm.shape[0], :f.anm.shape[1]] = f.anm
+    values = to_grid_batch(packed, base_grid, kernel, fields[0].GM, fields[0].R, device_output=True)
+    rms = torch.sqrt(torch.sum(values * values, dim=0) / len(fields))
+    grid = base_grid.copy()
+    grid.values = rms.cpu().numpy().reshape(-1)
+    return grid

@@ -1,0 +1,191 @@
+"""Regular grids (parallels x meridians on the ellipsoid) with GPU-backed analysis and
+covariance propagation.  Mirrors RegularGrid / GeographicGrid / GaussGrid of grates.grid
+(reference grid.py:510-839, :1123-1204) for the spherical-harmonic hot path: same
+constructor arguments, attributes (``parallels``, ``meridians``, ``value_array``, ``values``,
+``area``, ``epoch``), return types and error behaviour.  Irregular point sets are not part of
+this path and raise instead of falling back to the CPU.
+"""
+import numpy as np
+import torch
+
+from . import plan as _plan
+
+GM_DEFAULT = 3.9860044150e+14
+R_DEFAULT = 6.3781363000e+06
+
+
+class RegularGrid:
+    """Global regular point distribution defined by meridians [rad] and parallels [rad]
+    (north to south).  area_elements: optional [nlat, nlon] weights (reference grid.py:529-542)."""
+
+    def __init__(self, meridians, parallels, area_elements=None, a=6378137.0, f=298.2572221010 ** -1):
+        self.parallels = np.asarray(parallels, dtype=float)
+        self.meridians = np.asarray(meridians, dtype=float)
+        self._a, self._f = a, f
+        if area_elements is None:
+            lon_edges = np.concatenate(([-np.pi], self.meridians[0:-1] + 0.5 * np.diff(self.meridians), [np.pi]))
+            lat_edges = np.concatenate(([0.5 * np.pi], self.parallels[0:-1] + 0.5 * np.diff(self.parallels), [-0.5 * np.pi]))
+            area_elements = 2.0 * (np.sin(np.abs(np.diff(lat_edges)) * 0.5) * np.cos(self.parallels))[:, None] * np.diff(lon_edges)
+        self._areas = area_elements
+        self.value_array = None
+        self.epoch = None
+
+    # -- container behaviour (reference grid.py:544-625) ----------------------------------
+    def copy(self):
+        grid = RegularGrid(self.meridians.copy(), self.parallels.copy(), self._areas.copy(), self._a, self._f)
+        if self.value_array is not None:
+            grid.values = self.values.copy()
+        grid.epoch = self.epoch
+        return grid
+
+    @property
+    def semimajor_axis(self):
+        return self._a
+
+    @property
+    def flattening(self):
+        return self._f
+
+    @property
+    def point_count(self):
+        return self.parallels.size * self.meridians.size
+
+    @property
+    def size(self):
+        return self.point_count
+
+    @property
+    def longitude(self):
+        return np.tile(self.meridians, self.parallels.size)
+
+    @property
+    def latitude(self):
+        return np.repeat(self.parallels, self.meridians.size)
+
+    @property
+    def area(self):
+        return self._areas.ravel()
+
+    @property
+    def values(self):
+        if self.value_array is not None:
+            return self.value_array.ravel()
+
+    @values.setter
+    def values(self, val):
+        if val is None:
+            self.value_array = None
+        elif isinstance(val, np.ndarray):
+            if val.ndim > 1:
+                raise ValueError("unable to assign values of dimension {0:d} to grid".format(val.ndim))
+            if val.size != self.point_count:
+                raise ValueError("unable to assign values of size {0:d} to grid with {1:d} points".format(val.size, self.point_count))
+            self.value_array = np.reshape(val, (self.parallels.size, self.meridians.size))
+        else:
+            raise ValueError("grid values must be either None or " + str(np.ndarray))
+
+    def is_compatible(self, other):
+        if self.point_count == other.point_count:
+            return np.allclose(self.longitude, other.longitude) and np.allclose(self.latitude, other.latitude)
+        return False
+
+    # -- weighted statistics (reference grid.py:174-260) ----------------------------------
+    def _masked(self, mask):
+        mask = np.ones(self.point_count, dtype=bool) if mask is None else mask
+        return self.area[mask], self.values[mask]
+
+    def mean(self, mask=None):
+        w, v = self._masked(mask)
+        return np.sum(w * v) / np.sum(w)
+
+    def rms(self, mask=None):
+        w, v = self._masked(mask)
+        return np.sqrt(np.sum(w * v ** 2) / np.sum(w))
+
+    def std(self, mask=None):
+        w, v = self._masked(mask)
+        v = v - self.mean(mask)
+        return np.sqrt(np.sum(w * v ** 2) / np.sum(w))
+
+    # -- hot path ------------------------------------------------------------------------
+    def to_potential_coefficients(self, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+        """Spherical-harmonic analysis of the grid values on the GPU; same estimator as the
+        reference's order-by-order area-weighted least squares (grid.py:752-790).
+
+        Returns a PotentialCoefficients whose degrees below ``min_degree`` are zero.
+        Raises ValueError if the grid holds no values.
+        """
+        from .gravityfield import PotentialCoefficients
+        if self.values is None:
+            raise ValueError('grid has no values to propagate to potential coefficients')
+        anm = analysis_batch(self.value_array[None], self, min_degree, max_degree, kernel, GM, R)[0]
+        coeffs = PotentialCoefficients(GM, R)
+        coeffs.anm = anm
+        return coeffs
+
+    def covariance_propagation(self, covariance_matrix, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+        """Propagate a degree-wise ordered coefficient covariance matrix to grid-point standard
+        deviations, sqrt(diag(A Sigma A')), on the GPU.  Like the reference (grid.py:792-839)
+        this also stores the result in ``self.values`` and returns a 1-d array."""
+        p = _plan.get_plan(self, max_degree, kernel, GM, R)
+        sigma = torch.as_tensor(np.ascontiguousarray(covariance_matrix, dtype=np.float64)).to(torch.device("cuda", p.device))
+        std = p.covariance_propagation(sigma, min_degree).cpu().numpy().ravel()
+        self.values = std
+        return std.copy()
+
+
+class GeographicGrid(RegularGrid):
+    """Equi-angular geographic grid of pixel centres (reference grid.py:1141-1162)."""
+
+    def __init__(self, dlon=0.5, dlat=0.5, a=6378137.0, f=298.2572221010 ** -1):
+        self._dlon, self._dlat = dlon, dlat
+        nlons, nlats = 360 / dlon, 180 / dlat
+        meridians = np.linspace(-np.pi + dlon / 180 * np.pi * 0.5, np.pi - dlon / 180 * np.pi * 0.5, int(nlons))
+        parallels = -np.linspace(-np.pi * 0.5 + dlat / 180 * np.pi * 0.5, np.pi * 0.5 - dlat / 180 * np.pi * 0.5, int(nlats))
+        areas = np.tile(2.0 * dlon / 180 * np.pi * np.sin(dlat * 0.5 / 180 * np.pi) * np.cos(parallels)[:, None], (1, meridians.size))
+        super().__init__(meridians, parallels, areas, a, f)
+
+    def copy(self):
+        grid = GeographicGrid(self._dlon, self._dlat, self.semimajor_axis, self.flattening)
+        if self.values is not None:
+            grid.values = self.values.copy()
+        grid.epoch = self.epoch
+        return grid
+
+
+class GaussGrid(RegularGrid):
+    """Gaussian grid: parallels at the Legendre roots (reference grid.py:1181-1204)."""
+
+    def __init__(self, parallel_count, a=6378137.0, f=298.2572221010 ** -1):
+        from scipy.special import roots_legendre
+        zeros, weights, _ = roots_legendre(parallel_count, mu=True)
+        dlon = np.pi / parallel_count
+        meridians = np.linspace(-np.pi + dlon * 0.5, np.pi - dlon * 0.5, 2 * parallel_count)
+        cosine_theta = -zeros
+        sine_theta = np.sqrt(1 - cosine_theta ** 2)
+        parallels = np.arctan2(cosine_theta, (1 - f) ** 2 * sine_theta)
+        areas = np.tile(dlon * weights[:, None], (1, meridians.size))
+        super().__init__(meridians, parallels, areas, a, f)
+
+    def copy(self):
+        grid = GaussGrid(self.parallels.size, self.semimajor_axis, self.flattening)
+        if self.value_array is not None:
+            grid.values = self.values.copy()
+        grid.epoch = self.epoch
+        return grid
+
+
+def analysis_batch(values, grid, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT, device_output=False):
+    """Batched analysis: values [E, nlat, nlon] (numpy or CUDA tensor) -> packed anm [E, L, L].
+    New entry point (the reference loops over epochs and rebuilds its operators every call)."""
+    if min_degree < 0 or max_degree < min_degree:
+        raise ValueError("invalid degree range [{0}, {1}]".format(min_degree, max_degree))
+    p = _plan.get_plan(grid, max_degree, kernel, GM, R)
+    p.set_analysis(min_degree, grid.area.reshape(p.nlat, p.nlon))
+    if isinstance(values, torch.Tensor):
+        out = p.analysis(values)
+        return out if device_output else out.cpu().numpy()
+    out = p.analysis_host(np.asarray(values, dtype=float))
+    if device_output:
+        return torch.as_tensor(out).to(torch.device("cuda", p.device))
+    return out

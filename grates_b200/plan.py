@@ -1,0 +1,325 @@
+"""Plans: the epoch-independent device tables of one (grid geometry, degree, kernel, GM, R)
+combination, cached so that repeated ``to_grid`` / analysis / covariance calls pay for table
+construction once.  torch is used for device memory and streams only.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib, kernel as _kernel, utilities
+
+_cache = {}
+_cache_lock = threading.Lock()
+_MAX_CACHED_PLANS = 16
+
+
+def _current_device(device=None):
+    _lib.require_device()
+    if device is None:
+        return torch.cuda.current_device()
+    return torch.device(device).index if not isinstance(device, int) else device
+
+
+def _ptr(array):
+    return array.ctypes.data_as(ctypes.c_void_p)
+
+
+def _stream_handle(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class PinnedArray:
+    """numpy view on page-locked host memory from gb_host_alloc (full PCIe rate for *_host calls)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._lib = _lib.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._raw = ctypes.c_void_p()
+        _lib.check(self._lib.gb_host_alloc(ctypes.byref(self._raw), self.nbytes))
+        buf = (ctypes.c_char * max(self.nbytes, 1)).from_address(self._raw.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._raw is not None and self._raw.value:
+            self.array = None
+            self._lib.gb_host_free(self._raw)
+            self._raw = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SHPlan:
+    """Device-resident tables for one regular grid + kernel; wraps ``gb_plan``.
+
+    Parameters mirror what reference ``to_grid`` derives per call (gravityfield.py:353-365):
+    parallels / meridians in radians, ellipsoid (a, f), maximum degree, kernel name, GM, R.
+    """
+
+    def __init__(self, meridians, parallels, a, f, max_degree, kernel='ewh',
+                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
+        self._lib = _lib.load()
+        self.device = _current_device(device)
+        self.max_degree = int(max_degree)
+        self.meridians = np.ascontiguousarray(meridians, dtype=float)
+        self.parallels = np.ascontiguousarray(parallels, dtype=float)
+        self.a, self.f = a, f
+        self.kernel, self.GM, self.R = kernel, GM, R
+        self.nlat, self.nlon = self.parallels.size, self.meridians.size
+        colat, kn = _kernel.degree_factors(kernel, self.max_degree, self.parallels, a, f, GM, R)
+        if not np.all(np.isfinite(kn)):
+            raise ValueError("kernel '{0}' has non-finite degree factors on this grid".format(kernel))
+        self.colat, self.kn = colat, kn
+        cos_t = np.ascontiguousarray(np.cos(colat))
+        sin_t = np.ascontiguousarray(np.sin(colat))
+        cos_ml, sin_ml = utilities.trig_tables(self.max_degree, self.meridians)
+        handle = ctypes.c_void_p()
+        _lib.check(self._lib.gb_plan_create(ctypes.byref(handle), self.max_degree, self.nlat, self.nlon,
+                                            _ptr(cos_t), _ptr(sin_t), _ptr(kn), _ptr(cos_ml), _ptr(sin_ml),
+                                            self.device))
+        self._handle = handle
+        self._analysis_nmin = None
+        self._areas_key = None
+
+    # -- life cycle ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.gb_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def L(self):
+        return self.max_degree + 1
+
+    def _check_anm(self, anm):
+        if anm.dim() != 3 or anm.shape[1] != self.L or anm.shape[2] != self.L:
+            raise ValueError("coefficients must have shape [epochs, {0}, {0}] (got {1})".format(self.L, tuple(anm.shape)))
+        if anm.dtype != torch.float64 or not anm.is_cuda or anm.device.index != self.device:
+            raise ValueError("coefficients must be a float64 CUDA tensor on device {0}".format(self.device))
+
+    # -- synthesis ----------------------------------------------------------------------
+    def synthesis(self, anm, out=None):
+        """anm: CUDA float64 tensor [E, L, L] (packed) -> CUDA tensor [E, nlat, nlon]."""
+        self._check_anm(anm)
+        anm = anm.contiguous()
+        E = anm.shape[0]
+        if out is None:
+            out = torch.empty((E, self.nlat, self.nlon), dtype=torch.float64, device=anm.device)
+        elif tuple(out.shape) != (E, self.nlat, self.nlon) or out.dtype != torch.float64 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float64 tensor of shape [E, nlat, nlon]")
+        _lib.check(self._lib.gb_synthesis(self._handle, ctypes.c_void_p(anm.data_ptr()), E,
+                                          ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+        return out
+
+    def synthesis_host(self, anm, out=None):
+        """anm: numpy [E, L, L] -> numpy [E, nlat, nlon]; copies both ways inside the call."""
+        anm = np.ascontiguousarray(anm, dtype=np.float64)
+        if anm.ndim != 3 or anm.shape[1:] != (self.L, self.L):
+            raise ValueError("coefficients must have shape [epochs, {0}, {0}] (got {1})".format(self.L, anm.shape))
+        E = anm.shape[0]
+        if out is None:
+            out = np.empty((E, self.nlat, self.nlon))
+        elif out.shape != (E, self.nlat, self.nlon) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape [E, nlat, nlon]")
+        _lib.check(self._lib.gb_synthesis_host(self._handle, _ptr(anm), E, _ptr(out)))
+        return out
+
+    def legendre_table(self, scaled=False):
+        """Packed Legendre table [nlat, L, L] from the on-the-fly recursion (parity hook)."""
+        out = torch.empty((self.nlat, self.L, self.L), dtype=torch.float64, device=torch.device("cuda", self.device))
+        _lib.check(self._lib.gb_legendre_table(self._handle, ctypes.c_void_p(out.data_ptr()), int(bool(scaled)),
+                                               _stream_handle(self.device)))
+        return out
+
+    # -- analysis -----------------------------------------------------------------------
+    def set_analysis(self, min_degree, areas):
+        """Build the separable least-squares operators of reference grid.py:665-696 for the
+        plan's grid (host, once) and upload them.  areas: [nlat, nlon] area weights."""
+        areas = np.asarray(areas, dtype=float).reshape(self.nlat, self.nlon)
+        key = (int(min_degree), hash(areas.tobytes()))
+        if self._analysis_nmin == key:
+            return
+        if 2 * self.max_degree >= self.nlon:
+            raise ValueError("analysis up to degree {0} needs more than {1} meridians (got {2})"
+                             .format(self.max_degree, 2 * self.max_degree, self.nlon))
+        w_lat, u_lon = separable_weights(areas)
+        lon_ops, lat_ops, offsets = analysis_operators(self, int(min_degree), w_lat, u_lon)
+        _lib.check(self._lib.gb_plan_set_analysis(self._handle, int(min_degree), _ptr(lon_ops), _ptr(lat_ops),
+                                                  _ptr(offsets)))
+        self._analysis_nmin = key
+        self.analysis_min_degree = int(min_degree)
+
+    def analysis(self, values, out=None):
+        """values: CUDA tensor [E, nlat, nlon] -> packed coefficients [E, L, L] (CUDA)."""
+        if self._analysis_nmin is None:
+            raise RuntimeError("call set_analysis() first")
+        if values.dim() != 3 or tuple(values.shape[1:]) != (self.nlat, self.nlon):
+            raise ValueError("grid values must have shape [epochs, {0}, {1}]".format(self.nlat, self.nlon))
+        if values.dtype != torch.float64 or not values.is_cuda or values.device.index != self.device:
+            raise ValueError("grid values must be a float64 CUDA tensor on device {0}".format(self.device))
+        values = values.contiguous()
+        E = values.shape[0]
+        if out is None:
+            out = torch.empty((E, self.L, self.L), dtype=torch.float64, device=values.device)
+        _lib.check(self._lib.gb_analysis(self._handle, ctypes.c_void_p(values.data_ptr()), E,
+                                         ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+        return out
+
+    def analysis_host(self, values, out=None):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if values.ndim != 3 or values.shape[1:] != (self.nlat, self.nlon):
+            raise ValueError("grid values must have shape [epochs, {0}, {1}]".format(self.nlat, self.nlon))
+        if self._analysis_nmin is None:
+            raise RuntimeError("call set_analysis() first")
+        E = values.shape[0]
+        if out is None:
+            out = np.empty((E, self.L, self.L))
+        _lib.check(self._lib.gb_analysis_host(self._handle, _ptr(values), E, _ptr(out)))
+        return out
+
+    # -- covariance propagation ---------------------------------------------------------
+    def covariance_propagation(self, sigma, min_degree, row0=0, nrows=None, take_sqrt=True, out=None):
+        """sigma: CUDA tensor [K', K'] (degree-wise order, offset min_degree^2) ->
+        [nrows, nlon] standard deviations (or variances) for parallels row0..row0+nrows."""
+        nrows = self.nlat - row0 if nrows is None else nrows
+        kp = self.L ** 2 - min_degree ** 2
+        if sigma.dim() != 2 or tuple(sigma.shape) != (kp, kp):
+            raise ValueError("covariance matrix must have shape [{0}, {0}] (got {1})".format(kp, tuple(sigma.shape)))
+        if sigma.dtype != torch.float64 or not sigma.is_cuda or sigma.device.index != self.device:
+            raise ValueError("covariance matrix must be a float64 CUDA tensor on device {0}".format(self.device))
+        sigma = sigma.contiguous()
+        if out is None:
+            out = torch.empty((nrows, self.nlon), dtype=torch.float64, device=sigma.device)
+        _lib.check(self._lib.gb_covariance_propagation(self._handle, ctypes.c_void_p(sigma.data_ptr()),
+                                                       int(min_degree), int(row0), int(nrows),
+                                                       ctypes.c_void_p(out.data_ptr()), int(bool(take_sqrt)),
+                                                       _stream_handle(self.device)))
+        return out
+
+
+def separable_weights(areas):
+    """Factor areas[nlat, nlon] into w_lat[:, None] * u_lon[None, :].  The order-by-order analysis
+    of the reference is only separable for rank-one area weights (all grids it constructs itself
+    have them: grid.py:540, :1151, :1193); anything else is rejected, not approximated."""
+    j0 = int(np.argmax(np.abs(areas).sum(axis=0)))
+    i0 = int(np.argmax(np.abs(areas[:, j0])))
+    if areas[i0, j0] == 0:
+        raise ValueError('area elements are all zero')
+    w_lat = areas[:, j0].copy()
+    u_lon = areas[i0, :] / areas[i0, j0]
+    if not np.allclose(w_lat[:, None] * u_lon[None, :], areas, rtol=1e-12, atol=0):
+        raise ValueError('area elements are not separable into latitude and longitude factors; '
+                         'the B200 analysis path does not support this grid')
+    return w_lat, u_lon
+
+
+def _legendre_per_order_host(nmax, m, colat):
+    """Per-order Legendre columns with s = sqrt(1 - t^2), the variant the reference's analysis
+    uses (utilities.py:62-115, order 0 via :138-151).  Host side: enters only the small
+    plan-time least-squares operators."""
+    t = np.cos(colat)
+    cnt = nmax + 1 - m
+    out = np.empty((t.size, cnt))
+    if m == 0:
+        out[:, 0] = 1
+        if nmax >= 1:
+            out[:, 1] = np.sqrt(3) * t
+        for n in range(2, nmax + 1):
+            out[:, n] = np.sqrt((2.0 * n - 1.0) * (2.0 * n + 1.0)) / n * t * out[:, n - 1] - \
+                np.sqrt((2.0 * n + 1.0) / (2.0 * n - 3.0)) * (n - 1.0) / n * out[:, n - 2]
+        return out
+    s = np.sqrt(1 - t ** 2)
+    pmm = np.sqrt(3) * s
+    for n in range(2, m + 1):
+        pmm = np.sqrt((2 * n + 1) / (2 * n)) * s * pmm
+    out[:, 0] = pmm
+    if cnt > 1:
+        out[:, 1] = np.sqrt(2 * m + 3) * t * out[:, 0]
+    for n in range(m + 2, nmax + 1):
+        out[:, n - m] = np.sqrt((2 * n - 1) / (n - m) * (2 * n + 1) / (n + m)) * t * out[:, n - 1 - m] - \
+            np.sqrt((2 * n + 1) / (2 * n - 3) * (n - m - 1) / (n - m) * (n + m - 1) / (n + m)) * out[:, n - 2 - m]
+    return out
+
+
+def analysis_operators(plan, min_degree, w_lat, u_lon):
+    """Host construction of the separable analysis operators (see gb_plan_set_analysis)."""
+    L, nlon, nlat = plan.L, plan.nlon, plan.nlat
+    lam = plan.meridians
+    lon_ops = np.zeros((2 * L, nlon))
+    for m in range(L):
+        c = np.cos(m * lam)
+        lon_ops[2 * m] = u_lon * c / np.sum(u_lon * c * c)
+        if m > 0:
+            s = np.sin(m * lam)
+            lon_ops[2 * m + 1] = u_lon * s / np.sum(u_lon * s * s)
+    blocks, offsets = [], np.zeros(L + 1, dtype=np.int64)
+    for m in range(L):
+        P = (_legendre_per_order_host(plan.max_degree, m, plan.colat) * plan.kn[:, m:])[:, max(min_degree - m, 0):]
+        if P.shape[1] == 0:
+            op = np.zeros((0, nlat))
+        else:
+            PW = (P * w_lat[:, None]).T
+            op = np.linalg.solve(PW @ P, PW)
+        blocks.append(np.ascontiguousarray(op).ravel())
+        offsets[m + 1] = offsets[m] + op.size
+    lat_ops = np.concatenate(blocks) if offsets[-1] > 0 else np.zeros(1)
+    return np.ascontiguousarray(lon_ops), np.ascontiguousarray(lat_ops), offsets
+
+
+def get_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
+    """Cached plan for a regular grid object exposing .meridians/.parallels/.semimajor_axis/.flattening."""
+    try:
+        meridians, parallels = grid.meridians, grid.parallels
+    except AttributeError:
+        raise NotImplementedError("the B200 path handles regular grids (meridians x parallels); "
+                                  "irregular point sets are not supported and there is no CPU fallback") from None
+    dev = _current_device(device)
+    key = (np.asarray(meridians, dtype=float).tobytes(), np.asarray(parallels, dtype=float).tobytes(),
+           float(grid.semimajor_axis), float(grid.flattening), int(max_degree), kernel.lower(), float(GM), float(R), dev)
+    with _cache_lock:
+        plan = _cache.get(key)
+        if plan is None:
+            plan = SHPlan(meridians, parallels, grid.semimajor_axis, grid.flattening, max_degree, kernel, GM, R, dev)
+            if len(_cache) >= _MAX_CACHED_PLANS:
+                _cache.pop(next(iter(_cache))).close()
+            _cache[key] = plan
+        return plan
+
+
+def clear_plan_cache():
+    with _cache_lock:
+        for plan in _cache.values():
+            plan.close()
+        _cache.clear()
+
+
+def legendre_table_for_colatitudes(max_degree, colat, device=None):
+    """utilities.legendre_functions for arbitrary colatitudes via the device recursion."""
+    lib = _lib.load()
+    dev = _current_device(device)
+    L = max_degree + 1
+    cos_t = np.ascontiguousarray(np.cos(colat))
+    sin_t = np.ascontiguousarray(np.sin(colat))
+    kn = np.ones((colat.size, L))
+    dummy = np.ones((L, 1))
+    handle = ctypes.c_void_p()
+    _lib.check(lib.gb_plan_create(ctypes.byref(handle), max_degree, colat.size, 1, _ptr(cos_t), _ptr(sin_t), _ptr(kn),
+                                  _ptr(dummy), _ptr(dummy), dev))
+    try:
+        out = torch.empty((colat.size, L, L), dtype=torch.float64, device=torch.device("cuda", dev))
+        _lib.check(lib.gb_legendre_table(handle, ctypes.c_void_p(out.data_ptr()), 0, _stream_handle(dev)))
+        result = out.cpu().numpy()
+    finally:
+        lib.gb_plan_destroy(handle)
+    return result

@@ -1,0 +1,155 @@
+/*
+ * grates_b200 -- C ABI of the B200 (sm_100a) spherical-harmonic hot path of akvas/grates.
+ *
+ * The reference (pure Python/numpy) has no FFI; the boundary it offers is its Python method
+ * signatures.  Each entry point below replaces the numpy/BLAS body of one of those methods
+ * (citations are relative to /root/reference/grates/).  The Python host side
+ * (grates_b200/*.py) builds the small epoch-independent tables with the reference's exact
+ * numpy expressions and calls these functions through ctypes; see INTEGRATION.md for the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - All floating-point data are IEEE double, C-contiguous.
+ *  - "packed" coefficient arrays are the reference's anm[L][L] layout (gravityfield.py:149-159):
+ *    C_nm = anm[n][m] (m <= n), S_nm = anm[m-1][n] (m >= 1), L = nmax + 1.
+ *  - Grid values are [nlat][nlon], rows north -> south, columns west -> east (grid.py:1149-1150).
+ *  - Covariance matrices and ravelled vectors are in the degree-wise order of
+ *    utilities.py:310-360 (index of C_nm = n^2 + max(2m-1, 0), of S_nm = n^2 + 2m), offset nmin^2.
+ *  - Pointers named d_* are device pointers on the plan's device, h_* are host pointers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
+ *    points are asynchronous with respect to the host; *_host entry points return after the
+ *    result is in the host buffer.
+ *  - The library never frees caller memory and returns no owning pointer except gb_plan*.
+ *  - Return value: GB_OK or an error code; gb_last_error() gives the thread-local message.
+ *  - There is no CPU fallback anywhere: without a CUDA device every compute call fails.
+ */
+#ifndef GRATES_B200_H
+#define GRATES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_OK 0
+#define GB_ERR_ARGUMENT 1
+#define GB_ERR_CUDA 2
+#define GB_ERR_UNSUPPORTED 3
+#define GB_ERR_MEMORY 4
+
+typedef struct gb_plan gb_plan;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int gb_version(void);
+
+/* Thread-local description of the last error returned on this thread. */
+const char* gb_last_error(void);
+
+/* Number of visible CUDA devices (fails with GB_ERR_CUDA if the driver is unusable). */
+int gb_device_count(int* count);
+
+/*
+ * Plan = the epoch-independent tables of one (grid geometry, nmax, kernel, GM, R) combination,
+ * resident on one device.  Replaces the per-call table construction of
+ * PotentialCoefficients.to_grid (gravityfield.py:353-365) and
+ * RegularGrid.covariance_propagation (grid.py:819-831).
+ *
+ *   cos_theta, sin_theta [nlat]   cos / sin of the geocentric colatitude of each parallel
+ *                                 (utilities.py:438-459 then np.cos / np.sin, utilities.py:38-39)
+ *   kn [nlat][nmax+1]             inverse kernel factor x upward continuation x GM/R
+ *                                 (gravityfield.py:356 == grid.py:657 == grid.py:823)
+ *   cos_mlon, sin_mlon [nmax+1][nlon]   cos(m*lon_j), sin(m*lon_j) (utilities.py:271-273)
+ *
+ * The fully normalised Legendre functions themselves are NOT passed in: the kernels run the
+ * recursion of utilities.py:37-54 on the fly, per latitude tile, with unfused IEEE multiplies
+ * and subtracts so that every P_nm is bit-identical to the reference's table.
+ */
+int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon,
+                   const double* cos_theta, const double* sin_theta, const double* kn,
+                   const double* cos_mlon, const double* sin_mlon, int device);
+int gb_plan_destroy(gb_plan* plan);
+
+/* Geometry queries (for the host wrapper). */
+int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon, int* device);
+
+/*
+ * Spherical-harmonic synthesis of n_epochs coefficient sets onto the plan's grid.
+ * Replaces the body of PotentialCoefficients.to_grid, gravityfield.py:358-368, for a batch:
+ *   out[e][i][j] = sum_n kn[i][n] sum_m P_nm(theta_i) (C_nm^e cos m lon_j + S_nm^e sin m lon_j)
+ *   d_anm [n_epochs][L][L] packed, d_out [n_epochs][nlat][nlon].
+ */
+int gb_synthesis(gb_plan* plan, const double* d_anm, int n_epochs, double* d_out, void* stream);
+
+/*
+ * Same through host buffers: copies the coefficients to the device, runs the kernels in
+ * epoch chunks and copies each finished chunk back while the next one computes.
+ * Pinned host buffers (gb_host_alloc) give the full PCIe rate; pageable ones work too.
+ */
+int gb_synthesis_host(gb_plan* plan, const double* h_anm, int n_epochs, double* h_out);
+
+/*
+ * Bit-exact check hook: the on-the-fly Legendre recursion written out as a table, scaled by
+ * kn, in the reference's packed layout.  d_out [nlat][L][L]; with scaled == 0 the kn factor is
+ * left out and the result equals utilities.legendre_functions (utilities.py:13-59) bit for bit.
+ */
+int gb_legendre_table(gb_plan* plan, double* d_out, int scaled, void* stream);
+
+/*
+ * Spherical-harmonic analysis (area-weighted least squares, order by order), batched.
+ * Replaces RegularGrid.to_potential_coefficients, grid.py:776-785.  The per-order operators
+ * solve(A'WA, A'W) of grid.py:690-696 are separable on a regular grid with rank-one area
+ * weights; the host builds the small Legendre-side factor once per plan:
+ *
+ *   lon_ops [2L][nlon]     row 2m   : u_j cos(m lon_j) / sum_j u_j cos^2(m lon_j)
+ *                          row 2m+1 : u_j sin(m lon_j) / sum_j u_j sin^2(m lon_j)   (row 1 = 0)
+ *   lat_ops                concatenation over m = 0..nmax of op_m [cnt_m][nlat] row-major,
+ *                          cnt_m = nmax + 1 - max(m, nmin); op_m = solve(P'WP, P'W)
+ *   lat_op_offsets [L+1]   element offsets of op_m inside lat_ops
+ */
+int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_ops, const double* lat_ops,
+                         const int64_t* lat_op_offsets);
+/*   d_grid [n_epochs][nlat][nlon] -> d_anm [n_epochs][L][L] packed (degrees < nmin zero). */
+int gb_analysis(gb_plan* plan, const double* d_grid, int n_epochs, double* d_anm, void* stream);
+int gb_analysis_host(gb_plan* plan, const double* h_grid, int n_epochs, double* h_anm);
+
+/*
+ * Covariance propagation to per-point variances, diag(F Sigma F'), for the parallels
+ * [row0, row0 + nrows) of the plan's grid.  Replaces grid.py:833-835 (the reference then takes
+ * the square root, grid.py:837-839; pass take_sqrt = 1 for that).
+ *   d_sigma [K'][K'] row-major, K' = (nmax+1)^2 - nmin^2, degree-wise order
+ *   d_out   [nrows][nlon]
+ */
+int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
+                              double* d_out, int take_sqrt, void* stream);
+
+/*
+ * Order-wise block filter, batched over epochs.  Replaces OrderWiseFilter.filter,
+ * filter.py:180-189: order 0 block on C_n0, blocks 2m-1 / 2m on C_nm / S_nm, each block
+ * truncated to its top-left (nmax+1-m)^2 corner; degrees 0 and 1 pass through unchanged.
+ *   d_blocks        all blocks concatenated; block b is [(nf+1-m_b)][(nf+1-m_b)] row-major
+ *   block_offsets   [2*nf+2] element offsets of each block inside d_blocks (host array)
+ *   nf              maximum degree of the filter; nmax <= nf required
+ *   d_anm_in/out    [n_epochs][L][L] packed (may not alias)
+ */
+int gb_orderwise_filter(const double* d_blocks, const int64_t* block_offsets, int nf,
+                        const double* d_anm_in, int n_epochs, int nmax, double* d_anm_out,
+                        int device, void* stream);
+
+/* Pinned host memory for the *_host entry points. */
+int gb_host_alloc(void** ptr, uint64_t bytes);
+int gb_host_free(void* ptr);
+
+/*
+ * FP64 pipe probes used by bench.py for the roofline denominator (MEASURED_PEAKS.json holds
+ * no FP64 figure): sustained DMMA (tensor) and DFMA (vector) rate in TFLOP/s on `device`.
+ */
+int gb_probe_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
+
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+int64_t gb_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRATES_B200_H */

@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (through the Python host mirror -> ctypes -> C ABI) against
+(a) golden outputs of the unmodified reference (tests/golden) and (b) the CPU oracle on the same
+seeded inputs.  Parity metric: max|d| / max|ref|; tolerance 1e-12
+(1e-10 at degree >= 180) as stated by BASELINE.json north_star; Legendre tables bit-exact."""
+import datetime
+
+import numpy as np
+import pytest
+
+from conftest import maxnorm_err
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+KERNELS = ("ewh", "obp", "potential", "geoid", "surface_density", "anomaly", "deformation", "uplift")
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def gb():
+    import grates_b200
+    grates_b200._lib.require_device()
+    return grates_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import sh_oracle
+    return sh_oracle
+
+
+def _pc(gb, anm, GM=None, R=None):
+    pc = gb.PotentialCoefficients() if GM is None else gb.PotentialCoefficients(GM, R)
+    pc.anm = np.array(anm, dtype=float)
+    return pc
+
+
+# ------------------------------------------------------------------------------ Legendre
+def test_legendre_bit_exact_vs_reference(gb, golden):
+    g = golden("l1_numerics")
+    for N in (5, 40):
+        out = gb.utilities.legendre_functions(N, g["colat"])
+        np.testing.assert_array_equal(out, g["legendre_%d" % N])
+    out = gb.utilities.legendre_functions(200, g["colat"][::4])
+    np.testing.assert_array_equal(out, g["legendre_200"])       # includes polar underflow to denormals / 0
+
+
+def test_legendre_scaled_table(gb, orc):
+    grid = gb.GeographicGrid(5.0, 5.0)
+    plan = gb.get_plan(grid, 30, "ewh")
+    colat, kn = orc.kn_table("ewh", 30, grid.parallels)
+    ref = orc._scale_packed_by_degree(orc.legendre_functions(30, colat), kn)
+    np.testing.assert_array_equal(plan.legendre_table(scaled=True).cpu().numpy(), ref)
+    np.testing.assert_array_equal(plan.kn, kn)
+
+
+# ------------------------------------------------------------------------------ synthesis
+def test_synthesis_config1_golden(gb, golden):
+    g = golden("synthesis")
+    grid = gb.GeographicGrid(1.0, 1.0)
+    out = _pc(gb, g["c1_anm"]).to_grid(grid, "ewh")
+    assert type(out) is gb.GeographicGrid and out.value_array.shape == (180, 360)
+    assert grid.value_array is None                                # input grid untouched
+    assert maxnorm_err(out.value_array, g["c1_ewh"]) < TOL
+    assert out.values.shape == (64800,)
+
+
+@pytest.mark.parametrize("name", KERNELS)
+def test_synthesis_kernels_golden(gb, golden, name):
+    g = golden("synthesis")
+    grid = gb.GeographicGrid(10.0, 10.0)
+    batch = gb.to_grid_batch(g["s_anm"], grid, name)
+    assert batch.shape == (3, 18, 36)
+    assert maxnorm_err(batch, g["s_" + name]) < TOL
+    for e in range(3):
+        single = _pc(gb, g["s_anm"][e]).to_grid(grid, name).value_array
+        assert maxnorm_err(single, g["s_" + name][e]) < TOL
+
+
+def test_synthesis_variants_golden(gb, golden):
+    g = golden("synthesis")
+    grid = gb.GeographicGrid(10.0, 10.0)
+    out = _pc(gb, g["s_anm"][0], g["s_gmr"][0], g["s_gmr"][1]).to_grid(grid, "ewh")
+    assert maxnorm_err(out.value_array, g["s_ewh_gmr"]) < TOL
+    from oracle import sh_oracle as orc
+    anm20 = orc.synthetic_coefficients(20, 0)
+    gg = gb.GaussGrid(24)
+    out = _pc(gb, anm20).to_grid(gg, "ewh")
+    assert type(out) is gb.GaussGrid and maxnorm_err(out.value_array, g["gauss_ewh"]) < TOL
+    rg = gb.RegularGrid(g["reg_meridians"], g["reg_parallels"])
+    assert maxnorm_err(_pc(gb, anm20).to_grid(rg, "geoid").value_array, g["reg_geoid"]) < TOL
+    assert maxnorm_err(_pc(gb, np.array([[1.0]])).to_grid(grid, "potential").value_array, g["deg0_potential"]) < TOL
+    rp = gb.RegularGrid(g["hi_meridians"], g["hi_parallels"])
+    hi = _pc(gb, g["hi_anm"]).to_grid(rp, "ewh").value_array       # degree 200, polar underflow
+    assert np.all(np.isfinite(hi)) and maxnorm_err(hi, g["hi_ewh"]) < 1e-10
+
+
+def test_synthesis_default_grid_and_epoch(gb, orc):
+    pc = _pc(gb, orc.synthetic_coefficients(8, 3))
+    out = pc.to_grid()                                             # default 0.5 degree grid, ewh
+    assert out.value_array.shape == (360, 720)
+    ref = orc.synthesis(pc.anm, orc.geographic_grid(0.5, 0.5), "ewh")
+    assert maxnorm_err(out.value_array, ref) < TOL
+    g = gb.GeographicGrid(5.0, 5.0)
+    g.epoch = datetime.datetime(2005, 1, 1)
+    assert pc.to_grid(g, "ewh").epoch == g.epoch
+
+
+def test_synthesis_tensor_core_vs_plain_kernel(gb, orc, monkeypatch):
+    """The DMMA stage-2 kernel and the one-thread-per-output kernel agree to rounding."""
+    grid = gb.GeographicGrid(2.0, 2.0)
+    anm = np.stack([orc.synthetic_coefficients(45, e) for e in range(5)])
+    fast = gb.to_grid_batch(anm, grid, "ewh")
+    monkeypatch.setenv("GB_NAIVE_STAGE2", "1")
+    plain = gb.to_grid_batch(anm, grid, "ewh")
+    monkeypatch.delenv("GB_NAIVE_STAGE2")
+    assert maxnorm_err(fast, plain) < 1e-14
+    ref = np.stack([orc.synthesis(a, orc.geographic_grid(2.0, 2.0), "ewh") for a in anm])
+    assert maxnorm_err(fast, ref) < TOL
+
+
+@pytest.mark.parametrize("nmax,dlon,dlat,E", [(1, 30.0, 30.0, 1), (2, 90.0, 45.0, 2), (17, 7.5, 4.0, 7),
+                                              (33, 3.0, 3.0, 2), (96, 1.0, 0.5, 3)])
+def test_synthesis_ragged_shapes_vs_oracle(gb, orc, nmax, dlon, dlat, E):
+    grid = gb.GeographicGrid(dlon, dlat)
+    anm = np.stack([orc.synthetic_coefficients(nmax, e) for e in range(E)])
+    if nmax < 2:
+        anm[:, 0, 0] = 1.0
+    out = gb.to_grid_batch(anm, grid, "ewh")
+    og = orc.geographic_grid(dlon, dlat)
+    ref = np.stack([orc.synthesis(a, og, "ewh") for a in anm])
+    assert maxnorm_err(out, ref) < TOL
+
+
+def test_synthesis_odd_meridian_count(gb, orc):
+    mer = np.linspace(-3.0, 3.0, 37)
+    par = np.linspace(1.4, -1.4, 9)
+    anm = orc.synthetic_coefficients(12, 1)
+    out = _pc(gb, anm).to_grid(gb.RegularGrid(mer, par), "potential").value_array
+    assert maxnorm_err(out, orc.synthesis(anm, orc.OracleGrid(mer, par), "potential")) < TOL
+
+
+def test_synthesis_headline_shape_properties(gb, orc):
+    """BASELINE config 2 at full size (degree 96 -> 0.5 deg, 240 epochs): device-resident batch.
+    The oracle checks 3 epochs directly; the rest through linearity and batch-independence."""
+    E, N = 240, 96
+    grid = gb.GeographicGrid(0.5, 0.5)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    dev = torch.device("cuda")
+    x = torch.as_tensor(anm).to(dev)
+    out = gb.to_grid_batch(x, grid, "ewh")
+    assert out.is_cuda and tuple(out.shape) == (E, 360, 720)
+    og = orc.geographic_grid(0.5, 0.5)
+    for e in (0, 117, 239):
+        assert maxnorm_err(out[e].cpu().numpy(), orc.synthesis(anm[e], og, "ewh")) < TOL
+    # batch independence: any sub-batch gives bit-identical rows
+    sub = gb.to_grid_batch(x[100:103].contiguous(), grid, "ewh")
+    assert torch.equal(sub, out[100:103])
+    # linearity: synth(a x_p + b x_q) = a synth(x_p) + b synth(x_q)
+    mix = (0.3 * x[5] - 1.7 * x[200])[None].contiguous()
+    lin = 0.3 * out[5] - 1.7 * out[200]
+    assert maxnorm_err(gb.to_grid_batch(mix, grid, "ewh")[0].cpu().numpy(), lin.cpu().numpy()) < 1e-13
+    # host-buffer entry point agrees with the device one
+    host = gb.to_grid_batch(anm[:40], grid, "ewh")
+    assert isinstance(host, np.ndarray) and np.array_equal(host, out[:40].cpu().numpy())
+
+
+def test_time_series_and_rms(gb, orc):
+    data = []
+    for e in range(6):
+        pc = _pc(gb, orc.synthetic_coefficients(20, e))
+        pc.epoch = datetime.datetime(2002, 4, 15) + datetime.timedelta(days=30.4375 * (5 - e))
+        data.append(pc)
+    ts = gb.TimeSeries(data)
+    assert ts.epochs() == sorted(ts.epochs())
+    grid = gb.GeographicGrid(5.0, 5.0)
+    vals = ts.to_grid(grid, "ewh")
+    og = orc.geographic_grid(5.0, 5.0)
+    ref = np.stack([orc.synthesis(d.anm, og, "ewh") for _, d in ts.items()])
+    assert maxnorm_err(vals, ref) < TOL
+    np.testing.assert_array_equal(ts.to_array(), orc.ravel_coefficients(np.stack([d.anm for _, d in ts.items()])))
+    rms = gb.gridded_rms(ts, ts.epochs(), "ewh", grid)
+    assert maxnorm_err(rms.value_array, np.sqrt((ref ** 2).mean(axis=0))) < TOL
+
+
+# ------------------------------------------------------------------------------ analysis
+def test_analysis_golden(gb, golden):
+    g = golden("analysis")
+    for name in ("ewh", "potential"):
+        for lo, hi in ((0, 12), (2, 12), (3, 9)):
+            grid = gb.GeographicGrid(10.0, 10.0)
+            grid.values = g["in_" + name].ravel().copy()
+            pc = grid.to_potential_coefficients(lo, hi, name)
+            assert isinstance(pc, gb.PotentialCoefficients) and pc.anm.shape == (hi + 1, hi + 1)
+            assert maxnorm_err(pc.anm, g["anm_%s_%d_%d" % (name, lo, hi)]) < TOL
+    gg = gb.GaussGrid(14)
+    gg.values = g["gauss_in"].ravel().copy()
+    assert maxnorm_err(gg.to_potential_coefficients(0, 10, "ewh").anm, g["gauss_anm_0_10"]) < TOL
+    rg = gb.RegularGrid(g["reg_meridians"], g["reg_parallels"])
+    rg.values = g["reg_in"].ravel().copy()
+    assert maxnorm_err(rg.to_potential_coefficients(0, 8, "geoid").anm, g["reg_anm_0_8"]) < 1e-11
+
+
+def test_analysis_round_trip_batch(gb, orc):
+    N, E = 60, 5
+    grid = gb.GeographicGrid(1.0, 1.0)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    vals = gb.to_grid_batch(anm, grid, "ewh")
+    back = gb.analysis_batch(vals, grid, 0, N, "ewh")
+    assert back.shape == (E, N + 1, N + 1)
+    assert maxnorm_err(back, anm) < 1e-11
+    ref = orc.analysis_separable(vals[:2], orc.geographic_grid(1.0, 1.0), 0, N, "ewh")
+    assert maxnorm_err(back[:2], ref) < TOL
+    dev = gb.analysis_batch(torch.as_tensor(vals).cuda(), grid, 2, N, "ewh", device_output=True)
+    assert dev.is_cuda and float(dev[:, :2, :2].abs().max()) == 0.0
+
+
+def test_analysis_errors(gb):
+    grid = gb.GeographicGrid(10.0, 10.0)
+    with pytest.raises(ValueError):
+        grid.to_potential_coefficients(0, 8)                      # no values
+    grid.values = np.zeros(grid.point_count)
+    with pytest.raises(ValueError):
+        grid.to_potential_coefficients(0, 18)                     # N >= nlon / 2
+    rng = np.random.default_rng(0)
+    bad = gb.RegularGrid(grid.meridians, grid.parallels, rng.uniform(1, 2, (18, 36)))
+    bad.values = np.zeros(bad.point_count)
+    with pytest.raises(ValueError):
+        bad.to_potential_coefficients(0, 8)                       # non-separable area weights
+
+
+# ------------------------------------------------------------------------------ covariance
+def test_covariance_golden(gb, golden):
+    g = golden("covariance")
+    grid = gb.GeographicGrid(15.0, 15.0)
+    std = grid.covariance_propagation(g["sigma"], 0, 8, "ewh")
+    assert std.shape == (288,) and maxnorm_err(std, g["std_ewh_0_8"]) < TOL
+    np.testing.assert_array_equal(grid.values, std)               # reference also stores the std-devs
+    std = gb.GeographicGrid(15.0, 15.0).covariance_propagation(g["sigma"][4:, 4:], 2, 8, "potential")
+    assert maxnorm_err(std, g["std_potential_2_8"]) < TOL
+    std = gb.GaussGrid(10).covariance_propagation(g["sigma"], 0, 8, "geoid")
+    assert maxnorm_err(std, g["std_gauss_geoid"]) < TOL
+
+
+def test_covariance_vs_oracle_and_row_blocks(gb, orc):
+    N = 30
+    sigma = orc.synthetic_covariance(N, rank=24)
+    grid = gb.GeographicGrid(4.0, 6.0)
+    og = orc.geographic_grid(4.0, 6.0)
+    ref = orc.covariance_propagation(sigma, og, 0, N, "ewh")
+    std = grid.covariance_propagation(sigma, 0, N, "ewh")
+    assert maxnorm_err(std, ref) < TOL
+    plan = gb.get_plan(grid, N, "ewh")
+    s = torch.as_tensor(sigma).cuda()
+    parts = [plan.covariance_propagation(s, 0, r0, 10) for r0 in (0, 10, 20)]   # row-block sharding
+    assert maxnorm_err(torch.cat(parts).cpu().numpy().ravel(), ref) < TOL
+    var = plan.covariance_propagation(s, 0, take_sqrt=False).cpu().numpy().ravel()
+    assert maxnorm_err(var, ref ** 2) < TOL
+    # closed form: Sigma = I  ->  var_p = sum_a F_pa^2
+    eye = torch.eye((N + 1) ** 2, dtype=torch.float64, device="cuda")
+    v = plan.covariance_propagation(eye, 0, take_sqrt=False).cpu().numpy()
+    P = orc.ravel_coefficients(orc._scale_packed_by_degree(orc.legendre_functions(N, plan.colat), plan.kn))
+    T = orc.ravel_coefficients(orc.trigonometric_functions(N, grid.meridians))
+    assert maxnorm_err(v, (P ** 2) @ (T ** 2).T) < TOL
+    with pytest.raises(ValueError):
+        plan.covariance_propagation(s[:-1, :-1], 0)
+
+
+# ------------------------------------------------------------------------------ filter
+def test_orderwise_filter_golden(gb, golden):
+    g = golden("filters")
+    blocks = [g["block_%02d" % i] for i in range(25)]
+    flt = gb.OrderWiseFilter(blocks)
+    for tag in ("12", "9"):
+        pc = _pc(gb, g["in_" + tag])
+        out = flt.filter(pc)
+        assert isinstance(out, gb.PotentialCoefficients) and out is not pc
+        assert maxnorm_err(out.anm, g["out_" + tag]) < 1e-14
+        np.testing.assert_array_equal(out.anm[0:2, 0:2], g["in_" + tag][0:2, 0:2])
+    np.testing.assert_array_equal(flt.matrix(2, 9), g["matrix_2_9"])
+    with pytest.raises(ValueError):
+        flt.filter(_pc(gb, np.zeros((14, 14))))
+    with pytest.raises(TypeError):
+        flt.filter(np.zeros((5, 5)))
+
+
+def test_orderwise_filter_batch_then_synthesis(gb, orc):
+    """BASELINE config 5 in small: block filter over an epoch batch feeding the synthesis."""
+    nf, N, E = 40, 36, 11
+    blocks = orc.synthetic_filter_blocks(nf)
+    flt = gb.OrderWiseFilter(blocks)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    out = flt.filter_batch(anm)
+    ref = np.stack([orc.orderwise_filter(blocks, a) for a in anm])
+    assert maxnorm_err(out, ref) < 1e-14
+    dev = flt.filter_batch(torch.as_tensor(anm).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), out)
+    grid = gb.GeographicGrid(3.0, 3.0)
+    vals = gb.to_grid_batch(dev, grid, "ewh").cpu().numpy()
+    og = orc.geographic_grid(3.0, 3.0)
+    assert maxnorm_err(vals, np.stack([orc.synthesis(a, og, "ewh") for a in ref])) < TOL
+
+
+# ------------------------------------------------------------------------------ API behaviour
+def test_api_errors(gb):
+    with pytest.raises(ValueError):
+        gb.PotentialCoefficients(max_degree=3).to_grid(gb.GeographicGrid(30.0, 30.0), "no_such_kernel")
+
+    class Irregular:
+        longitude = np.zeros(3)
+        latitude = np.zeros(3)
+    with pytest.raises(NotImplementedError):
+        gb.PotentialCoefficients(max_degree=3).to_grid(Irregular(), "ewh")
+    plan = gb.get_plan(gb.GeographicGrid(30.0, 30.0), 3, "ewh")
+    with pytest.raises(ValueError):
+        plan.synthesis(torch.zeros((1, 5, 5), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        plan.synthesis(torch.zeros((1, 4, 4), dtype=torch.float32, device="cuda"))
+    assert plan.synthesis(torch.zeros((0, 4, 4), dtype=torch.float64, device="cuda")).shape == (0, 6, 12)
+    assert gb.get_plan(gb.GeographicGrid(30.0, 30.0), 3, "ewh") is plan       # cached
