@@ -35,6 +35,8 @@ SIGNATURES = {
     "gb_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "gb_host_free": (ctypes.c_int, [_vp]),
     "gb_probe_fp64_peak": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p]),
+    "gb_plan_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "gb_plan_stage_times": (ctypes.c_int, [_vp, _c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "gb_launch_count": (ctypes.c_int64, [ctypes.c_int]),
 }
 

@@ -67,6 +67,9 @@ struct gb_plan {
     double* d_lat_ops = nullptr;
     long long* d_lat_off = nullptr;  // [L+1]
     long long* h_lat_off = nullptr;
+    // optional per-kernel event timing (gb_plan_set_profiling)
+    cudaEvent_t* prof_ev = nullptr;  // [capacity][4]
+    int prof_capacity = 0, prof_count = 0;
     // device facts
     int sm_count = 0;
 };

@@ -128,6 +128,10 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);
     cudaFree(p->d_lon_ops); cudaFree(p->d_lat_ops); cudaFree(p->d_lat_off);
     delete[] p->h_lat_off;
+    if (p->prof_ev) {
+        for (int i = 0; i < p->prof_capacity * 4; ++i) cudaEventDestroy(p->prof_ev[i]);
+        delete[] p->prof_ev;
+    }
     if (p->s_compute) cudaStreamDestroy(p->s_compute);
     if (p->s_copy) cudaStreamDestroy(p->s_copy);
     for (auto& e : p->ev)
@@ -154,6 +158,42 @@ int gb_plan_ensure_workspace(gb_plan* p, int n_epochs) {
     GB_CUDA(cudaDeviceSynchronize());
     p->ws_epochs = n_epochs;
     p->ws_mpad = mpad;
+    return GB_OK;
+}
+
+extern "C" int gb_plan_set_profiling(gb_plan* p, int capacity) {
+    GB_REQUIRE(p != nullptr && capacity >= 0, "gb_plan_set_profiling: bad argument");
+    GB_CUDA(cudaSetDevice(p->device));
+    if (p->prof_ev) {
+        GB_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < p->prof_capacity * 4; ++i) cudaEventDestroy(p->prof_ev[i]);
+        delete[] p->prof_ev;
+        p->prof_ev = nullptr;
+    }
+    p->prof_capacity = 0;
+    p->prof_count = 0;
+    if (capacity > 0) {
+        p->prof_ev = new cudaEvent_t[(size_t)capacity * 4];
+        for (int i = 0; i < capacity * 4; ++i) GB_CUDA(cudaEventCreate(&p->prof_ev[i]));
+        p->prof_capacity = capacity;
+    }
+    return GB_OK;
+}
+
+extern "C" int gb_plan_stage_times(gb_plan* p, double* ms, int max_calls, int* n_calls) {
+    GB_REQUIRE(p != nullptr && ms != nullptr && n_calls != nullptr, "gb_plan_stage_times: NULL argument");
+    const int n = p->prof_count < max_calls ? p->prof_count : max_calls;
+    for (int c = 0; c < n; ++c) {
+        cudaEvent_t* ev = p->prof_ev + (size_t)c * 4;
+        GB_CUDA(cudaEventSynchronize(ev[3]));
+        for (int s = 0; s < 3; ++s) {
+            float t = 0.f;
+            GB_CUDA(cudaEventElapsedTime(&t, ev[s], ev[s + 1]));
+            ms[c * 3 + s] = t;
+        }
+    }
+    *n_calls = n;
+    p->prof_count = 0;
     return GB_OK;
 }
 

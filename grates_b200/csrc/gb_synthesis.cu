@@ -289,11 +289,14 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     const int L = p->L;
     const long long M = (long long)E * p->nlat;
     const long long mpad = p->ws_mpad;
+    cudaEvent_t* prof = (p->prof_ev && p->prof_count < p->prof_capacity) ? p->prof_ev + (size_t)p->prof_count * 4 : nullptr;
+    if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
     {
         dim3 grid((unsigned)(((long long)L * 2 * E + 255) / 256), L);
         gb_pack_orderwise<<<grid, 256, 0, st>>>(d_anm, p->d_x, L, E);
         GB_LAUNCH_CHECK();
     }
+    if (prof) GB_CUDA(cudaEventRecord(prof[1], st));
     {
         dim3 grid((p->nlat + S1_TI - 1) / S1_TI, L);
         const size_t smem = (size_t)L * S1_TI * sizeof(double);
@@ -303,6 +306,7 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
                                                     p->d_rc, L, p->nlat, E, mpad);
         GB_LAUNCH_CHECK();
     }
+    if (prof) GB_CUDA(cudaEventRecord(prof[2], st));
     if (env_flag("GB_NAIVE_STAGE2")) {
         const long long total = M * p->nlon;
         gb_fourier_stage2_naive<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p->d_ab, mpad, p->d_trig, p->nlp,
@@ -317,6 +321,10 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         gb_fourier_stage2<<<grid, S2_THREADS, S2_SMEM, st>>>(p->d_ab, mpad, p->d_trig, p->nlp, p->kpad, d_out, M,
                                                              p->nlon, n_mtiles, n_ntiles);
         GB_LAUNCH_CHECK();
+    }
+    if (prof) {
+        GB_CUDA(cudaEventRecord(prof[3], st));
+        p->prof_count++;
     }
     return GB_OK;
 }

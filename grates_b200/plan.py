@@ -142,6 +142,18 @@ class SHPlan:
                                                _stream_handle(self.device)))
         return out
 
+    def set_profiling(self, capacity):
+        """Record per-kernel CUDA events for the next ``capacity`` synthesis calls (0 = off)."""
+        _lib.check(self._lib.gb_plan_set_profiling(self._handle, int(capacity)))
+
+    def stage_times(self, max_calls=4096):
+        """[calls, 3] device milliseconds of (pack, Legendre stage 1, Fourier stage 2)."""
+        buf = np.zeros((max_calls, 3))
+        n = ctypes.c_int(0)
+        _lib.check(self._lib.gb_plan_stage_times(self._handle, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                 max_calls, ctypes.byref(n)))
+        return buf[:n.value].copy()
+
     # -- analysis -----------------------------------------------------------------------
     def set_analysis(self, min_degree, areas):
         """Build the separable least-squares operators of reference grid.py:665-696 for the

@@ -146,6 +146,17 @@ int gb_host_free(void* ptr);
  */
 int gb_probe_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
 
+/*
+ * Per-kernel device timing of gb_synthesis calls (for the roofline figures of bench.py):
+ * with capacity > 0 every following gb_synthesis on this plan records CUDA events on the
+ * caller's stream around its three kernels (pack, Legendre stage 1, Fourier stage 2), for up to
+ * `capacity` calls; capacity = 0 switches it off.  gb_plan_stage_times synchronises those events,
+ * writes ms[call][3] for the recorded calls (at most max_calls), returns their number in
+ * n_calls and clears the record.
+ */
+int gb_plan_set_profiling(gb_plan* plan, int capacity);
+int gb_plan_stage_times(gb_plan* plan, double* ms, int max_calls, int* n_calls);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 int64_t gb_launch_count(int reset);
 
