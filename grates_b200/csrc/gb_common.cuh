@@ -51,6 +51,7 @@ struct gb_plan {
     double* d_rb = nullptr;     // [L][L]      recursion coefficient b_nm (utilities.py:54)
     double* d_rc = nullptr;     // [L]         sqrt(2n+1), first off-diagonal (utilities.py:46)
     double* d_trig = nullptr;   // [kpad][nlp] row 2m: cos(m lon_j), row 2m+1: sin(m lon_j)
+    double* d_zero = nullptr;   // 4 KB of zeros (source of padding rows for bulk copies)
     // synthesis workspace, grown on demand (epochs)
     int ws_epochs = 0;
     long long ws_mpad = 0;

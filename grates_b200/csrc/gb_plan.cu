@@ -103,7 +103,7 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
     int rc_ = GB_OK;
     if ((rc_ = upload(&p->d_ct, ct)) || (rc_ = upload(&p->d_kn, knv)) || (rc_ = upload(&p->d_pmm, pmm)) ||
         (rc_ = upload(&p->d_ra, ra)) || (rc_ = upload(&p->d_rb, rb)) || (rc_ = upload(&p->d_rc, rc)) ||
-        (rc_ = upload(&p->d_trig, trig))) {
+        (rc_ = upload(&p->d_trig, trig)) || (rc_ = upload(&p->d_zero, std::vector<double>(512, 0.0)))) {
         gb_plan_destroy(p);
         return rc_;
     }
@@ -124,7 +124,7 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     if (!p) return GB_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_ct); cudaFree(p->d_kn); cudaFree(p->d_pmm); cudaFree(p->d_ra); cudaFree(p->d_rb);
-    cudaFree(p->d_rc); cudaFree(p->d_trig); cudaFree(p->d_x); cudaFree(p->d_ab);
+    cudaFree(p->d_rc); cudaFree(p->d_trig); cudaFree(p->d_zero); cudaFree(p->d_x); cudaFree(p->d_ab);
     cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);
     cudaFree(p->d_lon_ops); cudaFree(p->d_lat_ops); cudaFree(p->d_lat_off);
     delete[] p->h_lat_off;

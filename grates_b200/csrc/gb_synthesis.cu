@@ -71,7 +71,7 @@ __device__ __forceinline__ void legendre_column(int m, int L, double ct, double 
 constexpr int S1_TI = 32;  // latitudes per CTA
 
 __global__ void __launch_bounds__(256)
-gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const double* __restrict__ ct,
+gb_legendre_stage1_simple(const double* __restrict__ X, double* __restrict__ AB, const double* __restrict__ ct,
                    const double* __restrict__ kn, const double* __restrict__ pmm, const double* __restrict__ ra,
                    const double* __restrict__ rb, const double* __restrict__ rc, int L, int nlat, int E,
                    long long mpad) {
@@ -120,6 +120,168 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const 
         if (i + 1 < nlat) dst[1] = a1;
         if (i + 2 < nlat) dst[2] = a2;
         if (i + 3 < nlat) dst[3] = a3;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// stage 1 on the FP64 tensor cores.  One CTA = (order m, 64 parallels, 240 columns (e, cos|sin)):
+//   D[i, col] = sum_n Pk[i, n] X_m[n, col],  Pk = kn * P_nm produced ON THE FLY:
+//   two Legendre warps (lane = parallel) advance the recursion 16 degrees at a time and write the
+//   chunk k-major into shared memory; a copy warp streams the matching 16 rows of X_m with bulk
+//   copies; twelve consumer warps (2 x 6, 32 x 40 register tiles) issue DMMA.8x8x4.
+// Degrees beyond nmax in the last chunk are fed from a zero row, parallels beyond nlat are zero.
+// ---------------------------------------------------------------------------------------------
+constexpr int T1_TM = 64, T1_TN = 240, T1_KC = 16, T1_STAGES = 4;
+constexpr int T1_LDA = T1_TM + 4;    // 68
+constexpr int T1_LDB = T1_TN + 4;    // 244
+constexpr int T1_CONSUMER_WARPS = 12;
+constexpr int T1_THREADS = 32 * (T1_CONSUMER_WARPS + 3);   // + copy warp + 2 Legendre warps
+constexpr int T1_STAGE_DOUBLES = T1_KC * (T1_LDA + T1_LDB);
+constexpr size_t T1_SMEM = (size_t)T1_STAGES * T1_STAGE_DOUBLES * sizeof(double) + 2 * T1_STAGES * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(T1_THREADS, 1)
+gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const double* __restrict__ ct,
+                   const double* __restrict__ kn, const double* __restrict__ pmm, const double* __restrict__ ra,
+                   const double* __restrict__ rb, const double* __restrict__ rc, const double* __restrict__ zeros,
+                   int L, int nlat, int E, long long mpad, int n_coltiles) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tiles = reinterpret_cast<double*>(s_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)T1_STAGES * T1_STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + T1_STAGES;
+
+    const int m = blockIdx.y;
+    const int it = blockIdx.x / n_coltiles;
+    const int ctile = blockIdx.x % n_coltiles;
+    const int i0 = it * T1_TM;
+    const int cols = 2 * E;
+    const int c0 = ctile * T1_TN;
+    const int width = min(T1_TN, cols - c0);       // even
+    const int Kn = L - m;
+    const int n_chunks = (Kn + T1_KC - 1) / T1_KC;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T1_STAGES; ++s) {
+            gb::mbar_init(&full[s], 3);                      // copy warp (+tx bytes) and two Legendre warps
+            gb::mbar_init(&empty[s], T1_CONSUMER_WARPS);
+        }
+        gb::fence_mbar_init();
+    }
+    // recursion coefficients of this order, padded to whole chunks.  Entry 1 (n = m+1) uses
+    // a = sqrt(2n+1), b = 0: (a ct) p1 - 0 * 0 is bit-identical to utilities.py:46.
+    double* s_ra = reinterpret_cast<double*>(empty + T1_STAGES);
+    double* s_rb = s_ra + n_chunks * T1_KC;
+    for (int nn = threadIdx.x; nn < n_chunks * T1_KC; nn += blockDim.x) {
+        const int n = m + nn;
+        double a = 0.0, b = 0.0;
+        if (nn == 1 && n < L) a = rc[n];
+        else if (nn >= 2 && n < L) { a = ra[(size_t)n * L + m]; b = rb[(size_t)n * L + m]; }
+        s_ra[nn] = a;
+        s_rb[nn] = b;
+    }
+    __syncthreads();
+
+    int stage = 0;
+    uint32_t phase = 0;
+    if (warp == T1_CONSUMER_WARPS) {
+        // ===== copy warp: 16 rows of X_m per chunk =====
+        const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
+        const double* Xm = X + xo + c0;
+        for (int c = 0; c < n_chunks; ++c) {
+            gb::mbar_wait(&empty[stage], phase ^ 1u);
+            double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA;
+            if (lane == 0) gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(T1_KC * width * sizeof(double)));
+            __syncwarp();
+            if (lane < T1_KC) {
+                const int nn = c * T1_KC + lane;
+                const double* src = (nn < Kn) ? Xm + (size_t)nn * cols : zeros;
+                gb::bulk_g2s(sB + lane * T1_LDB, src, (uint32_t)(width * sizeof(double)), &full[stage]);
+            }
+            if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp > T1_CONSUMER_WARPS) {
+        // ===== Legendre warps: lane = parallel, recursion state lives in registers =====
+        const int li = (warp - T1_CONSUMER_WARPS - 1) * 32 + lane;
+        const int i = i0 + li;
+        const bool live = i < nlat;
+        const double cti = live ? ct[i] : 0.0;
+        const double* kn_i = kn + (size_t)(live ? i : 0) * L + m;
+        double p1 = 0.0, p2 = 0.0;
+        for (int c = 0; c < n_chunks; ++c) {
+            // factors and recursion coefficients of the chunk first (independent loads in flight
+            // together), then the serial chain: per degree one dependent multiply + subtract
+            double knv[T1_KC], act[T1_KC];
+#pragma unroll
+            for (int kk = 0; kk < T1_KC; ++kk) {
+                const int nn = c * T1_KC + kk;
+                knv[kk] = (live && nn < Kn) ? __ldg(kn_i + nn) : 0.0;
+                act[kk] = __dmul_rn(s_ra[nn], cti);
+            }
+            gb::mbar_wait(&empty[stage], phase ^ 1u);
+            double* sA = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + li;
+#pragma unroll
+            for (int kk = 0; kk < T1_KC; ++kk) {
+                const int nn = c * T1_KC + kk;
+                double pn;
+                if (nn == 0) pn = live ? pmm[(size_t)i * L + m] : 0.0;
+                else pn = __dsub_rn(__dmul_rn(act[kk], p1), __dmul_rn(s_rb[nn], p2));
+                p2 = p1;
+                p1 = pn;
+                sA[kk * T1_LDA] = __dmul_rn(pn, knv[kk]);   // knv = 0 beyond nmax / nlat
+            }
+            __syncwarp();
+            if (lane == 0) gb::mbar_arrive(&full[stage]);
+            if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else {
+        // ===== consumer warps =====
+        const int wm = warp / 6;
+        const int wn = warp % 6;
+        const int g = lane >> 2, q = lane & 3;
+        double acc[4][5][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int c = 0; c < n_chunks; ++c) {
+            gb::mbar_wait(&full[stage], phase);
+            const double* sA = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + wm * 32 + g;
+            const double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA + wn * 40 + g;
+#pragma unroll
+            for (int kk = 0; kk < T1_KC; kk += 4) {
+                double a[4], b[5];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * T1_LDA + mi * 8];
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * T1_LDB + ni * 8];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) gb::mbar_arrive(&empty[stage]);
+            if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        // epilogue: column pair (2q, 2q+1) of a fragment = (cos, sin) of one epoch
+#pragma unroll
+        for (int ni = 0; ni < 5; ++ni) {
+            const int col = c0 + wn * 40 + ni * 8 + 2 * q;
+            if (col >= cols) continue;
+            const int e = col >> 1;
+            double* dc = AB + (size_t)(2 * m) * mpad + (size_t)e * nlat;
+            double* ds = dc + mpad;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int i = i0 + wm * 32 + mi * 8 + g;
+                if (i < nlat) {
+                    dc[i] = acc[mi][ni][0];
+                    ds[i] = acc[mi][ni][1];
+                }
+            }
+        }
     }
 }
 
@@ -297,13 +459,23 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         GB_LAUNCH_CHECK();
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[1], st));
-    {
+    if (env_flag("GB_SIMPLE_STAGE1")) {
         dim3 grid((p->nlat + S1_TI - 1) / S1_TI, L);
         const size_t smem = (size_t)L * S1_TI * sizeof(double);
         if (smem > 48 * 1024)
-            GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gb_legendre_stage1<<<grid, 256, smem, st>>>(p->d_x, p->d_ab, p->d_ct, p->d_kn, p->d_pmm, p->d_ra, p->d_rb,
-                                                    p->d_rc, L, p->nlat, E, mpad);
+            GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gb_legendre_stage1_simple<<<grid, 256, smem, st>>>(p->d_x, p->d_ab, p->d_ct, p->d_kn, p->d_pmm, p->d_ra,
+                                                           p->d_rb, p->d_rc, L, p->nlat, E, mpad);
+        GB_LAUNCH_CHECK();
+    } else {
+        const int n_coltiles = (2 * E + T1_TN - 1) / T1_TN;
+        const int n_lattiles = (p->nlat + T1_TM - 1) / T1_TM;
+        dim3 grid(n_lattiles * n_coltiles, L);
+        const size_t smem1 = T1_SMEM + 2 * (size_t)((L + T1_KC - 1) / T1_KC * T1_KC) * sizeof(double);
+        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        gb_legendre_stage1<<<grid, T1_THREADS, smem1, st>>>(p->d_x, p->d_ab, p->d_ct, p->d_kn, p->d_pmm, p->d_ra,
+                                                              p->d_rb, p->d_rc, p->d_zero, L, p->nlat, E, mpad,
+                                                              n_coltiles);
         GB_LAUNCH_CHECK();
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[2], st));

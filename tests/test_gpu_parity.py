@@ -116,6 +116,10 @@ def test_synthesis_tensor_core_vs_plain_kernel(gb, orc, monkeypatch):
     plain = gb.to_grid_batch(anm, grid, "ewh")
     monkeypatch.delenv("GB_NAIVE_STAGE2")
     assert maxnorm_err(fast, plain) < 1e-14
+    monkeypatch.setenv("GB_SIMPLE_STAGE1", "1")            # FMA stage 1 instead of the DMMA one
+    simple = gb.to_grid_batch(anm, grid, "ewh")
+    monkeypatch.delenv("GB_SIMPLE_STAGE1")
+    assert maxnorm_err(fast, simple) < 1e-14
     ref = np.stack([orc.synthesis(a, orc.geographic_grid(2.0, 2.0), "ewh") for a in anm])
     assert maxnorm_err(fast, ref) < TOL
 

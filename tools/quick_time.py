@@ -17,6 +17,12 @@ def run(N, d, E, reps=10):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); plan.synthesis(x, out=out); e1.record(); e1.synchronize()
         ts.append(e0.elapsed_time(e1))
+    plan.set_profiling(reps)
+    for _ in range(reps):
+        plan.synthesis(x, out=out)
+    st = plan.stage_times(reps).mean(axis=0)
+    plan.set_profiling(0)
+    print("   stages (pack, stage1, stage2) ms:", np.round(st, 4))
     L = N + 1
     flops = 2.0 * E * plan.nlat * L * L + 2.0 * (2 * L - 1) * E * plan.nlat * plan.nlon
     best, med = min(ts), sorted(ts)[len(ts) // 2]
