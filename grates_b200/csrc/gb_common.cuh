@@ -36,6 +36,24 @@ void gb_count_launch(int n = 1);
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// tiled HBM layouts shared by the synthesis kernels
+//   AB   [row tile][spectral row k][GB_LDA]   128 grid rows (e, i) per tile, 4 pad doubles so that a
+//        chunk of consecutive k lands in shared memory with one bulk copy AND with the k-rows 4
+//        doubles apart modulo 16 (conflict-free DMMA fragment loads)
+//   trig [column tile][k][tile width + 4]     same idea for the longitude tables
+// ---------------------------------------------------------------------------------------------
+constexpr int GB_TM = 128;          // grid rows per AB tile
+constexpr int GB_LDA = GB_TM + 4;   // 132
+constexpr int GB_S2_TN = 120;       // meridians per tile, general stage 2
+constexpr int GB_S2_LDB = GB_S2_TN + 4;
+constexpr int GB_Q_TN = 32;         // first-quadrant meridians per tile, symmetric stage 2
+constexpr int GB_Q_LDB = GB_Q_TN + 4;
+
+__host__ __device__ __forceinline__ size_t gb_ab_offset(long long row, int k, int ab_rows) {
+    return ((size_t)(row >> 7) * ab_rows + k) * GB_LDA + (size_t)(row & 127);
+}
+
+// ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
 struct gb_plan {
@@ -52,11 +70,24 @@ struct gb_plan {
     double* d_rc = nullptr;     // [L]         sqrt(2n+1), first off-diagonal (utilities.py:46)
     double* d_trig = nullptr;   // [kpad][nlp] row 2m: cos(m lon_j), row 2m+1: sin(m lon_j)
     double* d_zero = nullptr;   // 4 KB of zeros (source of padding rows for bulk copies)
+    // four-fold longitude symmetry (meridians symmetric about 0 and invariant under a half turn):
+    // spectral rows regrouped as [even-m cos | odd-m cos | even-m sin | odd-m sin], each padded to 4
+    int sym = 0;                // 1 if the meridians allow the symmetric stage 2
+    int kpad_s = 0;             // rows of AB in the symmetric layout (incl. 4 dummy rows at the end)
+    int grp_off[5] = {0, 0, 0, 0, 0};
+    int nq = 0, nqp = 0;        // first-quadrant meridians, padded to a multiple of 8
+    int* d_krow_id = nullptr;   // [kpad] k = 2m+cs -> AB row, general layout (identity)
+    int* d_krow_sym = nullptr;  // [kpad] k = 2m+cs -> AB row, symmetric layout
+    double* d_trig_q = nullptr; // [kpad_s][nqp] first-quadrant trig table in the symmetric row order
+    double* d_trig_t = nullptr;   // tiled copy of d_trig:   [n_ntiles][kpad][GB_S2_LDB]
+    double* d_trig_q_t = nullptr; // tiled copy of d_trig_q: [n_qtiles][kpad_s][GB_Q_LDB]
+    int n_ntiles = 0, n_qtiles = 0;
+    int ab_rows = 0;            // spectral rows allocated per AB tile = max(kpad, kpad_s)
     // synthesis workspace, grown on demand (epochs)
     int ws_epochs = 0;
     long long ws_mpad = 0;
     double* d_x = nullptr;      // order-wise packed coefficients, see gb_synthesis.cu
-    double* d_ab = nullptr;     // [kpad][mpad] spectral intermediate
+    double* d_ab = nullptr;     // [mpad/128][ab_rows][GB_LDA] spectral intermediate (see above)
     // host-buffer pipeline
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -89,7 +120,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 // D(8x8) += A(8x4, row) * B(4x8, col); FP64 tensor op, SASS DMMA.8x8x4
 __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }

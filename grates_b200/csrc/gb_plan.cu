@@ -100,10 +100,80 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
         }
     std::vector<double> ct(cos_theta, cos_theta + nlat), knv(kn, kn + (size_t)nlat * L);
 
+    // Four-fold longitude symmetry: with h = nlon/2, q = nlon/4 and mu = lon[h + j'] in (0, pi/2),
+    //   lon[nlon-1-j'] = pi - mu,  lon[h-1-j'] = -mu,  lon[j'] = mu - pi.
+    // Checked on the tables themselves (they are what the kernels multiply with).
+    std::vector<int> krow_id(p->kpad), krow_sym(p->kpad, 0);
+    for (int k = 0; k < p->kpad; ++k) krow_id[k] = k;
+    std::vector<double> trig_q;
+    {
+        bool sym = (nlon % 8 == 0);   // first quadrant must hold an even number of meridians
+        const int h = nlon / 2, q = nlon / 4;
+        for (int m = 0; m < L && sym; ++m) {
+            // numpy evaluates cos(m * lon): the product is rounded (half an ulp of |m lon| <= m pi) and lon
+            // itself carries half an ulp of pi, so mirrored table entries differ by a few (m+1) * 1e-15
+            const double tol = 4.0 * (m + 1) * 2.220446049250313e-16 * 3.141592653589793;
+            const double sg = (m & 1) ? -1.0 : 1.0;
+            const double* c = cos_mlon + (size_t)m * nlon;
+            const double* s = sin_mlon + (size_t)m * nlon;
+            for (int j = 0; j < q; ++j) {
+                const double cq = c[h + j], sq = s[h + j];
+                if (std::fabs(c[nlon - 1 - j] - sg * cq) > tol || std::fabs(s[nlon - 1 - j] + sg * sq) > tol ||
+                    std::fabs(c[h - 1 - j] - cq) > tol || std::fabs(s[h - 1 - j] + sq) > tol ||
+                    std::fabs(c[j] - sg * cq) > tol || std::fabs(s[j] - sg * sq) > tol) {
+                    sym = false;
+                    break;
+                }
+            }
+        }
+        p->sym = sym ? 1 : 0;
+        if (sym) {
+            p->nq = q;
+            p->nqp = (q + 7) / 8 * 8;
+            const int cnt[4] = {nmax / 2 + 1, (nmax + 1) / 2, nmax / 2, (nmax + 1) / 2};
+            for (int g = 0; g < 4; ++g) p->grp_off[g + 1] = p->grp_off[g] + (cnt[g] + 3) / 4 * 4;
+            p->kpad_s = p->grp_off[4] + 4;
+            trig_q.assign((size_t)p->kpad_s * p->nqp, 0.0);
+            for (int m = 0; m < L; ++m) {
+                const int rc_row = p->grp_off[m & 1] + m / 2;
+                krow_sym[2 * m] = rc_row;
+                int rs_row = p->kpad_s - 1;   // (m = 0, sin) does not exist: dummy row
+                if (m > 0) rs_row = p->grp_off[2 + (m & 1)] + ((m & 1) ? m / 2 : m / 2 - 1);
+                krow_sym[2 * m + 1] = rs_row;
+                for (int j = 0; j < q; ++j) {
+                    trig_q[(size_t)rc_row * p->nqp + j] = cos_mlon[(size_t)m * nlon + h + j];
+                    if (m > 0) trig_q[(size_t)rs_row * p->nqp + j] = sin_mlon[(size_t)m * nlon + h + j];
+                }
+            }
+            for (int k = 2 * L; k < p->kpad; ++k) krow_sym[k] = p->kpad_s - 1;
+        }
+    }
+
+    // tiled + padded copies of the longitude tables (one bulk copy per pipeline stage)
+    p->ab_rows = p->kpad > p->kpad_s ? p->kpad : p->kpad_s;
+    p->n_ntiles = (p->nlp + GB_S2_TN - 1) / GB_S2_TN;
+    std::vector<double> trig_t((size_t)p->n_ntiles * p->kpad * GB_S2_LDB, 0.0);
+    for (int t = 0; t < p->n_ntiles; ++t)
+        for (int k = 0; k < p->kpad; ++k)
+            for (int c = 0; c < GB_S2_TN && t * GB_S2_TN + c < p->nlp; ++c)
+                trig_t[((size_t)t * p->kpad + k) * GB_S2_LDB + c] = trig[(size_t)k * p->nlp + t * GB_S2_TN + c];
+    std::vector<double> trig_q_t;
+    if (p->sym) {
+        p->n_qtiles = (p->nqp + GB_Q_TN - 1) / GB_Q_TN;
+        trig_q_t.assign((size_t)p->n_qtiles * p->kpad_s * GB_Q_LDB, 0.0);
+        for (int t = 0; t < p->n_qtiles; ++t)
+            for (int k = 0; k < p->kpad_s; ++k)
+                for (int c = 0; c < GB_Q_TN && t * GB_Q_TN + c < p->nqp; ++c)
+                    trig_q_t[((size_t)t * p->kpad_s + k) * GB_Q_LDB + c] = trig_q[(size_t)k * p->nqp + t * GB_Q_TN + c];
+    }
+
     int rc_ = GB_OK;
-    if ((rc_ = upload(&p->d_ct, ct)) || (rc_ = upload(&p->d_kn, knv)) || (rc_ = upload(&p->d_pmm, pmm)) ||
+    if ((rc_ = upload(&p->d_trig_t, trig_t)) || (p->sym && (rc_ = upload(&p->d_trig_q_t, trig_q_t))) ||
+        (rc_ = upload(&p->d_ct, ct)) || (rc_ = upload(&p->d_kn, knv)) || (rc_ = upload(&p->d_pmm, pmm)) ||
         (rc_ = upload(&p->d_ra, ra)) || (rc_ = upload(&p->d_rb, rb)) || (rc_ = upload(&p->d_rc, rc)) ||
-        (rc_ = upload(&p->d_trig, trig)) || (rc_ = upload(&p->d_zero, std::vector<double>(512, 0.0)))) {
+        (rc_ = upload(&p->d_trig, trig)) || (rc_ = upload(&p->d_zero, std::vector<double>(512, 0.0))) ||
+        (rc_ = upload(&p->d_krow_id, krow_id)) || (rc_ = upload(&p->d_krow_sym, krow_sym)) ||
+        (p->sym && (rc_ = upload(&p->d_trig_q, trig_q)))) {
         gb_plan_destroy(p);
         return rc_;
     }
@@ -124,7 +194,9 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     if (!p) return GB_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_ct); cudaFree(p->d_kn); cudaFree(p->d_pmm); cudaFree(p->d_ra); cudaFree(p->d_rb);
-    cudaFree(p->d_rc); cudaFree(p->d_trig); cudaFree(p->d_zero); cudaFree(p->d_x); cudaFree(p->d_ab);
+    cudaFree(p->d_rc); cudaFree(p->d_trig); cudaFree(p->d_zero);
+    cudaFree(p->d_krow_id); cudaFree(p->d_krow_sym); cudaFree(p->d_trig_q);
+    cudaFree(p->d_trig_t); cudaFree(p->d_trig_q_t); cudaFree(p->d_x); cudaFree(p->d_ab);
     cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);
     cudaFree(p->d_lon_ops); cudaFree(p->d_lat_ops); cudaFree(p->d_lat_off);
     delete[] p->h_lat_off;
@@ -152,9 +224,10 @@ int gb_plan_ensure_workspace(gb_plan* p, int n_epochs) {
     const long long mpad = (m + 127) / 128 * 128;
     const size_t x_elems = (size_t)p->L * (p->L + 1) / 2 * 2 * (size_t)n_epochs;
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_x), x_elems * sizeof(double)));
-    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ab), (size_t)p->kpad * mpad * sizeof(double)));
-    // rows k >= 2L and padded columns must stay finite (they meet zero trig rows / masked stores)
-    GB_CUDA(cudaMemset(p->d_ab, 0, (size_t)p->kpad * mpad * sizeof(double)));
+    const size_t ab_elems = (size_t)(mpad / GB_TM) * p->ab_rows * GB_LDA;
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ab), ab_elems * sizeof(double)));
+    // padding rows and padded columns must stay finite (they meet zero trig rows / masked stores)
+    GB_CUDA(cudaMemset(p->d_ab, 0, ab_elems * sizeof(double)));
     GB_CUDA(cudaDeviceSynchronize());
     p->ws_epochs = n_epochs;
     p->ws_mpad = mpad;

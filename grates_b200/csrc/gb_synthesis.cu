@@ -8,8 +8,9 @@
 // HBM layout
 //   anm   [E][L][L]          packed coefficients as the reference stores them
 //   X     order-wise packed  X_m[n-m][2e+cs], block of order m at offset 2E*(m*L - m(m-1)/2)
-//   AB    [kpad][mpad]       spectral intermediate, row k = 2m+cs, column = e*nlat + i
-//   trig  [kpad][nlp]        row 2m = cos(m lon_j), row 2m+1 = sin(m lon_j)
+//   AB    [row tile][k][132]  spectral intermediate, tiled by 128 grid rows (e*nlat + i), see gb_common.cuh;
+//                            row order k = 2m+cs, or [CE|CO|SE|SO] groups for the symmetric stage 2
+//   trig  [col tile][k][124]  row 2m = cos(m lon_j), row 2m+1 = sin(m lon_j) (first quadrant only when symmetric)
 //   V     [E][nlat][nlon]    output
 //
 // Kernels
@@ -73,8 +74,8 @@ constexpr int S1_TI = 32;  // latitudes per CTA
 __global__ void __launch_bounds__(256)
 gb_legendre_stage1_simple(const double* __restrict__ X, double* __restrict__ AB, const double* __restrict__ ct,
                    const double* __restrict__ kn, const double* __restrict__ pmm, const double* __restrict__ ra,
-                   const double* __restrict__ rb, const double* __restrict__ rc, int L, int nlat, int E,
-                   long long mpad) {
+                   const double* __restrict__ rb, const double* __restrict__ rc, const int* __restrict__ krow, int L,
+                   int nlat, int E, int ab_rows) {
     extern __shared__ double s_pk[];  // [Kn][S1_TI]
     const int m = blockIdx.y;
     const int i0 = blockIdx.x * S1_TI;
@@ -115,11 +116,12 @@ gb_legendre_stage1_simple(const double* __restrict__ X, double* __restrict__ AB,
         }
         const int e = col >> 1, cs = col & 1;
         const int i = i0 + ig * 4;
-        double* dst = AB + (size_t)(2 * m + cs) * mpad + (size_t)e * nlat + i;
-        if (i + 0 < nlat) dst[0] = a0;
-        if (i + 1 < nlat) dst[1] = a1;
-        if (i + 2 < nlat) dst[2] = a2;
-        if (i + 3 < nlat) dst[3] = a3;
+        const int k = krow[2 * m + cs];
+        const long long row = (long long)e * nlat + i;
+        if (i + 0 < nlat) AB[gb_ab_offset(row + 0, k, ab_rows)] = a0;
+        if (i + 1 < nlat) AB[gb_ab_offset(row + 1, k, ab_rows)] = a1;
+        if (i + 2 < nlat) AB[gb_ab_offset(row + 2, k, ab_rows)] = a2;
+        if (i + 3 < nlat) AB[gb_ab_offset(row + 3, k, ab_rows)] = a3;
     }
 }
 
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(T1_THREADS, 1)
 gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const double* __restrict__ ct,
                    const double* __restrict__ kn, const double* __restrict__ pmm, const double* __restrict__ ra,
                    const double* __restrict__ rb, const double* __restrict__ rc, const double* __restrict__ zeros,
-                   int L, int nlat, int E, long long mpad, int n_coltiles) {
+                   const int* __restrict__ krow, int L, int nlat, int E, int ab_rows, int n_coltiles) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)T1_STAGES * T1_STAGE_DOUBLES * sizeof(double));
@@ -271,14 +273,14 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const 
             const int col = c0 + wn * 40 + ni * 8 + 2 * q;
             if (col >= cols) continue;
             const int e = col >> 1;
-            double* dc = AB + (size_t)(2 * m) * mpad + (size_t)e * nlat;
-            double* ds = dc + mpad;
+            const int kc_row = krow[2 * m], ks_row = krow[2 * m + 1];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const int i = i0 + wm * 32 + mi * 8 + g;
                 if (i < nlat) {
-                    dc[i] = acc[mi][ni][0];
-                    ds[i] = acc[mi][ni][1];
+                    const long long row = (long long)e * nlat + i;
+                    AB[gb_ab_offset(row, kc_row, ab_rows)] = acc[mi][ni][0];
+                    AB[gb_ab_offset(row, ks_row, ab_rows)] = acc[mi][ni][1];
                 }
             }
         }
@@ -291,6 +293,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const 
 constexpr int S2_WM = 4, S2_WN = 3;            // consumer warp grid
 constexpr int S2_TM = 32 * S2_WM;              // 128 rows per CTA tile
 constexpr int S2_TN = 40 * S2_WN;              // 120 columns per CTA tile
+static_assert(S2_TM == GB_TM && S2_TN == GB_S2_TN, "tile shape must match the tiled HBM layouts");
 constexpr int S2_KC = 28;                      // spectral rows per pipeline stage
 constexpr int S2_STAGES = 3;
 constexpr int S2_LDA = S2_TM + 4;              // 132: k-rows land 4 doubles apart mod 16 -> conflict-free fragments
@@ -301,7 +304,7 @@ constexpr int S2_STAGE_DOUBLES = S2_KC * (S2_LDA + S2_LDB);
 constexpr size_t S2_SMEM = (size_t)S2_STAGES * S2_STAGE_DOUBLES * sizeof(double) + 2 * S2_STAGES * sizeof(uint64_t);
 
 __global__ void __launch_bounds__(S2_THREADS, 1)
-gb_fourier_stage2(const double* __restrict__ AB, long long mpad, const double* __restrict__ trig, int nlp, int kpad,
+gb_fourier_stage2(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig_t, int kpad,
                   double* __restrict__ out, long long M, int nlon, int n_mtiles, int n_ntiles) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
@@ -324,28 +327,23 @@ gb_fourier_stage2(const double* __restrict__ AB, long long mpad, const double* _
     uint32_t phase = 0;
 
     if (warp == S2_CONSUMER_WARPS) {
-        // ===== producer warp: one bulk copy per spectral row of each operand =====
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const long long mt = t / n_ntiles;
-            const int nt = (int)(t % n_ntiles);
-            const long long m0 = mt * S2_TM;
-            const int n0 = nt * S2_TN;
-            const int width = min(S2_TN, nlp - n0);
-            for (int k0 = 0; k0 < kpad; k0 += S2_KC) {
-                const int kc = min(S2_KC, kpad - k0);
-                gb::mbar_wait(&empty[stage], phase ^ 1u);
-                double* sA = s_tiles + (size_t)stage * S2_STAGE_DOUBLES;
-                double* sB = sA + S2_KC * S2_LDA;
-                if (lane == 0)
-                    gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(kc * (S2_TM + width) * sizeof(double)));
-                __syncwarp();
-                if (lane < kc) {
-                    gb::bulk_g2s(sA + lane * S2_LDA, AB + (size_t)(k0 + lane) * mpad + m0,
-                                 (uint32_t)(S2_TM * sizeof(double)), &full[stage]);
-                    gb::bulk_g2s(sB + lane * S2_LDB, trig + (size_t)(k0 + lane) * nlp + n0,
-                                 (uint32_t)(width * sizeof(double)), &full[stage]);
+        // ===== producer warp: the tiled layouts make every chunk one contiguous block per operand =====
+        if (lane == 0) {
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const long long mt = t / n_ntiles;
+                const int nt = (int)(t % n_ntiles);
+                for (int k0 = 0; k0 < kpad; k0 += S2_KC) {
+                    const int kc = min(S2_KC, kpad - k0);
+                    gb::mbar_wait(&empty[stage], phase ^ 1u);
+                    double* sA = s_tiles + (size_t)stage * S2_STAGE_DOUBLES;
+                    double* sB = sA + S2_KC * S2_LDA;
+                    const uint32_t bytes_a = (uint32_t)(kc * S2_LDA * sizeof(double));
+                    const uint32_t bytes_b = (uint32_t)(kc * S2_LDB * sizeof(double));
+                    gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
+                    gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * S2_LDA, bytes_a, &full[stage]);
+                    gb::bulk_g2s(sB, trig_t + ((size_t)nt * kpad + k0) * S2_LDB, bytes_b, &full[stage]);
+                    if (++stage == S2_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                if (++stage == S2_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
@@ -368,8 +366,9 @@ gb_fourier_stage2(const double* __restrict__ AB, long long mpad, const double* _
                 gb::mbar_wait(&full[stage], phase);
                 const double* sA = s_tiles + (size_t)stage * S2_STAGE_DOUBLES + wm * 32 + g;
                 const double* sB = s_tiles + (size_t)stage * S2_STAGE_DOUBLES + S2_KC * S2_LDA + wn * 40 + g;
-#pragma unroll 1
-                for (int kk = 0; kk < kc; kk += 4) {
+#pragma unroll
+                for (int kk = 0; kk < S2_KC; kk += 4) {
+                    if (kk >= kc) break;
                     double a[4], b[5];
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * S2_LDA + mi * 8];
@@ -409,16 +408,165 @@ gb_fourier_stage2(const double* __restrict__ AB, long long mpad, const double* _
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// stage 2 with four-fold longitude symmetry.  For mu = lon[h + j'] in the first quadrant
+//   CE = sum_{m even} A_m cos(m mu)   CO = sum_{m odd} A_m cos(m mu)
+//   SE = sum_{m even} B_m sin(m mu)   SO = sum_{m odd} B_m sin(m mu)
+//   V(mu)      = CE + CO + SE + SO  -> column h + j'        V(pi - mu) = CE - CO - SE + SO -> nlon-1-j'
+//   V(-mu)     = CE + CO - SE - SO  -> column h - 1 - j'    V(mu - pi) = CE - CO + SE - SO -> j'
+// so one quarter of the multiply-adds of the direct contraction produce all four columns.
+// AB rows are grouped [CE | CO | SE | SO] (gb_plan::grp_off); the K loop walks the groups in
+// turn, each feeding its own accumulator set.  CTA tile: 128 rows x 32 first-quadrant columns
+// (= 128 x 128 outputs), 8 consumer warps (4 x 2) with 32 x 16 x 4-set register tiles.
+// ---------------------------------------------------------------------------------------------
+constexpr int Q_WM = 4, Q_WN = 2;
+constexpr int Q_TM = 32 * Q_WM;               // 128
+constexpr int Q_TN = 16 * Q_WN;               // 32 first-quadrant columns
+static_assert(Q_TM == GB_TM && Q_TN == GB_Q_TN, "tile shape must match the tiled HBM layouts");
+constexpr int Q_KC = 28;
+constexpr int Q_STAGES = 4;
+constexpr int Q_LDA = Q_TM + 4;               // 132
+constexpr int Q_LDB = Q_TN + 4;               // 36
+constexpr int Q_CONSUMER_WARPS = Q_WM * Q_WN;
+constexpr int Q_THREADS = 32 * (Q_CONSUMER_WARPS + 1);
+constexpr int Q_STAGE_DOUBLES = Q_KC * (Q_LDA + Q_LDB);
+constexpr size_t Q_SMEM = (size_t)Q_STAGES * Q_STAGE_DOUBLES * sizeof(double) + 2 * Q_STAGES * sizeof(uint64_t);
+
+struct QGroups { int off[5]; };
+
+__global__ void __launch_bounds__(Q_THREADS, 1)
+gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig_q_t, int kpad_s,
+                      QGroups grp, double* __restrict__ out, long long M, int nlon, int nq, int n_mtiles,
+                      int n_ntiles) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tiles = reinterpret_cast<double*>(s_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)Q_STAGES * Q_STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + Q_STAGES;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Q_STAGES; ++s) {
+            gb::mbar_init(&full[s], 1);
+            gb::mbar_init(&empty[s], Q_CONSUMER_WARPS);
+        }
+        gb::fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long n_tiles = (long long)n_mtiles * n_ntiles;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (warp == Q_CONSUMER_WARPS) {
+        if (lane == 0) {
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const long long mt = t / n_ntiles;
+                const int nt = (int)(t % n_ntiles);
+                for (int k0 = 0; k0 < grp.off[4];) {
+                    // chunks never straddle a group boundary
+                    int gend = grp.off[1];
+#pragma unroll
+                    for (int s = 1; s < 4; ++s)
+                        if (k0 >= grp.off[s]) gend = grp.off[s + 1];
+                    const int kc = min(Q_KC, gend - k0);
+                    gb::mbar_wait(&empty[stage], phase ^ 1u);
+                    double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES;
+                    double* sB = sA + Q_KC * Q_LDA;
+                    const uint32_t bytes_a = (uint32_t)(kc * Q_LDA * sizeof(double));
+                    const uint32_t bytes_b = (uint32_t)(kc * Q_LDB * sizeof(double));
+                    gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
+                    gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * Q_LDA, bytes_a, &full[stage]);
+                    gb::bulk_g2s(sB, trig_q_t + ((size_t)nt * kpad_s + k0) * Q_LDB, bytes_b, &full[stage]);
+                    if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+                    k0 += kc;
+                }
+            }
+        }
+    } else {
+        const int wm = warp / Q_WN;
+        const int wn = warp % Q_WN;
+        const int g = lane >> 2, q = lane & 3;
+        const int h = nlon >> 1;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long mt = t / n_ntiles;
+            const int nt = (int)(t % n_ntiles);
+            double acc[4][4][2][2];   // [set][mi][ni][2]
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) acc[s][mi][ni][0] = acc[s][mi][ni][1] = 0.0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                for (int k0 = grp.off[s]; k0 < grp.off[s + 1];) {
+                    const int kc = min(Q_KC, grp.off[s + 1] - k0);
+                    gb::mbar_wait(&full[stage], phase);
+                    const double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES + wm * 32 + g;
+                    const double* sB = s_tiles + (size_t)stage * Q_STAGE_DOUBLES + Q_KC * Q_LDA + wn * 16 + g;
+#pragma unroll
+                    for (int kk = 0; kk < Q_KC; kk += 4) {
+                        if (kk >= kc) break;
+                        double a[4], b[2];
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * Q_LDA + mi * 8];
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) b[ni] = sB[(kk + q) * Q_LDB + ni * 8];
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                            for (int ni = 0; ni < 2; ++ni)
+                                gb::dmma_884(acc[s][mi][ni][0], acc[s][mi][ni][1], a[mi], b[ni]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                    if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+                    k0 += kc;
+                }
+            }
+            // butterfly epilogue: four output columns per first-quadrant column
+            const long long row_base = mt * Q_TM + wm * 32 + g;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const long long row = row_base + mi * 8;
+                if (row >= M) continue;
+                double* orow = out + (size_t)row * nlon;
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    const int jq = nt * Q_TN + wn * 16 + ni * 8 + 2 * q;   // even; nq is even too
+                    if (jq >= nq) continue;
+                    double v1[2], v2[2], v3[2], v4[2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const double ce = acc[0][mi][ni][r], co = acc[1][mi][ni][r];
+                        const double se = acc[2][mi][ni][r], so = acc[3][mi][ni][r];
+                        const double cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
+                        v1[r] = cp + sp;   // mu
+                        v2[r] = cm - sm;   // pi - mu
+                        v3[r] = cp - sp;   // -mu
+                        v4[r] = cm + sm;   // mu - pi
+                    }
+                    gb::st_cs_v2(orow + h + jq, v1[0], v1[1]);
+                    gb::st_cs_v2(orow + nlon - 2 - jq, v2[1], v2[0]);
+                    gb::st_cs_v2(orow + h - 2 - jq, v3[1], v3[0]);
+                    gb::st_cs_v2(orow + jq, v4[0], v4[1]);
+                }
+            }
+        }
+    }
+}
+
 // Plain one-thread-per-output stage 2 (debug cross-check of the tensor-core kernel, GB_NAIVE_STAGE2=1).
 __global__ void __launch_bounds__(256)
-gb_fourier_stage2_naive(const double* __restrict__ AB, long long mpad, const double* __restrict__ trig, int nlp,
+gb_fourier_stage2_naive(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig, int nlp,
                         int kpad, double* __restrict__ out, long long M, int nlon) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * nlon) return;
     const long long row = idx / nlon;
     const int j = (int)(idx % nlon);
     double s = 0.0;
-    for (int k = 0; k < kpad; ++k) s = fma(AB[(size_t)k * mpad + row], trig[(size_t)k * nlp + j], s);
+    for (int k = 0; k < kpad; ++k) s = fma(AB[gb_ab_offset(row, k, ab_rows)], trig[(size_t)k * nlp + j], s);
     out[idx] = s;
 }
 
@@ -450,7 +598,6 @@ bool env_flag(const char* name) {
 static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_out, cudaStream_t st) {
     const int L = p->L;
     const long long M = (long long)E * p->nlat;
-    const long long mpad = p->ws_mpad;
     cudaEvent_t* prof = (p->prof_ev && p->prof_count < p->prof_capacity) ? p->prof_ev + (size_t)p->prof_count * 4 : nullptr;
     if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
     {
@@ -459,13 +606,16 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         GB_LAUNCH_CHECK();
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[1], st));
+    const bool naive2 = env_flag("GB_NAIVE_STAGE2");
+    const bool use_sym = p->sym && !naive2 && !env_flag("GB_NO_SYMMETRY");
+    const int* d_krow = use_sym ? p->d_krow_sym : p->d_krow_id;
     if (env_flag("GB_SIMPLE_STAGE1")) {
         dim3 grid((p->nlat + S1_TI - 1) / S1_TI, L);
         const size_t smem = (size_t)L * S1_TI * sizeof(double);
         if (smem > 48 * 1024)
             GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gb_legendre_stage1_simple<<<grid, 256, smem, st>>>(p->d_x, p->d_ab, p->d_ct, p->d_kn, p->d_pmm, p->d_ra,
-                                                           p->d_rb, p->d_rc, L, p->nlat, E, mpad);
+                                                           p->d_rb, p->d_rc, d_krow, L, p->nlat, E, p->ab_rows);
         GB_LAUNCH_CHECK();
     } else {
         const int n_coltiles = (2 * E + T1_TN - 1) / T1_TN;
@@ -474,23 +624,34 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         const size_t smem1 = T1_SMEM + 2 * (size_t)((L + T1_KC - 1) / T1_KC * T1_KC) * sizeof(double);
         GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         gb_legendre_stage1<<<grid, T1_THREADS, smem1, st>>>(p->d_x, p->d_ab, p->d_ct, p->d_kn, p->d_pmm, p->d_ra,
-                                                              p->d_rb, p->d_rc, p->d_zero, L, p->nlat, E, mpad,
-                                                              n_coltiles);
+                                                            p->d_rb, p->d_rc, p->d_zero, d_krow, L, p->nlat, E,
+                                                            p->ab_rows, n_coltiles);
         GB_LAUNCH_CHECK();
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[2], st));
-    if (env_flag("GB_NAIVE_STAGE2")) {
+    if (naive2) {
         const long long total = M * p->nlon;
-        gb_fourier_stage2_naive<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p->d_ab, mpad, p->d_trig, p->nlp,
+        gb_fourier_stage2_naive<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p->d_ab, p->ab_rows, p->d_trig, p->nlp,
                                                                                 p->kpad, d_out, M, p->nlon);
+        GB_LAUNCH_CHECK();
+    } else if (use_sym) {
+        const int n_mtiles = (int)((M + Q_TM - 1) / Q_TM);
+        const int n_ntiles = p->n_qtiles;
+        const long long n_tiles = (long long)n_mtiles * n_ntiles;
+        const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
+        QGroups grp;
+        for (int g = 0; g < 5; ++g) grp.off[g] = p->grp_off[g];
+        GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+        gb_fourier_stage2_sym<<<grid, Q_THREADS, Q_SMEM, st>>>(p->d_ab, p->ab_rows, p->d_trig_q_t, p->kpad_s, grp, d_out, M,
+                                                               p->nlon, p->nq, n_mtiles, n_ntiles);
         GB_LAUNCH_CHECK();
     } else {
         const int n_mtiles = (int)((M + S2_TM - 1) / S2_TM);
-        const int n_ntiles = (p->nlp + S2_TN - 1) / S2_TN;
+        const int n_ntiles = p->n_ntiles;
         const long long n_tiles = (long long)n_mtiles * n_ntiles;
         const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
         GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
-        gb_fourier_stage2<<<grid, S2_THREADS, S2_SMEM, st>>>(p->d_ab, mpad, p->d_trig, p->nlp, p->kpad, d_out, M,
+        gb_fourier_stage2<<<grid, S2_THREADS, S2_SMEM, st>>>(p->d_ab, p->ab_rows, p->d_trig_t, p->kpad, d_out, M,
                                                              p->nlon, n_mtiles, n_ntiles);
         GB_LAUNCH_CHECK();
     }

@@ -124,6 +124,25 @@ def test_synthesis_tensor_core_vs_plain_kernel(gb, orc, monkeypatch):
     assert maxnorm_err(fast, ref) < TOL
 
 
+@pytest.mark.parametrize("nmax,dlon,E", [(0, 5.0, 1), (1, 5.0, 2), (2, 45.0, 1), (45, 1.5, 5), (96, 0.5, 2), (97, 1.0, 3)])
+def test_synthesis_symmetric_vs_general_path(gb, orc, monkeypatch, nmax, dlon, E):
+    """Meridian counts divisible by 8 take the four-fold symmetric stage 2; it must agree with the
+    general contraction (GB_NO_SYMMETRY=1) to rounding and with the oracle to tolerance."""
+    grid = gb.GeographicGrid(dlon, 3.0)
+    anm = np.stack([orc.synthetic_coefficients(nmax, e) for e in range(E)])
+    anm[:, 0, 0] = 1e-6
+    if nmax >= 1:
+        anm[:, 1, 0], anm[:, 1, 1], anm[:, 0, 1] = 2e-6, -3e-6, 4e-6
+    sym = gb.to_grid_batch(anm, grid, "ewh")
+    monkeypatch.setenv("GB_NO_SYMMETRY", "1")
+    gen = gb.to_grid_batch(anm, grid, "ewh")
+    monkeypatch.delenv("GB_NO_SYMMETRY")
+    assert maxnorm_err(sym, gen) < 2e-13
+    og = orc.geographic_grid(dlon, 3.0)
+    ref = np.stack([orc.synthesis(a, og, "ewh") for a in anm])
+    assert maxnorm_err(sym, ref) < TOL and maxnorm_err(gen, ref) < TOL
+
+
 @pytest.mark.parametrize("nmax,dlon,dlat,E", [(1, 30.0, 30.0, 1), (2, 90.0, 45.0, 2), (17, 7.5, 4.0, 7),
                                               (33, 3.0, 3.0, 2), (96, 1.0, 0.5, 3)])
 def test_synthesis_ragged_shapes_vs_oracle(gb, orc, nmax, dlon, dlat, E):

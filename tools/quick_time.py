@@ -30,6 +30,9 @@ def run(N, d, E, reps=10):
           f"{E*plan.nlat*plan.nlon/best/1e6:.3f} Gpt.ep/s")
 
 if __name__ == "__main__":
-    run(96, 0.5, 240)
-    run(60, 1.0, 1)
-    run(180, 0.25, 120)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2":
+        run(96, 0.5, 240, reps=2)
+    else:
+        run(96, 0.5, 240)
+        run(60, 1.0, 1)
+        run(180, 0.25, 120)
