@@ -190,6 +190,8 @@ extern "C" int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon
     return GB_OK;
 }
 
+extern "C" int gb_plan_is_symmetric(const gb_plan* plan) { return (plan && plan->sym) ? 1 : 0; }
+
 extern "C" int gb_plan_destroy(gb_plan* p) {
     if (!p) return GB_OK;
     cudaSetDevice(p->device);

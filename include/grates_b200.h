@@ -74,6 +74,15 @@ int gb_plan_destroy(gb_plan* plan);
 int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon, int* device);
 
 /*
+ * 1 if the plan's meridians are symmetric about 0 and invariant under a half turn (all grids the
+ * reference constructs itself: GeographicGrid, GaussGrid with a meridian count divisible by 8).
+ * gb_synthesis then evaluates only the first quadrant of meridians and obtains the other three by
+ * sign changes (one quarter of the multiply-adds of the direct longitude contraction); set the
+ * environment variable GB_NO_SYMMETRY=1 to force the direct contraction.
+ */
+int gb_plan_is_symmetric(const gb_plan* plan);
+
+/*
  * Spherical-harmonic synthesis of n_epochs coefficient sets onto the plan's grid.
  * Replaces the body of PotentialCoefficients.to_grid, gravityfield.py:358-368, for a batch:
  *   out[e][i][j] = sum_n kn[i][n] sum_m P_nm(theta_i) (C_nm^e cos m lon_j + S_nm^e sin m lon_j)
