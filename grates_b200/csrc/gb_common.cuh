@@ -108,6 +108,12 @@ struct gb_plan {
 
 int gb_plan_ensure_workspace(gb_plan* p, int n_epochs);
 
+// Recursion coefficients a_nm, b_nm [L][L], sqrt(2n+1) [L] and sectorial seeds P_mm [npts][L],
+// evaluated in IEEE double in the operation order of reference utilities.py:37-54.
+#include <vector>
+void gb_recursion_tables(int nmax, int npts, const double* sin_theta, std::vector<double>& ra,
+                         std::vector<double>& rb, std::vector<double>& rc, std::vector<double>& pmm);
+
 // ---------------------------------------------------------------------------------------------
 // PTX helpers (device)
 // ---------------------------------------------------------------------------------------------

@@ -37,6 +37,39 @@ static int upload(T** d, const std::vector<T>& h) {
     return GB_OK;
 }
 
+void gb_recursion_tables(int nmax, int npts, const double* sin_theta, std::vector<double>& ra,
+                         std::vector<double>& rb, std::vector<double>& rc, std::vector<double>& pmm) {
+    const int L = nmax + 1;
+    // Recursion coefficients, evaluated exactly as utilities.py:46,52,54 (IEEE double, same
+    // operation order), so that the device recursion reproduces the reference table bit for bit.
+    ra.assign((size_t)L * L, 0.0);
+    rb.assign((size_t)L * L, 0.0);
+    rc.assign(L, 0.0);
+    for (int n = 0; n < L; ++n) rc[n] = std::sqrt((double)(2 * n + 1));
+    for (int n = 2; n < L; ++n)
+        for (int m = 0; m <= n - 2; ++m) {
+            const double dn = n, dm = m;
+            ra[(size_t)n * L + m] = std::sqrt((2.0 * dn - 1.0) / (dn - dm) * (2.0 * dn + 1.0) / (dn + dm));
+            rb[(size_t)n * L + m] =
+                std::sqrt((2.0 * dn + 1.0) / (2.0 * dn - 3.0) * (dn - dm - 1.0) / (dn - dm) * (dn + dm - 1.0) / (dn + dm));
+        }
+    // Sectorial seeds P_mm(theta_i) (utilities.py:37,39,41-43): O(npts * L) values, the only part
+    // of the Legendre triangle that is tabulated; everything below the diagonal is recomputed on
+    // the fly inside the kernels.
+    pmm.assign((size_t)npts * L, 0.0);
+    for (int i = 0; i < npts; ++i) {
+        double* row = &pmm[(size_t)i * L];
+        row[0] = 1.0;
+        if (L > 1) row[1] = std::sqrt(3.0) * sin_theta[i];
+        for (int n = 2; n < L; ++n) {
+            const double dn = n;
+            const double f = std::sqrt((2.0 * dn + 1.0) / (2.0 * dn));
+            const double fs = f * sin_theta[i];
+            row[n] = fs * row[n - 1];
+        }
+    }
+}
+
 extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, const double* cos_theta,
                               const double* sin_theta, const double* kn, const double* cos_mlon,
                               const double* sin_mlon, int device) {
@@ -66,32 +99,8 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
     p->sm_count = prop.multiProcessorCount;
     const int L = p->L;
 
-    // Recursion coefficients, evaluated exactly as utilities.py:46,52,54 (IEEE double, same
-    // operation order), so that the device recursion reproduces the reference table bit for bit.
-    std::vector<double> ra((size_t)L * L, 0.0), rb((size_t)L * L, 0.0), rc(L, 0.0);
-    for (int n = 0; n < L; ++n) rc[n] = std::sqrt((double)(2 * n + 1));
-    for (int n = 2; n < L; ++n)
-        for (int m = 0; m <= n - 2; ++m) {
-            const double dn = n, dm = m;
-            ra[(size_t)n * L + m] = std::sqrt((2.0 * dn - 1.0) / (dn - dm) * (2.0 * dn + 1.0) / (dn + dm));
-            rb[(size_t)n * L + m] =
-                std::sqrt((2.0 * dn + 1.0) / (2.0 * dn - 3.0) * (dn - dm - 1.0) / (dn - dm) * (dn + dm - 1.0) / (dn + dm));
-        }
-    // Sectorial seeds P_mm(theta_i) (utilities.py:37,39,41-43): O(nlat * L) values, the only part
-    // of the Legendre triangle that is tabulated; everything below the diagonal is recomputed on
-    // the fly inside the kernels.
-    std::vector<double> pmm((size_t)nlat * L);
-    for (int i = 0; i < nlat; ++i) {
-        double* row = &pmm[(size_t)i * L];
-        row[0] = 1.0;
-        if (L > 1) row[1] = std::sqrt(3.0) * sin_theta[i];
-        for (int n = 2; n < L; ++n) {
-            const double dn = n;
-            const double f = std::sqrt((2.0 * dn + 1.0) / (2.0 * dn));
-            const double fs = f * sin_theta[i];
-            row[n] = fs * row[n - 1];
-        }
-    }
+    std::vector<double> ra, rb, rc, pmm;
+    gb_recursion_tables(nmax, nlat, sin_theta, ra, rb, rc, pmm);
     std::vector<double> trig((size_t)p->kpad * p->nlp, 0.0);
     for (int m = 0; m < L; ++m)
         for (int j = 0; j < nlon; ++j) {

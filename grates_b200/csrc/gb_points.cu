@@ -1,0 +1,357 @@
+// Arbitrary point sets (the reference's IrregularGrid path): synthesis and covariance propagation.
+//
+//   gb_points_synthesis    replaces the irregular branch of PotentialCoefficients.to_grid
+//                          (reference gravityfield.py:370-388): per point the Legendre recursion runs
+//                          on the fly (bit-identical values), scaled by kn[p,n], contracted against an
+//                          epoch tile of coefficients held in shared memory.
+//   gb_points_covariance   replaces IrregularGrid.covariance_propagation (reference grid.py:1096-1120):
+//                          var[p] = sum_ab F[p,a] Sigma[a,b] F[p,b] -- the direct, blocked
+//                          diag(F Sigma F') of the north star: F tiles generated on the fly
+//                          (gb_points_design), T = F Sigma on the FP64 tensor cores with Sigma rows
+//                          staged by the TMA unit (cp.async.bulk + mbarrier pipeline), and the
+//                          row-wise product with F folded into the epilogue with warp shuffles.
+//                          2 P K^2 flops, nothing assumed about the point geometry.
+#include <vector>
+#include <cmath>
+#include "gb_common.cuh"
+
+struct gb_points {
+    int device = 0, nmax = 0, L = 0, npts = 0, sm_count = 0;
+    double *d_ct = nullptr, *d_kn = nullptr, *d_pmm = nullptr, *d_cml = nullptr, *d_sml = nullptr;
+    double *d_ra = nullptr, *d_rb = nullptr, *d_rc = nullptr;
+};
+
+namespace {
+
+template <typename F>
+__device__ __forceinline__ void legendre_column(int m, int L, double ct, double pmm, const double* __restrict__ ra,
+                                                const double* __restrict__ rb, const double* __restrict__ rc, F&& f) {
+    double p2 = pmm;
+    f(m, p2);
+    if (m + 1 >= L) return;
+    double p1 = __dmul_rn(__dmul_rn(rc[m + 1], ct), p2);
+    f(m + 1, p1);
+    for (int n = m + 2; n < L; ++n) {
+        const double p = __dsub_rn(__dmul_rn(__dmul_rn(ra[(size_t)n * L + m], ct), p1),
+                                   __dmul_rn(rb[(size_t)n * L + m], p2));
+        f(n, p);
+        p2 = p1;
+        p1 = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthesis at points: thread = point, CTA = 128 points x 8 epochs, loop over orders
+// ---------------------------------------------------------------------------------------------
+constexpr int PE = 8;
+
+__global__ void __launch_bounds__(128)
+gb_points_synthesis_kernel(const double* __restrict__ anm, double* __restrict__ out, const double* __restrict__ ct,
+                           const double* __restrict__ kn, const double* __restrict__ pmm,
+                           const double* __restrict__ cml, const double* __restrict__ sml,
+                           const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc,
+                           int L, int npts, int E) {
+    extern __shared__ double s_coef[];   // [2][PE][L]
+    double* sC = s_coef;
+    double* sS = s_coef + PE * L;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e0 = blockIdx.y * PE;
+    const int ne = min(PE, E - e0);
+    const bool live = p < npts;
+    const double ctp = live ? ct[p] : 0.0;
+    const double* kn_p = kn + (size_t)(live ? p : 0) * L;
+    double v[PE];
+#pragma unroll
+    for (int e = 0; e < PE; ++e) v[e] = 0.0;
+    for (int m = 0; m < L; ++m) {
+        __syncthreads();
+        const int cnt = L - m;
+        for (int idx = threadIdx.x; idx < PE * cnt; idx += blockDim.x) {
+            const int e = idx / cnt, nn = idx % cnt;
+            const int n = m + nn;
+            double c = 0.0, s = 0.0;
+            if (e < ne) {
+                const double* a = anm + (size_t)(e0 + e) * L * L;
+                c = a[(size_t)n * L + m];
+                if (m > 0) s = a[(size_t)(m - 1) * L + n];
+            }
+            sC[e * L + nn] = c;
+            sS[e * L + nn] = s;
+        }
+        __syncthreads();
+        if (!live) continue;
+        double ac[PE], as[PE];
+#pragma unroll
+        for (int e = 0; e < PE; ++e) ac[e] = as[e] = 0.0;
+        legendre_column(m, L, ctp, pmm[(size_t)p * L + m], ra, rb, rc, [&](int n, double pn) {
+            const double pk = __dmul_rn(pn, kn_p[n]);
+            const int nn = n - m;
+#pragma unroll
+            for (int e = 0; e < PE; ++e) {
+                ac[e] = fma(pk, sC[e * L + nn], ac[e]);
+                as[e] = fma(pk, sS[e * L + nn], as[e]);
+            }
+        });
+        const double cm = cml[(size_t)p * L + m], sm = sml[(size_t)p * L + m];
+#pragma unroll
+        for (int e = 0; e < PE; ++e) v[e] = fma(cm, ac[e], fma(sm, as[e], v[e]));
+    }
+    if (live)
+        for (int e = 0; e < ne; ++e) out[(size_t)(e0 + e) * npts + p] = v[e];
+}
+
+// ---------------------------------------------------------------------------------------------
+// design matrix F^T in the tiled layout [point tile][a][GB_LDA], a = degree-wise index - nmin^2
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gb_points_design(double* __restrict__ FT, const double* __restrict__ ct, const double* __restrict__ kn,
+                 const double* __restrict__ pmm, const double* __restrict__ cml, const double* __restrict__ sml,
+                 const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc, int L,
+                 int nmin, int npts, int rows) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (p >= npts) return;
+    const double* kn_p = kn + (size_t)p * L;
+    const double cm = cml[(size_t)p * L + m], sm = sml[(size_t)p * L + m];
+    const int off = nmin * nmin;
+    legendre_column(m, L, ct[p], pmm[(size_t)p * L + m], ra, rb, rc, [&](int n, double pn) {
+        if (n < nmin) return;
+        const double pk = __dmul_rn(pn, kn_p[n]);
+        const int a = n * n + (m == 0 ? 0 : 2 * m - 1) - off;
+        FT[gb_ab_offset(p, a, rows)] = __dmul_rn(pk, cm);
+        if (m > 0) FT[gb_ab_offset(p, a + 1, rows)] = __dmul_rn(pk, sm);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocked diag(F Sigma F'): tile = 128 points x 120 columns b; K loop over a in chunks of 28
+// ---------------------------------------------------------------------------------------------
+constexpr int C_WM = 4, C_WN = 3, C_TM = 128, C_TN = 120, C_KC = 28, C_STAGES = 3;
+constexpr int C_LDA = GB_LDA, C_LDB = C_TN + 4;
+constexpr int C_CONSUMER_WARPS = C_WM * C_WN;
+constexpr int C_THREADS = 32 * (C_CONSUMER_WARPS + 1);
+constexpr int C_STAGE_DOUBLES = C_KC * (C_LDA + C_LDB);
+constexpr size_t C_SMEM = (size_t)C_STAGES * C_STAGE_DOUBLES * sizeof(double) + 2 * C_STAGES * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(C_THREADS, 1)
+gb_points_quadform(const double* __restrict__ FT, int rows, const double* __restrict__ sig, long long lds, int Kp,
+                   long long Kc, double* __restrict__ var, int npts, int n_mtiles, int n_ntiles) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tiles = reinterpret_cast<double*>(s_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)C_STAGES * C_STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + C_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C_STAGES; ++s) {
+            gb::mbar_init(&full[s], 1);
+            gb::mbar_init(&empty[s], C_CONSUMER_WARPS);
+        }
+        gb::fence_mbar_init();
+    }
+    __syncthreads();
+    const long long n_tiles = (long long)n_mtiles * n_ntiles;
+    int stage = 0;
+    uint32_t phase = 0;
+    if (warp == C_CONSUMER_WARPS) {
+        // producer: one bulk copy for the F^T chunk, one per covariance row
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long mt = t / n_ntiles;
+            const int n0 = (int)(t % n_ntiles) * C_TN;
+            long long w = Kc - n0;
+            if (w > C_TN) w = C_TN;
+            const int width = (int)((w + 1) & ~1LL);     // even number of doubles (16-byte granules)
+            for (int k0 = 0; k0 < Kp; k0 += C_KC) {
+                const int kc = min(C_KC, Kp - k0);
+                gb::mbar_wait(&empty[stage], phase ^ 1u);
+                double* sA = s_tiles + (size_t)stage * C_STAGE_DOUBLES;
+                double* sB = sA + C_KC * C_LDA;
+                if (lane == 0) {
+                    const uint32_t bytes_a = (uint32_t)(kc * C_LDA * sizeof(double));
+                    gb::mbar_arrive_expect_tx(&full[stage], bytes_a + (uint32_t)(kc * width * sizeof(double)));
+                    gb::bulk_g2s(sA, FT + ((size_t)mt * rows + k0) * C_LDA, bytes_a, &full[stage]);
+                }
+                __syncwarp();
+                if (lane < kc)
+                    gb::bulk_g2s(sB + lane * C_LDB, sig + (size_t)(k0 + lane) * lds + n0,
+                                 (uint32_t)(width * sizeof(double)), &full[stage]);
+                if (++stage == C_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        const int wm = warp / C_WN, wn = warp % C_WN;
+        const int g = lane >> 2, q = lane & 3;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long mt = t / n_ntiles;
+            const int n0 = (int)(t % n_ntiles) * C_TN;
+            double acc[4][5][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int k0 = 0; k0 < Kp; k0 += C_KC) {
+                const int kc = min(C_KC, Kp - k0);
+                gb::mbar_wait(&full[stage], phase);
+                const double* sA = s_tiles + (size_t)stage * C_STAGE_DOUBLES + wm * 32 + g;
+                const double* sB = s_tiles + (size_t)stage * C_STAGE_DOUBLES + C_KC * C_LDA + wn * 40 + g;
+#pragma unroll
+                for (int kk = 0; kk < C_KC; kk += 4) {
+                    if (kk >= kc) break;
+                    double a[4], b[5];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * C_LDA + mi * 8];
+#pragma unroll
+                    for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * C_LDB + ni * 8];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                }
+                __syncwarp();
+                if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                if (++stage == C_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            // epilogue: var[p] += sum_b T[p,b] F[p,b] over this tile's columns
+            const double* ft = FT + (size_t)mt * rows * C_LDA;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int r = wm * 32 + mi * 8 + g;
+                double part = 0.0;
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni) {
+                    const long long b = (long long)n0 + wn * 40 + ni * 8 + 2 * q;
+                    if (b < Kc) part = fma(acc[mi][ni][0], ft[(size_t)b * C_LDA + r], part);
+                    if (b + 1 < Kc) part = fma(acc[mi][ni][1], ft[(size_t)(b + 1) * C_LDA + r], part);
+                }
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                const long long p = mt * C_TM + r;
+                if (q == 0 && p < npts) atomicAdd(var + p, part);
+            }
+        }
+    }
+}
+
+__global__ void gb_points_sqrt(double* v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = sqrt(v[i]);
+}
+
+template <typename T>
+int upload(T** d, const std::vector<T>& h) {
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(d), (h.size() ? h.size() : 1) * sizeof(T)));
+    GB_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return GB_OK;
+}
+
+}  // namespace
+
+extern "C" int gb_points_create(gb_points** out, int nmax, int npts, const double* cos_theta, const double* sin_theta,
+                                const double* kn, const double* cos_mlon, const double* sin_mlon, int device) {
+    GB_REQUIRE(out != nullptr, "gb_points_create: out is NULL");
+    *out = nullptr;
+    GB_REQUIRE(nmax >= 0 && nmax <= 2047, "gb_points_create: nmax=%d out of range [0, 2047]", nmax);
+    GB_REQUIRE(npts >= 1, "gb_points_create: empty point set");
+    GB_REQUIRE(cos_theta && sin_theta && kn && cos_mlon && sin_mlon, "gb_points_create: NULL table pointer");
+    int ndev = 0;
+    GB_CUDA(cudaGetDeviceCount(&ndev));
+    GB_REQUIRE(device >= 0 && device < ndev, "gb_points_create: device %d not available (%d visible)", device, ndev);
+    GB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return gb_set_error(GB_ERR_UNSUPPORTED, "gb_points_create: device %d is sm_%d%d; built for sm_100a", device,
+                            prop.major, prop.minor);
+    gb_points* p = new gb_points();
+    p->device = device;
+    p->nmax = nmax;
+    p->L = nmax + 1;
+    p->npts = npts;
+    p->sm_count = prop.multiProcessorCount;
+    const int L = p->L;
+    std::vector<double> ra, rb, rc, pmm;
+    gb_recursion_tables(nmax, npts, sin_theta, ra, rb, rc, pmm);
+    const size_t tl = (size_t)npts * L;
+    int rc_ = GB_OK;
+    if ((rc_ = upload(&p->d_ct, std::vector<double>(cos_theta, cos_theta + npts))) ||
+        (rc_ = upload(&p->d_kn, std::vector<double>(kn, kn + tl))) || (rc_ = upload(&p->d_pmm, pmm)) ||
+        (rc_ = upload(&p->d_cml, std::vector<double>(cos_mlon, cos_mlon + tl))) ||
+        (rc_ = upload(&p->d_sml, std::vector<double>(sin_mlon, sin_mlon + tl))) || (rc_ = upload(&p->d_ra, ra)) ||
+        (rc_ = upload(&p->d_rb, rb)) || (rc_ = upload(&p->d_rc, rc))) {
+        gb_points_destroy(p);
+        return rc_;
+    }
+    *out = p;
+    return GB_OK;
+}
+
+extern "C" int gb_points_destroy(gb_points* p) {
+    if (!p) return GB_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_ct); cudaFree(p->d_kn); cudaFree(p->d_pmm); cudaFree(p->d_cml); cudaFree(p->d_sml);
+    cudaFree(p->d_ra); cudaFree(p->d_rb); cudaFree(p->d_rc);
+    delete p;
+    return GB_OK;
+}
+
+extern "C" int gb_points_synthesis(gb_points* p, const double* d_anm, int n_epochs, double* d_out, void* stream) {
+    GB_REQUIRE(p != nullptr, "gb_points_synthesis: point set is NULL");
+    GB_REQUIRE(n_epochs >= 0, "gb_points_synthesis: n_epochs=%d is negative", n_epochs);
+    if (n_epochs == 0) return GB_OK;
+    GB_REQUIRE(d_anm && d_out, "gb_points_synthesis: NULL device pointer");
+    GB_CUDA(cudaSetDevice(p->device));
+    dim3 grid((p->npts + 127) / 128, (n_epochs + PE - 1) / PE);
+    const size_t smem = (size_t)2 * PE * p->L * sizeof(double);
+    if (smem > 48 * 1024)
+        GB_CUDA(cudaFuncSetAttribute(gb_points_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gb_points_synthesis_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        d_anm, d_out, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra, p->d_rb, p->d_rc, p->L, p->npts,
+        n_epochs);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}
+
+extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmin, double* d_out, int take_sqrt,
+                                    void* stream) {
+    GB_REQUIRE(p != nullptr, "gb_points_covariance: point set is NULL");
+    GB_REQUIRE(nmin >= 0 && nmin <= p->nmax, "gb_points_covariance: min_degree=%d outside [0, %d]", nmin, p->nmax);
+    GB_REQUIRE(d_sigma && d_out, "gb_points_covariance: NULL device pointer");
+    GB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int L = p->L;
+    const long long Kc = (long long)L * L - (long long)nmin * nmin;   // coefficients
+    const int Kp = (int)((Kc + 3) / 4 * 4);                            // padded to whole k4 steps
+    const long long lds = (Kc + 1) / 2 * 2 + 2;                        // even leading dimension, room for the tail
+    const int n_mtiles = (p->npts + C_TM - 1) / C_TM;
+    const int n_ntiles = (int)((Kc + C_TN - 1) / C_TN);
+    double *d_ft = nullptr, *d_sig = nullptr;
+    const size_t ft_elems = (size_t)n_mtiles * Kp * C_LDA;
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ft), ft_elems * sizeof(double), st));
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_sig), (size_t)Kp * lds * sizeof(double), st));
+    GB_CUDA(cudaMemsetAsync(d_ft, 0, ft_elems * sizeof(double), st));
+    GB_CUDA(cudaMemsetAsync(d_sig, 0, (size_t)Kp * lds * sizeof(double), st));
+    GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->npts * sizeof(double), st));
+    // covariance rows re-pitched to an even leading dimension (16-byte aligned rows for the bulk copies)
+    GB_CUDA(cudaMemcpy2DAsync(d_sig, lds * sizeof(double), d_sigma, Kc * sizeof(double), Kc * sizeof(double), Kc,
+                              cudaMemcpyDeviceToDevice, st));
+    {
+        dim3 grid((p->npts + 127) / 128, L);
+        gb_points_design<<<grid, 128, 0, st>>>(d_ft, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra, p->d_rb,
+                                              p->d_rc, L, nmin, p->npts, Kp);
+        GB_LAUNCH_CHECK();
+    }
+    {
+        const long long n_tiles = (long long)n_mtiles * n_ntiles;
+        const int grid = (int)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
+        GB_CUDA(cudaFuncSetAttribute(gb_points_quadform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM));
+        gb_points_quadform<<<grid, C_THREADS, C_SMEM, st>>>(d_ft, Kp, d_sig, lds, Kp, Kc, d_out, p->npts, n_mtiles,
+                                                            n_ntiles);
+        GB_LAUNCH_CHECK();
+    }
+    if (take_sqrt) {
+        gb_points_sqrt<<<(p->npts + 255) / 256, 256, 0, st>>>(d_out, p->npts);
+        GB_LAUNCH_CHECK();
+    }
+    GB_CUDA(cudaFreeAsync(d_ft, st));
+    GB_CUDA(cudaFreeAsync(d_sig, st));
+    return GB_OK;
+}

@@ -111,14 +111,25 @@ class PotentialCoefficients:
         """Gridded values of the coefficient set on a regular grid, computed on the GPU.
 
         Parameters and return value as reference gravityfield.py:331-390: returns a deep copy
-        of ``grid`` (same class) whose ``value_array`` holds the synthesis; the input grid is
-        left untouched.  Irregular grids raise NotImplementedError (no CPU fallback).
+        of ``grid`` (same class) whose values hold the synthesis; the input grid is left
+        untouched.  Regular grids (``parallels`` x ``meridians``) take the two-stage tensor-core path,
+        any other grid with ``longitude`` / ``latitude`` the point-set kernels (the reference's
+        irregular branch, gravityfield.py:370-388).  There is no CPU fallback.
         """
         grid = GeographicGrid() if grid is None else grid
-        p = _plan.get_plan(grid, self.max_degree, kernel, self.GM, self.R)
+        anm = np.ascontiguousarray(self.anm, dtype=float)[None]
+        if not (_plan.is_regular(grid) or (hasattr(grid, "longitude") and hasattr(grid, "latitude"))):
+            raise TypeError("grid must expose parallels/meridians or longitude/latitude")
         output_grid = grid.copy()
-        result = p.synthesis_host(np.ascontiguousarray(self.anm, dtype=float)[None])
-        output_grid.values = result.reshape(-1)
+        if _plan.is_regular(grid):
+            p = _plan.get_plan(grid, self.max_degree, kernel, self.GM, self.R)
+            output_grid.values = p.synthesis_host(anm).reshape(-1)
+        elif hasattr(grid, "longitude") and hasattr(grid, "latitude"):
+            p = _plan.get_points_plan(grid, self.max_degree, kernel, self.GM, self.R)
+            dev = torch.device("cuda", p.device)
+            output_grid.values = p.synthesis(torch.as_tensor(anm).to(dev)).cpu().numpy().reshape(-1)
+        else:
+            raise TypeError("grid must expose parallels/meridians or longitude/latitude")
         return output_grid
 
 
@@ -201,6 +212,12 @@ def to_grid_batch(anm, grid=None, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT, devi
     result stays on the device, otherwise it is copied to the host inside the call."""
     grid = GeographicGrid() if grid is None else grid
     L = anm.shape[-1]
+    if not _plan.is_regular(grid):
+        p = _plan.get_points_plan(grid, L - 1, kernel, GM, R)      # -> [E, points]
+        on_device = isinstance(anm, torch.Tensor)
+        x = anm if on_device else torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", p.device))
+        vals = p.synthesis(x, out=out if on_device or device_output else None)
+        return vals if (on_device or device_output) else vals.cpu().numpy()
     p = _plan.get_plan(grid, L - 1, kernel, GM, R)
     if isinstance(anm, torch.Tensor):
         return p.synthesis(anm, out=out)

@@ -134,6 +134,60 @@ class RegularGrid:
         return std.copy()
 
 
+class IrregularGrid:
+    """Arbitrary point distribution on the ellipsoid (reference grid.py:842-1120): longitude /
+    latitude pairs in radians, optional per-point area elements (default 4 pi / point count)."""
+
+    def __init__(self, longitude, latitude, area_element=None, a=6378137.0, f=298.2572221010 ** -1):
+        self._lons = np.asarray(longitude, dtype=float)
+        self._lats = np.asarray(latitude, dtype=float)
+        self._areas = np.full(self._lons.size, 4 * np.pi / self._lons.size) if area_element is None else area_element
+        self._a, self._f = a, f
+        self._values = None
+        self.epoch = None
+
+    def copy(self):
+        grid = IrregularGrid(self._lons.copy(), self._lats.copy(), self._areas.copy(), self._a, self._f)
+        if self._values is not None:
+            grid.values = self._values.copy()
+        grid.epoch = self.epoch
+        return grid
+
+    semimajor_axis = property(lambda self: self._a)
+    flattening = property(lambda self: self._f)
+    longitude = property(lambda self: self._lons)
+    latitude = property(lambda self: self._lats)
+    area = property(lambda self: self._areas)
+    point_count = property(lambda self: self._lons.size)
+    size = property(lambda self: self._lons.size)
+
+    @property
+    def values(self):
+        return self._values
+
+    @values.setter
+    def values(self, val):
+        if val is None:
+            self._values = None
+        elif isinstance(val, np.ndarray):
+            if val.ndim > 1:
+                raise ValueError("unable to assign values of dimension {0:d} to grid".format(val.ndim))
+            if val.size != self.point_count:
+                raise ValueError("unable to assign values of size {0:d} to grid with {1:d} points".format(val.size, self.point_count))
+            self._values = val
+        else:
+            raise ValueError("grid values must be either None or " + str(np.ndarray))
+
+    def covariance_propagation(self, covariance_matrix, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+        """sqrt(diag(F Sigma F')) at every point on the GPU (reference grid.py:1071-1120: 256-point
+        blocks of dense products); stores the standard deviations in ``self.values`` as the reference does."""
+        p = _plan.get_points_plan(self, max_degree, kernel, GM, R)
+        sigma = torch.as_tensor(np.ascontiguousarray(covariance_matrix, dtype=np.float64)).to(torch.device("cuda", p.device))
+        std = p.covariance_propagation(sigma, min_degree).cpu().numpy()
+        self.values = std
+        return std.copy()
+
+
 class GeographicGrid(RegularGrid):
     """Equi-angular geographic grid of pixel centres (reference grid.py:1141-1162)."""
 

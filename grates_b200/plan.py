@@ -296,13 +296,106 @@ def analysis_operators(plan, min_degree, w_lat, u_lon):
     return np.ascontiguousarray(lon_ops), np.ascontiguousarray(lat_ops), offsets
 
 
+class PointsPlan:
+    """Device tables for an arbitrary point set (reference IrregularGrid path); wraps ``gb_points``."""
+
+    def __init__(self, longitude, latitude, a, f, max_degree, kernel='ewh',
+                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
+        self._lib = _lib.load()
+        self.device = _current_device(device)
+        self.max_degree = int(max_degree)
+        self.longitude = np.ascontiguousarray(longitude, dtype=float)
+        self.latitude = np.ascontiguousarray(latitude, dtype=float)
+        if self.longitude.shape != self.latitude.shape or self.longitude.ndim != 1:
+            raise ValueError("longitude and latitude must be 1-d arrays of equal length")
+        self.npts = self.longitude.size
+        colat, kn = _kernel.degree_factors(kernel, self.max_degree, self.latitude, a, f, GM, R)
+        if not np.all(np.isfinite(kn)):
+            raise ValueError("kernel '{0}' has non-finite degree factors on this point set".format(kernel))
+        self.colat, self.kn = colat, kn
+        cos_t = np.ascontiguousarray(np.cos(colat))
+        sin_t = np.ascontiguousarray(np.sin(colat))
+        m = np.arange(self.max_degree + 1)[None, :]
+        arg = self.longitude[:, None] * m                 # == m * lon, reference utilities.py:303-304
+        cos_ml = np.ascontiguousarray(np.cos(arg))
+        sin_ml = np.ascontiguousarray(np.sin(arg))
+        handle = ctypes.c_void_p()
+        _lib.check(self._lib.gb_points_create(ctypes.byref(handle), self.max_degree, self.npts, _ptr(cos_t), _ptr(sin_t),
+                                              _ptr(kn), _ptr(cos_ml), _ptr(sin_ml), self.device))
+        self._handle = handle
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.gb_points_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def L(self):
+        return self.max_degree + 1
+
+    def synthesis(self, anm, out=None):
+        """anm: CUDA float64 [E, L, L] -> CUDA tensor [E, npts]."""
+        if anm.dim() != 3 or anm.shape[1] != self.L or anm.shape[2] != self.L:
+            raise ValueError("coefficients must have shape [epochs, {0}, {0}] (got {1})".format(self.L, tuple(anm.shape)))
+        if anm.dtype != torch.float64 or not anm.is_cuda or anm.device.index != self.device:
+            raise ValueError("coefficients must be a float64 CUDA tensor on device {0}".format(self.device))
+        anm = anm.contiguous()
+        E = anm.shape[0]
+        if out is None:
+            out = torch.empty((E, self.npts), dtype=torch.float64, device=anm.device)
+        _lib.check(self._lib.gb_points_synthesis(self._handle, ctypes.c_void_p(anm.data_ptr()), E,
+                                                 ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+        return out
+
+    def covariance_propagation(self, sigma, min_degree, take_sqrt=True):
+        """sigma: CUDA tensor [K', K'] in degree-wise order -> [npts] standard deviations / variances."""
+        kp = self.L ** 2 - min_degree ** 2
+        if sigma.dim() != 2 or tuple(sigma.shape) != (kp, kp):
+            raise ValueError("covariance matrix must have shape [{0}, {0}] (got {1})".format(kp, tuple(sigma.shape)))
+        if sigma.dtype != torch.float64 or not sigma.is_cuda or sigma.device.index != self.device:
+            raise ValueError("covariance matrix must be a float64 CUDA tensor on device {0}".format(self.device))
+        sigma = sigma.contiguous()
+        out = torch.empty((self.npts,), dtype=torch.float64, device=sigma.device)
+        _lib.check(self._lib.gb_points_covariance(self._handle, ctypes.c_void_p(sigma.data_ptr()), int(min_degree),
+                                                  ctypes.c_void_p(out.data_ptr()), int(bool(take_sqrt)),
+                                                  _stream_handle(self.device)))
+        return out
+
+
+def get_points_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
+    """Cached PointsPlan for a grid object exposing .longitude/.latitude/.semimajor_axis/.flattening."""
+    dev = _current_device(device)
+    lon = np.asarray(grid.longitude, dtype=float)
+    lat = np.asarray(grid.latitude, dtype=float)
+    key = ("points", lon.tobytes(), lat.tobytes(), float(grid.semimajor_axis), float(grid.flattening),
+           int(max_degree), kernel.lower(), float(GM), float(R), dev)
+    with _cache_lock:
+        plan = _cache.get(key)
+        if plan is None:
+            plan = PointsPlan(lon, lat, grid.semimajor_axis, grid.flattening, max_degree, kernel, GM, R, dev)
+            if len(_cache) >= _MAX_CACHED_PLANS:
+                _cache.pop(next(iter(_cache))).close()
+            _cache[key] = plan
+        return plan
+
+
+def is_regular(grid):
+    return hasattr(grid, "parallels") and hasattr(grid, "meridians")
+
+
 def get_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
     """Cached plan for a regular grid object exposing .meridians/.parallels/.semimajor_axis/.flattening."""
     try:
         meridians, parallels = grid.meridians, grid.parallels
     except AttributeError:
-        raise NotImplementedError("the B200 path handles regular grids (meridians x parallels); "
-                                  "irregular point sets are not supported and there is no CPU fallback") from None
+        raise NotImplementedError("this call needs a regular grid (meridians x parallels); use the point-set "
+                                  "entry points for irregular grids -- there is no CPU fallback") from None
     dev = _current_device(device)
     key = (np.asarray(meridians, dtype=float).tobytes(), np.asarray(parallels, dtype=float).tobytes(),
            float(grid.semimajor_axis), float(grid.flattening), int(max_degree), kernel.lower(), float(GM), float(R), dev)

@@ -145,6 +145,22 @@ int gb_orderwise_filter(const double* d_blocks, const int64_t* block_offsets, in
                         const double* d_anm_in, int n_epochs, int nmax, double* d_anm_out,
                         int device, void* stream);
 
+/*
+ * Arbitrary point sets (the reference's IrregularGrid path).  Tables are per point:
+ *   cos_theta, sin_theta [npts], kn [npts][nmax+1], cos_mlon, sin_mlon [npts][nmax+1]
+ *   (cos(m*lon_p), sin(m*lon_p), utilities.py:303-304).
+ * gb_points_synthesis replaces gravityfield.py:376-388: d_anm [n_epochs][L][L] -> d_out [n_epochs][npts].
+ * gb_points_covariance replaces grid.py:1103-1116: direct blocked diag(F Sigma F') with Sigma
+ *   [K'][K'] (degree-wise order, offset nmin^2) -> d_out [npts] variances (std-devs if take_sqrt).
+ */
+typedef struct gb_points gb_points;
+int gb_points_create(gb_points** points, int nmax, int npts, const double* cos_theta, const double* sin_theta,
+                     const double* kn, const double* cos_mlon, const double* sin_mlon, int device);
+int gb_points_destroy(gb_points* points);
+int gb_points_synthesis(gb_points* points, const double* d_anm, int n_epochs, double* d_out, void* stream);
+int gb_points_covariance(gb_points* points, const double* d_sigma, int nmin, double* d_out, int take_sqrt,
+                         void* stream);
+
 /* Pinned host memory for the *_host entry points. */
 int gb_host_alloc(void** ptr, uint64_t bytes);
 int gb_host_free(void* ptr);

@@ -290,6 +290,43 @@ def test_covariance_vs_oracle_and_row_blocks(gb, orc):
         plan.covariance_propagation(s[:-1, :-1], 0)
 
 
+# ------------------------------------------------------------------------------ irregular point sets
+def test_irregular_synthesis_golden(gb, golden, orc):
+    g = golden("synthesis")
+    ig = gb.IrregularGrid(g["irr_lon"], g["irr_lat"])
+    out = _pc(gb, g["irr_anm"]).to_grid(ig, "ewh")
+    assert type(out) is gb.IrregularGrid and out.values.shape == (700,) and ig.values is None
+    assert maxnorm_err(out.values, g["irr_ewh"]) < TOL
+    # batched, other kernel, against the oracle
+    rng = np.random.default_rng(3)
+    lon, lat = rng.uniform(-np.pi, np.pi, 1111), rng.uniform(-1.57, 1.57, 1111)
+    anm = np.stack([orc.synthetic_coefficients(40, e) for e in range(11)])
+    vals = gb.to_grid_batch(anm, gb.IrregularGrid(lon, lat), "geoid")
+    ref = np.stack([orc.synthesis_points(a, lon, lat, "geoid") for a in anm])
+    assert vals.shape == (11, 1111) and maxnorm_err(vals, ref) < TOL
+
+
+def test_irregular_covariance_golden(gb, golden, orc):
+    g = golden("covariance")
+    ig = gb.IrregularGrid(g["irr_lon"], g["irr_lat"])
+    std = ig.covariance_propagation(g["sigma"], 0, 8, "ewh")
+    assert std.shape == (300,) and maxnorm_err(std, g["std_irr_ewh"]) < TOL
+    np.testing.assert_array_equal(ig.values, std)
+    # larger: odd coefficient count, min_degree > 0, point count not a multiple of the tile
+    N, nmin = 24, 2
+    sigma = orc.synthetic_covariance(N, rank=16)[nmin * nmin:, nmin * nmin:]
+    rng = np.random.default_rng(9)
+    lon, lat = rng.uniform(-np.pi, np.pi, 777), rng.uniform(-1.57, 1.57, 777)
+    std = gb.IrregularGrid(lon, lat).covariance_propagation(sigma, nmin, N, "potential")
+    ref = orc.covariance_propagation_points(sigma, lon, lat, nmin, N, "potential")
+    assert maxnorm_err(std, ref) < TOL
+    # the direct point kernel and the structured regular-grid kernel agree on a regular grid
+    grid = gb.GeographicGrid(12.0, 9.0)
+    reg = grid.covariance_propagation(sigma, nmin, N, "potential")
+    pts = gb.IrregularGrid(grid.longitude, grid.latitude).covariance_propagation(sigma, nmin, N, "potential")
+    assert maxnorm_err(pts, reg) < TOL
+
+
 # ------------------------------------------------------------------------------ filter
 def test_orderwise_filter_golden(gb, golden):
     g = golden("filters")
@@ -330,11 +367,10 @@ def test_api_errors(gb):
     with pytest.raises(ValueError):
         gb.PotentialCoefficients(max_degree=3).to_grid(gb.GeographicGrid(30.0, 30.0), "no_such_kernel")
 
-    class Irregular:
-        longitude = np.zeros(3)
-        latitude = np.zeros(3)
+    with pytest.raises(TypeError):
+        gb.PotentialCoefficients(max_degree=3).to_grid(object(), "ewh")
     with pytest.raises(NotImplementedError):
-        gb.PotentialCoefficients(max_degree=3).to_grid(Irregular(), "ewh")
+        gb.get_plan(gb.IrregularGrid(np.zeros(3), np.zeros(3)), 3, "ewh")
     plan = gb.get_plan(gb.GeographicGrid(30.0, 30.0), 3, "ewh")
     with pytest.raises(ValueError):
         plan.synthesis(torch.zeros((1, 5, 5), dtype=torch.float64, device="cuda"))
