@@ -29,6 +29,8 @@ SIGNATURES = {
     "gb_plan_set_analysis": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),
     "gb_analysis": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
     "gb_analysis_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "gb_synthesis_matrix": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
+    "gb_analysis_matrix": (ctypes.c_int, [_vp, _vp, _vp]),
     "gb_covariance_propagation": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                                  ctypes.c_int, _vp]),
     "gb_orderwise_filter": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp,

@@ -123,6 +123,30 @@ class RegularGrid:
         coeffs.anm = anm
         return coeffs
 
+    def synthesis_matrix(self, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+        """Dense operator A [points, K'] mapping coefficients in degree-wise order to grid values
+        (reference grid.py:412-443), generated on the GPU."""
+        p = _plan.get_plan(self, max_degree, kernel, GM, R)
+        return p.synthesis_matrix(min_degree).cpu().numpy()
+
+    def synthesis_matrix_per_order(self, m, min_degree, max_degree, kernel, GM, R):
+        """Columns of the synthesis operator for one order: [points, n_m] for m = 0, else the tuple
+        (cosine part, sine part) (reference grid.py:627-663)."""
+        if m > max_degree:
+            raise ValueError('order exceeds maximum degree ({0:d} vs. {1:d})'.format(m, max_degree))
+        A = self.synthesis_matrix(min_degree, max_degree, kernel, GM, R)
+        n = np.arange(max(m, min_degree), max_degree + 1)
+        base = n * n - min_degree * min_degree
+        if m == 0:
+            return np.ascontiguousarray(A[:, base])
+        return np.ascontiguousarray(A[:, base + 2 * m - 1]), np.ascontiguousarray(A[:, base + 2 * m])
+
+    def analysis_matrix(self, min_degree, max_degree, kernel, GM=GM_DEFAULT, R=R_DEFAULT):
+        """Dense analysis operator [K', points], rows in degree-wise order (reference grid.py:698-730)."""
+        p = _plan.get_plan(self, max_degree, kernel, GM, R)
+        p.set_analysis(min_degree, self.area.reshape(p.nlat, p.nlon))
+        return p.analysis_matrix().cpu().numpy()
+
     def covariance_propagation(self, covariance_matrix, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
         """Propagate a degree-wise ordered coefficient covariance matrix to grid-point standard
         deviations, sqrt(diag(A Sigma A')), on the GPU.  Like the reference (grid.py:792-839)

@@ -195,6 +195,24 @@ class SHPlan:
                                          ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
 
+    def synthesis_matrix(self, min_degree=0):
+        """Dense synthesis operator [nlat*nlon, K'] (columns in degree-wise order) as a CUDA tensor."""
+        kp = self.L ** 2 - int(min_degree) ** 2
+        out = torch.zeros((self.nlat * self.nlon, kp), dtype=torch.float64, device=torch.device("cuda", self.device))
+        _lib.check(self._lib.gb_synthesis_matrix(self._handle, int(min_degree), ctypes.c_void_p(out.data_ptr()),
+                                                 _stream_handle(self.device)))
+        return out
+
+    def analysis_matrix(self):
+        """Dense analysis operator [K', nlat*nlon] for the min_degree of set_analysis() (CUDA tensor)."""
+        if self._analysis_nmin is None:
+            raise RuntimeError("call set_analysis() first")
+        kp = self.L ** 2 - self.analysis_min_degree ** 2
+        out = torch.empty((kp, self.nlat * self.nlon), dtype=torch.float64, device=torch.device("cuda", self.device))
+        _lib.check(self._lib.gb_analysis_matrix(self._handle, ctypes.c_void_p(out.data_ptr()),
+                                                _stream_handle(self.device)))
+        return out
+
     def analysis_host(self, values, out=None):
         values = np.ascontiguousarray(values, dtype=np.float64)
         if values.ndim != 3 or values.shape[1:] != (self.nlat, self.nlon):

@@ -123,6 +123,15 @@ int gb_analysis(gb_plan* plan, const double* d_grid, int n_epochs, double* d_anm
 int gb_analysis_host(gb_plan* plan, const double* h_grid, int n_epochs, double* h_anm);
 
 /*
+ * Explicit operators in degree-wise order (dense, for small grids / window matrices):
+ *   gb_synthesis_matrix  d_out [nlat*nlon][K'] , K' = (nmax+1)^2 - nmin^2   (Grid.synthesis_matrix, grid.py:412-443)
+ *   gb_analysis_matrix   d_out [K'][nlat*nlon] for the nmin of gb_plan_set_analysis (RegularGrid.analysis_matrix,
+ *                        grid.py:698-730)
+ */
+int gb_synthesis_matrix(gb_plan* plan, int nmin, double* d_out, void* stream);
+int gb_analysis_matrix(gb_plan* plan, double* d_out, void* stream);
+
+/*
  * Covariance propagation to per-point variances, diag(F Sigma F'), for the parallels
  * [row0, row0 + nrows) of the plan's grid.  Replaces grid.py:833-835 (the reference then takes
  * the square root, grid.py:837-839; pass take_sqrt = 1 for that).

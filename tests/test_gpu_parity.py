@@ -239,6 +239,22 @@ def test_analysis_round_trip_batch(gb, orc):
     assert dev.is_cuda and float(dev[:, :2, :2].abs().max()) == 0.0
 
 
+def test_dense_operators_golden(gb, golden):
+    g = golden("analysis")
+    grid = gb.GeographicGrid(30.0, 30.0)
+    A = grid.synthesis_matrix(1, 4, "ewh")
+    assert A.shape == (72, 24) and maxnorm_err(A, g["synthesis_matrix_1_4"]) < TOL
+    F = grid.analysis_matrix(0, 4, "ewh")
+    assert F.shape == (25, 72) and maxnorm_err(F, g["analysis_matrix_0_4"]) < TOL
+    A0 = grid.synthesis_matrix(0, 4, "ewh")
+    np.testing.assert_allclose(F @ A0, np.eye(25), atol=1e-10)          # analysis o synthesis = identity
+    c2, s2 = grid.synthesis_matrix_per_order(2, 1, 4, "ewh", 3.9860044150e+14, 6.3781363000e+06)
+    np.testing.assert_array_equal(c2, A[:, [4 + 3 - 1, 9 + 3 - 1, 16 + 3 - 1]])
+    np.testing.assert_array_equal(s2, A[:, [4 + 4 - 1, 9 + 4 - 1, 16 + 4 - 1]])
+    z = grid.synthesis_matrix_per_order(0, 1, 4, "ewh", 3.9860044150e+14, 6.3781363000e+06)
+    np.testing.assert_array_equal(z, A[:, [0, 3, 8, 15]])
+
+
 def test_analysis_errors(gb):
     grid = gb.GeographicGrid(10.0, 10.0)
     with pytest.raises(ValueError):
