@@ -14,9 +14,65 @@
 //              G [kpad][mpad] (same spectral layout as the synthesis intermediate AB),
 //              lat_ops concatenated [cnt_m][nlat] blocks, anm [E][L][L] packed (output).
 #include <vector>
+#include <cmath>
 #include "gb_common.cuh"
+#include "gb_gemm.cuh"
 
 namespace {
+
+// ---- longitude stage on the tensor cores ---------------------------------------------------------
+// gb_analysis_fold transposes V into the tiled k-major operand layout of gb_gemm.cuh.  With four-fold
+// symmetric meridians / weights it also folds the four mirrored meridians of every first-quadrant
+// longitude mu = lon[h+j'] (v1 = V(mu), v2 = V(pi-mu), v3 = V(-mu), v4 = V(mu-pi)):
+//   set 0 (even m, cos) (v1+v3)+(v2+v4)      set 1 (odd m, cos) (v1+v3)-(v2+v4)
+//   set 2 (even m, sin) (v1-v3)+(v4-v2)      set 3 (odd m, sin) (v1-v3)-(v4-v2)
+// so that the contraction runs over one quadrant only (a quarter of the multiply-adds).
+__global__ void __launch_bounds__(256)
+gb_analysis_fold(const double* __restrict__ V, double* __restrict__ VF, long long M, int nlon, int nsets, int kp,
+                 int kvalid) {
+    __shared__ double s_f[4][32][33];
+    const int j0 = blockIdx.x * 32;                 // first k (j or j') of this block
+    const long long r0 = (long long)blockIdx.y * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;   // 8 warps, 4 rows each
+    const int h = nlon >> 1;
+    for (int rr = w; rr < 32; rr += 8) {
+        const long long row = r0 + rr;
+        const int j = j0 + lane;
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+        if (row < M && j < kvalid) {
+            const double* v = V + (size_t)row * nlon;
+            if (nsets == 4) {
+                const double v1 = v[h + j], v2 = v[nlon - 1 - j], v3 = v[h - 1 - j], v4 = v[j];
+                const double p13 = v1 + v3, p24 = v2 + v4, m13 = v1 - v3, m42 = v4 - v2;
+                f0 = p13 + p24; f1 = p13 - p24; f2 = m13 + m42; f3 = m13 - m42;
+            } else {
+                f0 = v[j];
+            }
+        }
+        s_f[0][lane][rr] = f0;
+        if (nsets == 4) { s_f[1][lane][rr] = f1; s_f[2][lane][rr] = f2; s_f[3][lane][rr] = f3; }
+    }
+    __syncthreads();
+    const int a_rows = nsets * kp;
+    for (int idx = threadIdx.x; idx < nsets * 32 * 32; idx += 256) {
+        const int set = idx >> 10, jj = (idx >> 5) & 31, rr = idx & 31;
+        const int k = j0 + jj;
+        if (k >= kp) continue;
+        VF[gb_ab_offset(r0 + rr, set * kp + k, a_rows)] = s_f[set][jj][rr];
+    }
+}
+
+struct SpectralStore {   // epilogue: G[kmap[col]][row]
+    double* G;
+    long long mpad, M;
+    const int* kmap;
+    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
+        if (row >= M) return;
+        const int k0 = kmap[col], k1 = kmap[col + 1];
+        if (k0 >= 0) G[(size_t)k0 * mpad + row] = v0;
+        if (k1 >= 0) G[(size_t)k1 * mpad + row] = v1;
+    }
+};
 
 // ---- longitude stage: G[k][row] = sum_j V[row][j] * lonT[j][k] ;  64 x 64 tile, 4 x 4 per thread
 constexpr int LT = 64, LK = 16;
@@ -168,6 +224,70 @@ extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_o
     GB_CUDA(cudaMemcpy(p->d_lat_ops, lat_ops, total * sizeof(double), cudaMemcpyHostToDevice));
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_lat_off), (L + 1) * sizeof(long long)));
     GB_CUDA(cudaMemcpy(p->d_lat_off, p->h_lat_off, (L + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+
+    // ---- operator tiles for the tensor-core longitude stage ----
+    cudaFree(p->d_ana_w_t); p->d_ana_w_t = nullptr;
+    cudaFree(p->d_ana_kmap); p->d_ana_kmap = nullptr;
+    const int nlon = p->nlon, h = nlon / 2, q = nlon / 4;
+    bool sym = (nlon % 8 == 0);
+    for (int k = 0; k < 2 * L && sym; ++k) {
+        const int m = k >> 1;
+        const bool sine = (k & 1) != 0;
+        if (sine && m == 0) continue;
+        const double* row = lon_ops + (size_t)k * nlon;
+        double amax = 0.0;
+        for (int j = 0; j < nlon; ++j) amax = std::fmax(amax, std::fabs(row[j]));
+        const double tol = 4.0 * (m + 1) * 2.220446049250313e-16 * 3.141592653589793 * amax;
+        const double sg = (m & 1) ? -1.0 : 1.0;
+        for (int j = 0; j < q; ++j) {
+            const double c = row[h + j];
+            const double e2 = sine ? -sg * c : sg * c;   // at pi - mu
+            const double e3 = sine ? -c : c;             // at -mu
+            const double e4 = sg * c;                    // at mu - pi
+            if (std::fabs(row[nlon - 1 - j] - e2) > tol || std::fabs(row[h - 1 - j] - e3) > tol ||
+                std::fabs(row[j] - e4) > tol) {
+                sym = false;
+                break;
+            }
+        }
+    }
+    if (getenv("GB_NO_SYMMETRY") && getenv("GB_NO_SYMMETRY")[0] && getenv("GB_NO_SYMMETRY")[0] != '0') sym = false;
+    std::vector<std::vector<int>> cols;   // spectral rows (2m+cs) per set
+    if (sym) {
+        cols.resize(4);
+        for (int m = 0; m < L; ++m) {
+            cols[m & 1].push_back(2 * m);
+            if (m > 0) cols[2 + (m & 1)].push_back(2 * m + 1);
+        }
+        p->ana_nsets = 4;
+        p->ana_kp = (q + 3) / 4 * 4;
+    } else {
+        cols.resize(1);
+        for (int k = 0; k < 2 * L; ++k) cols[0].push_back(k);
+        p->ana_nsets = 1;
+        p->ana_kp = (nlon + 3) / 4 * 4;
+    }
+    size_t widest = 0;
+    for (auto& c : cols) widest = c.size() > widest ? c.size() : widest;
+    p->ana_tps = (int)((widest + GB_S2_TN - 1) / GB_S2_TN);
+    if (p->ana_tps < 1) p->ana_tps = 1;
+    const int ntiles = p->ana_nsets * p->ana_tps;
+    std::vector<double> wt((size_t)ntiles * p->ana_kp * GB_S2_LDB, 0.0);
+    std::vector<int> kmap((size_t)ntiles * GB_S2_TN, -1);
+    const int kvalid = sym ? q : nlon;
+    for (int s = 0; s < p->ana_nsets; ++s)
+        for (size_t c = 0; c < cols[s].size(); ++c) {
+            const int tile = s * p->ana_tps + (int)(c / GB_S2_TN), cc = (int)(c % GB_S2_TN);
+            const int k = cols[s][c];
+            kmap[(size_t)tile * GB_S2_TN + cc] = k;
+            const double* row = lon_ops + (size_t)k * nlon;
+            for (int j = 0; j < kvalid; ++j)
+                wt[((size_t)tile * p->ana_kp + j) * GB_S2_LDB + cc] = sym ? row[h + j] : row[j];
+        }
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_w_t), wt.size() * sizeof(double)));
+    GB_CUDA(cudaMemcpy(p->d_ana_w_t, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_kmap), kmap.size() * sizeof(int)));
+    GB_CUDA(cudaMemcpy(p->d_ana_kmap, kmap.data(), kmap.size() * sizeof(int), cudaMemcpyHostToDevice));
     p->ana_nmin = nmin;
     return GB_OK;
 }
@@ -177,10 +297,36 @@ static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_an
     const long long M = (long long)E * p->nlat;
     const long long mpad = p->ws_mpad;
     GB_CUDA(cudaMemsetAsync(d_anm, 0, (size_t)E * L * L * sizeof(double), st));
-    {
+    if (getenv("GB_SIMPLE_ANALYSIS") && getenv("GB_SIMPLE_ANALYSIS")[0] != '0') {
+        // plain FMA longitude stage (cross-check of the tensor-core path)
         dim3 grid((unsigned)((M + LT - 1) / LT), (p->kpad + LT - 1) / LT);
         gb_analysis_lon_kernel<<<grid, 256, 0, st>>>(d_grid, p->d_lon_ops, p->d_ab, M, p->nlon, p->kpad, mpad);
         GB_LAUNCH_CHECK();
+    } else {
+        // fold / transpose V into the tiled operand layout, then one persistent DMMA GEMM over all sets
+        const int n_mtiles = (int)((M + GB_TM - 1) / GB_TM);
+        const int a_rows = p->ana_nsets * p->ana_kp;
+        double* d_vf = nullptr;
+        GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_vf), (size_t)n_mtiles * a_rows * GB_LDA * sizeof(double), st));
+        {
+            dim3 grid((p->ana_kp + 31) / 32, n_mtiles * 4);
+            gb_analysis_fold<<<grid, 256, 0, st>>>(d_grid, d_vf, M, p->nlon, p->ana_nsets, p->ana_kp,
+                                                   p->ana_nsets == 4 ? p->nlon / 4 : p->nlon);
+            GB_LAUNCH_CHECK();
+        }
+        gbgemm::Shape sh;
+        sh.A_t = d_vf;
+        sh.a_rows = a_rows;
+        sh.a_koff_mul = p->ana_kp;
+        sh.tiles_per_group = p->ana_tps;
+        sh.B_t = p->d_ana_w_t;
+        sh.b_rows = p->ana_kp;
+        sh.klen = p->ana_kp;
+        sh.n_mtiles = n_mtiles;
+        sh.n_ntiles = p->ana_nsets * p->ana_tps;
+        int rc = gbgemm::launch(sh, SpectralStore{p->d_ab, mpad, M, p->d_ana_kmap}, p->sm_count, st);
+        if (rc) return rc;
+        GB_CUDA(cudaFreeAsync(d_vf, st));
     }
     {
         dim3 grid(L, (E + AE - 1) / AE);

@@ -99,6 +99,11 @@ struct gb_plan {
     double* d_lat_ops = nullptr;
     long long* d_lat_off = nullptr;  // [L+1]
     long long* h_lat_off = nullptr;
+    // longitude stage on the tensor cores: nsets = 4 folded inputs (four-fold symmetric meridians and
+    // weights) or 1 (plain transpose); operator tiles [nsets*tiles_per_set][ana_kp][GB_S2_LDB]
+    int ana_nsets = 0, ana_kp = 0, ana_tps = 0;
+    double* d_ana_w_t = nullptr;
+    int* d_ana_kmap = nullptr;       // [nsets*tiles_per_set*GB_S2_TN] output column -> spectral row 2m+cs, or -1
     // optional per-kernel event timing (gb_plan_set_profiling)
     cudaEvent_t* prof_ev = nullptr;  // [capacity][4]
     int prof_capacity = 0, prof_count = 0;

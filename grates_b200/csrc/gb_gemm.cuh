@@ -1,0 +1,144 @@
+// Persistent FP64 tensor-core GEMM building block (sm_100a), shared by synthesis stage 2 (direct
+// path) and the analysis longitude stage.
+//
+//   C[row, col] = sum_k A[k, row] * B[k, col]
+//
+// Operands live in HBM in the tiled + padded layouts of gb_common.cuh:
+//   A_t [row tile][k][GB_LDA]        (128 rows + 4 pad doubles per k)
+//   B_t [col tile][k][GB_S2_LDB]     (120 cols + 4 pad doubles per k)
+// so that every pipeline chunk (28 consecutive k) is ONE contiguous cp.async.bulk per operand and
+// lands in shared memory with k-rows 4 doubles apart modulo 16 (conflict-free DMMA.8x8x4 fragments).
+//
+// CTA: 12 consumer warps (4 x 3, 32 x 40 register tiles, 20 DMMA per k4 step) + 1 producer warp
+// (one elected lane), 3-stage mbarrier pipeline, static round-robin tile schedule over <= #SM CTAs.
+// The column tiles may be partitioned into groups that read different k ranges of A
+// (a_koff = (col tile / tiles_per_group) * a_koff_mul): the analysis uses this for its four folded
+// inputs.  The epilogue functor receives accumulator pairs (row, col, col+1).
+#pragma once
+#include "gb_common.cuh"
+
+namespace gbgemm {
+
+constexpr int WM = 4, WN = 3;
+constexpr int TM = 32 * WM;   // 128
+constexpr int TN = 40 * WN;   // 120
+constexpr int KC = 28;
+constexpr int STAGES = 3;
+constexpr int LDA = GB_LDA;
+constexpr int LDB = GB_S2_LDB;
+constexpr int CONSUMER_WARPS = WM * WN;
+constexpr int THREADS = 32 * (CONSUMER_WARPS + 1);
+constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
+constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+static_assert(TM == GB_TM && TN == GB_S2_TN, "tile shape must match the tiled HBM layouts");
+
+struct Shape {
+    const double* A_t;      // [n_mtiles][a_rows][LDA]
+    int a_rows;             // k rows allocated per A tile
+    int a_koff_mul;         // see above
+    int tiles_per_group;    // column tiles per group (>= 1)
+    const double* B_t;      // [n_ntiles][b_rows][LDB]
+    int b_rows;             // k rows per B tile
+    int klen;               // contraction length (multiple of 4), k = 0..klen-1 of B, a_koff.. of A
+    int n_mtiles, n_ntiles;
+};
+
+template <class Epilogue>
+__global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tiles = reinterpret_cast<double*>(s_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)STAGES * STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + STAGES;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            gb::mbar_init(&full[s], 1);
+            gb::mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        gb::fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long n_tiles = (long long)sh.n_mtiles * sh.n_ntiles;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (warp == CONSUMER_WARPS) {
+        if (lane == 0) {
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const long long mt = t / sh.n_ntiles;
+                const int nt = (int)(t % sh.n_ntiles);
+                const int a_koff = (nt / sh.tiles_per_group) * sh.a_koff_mul;
+                for (int k0 = 0; k0 < sh.klen; k0 += KC) {
+                    const int kc = min(KC, sh.klen - k0);
+                    gb::mbar_wait(&empty[stage], phase ^ 1u);
+                    double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES;
+                    double* sB = sA + KC * LDA;
+                    const uint32_t bytes_a = (uint32_t)(kc * LDA * sizeof(double));
+                    const uint32_t bytes_b = (uint32_t)(kc * LDB * sizeof(double));
+                    gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
+                    gb::bulk_g2s(sA, sh.A_t + ((size_t)mt * sh.a_rows + a_koff + k0) * LDA, bytes_a, &full[stage]);
+                    gb::bulk_g2s(sB, sh.B_t + ((size_t)nt * sh.b_rows + k0) * LDB, bytes_b, &full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        const int wm = warp / WN;
+        const int wn = warp % WN;
+        const int g = lane >> 2;
+        const int q = lane & 3;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long mt = t / sh.n_ntiles;
+            const int nt = (int)(t % sh.n_ntiles);
+            double acc[4][5][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int k0 = 0; k0 < sh.klen; k0 += KC) {
+                const int kc = min(KC, sh.klen - k0);
+                gb::mbar_wait(&full[stage], phase);
+                const double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 32 + g;
+                const double* sB = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
+#pragma unroll
+                for (int kk = 0; kk < KC; kk += 4) {
+                    if (kk >= kc) break;
+                    double a[4], b[5];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * LDA + mi * 8];
+#pragma unroll
+                    for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * LDB + ni * 8];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                }
+                __syncwarp();
+                if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            const long long row_base = mt * TM + wm * 32 + g;
+            const int col_base = nt * TN + wn * 40 + 2 * q;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni)
+                    epi(row_base + mi * 8, col_base + ni * 8, acc[mi][ni][0], acc[mi][ni][1]);
+        }
+    }
+}
+
+template <class Epilogue>
+inline int launch(const Shape& sh, const Epilogue& epi, int sm_count, cudaStream_t st) {
+    const long long n_tiles = (long long)sh.n_mtiles * sh.n_ntiles;
+    if (n_tiles == 0) return GB_OK;
+    const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+    GB_CUDA(cudaFuncSetAttribute(kernel<Epilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    kernel<Epilogue><<<grid, THREADS, SMEM, st>>>(sh, epi);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}
+
+}  // namespace gbgemm

@@ -210,6 +210,7 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     cudaFree(p->d_trig_t); cudaFree(p->d_trig_q_t); cudaFree(p->d_x); cudaFree(p->d_ab);
     cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);
     cudaFree(p->d_lon_ops); cudaFree(p->d_lat_ops); cudaFree(p->d_lat_off);
+    cudaFree(p->d_ana_w_t); cudaFree(p->d_ana_kmap);
     delete[] p->h_lat_off;
     if (p->prof_ev) {
         for (int i = 0; i < p->prof_capacity * 4; ++i) cudaEventDestroy(p->prof_ev[i]);

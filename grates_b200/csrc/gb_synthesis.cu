@@ -18,10 +18,11 @@
 //   gb_legendre_stage1   per (latitude tile, order m): runs the Legendre recursion on the fly
 //                        (unfused IEEE ops -> bit-identical to utilities.py:37-54), multiplies
 //                        kn[i,n] in, contracts against all epochs, writes AB
-//   gb_fourier_stage2    persistent FP64 tensor-core GEMM  V = AB^T * trig  (DMMA.8x8x4),
+//   gbgemm::kernel       persistent FP64 tensor-core GEMM  V = AB^T * trig  (DMMA.8x8x4, gb_gemm.cuh),
 //                        operands staged by the TMA unit (cp.async.bulk) through a 3-stage
 //                        mbarrier pipeline fed by a dedicated producer warp
 #include "gb_common.cuh"
+#include "gb_gemm.cuh"
 
 namespace {
 
@@ -288,126 +289,24 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// stage 2: V[row][j] = sum_k AB[k][row] * trig[k][j]   (M = E*nlat rows, K = kpad, N = nlon)
+// stage 2, direct contraction: V[row][j] = sum_k AB[k][row] * trig[k][j]  (M = E*nlat rows, K = kpad,
+// N = nlon) on the shared persistent DMMA GEMM (gb_gemm.cuh) with a streaming row-major epilogue.
 // ---------------------------------------------------------------------------------------------
-constexpr int S2_WM = 4, S2_WN = 3;            // consumer warp grid
-constexpr int S2_TM = 32 * S2_WM;              // 128 rows per CTA tile
-constexpr int S2_TN = 40 * S2_WN;              // 120 columns per CTA tile
-static_assert(S2_TM == GB_TM && S2_TN == GB_S2_TN, "tile shape must match the tiled HBM layouts");
-constexpr int S2_KC = 28;                      // spectral rows per pipeline stage
-constexpr int S2_STAGES = 3;
-constexpr int S2_LDA = S2_TM + 4;              // 132: k-rows land 4 doubles apart mod 16 -> conflict-free fragments
-constexpr int S2_LDB = S2_TN + 4;              // 124
-constexpr int S2_CONSUMER_WARPS = S2_WM * S2_WN;
-constexpr int S2_THREADS = 32 * (S2_CONSUMER_WARPS + 1);
-constexpr int S2_STAGE_DOUBLES = S2_KC * (S2_LDA + S2_LDB);
-constexpr size_t S2_SMEM = (size_t)S2_STAGES * S2_STAGE_DOUBLES * sizeof(double) + 2 * S2_STAGES * sizeof(uint64_t);
-
-__global__ void __launch_bounds__(S2_THREADS, 1)
-gb_fourier_stage2(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig_t, int kpad,
-                  double* __restrict__ out, long long M, int nlon, int n_mtiles, int n_ntiles) {
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    double* s_tiles = reinterpret_cast<double*>(s_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)S2_STAGES * S2_STAGE_DOUBLES * sizeof(double));
-    uint64_t* empty = full + S2_STAGES;
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S2_STAGES; ++s) {
-            gb::mbar_init(&full[s], 1);
-            gb::mbar_init(&empty[s], S2_CONSUMER_WARPS);
-        }
-        gb::fence_mbar_init();
-    }
-    __syncthreads();
-
-    const long long n_tiles = (long long)n_mtiles * n_ntiles;
-    int stage = 0;
-    uint32_t phase = 0;
-
-    if (warp == S2_CONSUMER_WARPS) {
-        // ===== producer warp: the tiled layouts make every chunk one contiguous block per operand =====
-        if (lane == 0) {
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const long long mt = t / n_ntiles;
-                const int nt = (int)(t % n_ntiles);
-                for (int k0 = 0; k0 < kpad; k0 += S2_KC) {
-                    const int kc = min(S2_KC, kpad - k0);
-                    gb::mbar_wait(&empty[stage], phase ^ 1u);
-                    double* sA = s_tiles + (size_t)stage * S2_STAGE_DOUBLES;
-                    double* sB = sA + S2_KC * S2_LDA;
-                    const uint32_t bytes_a = (uint32_t)(kc * S2_LDA * sizeof(double));
-                    const uint32_t bytes_b = (uint32_t)(kc * S2_LDB * sizeof(double));
-                    gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
-                    gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * S2_LDA, bytes_a, &full[stage]);
-                    gb::bulk_g2s(sB, trig_t + ((size_t)nt * kpad + k0) * S2_LDB, bytes_b, &full[stage]);
-                    if (++stage == S2_STAGES) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else {
-        // ===== consumer warps: 32 x 40 register tile each, DMMA.8x8x4 =====
-        const int wm = warp / S2_WN;
-        const int wn = warp % S2_WN;
-        const int g = lane >> 2;   // fragment row / column group
-        const int q = lane & 3;    // k index inside a k4 step
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const long long mt = t / n_ntiles;
-            const int nt = (int)(t % n_ntiles);
-            double acc[4][5][2];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-            for (int k0 = 0; k0 < kpad; k0 += S2_KC) {
-                const int kc = min(S2_KC, kpad - k0);
-                gb::mbar_wait(&full[stage], phase);
-                const double* sA = s_tiles + (size_t)stage * S2_STAGE_DOUBLES + wm * 32 + g;
-                const double* sB = s_tiles + (size_t)stage * S2_STAGE_DOUBLES + S2_KC * S2_LDA + wn * 40 + g;
-#pragma unroll
-                for (int kk = 0; kk < S2_KC; kk += 4) {
-                    if (kk >= kc) break;
-                    double a[4], b[5];
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * S2_LDA + mi * 8];
-#pragma unroll
-                    for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * S2_LDB + ni * 8];
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                        for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-                }
-                __syncwarp();
-                if (lane == 0) gb::mbar_arrive(&empty[stage]);
-                if (++stage == S2_STAGES) { stage = 0; phase ^= 1u; }
-            }
-
-            // epilogue: streaming stores straight from the accumulator fragments
-            const long long row_base = mt * S2_TM + wm * 32 + g;
-            const int col_base = nt * S2_TN + wn * 40 + 2 * q;
-            const bool vec_ok = (nlon & 1) == 0;
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                const long long row = row_base + mi * 8;
-                if (row >= M) continue;
-                double* orow = out + (size_t)row * nlon;
-#pragma unroll
-                for (int ni = 0; ni < 5; ++ni) {
-                    const int col = col_base + ni * 8;
-                    if (vec_ok && col + 1 < nlon) {
-                        gb::st_cs_v2(orow + col, acc[mi][ni][0], acc[mi][ni][1]);
-                    } else {
-                        if (col < nlon) gb::st_cs(orow + col, acc[mi][ni][0]);
-                        if (col + 1 < nlon) gb::st_cs(orow + col + 1, acc[mi][ni][1]);
-                    }
-                }
-            }
+struct RowMajorStore {
+    double* out;
+    long long M;
+    int nlon;
+    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
+        if (row >= M) return;
+        double* o = out + (size_t)row * nlon + col;
+        if ((nlon & 1) == 0 && col + 1 < nlon) {
+            gb::st_cs_v2(o, v0, v1);
+        } else {
+            if (col < nlon) gb::st_cs(o, v0);
+            if (col + 1 < nlon) gb::st_cs(o + 1, v1);
         }
     }
-}
-
+};
 
 // ---------------------------------------------------------------------------------------------
 // stage 2 with four-fold longitude symmetry.  For mu = lon[h + j'] in the first quadrant
@@ -646,14 +545,18 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
                                                                p->nlon, p->nq, n_mtiles, n_ntiles);
         GB_LAUNCH_CHECK();
     } else {
-        const int n_mtiles = (int)((M + S2_TM - 1) / S2_TM);
-        const int n_ntiles = p->n_ntiles;
-        const long long n_tiles = (long long)n_mtiles * n_ntiles;
-        const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
-        GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
-        gb_fourier_stage2<<<grid, S2_THREADS, S2_SMEM, st>>>(p->d_ab, p->ab_rows, p->d_trig_t, p->kpad, d_out, M,
-                                                             p->nlon, n_mtiles, n_ntiles);
-        GB_LAUNCH_CHECK();
+        gbgemm::Shape sh;
+        sh.A_t = p->d_ab;
+        sh.a_rows = p->ab_rows;
+        sh.a_koff_mul = 0;
+        sh.tiles_per_group = 1;
+        sh.B_t = p->d_trig_t;
+        sh.b_rows = p->kpad;
+        sh.klen = p->kpad;
+        sh.n_mtiles = (int)((M + gbgemm::TM - 1) / gbgemm::TM);
+        sh.n_ntiles = p->n_ntiles;
+        int rc = gbgemm::launch(sh, RowMajorStore{d_out, M, p->nlon}, p->sm_count, st);
+        if (rc) return rc;
     }
     if (prof) {
         GB_CUDA(cudaEventRecord(prof[3], st));

@@ -239,6 +239,28 @@ def test_analysis_round_trip_batch(gb, orc):
     assert dev.is_cuda and float(dev[:, :2, :2].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("nmax,dlon,dlat", [(30, 1.5, 3.0), (12, 10.0, 10.0), (50, 2.0, 1.0)])
+def test_analysis_paths_agree(gb, orc, monkeypatch, nmax, dlon, dlat):
+    """Tensor-core longitude stage (four-fold folded where the meridians allow, plain otherwise)
+    against the FMA cross-check kernel and the oracle."""
+    grid = gb.GeographicGrid(dlon, dlat)
+    og = orc.geographic_grid(dlon, dlat)
+    rng = np.random.default_rng(5)
+    vals = rng.standard_normal((3,) + og.shape)
+    ref = orc.analysis_separable(vals, og, 1, nmax, "potential")
+    results = {}
+    for tag, env in (("default", {}), ("nosym", {"GB_NO_SYMMETRY": "1"}), ("simple", {"GB_SIMPLE_ANALYSIS": "1"})):
+        gb.clear_plan_cache()
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        results[tag] = gb.analysis_batch(vals, grid, 1, nmax, "potential")
+        for k in env:
+            monkeypatch.delenv(k)
+    gb.clear_plan_cache()
+    for tag, out in results.items():
+        assert maxnorm_err(out, ref) < TOL, tag
+
+
 def test_dense_operators_golden(gb, golden):
     g = golden("analysis")
     grid = gb.GeographicGrid(30.0, 30.0)
