@@ -306,8 +306,16 @@ static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_an
         // fold / transpose V into the tiled operand layout, then one persistent DMMA GEMM over all sets
         const int n_mtiles = (int)((M + GB_TM - 1) / GB_TM);
         const int a_rows = p->ana_nsets * p->ana_kp;
-        double* d_vf = nullptr;
-        GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_vf), (size_t)n_mtiles * a_rows * GB_LDA * sizeof(double), st));
+        const size_t vf_elems = (size_t)n_mtiles * a_rows * GB_LDA;
+        if (vf_elems > p->ana_vf_elems) {   // grow-only workspace (a fresh 1 GB allocation per call costs milliseconds)
+            GB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(p->d_ana_vf);
+            p->d_ana_vf = nullptr;
+            p->ana_vf_elems = 0;
+            GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_vf), vf_elems * sizeof(double)));
+            p->ana_vf_elems = vf_elems;
+        }
+        double* d_vf = p->d_ana_vf;
         {
             dim3 grid((p->ana_kp + 31) / 32, n_mtiles * 4);
             gb_analysis_fold<<<grid, 256, 0, st>>>(d_grid, d_vf, M, p->nlon, p->ana_nsets, p->ana_kp,
@@ -326,7 +334,6 @@ static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_an
         sh.n_ntiles = p->ana_nsets * p->ana_tps;
         int rc = gbgemm::launch(sh, SpectralStore{p->d_ab, mpad, M, p->d_ana_kmap}, p->sm_count, st);
         if (rc) return rc;
-        GB_CUDA(cudaFreeAsync(d_vf, st));
     }
     {
         dim3 grid(L, (E + AE - 1) / AE);

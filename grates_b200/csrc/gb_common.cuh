@@ -104,6 +104,8 @@ struct gb_plan {
     int ana_nsets = 0, ana_kp = 0, ana_tps = 0;
     double* d_ana_w_t = nullptr;
     int* d_ana_kmap = nullptr;       // [nsets*tiles_per_set*GB_S2_TN] output column -> spectral row 2m+cs, or -1
+    double* d_ana_vf = nullptr;      // folded / transposed input tiles (grow-only workspace)
+    size_t ana_vf_elems = 0;
     // optional per-kernel event timing (gb_plan_set_profiling)
     cudaEvent_t* prof_ev = nullptr;  // [capacity][4]
     int prof_capacity = 0, prof_count = 0;

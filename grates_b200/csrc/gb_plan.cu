@@ -88,6 +88,14 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
         return gb_set_error(GB_ERR_UNSUPPORTED, "gb_plan_create: device %d is sm_%d%d; this library is built for sm_100a",
                             device, prop.major, prop.minor);
 
+    {   // keep stream-ordered workspace allocations in the pool between calls (default threshold 0
+        // returns them to the driver at every synchronisation: milliseconds per GB on the next call)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     gb_plan* p = new gb_plan();
     p->device = device;
     p->nmax = nmax;
@@ -210,7 +218,7 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     cudaFree(p->d_trig_t); cudaFree(p->d_trig_q_t); cudaFree(p->d_x); cudaFree(p->d_ab);
     cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);
     cudaFree(p->d_lon_ops); cudaFree(p->d_lat_ops); cudaFree(p->d_lat_off);
-    cudaFree(p->d_ana_w_t); cudaFree(p->d_ana_kmap);
+    cudaFree(p->d_ana_w_t); cudaFree(p->d_ana_kmap); cudaFree(p->d_ana_vf);
     delete[] p->h_lat_off;
     if (p->prof_ev) {
         for (int i = 0; i < p->prof_capacity * 4; ++i) cudaEventDestroy(p->prof_ev[i]);

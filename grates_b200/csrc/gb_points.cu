@@ -261,6 +261,14 @@ extern "C" int gb_points_create(gb_points** out, int nmax, int npts, const doubl
     if (prop.major < 10)
         return gb_set_error(GB_ERR_UNSUPPORTED, "gb_points_create: device %d is sm_%d%d; built for sm_100a", device,
                             prop.major, prop.minor);
+    {   // keep stream-ordered workspace allocations in the pool between calls (default threshold 0
+        // returns them to the driver at every synchronisation: milliseconds per GB on the next call)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     gb_points* p = new gb_points();
     p->device = device;
     p->nmax = nmax;
