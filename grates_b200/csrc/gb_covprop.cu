@@ -8,19 +8,25 @@
 //   H_i[k,k'] = sum_{a in k} sum_{b in k'} U_i[a] Sigma[a,b] U_i[b]        (k = (m, cos|sin) group)
 //   var[i,j]  = sum_k T[k,j] * ( sum_k' H_i[k,k'] T[k',j] )
 //
-// i.e. 2 nlat K^2 + 2 P kpad^2 flops (c4: 83.6 GF instead of 45.9 TF).  This restructuring is
-// declared in DESIGN.md and bench.py reports algorithmic and executed flops separately.
+// i.e. 2 nlat K^2 + 2 P (2L)^2 flops (config 4: 83.6 GF instead of 45.9 TF).  This restructuring is
+// DECLARED in DESIGN.md; bench_configs.py reports contract and executed flops separately, and the
+// direct kernel without any structure assumption is gb_points_covariance (gb_points.cu).
 //
-// Steps (all on the caller's stream):
-//   1. gb_cov_permute   Sigma (degree-wise order) -> Sigma' (order-wise: groups contiguous, each
-//                       padded to a multiple of 4 rows/cols with zeros)
-//   2. gb_cov_legendre  U[p][i]: on-the-fly Legendre recursion * kn for the requested parallels,
-//                       rows in the same order-wise padded order
-//   3. gb_cov_quadform  H[i][k][k'] for all group pairs
-//   4. gb_cov_longitude var[i][j] (optionally sqrt)
+// Both contractions run on the persistent DMMA GEMM of gb_gemm.cuh (operands staged by the TMA unit
+// with cp.async.bulk, 3-stage mbarrier pipeline); the second factor and the reduction over rows are
+// folded into the epilogues with warp shuffles + FP64 atomics.
+//
+//   1. gb_cov_permute    Sigma (degree-wise order) -> tiled operand St[row tile a'][b][132]: order-wise
+//                        order, groups padded to 8 rows (a') / 4 columns (b), zeros in the padding
+//   2. gb_cov_legendre   on-the-fly Legendre recursion * kn for the requested parallels -> U as GEMM
+//                        B tiles [group k' * nti + parallel tile][c][124]
+//   3. GEMM + QuadEpilogue   C_k'[a', i] = sum_{b in k'} St[a'][b] U[b][i];  H[i][k(a')][k'] += U[a'][i] C
+//   4. GEMM + LonEpilogue    W_i[k, j] = sum_k' H_i[k][k'] T[k'][j];          var[i][j] += T[k][j] W
+//   5. gb_cov_finish     optional sqrt
 #include <vector>
 #include <cmath>
 #include "gb_common.cuh"
+#include "gb_gemm.cuh"
 
 namespace {
 
@@ -41,107 +47,111 @@ __device__ __forceinline__ void legendre_column(int m, int L, double ct, double 
     }
 }
 
+// St[gb_ab_offset(a', b, Kp4)] = Sigma[perm8[a']][perm4[b]]  (0 where either index is padding)
 __global__ void __launch_bounds__(256)
-gb_cov_permute(const double* __restrict__ sigma, double* __restrict__ sp, const int* __restrict__ perm, int Kp,
-               long long K) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (c >= Kp) return;
-    const int pr = perm[r], pc = perm[c];
-    sp[(size_t)r * Kp + c] = (pr < 0 || pc < 0) ? 0.0 : sigma[(size_t)pr * K + pc];
+gb_cov_permute(const double* __restrict__ sigma, double* __restrict__ St, const int* __restrict__ perm8,
+               const int* __restrict__ perm4, int rows_a, int Kp4, long long K) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;   // a' fastest: coalesced writes
+    const int b = blockIdx.y;
+    if (a >= rows_a) return;
+    const int pa = perm8[a], pb = perm4[b];
+    St[gb_ab_offset(a, b, Kp4)] = (pa < 0 || pb < 0) ? 0.0 : sigma[(size_t)pa * K + pb];
 }
 
-// U[goff[2m+cs] + (n - n0)][i_local] = kn[i][n] * P_nm(theta_i),  n >= n0 = max(m, nmin)
+// U as B tiles: Ut[((k * nti + i/120) * Kg + (n - n0)) * 124 + i % 120] = kn[i][n] * P_nm(theta_i)
 __global__ void __launch_bounds__(128)
-gb_cov_legendre(double* __restrict__ U, const int* __restrict__ goff, const double* __restrict__ ct,
-                const double* __restrict__ kn, const double* __restrict__ pmm, const double* __restrict__ ra,
-                const double* __restrict__ rb, const double* __restrict__ rc, int L, int nmin, int row0, int nrows,
-                int ldu) {
+gb_cov_legendre(double* __restrict__ Ut, const double* __restrict__ ct, const double* __restrict__ kn,
+                const double* __restrict__ pmm, const double* __restrict__ ra, const double* __restrict__ rb,
+                const double* __restrict__ rc, int L, int nmin, int row0, int nrows, int nti, int Kg) {
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y;
     if (il >= nrows) return;
     const int i = row0 + il;
     const int n0 = max(m, nmin);
     const double* kn_i = kn + (size_t)i * L;
-    const int gc = goff[2 * m], gs = goff[2 * m + 1];
+    const int it = il / GB_S2_TN, ic = il % GB_S2_TN;
+    double* uc = Ut + ((size_t)(2 * m) * nti + it) * Kg * GB_S2_LDB + ic;
+    double* us = Ut + ((size_t)(2 * m + 1) * nti + it) * Kg * GB_S2_LDB + ic;
     legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int n, double p) {
         if (n < n0) return;
         const double v = __dmul_rn(p, kn_i[n]);
-        U[(size_t)(gc + n - n0) * ldu + il] = v;
-        if (m > 0) U[(size_t)(gs + n - n0) * ldu + il] = v;
+        uc[(size_t)(n - n0) * GB_S2_LDB] = v;
+        if (m > 0) us[(size_t)(n - n0) * GB_S2_LDB] = v;
     });
 }
 
-// H[i][k][k'] = sum_{r,c} U[gk+r][i] Sp[gk+r][gk'+c] U[gk'+c][i]; CTA per (k', k), threads over parallels.
-constexpr int QA = 32;  // rows of the Sigma' block staged per pass
-
-__global__ void __launch_bounds__(128)
-gb_cov_quadform(const double* __restrict__ sp, const double* __restrict__ U, double* __restrict__ H,
-                const int* __restrict__ goff, const int* __restrict__ gcnt, int Kp, int kpad, int nrows, int ldu) {
-    extern __shared__ double s_s[];  // [QA][cntc]
-    const int kc = blockIdx.x, kr = blockIdx.y;
-    const int cntr = gcnt[kr], cntc = gcnt[kc];
-    if (cntr == 0 || cntc == 0) {
-        for (int i = threadIdx.x; i < nrows; i += blockDim.x) H[((size_t)i * kpad + kr) * kpad + kc] = 0.0;
-        return;
-    }
-    const int gr = goff[kr], gcol = goff[kc];
-    for (int i0 = 0; i0 < nrows; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        const bool live = i < nrows;
-        double h = 0.0;
-        for (int a0 = 0; a0 < cntr; a0 += QA) {
-            const int na = min(QA, cntr - a0);
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < na * cntc; idx += blockDim.x) {
-                const int a = idx / cntc, c = idx % cntc;
-                s_s[idx] = sp[(size_t)(gr + a0 + a) * Kp + gcol + c];
-            }
-            __syncthreads();
-            if (live) {
-                for (int a = 0; a < na; ++a) {
-                    double z0 = 0.0, z1 = 0.0;
-                    const double* srow = s_s + a * cntc;
-                    int c = 0;
-                    for (; c + 1 < cntc; c += 2) {
-                        z0 = fma(srow[c], U[(size_t)(gcol + c) * ldu + i], z0);
-                        z1 = fma(srow[c + 1], U[(size_t)(gcol + c + 1) * ldu + i], z1);
-                    }
-                    if (c < cntc) z0 = fma(srow[c], U[(size_t)(gcol + c) * ldu + i], z0);
-                    h = fma(U[(size_t)(gr + a0 + a) * ldu + i], z0 + z1, h);
-                }
-            }
+// H[i][k][k'] accumulated in the A-tile layout of stage 4: Ht[((i * hmt + k/128) * kpad + k') * 132 + k%128]
+struct QuadEpilogue {
+    const double* Ut;        // B tiles of U (also the source of the row-side factor)
+    double* Ht;
+    const int* rowgroup;     // [rows_a / 8] group k of each 8-row slab, -1 for padding
+    const int* goff8;        // [kpad] first a' of each group
+    int nti, Kg, kpad, hmt, nrows;
+    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
+        const int k = rowgroup[row >> 3];                 // uniform over the 8 fragment rows
+        const int nt = col / GB_S2_TN, cc = col % GB_S2_TN;
+        const int kprime = nt / nti, it = nt % nti;
+        const int i = it * GB_S2_TN + cc;
+        double p0 = 0.0, p1 = 0.0;
+        if (k >= 0) {
+            const double* u = Ut + (((size_t)k * nti + it) * Kg + (row - goff8[k])) * GB_S2_LDB + cc;
+            p0 = v0 * u[0];
+            p1 = v1 * u[1];
         }
-        if (live) H[((size_t)i * kpad + kr) * kpad + kc] = h;
+        // sum over the 8 rows of the fragment (lanes with equal lane % 4)
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 4);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 4);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 8);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 8);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 16);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 16);
+        if ((threadIdx.x & 31) < 4 && k >= 0) {
+            double* h = Ht + (((size_t)i * hmt + (k >> 7)) * kpad + kprime) * GB_LDA + (k & 127);
+            if (i < nrows) atomicAdd(h, p0);
+            if (i + 1 < nrows) atomicAdd(h + (size_t)hmt * kpad * GB_LDA, p1);
+        }
     }
+};
+
+// var[i][j] += T[k][j] * W_i[k][j], rows of the GEMM = (i, k)
+struct LonEpilogue {
+    const double* trig;      // [kpad][nlp]
+    double* var;             // [nrows][nlon]
+    int hmt, kpad, nlp, nlon;
+    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
+        const int mt = (int)(row >> 7);
+        const int i = mt / hmt;
+        const int k = (mt % hmt) * 128 + (int)(row & 127);
+        double p0 = 0.0, p1 = 0.0;
+        if (k < kpad) {
+            const double* t = trig + (size_t)k * nlp + col;
+            if (col < nlp) p0 = v0 * t[0];
+            if (col + 1 < nlp) p1 = v1 * t[1];
+        }
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 4);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 4);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 8);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 8);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 16);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, 16);
+        if ((threadIdx.x & 31) < 4) {
+            double* o = var + (size_t)i * nlon + col;
+            if (col < nlon) atomicAdd(o, p0);
+            if (col + 1 < nlon) atomicAdd(o + 1, p1);
+        }
+    }
+};
+
+__global__ void gb_cov_finish(double* v, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = sqrt(v[i]);
 }
 
-// var[i][j] = sum_k T[k][j] * sum_k' H[i][k][k'] T[k'][j]; CTA per (j tile, i)
-__global__ void __launch_bounds__(128)
-gb_cov_longitude(const double* __restrict__ H, const double* __restrict__ trig, double* __restrict__ out, int kpad,
-                 int k_used, int nlon, int nlp, int take_sqrt) {
-    extern __shared__ double s_h[];  // one row of H_i at a time: [kpad]
-    const int i = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = j < nlon;
-    const double* Hi = H + (size_t)i * kpad * kpad;
-    double var = 0.0;
-    for (int k = 0; k < k_used; ++k) {
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < k_used; idx += blockDim.x) s_h[idx] = Hi[(size_t)k * kpad + idx];
-        __syncthreads();
-        if (live) {
-            double w0 = 0.0, w1 = 0.0;
-            int kk = 0;
-            for (; kk + 1 < k_used; kk += 2) {
-                w0 = fma(s_h[kk], trig[(size_t)kk * nlp + j], w0);
-                w1 = fma(s_h[kk + 1], trig[(size_t)(kk + 1) * nlp + j], w1);
-            }
-            if (kk < k_used) w0 = fma(s_h[kk], trig[(size_t)kk * nlp + j], w0);
-            var = fma(trig[(size_t)k * nlp + j], w0 + w1, var);
-        }
-    }
-    if (live) out[(size_t)i * nlon + j] = take_sqrt ? sqrt(var) : var;
+template <typename T>
+int to_device(T** d, const std::vector<T>& h, cudaStream_t st) {
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(d), (h.size() ? h.size() : 1) * sizeof(T), st));
+    GB_CUDA(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return GB_OK;
 }
 
 }  // namespace
@@ -160,72 +170,118 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
     const int L = p->L, kpad = p->kpad;
     const long long K = (long long)L * L - (long long)nmin * nmin;
 
-    // order-wise padded layout: group k = 2m + cs holds degrees n0(m)..nmax
-    std::vector<int> goff(kpad + 1, 0), gcnt(kpad, 0);
-    int Kp = 0;
+    // order-wise layouts: group k = 2m + cs holds degrees n0(m)..nmax
+    std::vector<int> gcnt(kpad, 0), goff8(kpad, 0), goff4(kpad, 0);
+    int Kp8 = 0, Kp4 = 0, Kg = 8;   // Kg: rows per U tile (covers the 8-padded groups read by the epilogue)
     for (int k = 0; k < kpad; ++k) {
         const int m = k >> 1, cs = k & 1;
         int cnt = 0;
         if (m < L && !(m == 0 && cs == 1)) cnt = L - (m > nmin ? m : nmin);
-        goff[k] = Kp;
         gcnt[k] = cnt;
-        Kp += (cnt + 3) / 4 * 4;
+        goff8[k] = Kp8;
+        goff4[k] = Kp4;
+        Kp8 += (cnt + 7) / 8 * 8;
+        Kp4 += (cnt + 3) / 4 * 4;
+        if ((cnt + 7) / 8 * 8 > Kg) Kg = (cnt + 7) / 8 * 8;
     }
-    goff[kpad] = Kp;
-    std::vector<int> perm(Kp, -1);
+    GB_REQUIRE(Kp4 <= 65535, "gb_covariance_propagation: degree %d is too large for this path", p->nmax);
+    const int n_atiles = (Kp8 + GB_TM - 1) / GB_TM;
+    const int rows_a = n_atiles * GB_TM;
+    std::vector<int> perm8(rows_a, -1), perm4(Kp4, -1), rowgroup(rows_a / 8, -1);
     for (int k = 0; k < kpad; ++k) {
         const int m = k >> 1, cs = k & 1;
         const int n0 = (m > nmin ? m : nmin);
         for (int r = 0; r < gcnt[k]; ++r) {
             const int n = n0 + r;
             const long long idx = (long long)n * n + (m == 0 ? 0 : 2 * m - 1 + cs) - (long long)nmin * nmin;
-            perm[goff[k] + r] = (int)idx;
+            perm8[goff8[k] + r] = (int)idx;
+            perm4[goff4[k] + r] = (int)idx;
         }
+        for (int r = 0; r < (gcnt[k] + 7) / 8; ++r) rowgroup[goff8[k] / 8 + r] = k;
     }
-    const int ldu = (nrows + 7) / 8 * 8;
-    int *d_goff = nullptr, *d_gcnt = nullptr, *d_perm = nullptr;
-    double *d_sp = nullptr, *d_U = nullptr, *d_H = nullptr;
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_goff), (kpad + 1) * sizeof(int), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_gcnt), kpad * sizeof(int), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_perm), Kp * sizeof(int), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_sp), (size_t)Kp * Kp * sizeof(double), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_U), (size_t)Kp * ldu * sizeof(double), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_H), (size_t)nrows * kpad * kpad * sizeof(double), st));
-    GB_CUDA(cudaMemcpyAsync(d_goff, goff.data(), (kpad + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaMemcpyAsync(d_gcnt, gcnt.data(), kpad * sizeof(int), cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaMemcpyAsync(d_perm, perm.data(), Kp * sizeof(int), cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope below; copies are tiny
-    GB_CUDA(cudaMemsetAsync(d_U, 0, (size_t)Kp * ldu * sizeof(double), st));
+    const int nti = (nrows + GB_S2_TN - 1) / GB_S2_TN;          // parallel tiles
+    const int n_ct = kpad * nti;                                // column tiles of the quadratic-form GEMM
+    std::vector<int> nt_koff(n_ct), nt_klen(n_ct);
+    for (int k = 0; k < kpad; ++k)
+        for (int it = 0; it < nti; ++it) {
+            nt_koff[k * nti + it] = goff4[k];
+            nt_klen[k * nti + it] = (gcnt[k] + 3) / 4 * 4;
+        }
+    const int hmt = (kpad + GB_TM - 1) / GB_TM;                 // row tiles of H_i
+
+    int *d_perm8 = nullptr, *d_perm4 = nullptr, *d_rowgroup = nullptr, *d_goff8 = nullptr, *d_koff = nullptr,
+        *d_klen = nullptr;
+    double *d_st = nullptr, *d_ut = nullptr, *d_ht = nullptr;
+    int rc = GB_OK;
+    if ((rc = to_device(&d_perm8, perm8, st)) || (rc = to_device(&d_perm4, perm4, st)) ||
+        (rc = to_device(&d_rowgroup, rowgroup, st)) || (rc = to_device(&d_goff8, goff8, st)) ||
+        (rc = to_device(&d_koff, nt_koff, st)) || (rc = to_device(&d_klen, nt_klen, st)))
+        return rc;
+    const size_t st_elems = (size_t)n_atiles * Kp4 * GB_LDA;
+    const size_t ut_elems = (size_t)n_ct * Kg * GB_S2_LDB;
+    const size_t ht_elems = (size_t)nrows * hmt * kpad * GB_LDA;
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_st), st_elems * sizeof(double), st));
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ut), ut_elems * sizeof(double), st));
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ht), ht_elems * sizeof(double), st));
+    GB_CUDA(cudaMemsetAsync(d_st, 0, st_elems * sizeof(double), st));    // pad columns 128..131 of every row
+    GB_CUDA(cudaMemsetAsync(d_ut, 0, ut_elems * sizeof(double), st));
+    GB_CUDA(cudaMemsetAsync(d_ht, 0, ht_elems * sizeof(double), st));
+    GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nrows * p->nlon * sizeof(double), st));
+    GB_CUDA(cudaStreamSynchronize(st));   // the host index vectors go out of scope; their copies are tiny
     {
-        dim3 grid((Kp + 255) / 256, Kp);
-        gb_cov_permute<<<grid, 256, 0, st>>>(d_sigma, d_sp, d_perm, Kp, K);
+        dim3 grid((rows_a + 255) / 256, Kp4);
+        gb_cov_permute<<<grid, 256, 0, st>>>(d_sigma, d_st, d_perm8, d_perm4, rows_a, Kp4, K);
         GB_LAUNCH_CHECK();
     }
     {
         dim3 grid((nrows + 127) / 128, L);
-        gb_cov_legendre<<<grid, 128, 0, st>>>(d_U, d_goff, p->d_ct, p->d_kn, p->d_pmm, p->d_ra, p->d_rb, p->d_rc, L,
-                                              nmin, row0, nrows, ldu);
+        gb_cov_legendre<<<grid, 128, 0, st>>>(d_ut, p->d_ct, p->d_kn, p->d_pmm, p->d_ra, p->d_rb, p->d_rc, L, nmin,
+                                              row0, nrows, nti, Kg);
         GB_LAUNCH_CHECK();
     }
     {
-        dim3 grid(kpad, kpad);
-        const size_t smem = (size_t)QA * L * sizeof(double);
-        if (smem > 48 * 1024)
-            GB_CUDA(cudaFuncSetAttribute(gb_cov_quadform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gb_cov_quadform<<<grid, 128, smem, st>>>(d_sp, d_U, d_H, d_goff, d_gcnt, Kp, kpad, nrows, ldu);
-        GB_LAUNCH_CHECK();
+        gbgemm::Shape sh;
+        sh.A_t = d_st;
+        sh.a_rows = Kp4;
+        sh.a_koff_mul = 0;
+        sh.tiles_per_group = 1;
+        sh.B_t = d_ut;
+        sh.b_rows = Kg;
+        sh.klen = 0;
+        sh.n_mtiles = n_atiles;
+        sh.n_ntiles = n_ct;
+        sh.nt_koff = d_koff;
+        sh.nt_klen = d_klen;
+        QuadEpilogue epi{d_ut, d_ht, d_rowgroup, d_goff8, nti, Kg, kpad, hmt, nrows};
+        if ((rc = gbgemm::launch(sh, epi, p->sm_count, st))) return rc;
     }
     {
-        dim3 grid((p->nlon + 127) / 128, nrows);
-        gb_cov_longitude<<<grid, 128, kpad * sizeof(double), st>>>(d_H, p->d_trig, d_out, kpad, 2 * L, p->nlon, p->nlp,
-                                                                   take_sqrt);
+        gbgemm::Shape sh;
+        sh.A_t = d_ht;
+        sh.a_rows = kpad;
+        sh.a_koff_mul = 0;
+        sh.tiles_per_group = 1;
+        sh.B_t = p->d_trig_t;
+        sh.b_rows = kpad;
+        sh.klen = kpad;
+        sh.n_mtiles = nrows * hmt;
+        sh.n_ntiles = p->n_ntiles;
+        LonEpilogue epi{p->d_trig, d_out, hmt, kpad, p->nlp, p->nlon};
+        if ((rc = gbgemm::launch(sh, epi, p->sm_count, st))) return rc;
+    }
+    if (take_sqrt) {
+        const long long n = (long long)nrows * p->nlon;
+        gb_cov_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_out, n);
         GB_LAUNCH_CHECK();
     }
-    GB_CUDA(cudaFreeAsync(d_goff, st));
-    GB_CUDA(cudaFreeAsync(d_gcnt, st));
-    GB_CUDA(cudaFreeAsync(d_perm, st));
-    GB_CUDA(cudaFreeAsync(d_sp, st));
-    GB_CUDA(cudaFreeAsync(d_U, st));
-    GB_CUDA(cudaFreeAsync(d_H, st));
+    GB_CUDA(cudaFreeAsync(d_perm8, st));
+    GB_CUDA(cudaFreeAsync(d_perm4, st));
+    GB_CUDA(cudaFreeAsync(d_rowgroup, st));
+    GB_CUDA(cudaFreeAsync(d_goff8, st));
+    GB_CUDA(cudaFreeAsync(d_koff, st));
+    GB_CUDA(cudaFreeAsync(d_klen, st));
+    GB_CUDA(cudaFreeAsync(d_st, st));
+    GB_CUDA(cudaFreeAsync(d_ut, st));
+    GB_CUDA(cudaFreeAsync(d_ht, st));
     return GB_OK;
 }

@@ -41,6 +41,8 @@ struct Shape {
     int b_rows;             // k rows per B tile
     int klen;               // contraction length (multiple of 4), k = 0..klen-1 of B, a_koff.. of A
     int n_mtiles, n_ntiles;
+    const int* nt_koff = nullptr;   // optional per-column-tile A k offset and contraction length
+    const int* nt_klen = nullptr;   // (overrides a_koff_mul / klen; used by the covariance quadratic form)
 };
 
 template <class Epilogue>
@@ -69,9 +71,10 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const long long mt = t / sh.n_ntiles;
                 const int nt = (int)(t % sh.n_ntiles);
-                const int a_koff = (nt / sh.tiles_per_group) * sh.a_koff_mul;
-                for (int k0 = 0; k0 < sh.klen; k0 += KC) {
-                    const int kc = min(KC, sh.klen - k0);
+                const int a_koff = sh.nt_koff ? sh.nt_koff[nt] : (nt / sh.tiles_per_group) * sh.a_koff_mul;
+                const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
+                for (int k0 = 0; k0 < klen; k0 += KC) {
+                    const int kc = min(KC, klen - k0);
                     gb::mbar_wait(&empty[stage], phase ^ 1u);
                     double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES;
                     double* sB = sA + KC * LDA;
@@ -97,8 +100,9 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            for (int k0 = 0; k0 < sh.klen; k0 += KC) {
-                const int kc = min(KC, sh.klen - k0);
+            const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
+            for (int k0 = 0; k0 < klen; k0 += KC) {
+                const int kc = min(KC, klen - k0);
                 gb::mbar_wait(&full[stage], phase);
                 const double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 32 + g;
                 const double* sB = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
