@@ -416,3 +416,64 @@ def test_api_errors(gb):
         plan.synthesis(torch.zeros((1, 4, 4), dtype=torch.float32, device="cuda"))
     assert plan.synthesis(torch.zeros((0, 4, 4), dtype=torch.float64, device="cuda")).shape == (0, 6, 12)
     assert gb.get_plan(gb.GeographicGrid(30.0, 30.0), 3, "ewh") is plan       # cached
+
+
+# ------------------------------------------------------------------------------ BASELINE full sizes
+def test_config3_full_size_round_trip(gb, orc):
+    """BASELINE config 3 geometry (degree 180 -> 0.25 deg, 720 x 1440): synthesis against the oracle
+    for one epoch (tolerance 1e-10 at degree >= 180), analysis through the round trip (size-independent
+    property) and against the separable oracle on one epoch."""
+    N, E = 180, 6
+    grid, og = gb.GeographicGrid(0.25, 0.25), orc.geographic_grid(0.25, 0.25)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    x = torch.as_tensor(anm).cuda()
+    vals = gb.to_grid_batch(x, grid, "ewh")
+    ref0 = orc.synthesis(anm[0], og, "ewh")
+    assert maxnorm_err(vals[0].cpu().numpy(), ref0) < 1e-10
+    back = gb.analysis_batch(vals, grid, 0, N, "ewh", device_output=True)
+    assert float((back - x).abs().max() / x.abs().max()) < 1e-10
+    assert maxnorm_err(back[0].cpu().numpy(), orc.analysis_separable(ref0, og, 0, N, "ewh")) < 1e-10
+
+
+def test_config4_full_size_properties(gb, orc):
+    """BASELINE config 4 at full size (K = 9409 coefficients, 360 x 720 grid): closed form for
+    Sigma = I, scaling (std is homogeneous of degree 1/2 in Sigma), row-block sharding and three
+    parallels against the oracle."""
+    N = 96
+    grid, og = gb.GeographicGrid(0.5, 0.5), orc.geographic_grid(0.5, 0.5)
+    plan = gb.get_plan(grid, N, "ewh")
+    K = (N + 1) ** 2
+    eye = torch.eye(K, dtype=torch.float64, device="cuda")
+    var = plan.covariance_propagation(eye, 0, take_sqrt=False).cpu().numpy()
+    P = orc.ravel_coefficients(orc._scale_packed_by_degree(orc.legendre_functions(N, plan.colat), plan.kn))
+    T = orc.ravel_coefficients(orc.trigonometric_functions(N, grid.meridians))
+    assert maxnorm_err(var, (P ** 2) @ (T ** 2).T) < TOL
+    del eye
+    sig_h = orc.synthetic_covariance(N)
+    sigma = torch.as_tensor(sig_h).cuda()
+    std = plan.covariance_propagation(sigma, 0)
+    ref = orc.covariance_propagation(sig_h, og, 0, N, "ewh", rows=[7, 180, 352])
+    assert maxnorm_err(std[[7, 180, 352]].cpu().numpy(), ref) < TOL
+    std4 = plan.covariance_propagation(sigma * 4.0, 0)
+    assert maxnorm_err(std4.cpu().numpy(), 2.0 * std.cpu().numpy()) < 1e-13
+    blocks = torch.cat([plan.covariance_propagation(sigma, 0, r0, 45) for r0 in range(0, 360, 45)])   # 8-GPU partition
+    assert maxnorm_err(blocks.cpu().numpy(), std.cpu().numpy()) < 1e-13
+
+
+def test_config5_filter_then_synthesis_full_degree(gb, orc):
+    """BASELINE config 5 geometry (degree 120 -> 0.25 deg) on a reduced epoch count: two epochs against
+    the oracle, linearity of filter + synthesis for the batch."""
+    N, E = 120, 12
+    grid, og = gb.GeographicGrid(0.25, 0.25), orc.geographic_grid(0.25, 0.25)
+    blocks = orc.synthetic_filter_blocks(N)
+    flt = gb.OrderWiseFilter(blocks)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    x = torch.as_tensor(anm).cuda()
+    vals = gb.to_grid_batch(flt.filter_batch(x), grid, "ewh")
+    for e in (0, E - 1):
+        ref = orc.synthesis(orc.orderwise_filter(blocks, anm[e]), og, "ewh")
+        assert maxnorm_err(vals[e].cpu().numpy(), ref) < TOL
+    mix = (2.0 * x[3] - 0.5 * x[9])[None].contiguous()
+    lin = 2.0 * vals[3] - 0.5 * vals[9]
+    got = gb.to_grid_batch(flt.filter_batch(mix), grid, "ewh")[0]
+    assert maxnorm_err(got.cpu().numpy(), lin.cpu().numpy()) < 1e-13
