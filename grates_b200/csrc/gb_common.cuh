@@ -48,6 +48,8 @@ constexpr int GB_S2_TN = 120;       // meridians per tile, general stage 2
 constexpr int GB_S2_LDB = GB_S2_TN + 4;
 constexpr int GB_Q_TN = 32;         // first-quadrant meridians per tile, symmetric stage 2
 constexpr int GB_Q_LDB = GB_Q_TN + 4;
+constexpr int GB_T1_TM = 64;        // parallels per stage-1 work item
+constexpr int GB_T1_KC = 16;        // degrees per stage-1 pipeline chunk
 
 __host__ __device__ __forceinline__ size_t gb_ab_offset(long long row, int k, int ab_rows) {
     return ((size_t)(row >> 7) * ab_rows + k) * GB_LDA + (size_t)(row & 127);
@@ -70,6 +72,14 @@ struct gb_plan {
     double* d_rc = nullptr;     // [L]         sqrt(2n+1), first off-diagonal (utilities.py:46)
     double* d_trig = nullptr;   // [kpad][nlp] row 2m: cos(m lon_j), row 2m+1: sin(m lon_j)
     double* d_zero = nullptr;   // 4 KB of zeros (source of padding rows for bulk copies)
+    // stage-1 tables, transposed and zero padded so that the Legendre warps read them coalesced and
+    // unguarded: parallels padded to GB_T1_TM, degrees of one order padded to whole GB_T1_KC chunks
+    int nlat_pad = 0, lpad = 0;
+    double* d_ct_pad = nullptr; // [nlat_pad]
+    double* d_kn_t = nullptr;   // [L + GB_T1_KC][nlat_pad]   kn_t[n][i]
+    double* d_pmm_t = nullptr;  // [L][nlat_pad]              pmm_t[m][i]
+    double* d_rec_a = nullptr;  // [L][lpad]  rec_a[m][n-m]: sqrt(2n+1) at n = m+1 (utilities.py:46), a_nm beyond
+    double* d_rec_b = nullptr;  // [L][lpad]  rec_b[m][n-m]: 0 at n = m+1, b_nm beyond
     // four-fold longitude symmetry (meridians symmetric about 0 and invariant under a half turn):
     // spectral rows regrouped as [even-m cos | odd-m cos | even-m sin | odd-m sin], each padded to 4
     int sym = 0;                // 1 if the meridians allow the symmetric stage 2

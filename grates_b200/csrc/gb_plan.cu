@@ -184,8 +184,29 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
                     trig_q_t[((size_t)t * p->kpad_s + k) * GB_Q_LDB + c] = trig_q[(size_t)k * p->nqp + t * GB_Q_TN + c];
     }
 
+    // stage-1 tables (see gb_common.cuh)
+    p->nlat_pad = (nlat + GB_T1_TM - 1) / GB_T1_TM * GB_T1_TM;
+    p->lpad = (L + GB_T1_KC - 1) / GB_T1_KC * GB_T1_KC;
+    std::vector<double> ct_pad(p->nlat_pad, 0.0), kn_t((size_t)(L + GB_T1_KC) * p->nlat_pad, 0.0),
+        pmm_t((size_t)L * p->nlat_pad, 0.0), rec_a((size_t)L * p->lpad, 0.0), rec_b((size_t)L * p->lpad, 0.0);
+    for (int i = 0; i < nlat; ++i) {
+        ct_pad[i] = ct[i];
+        for (int n = 0; n < L; ++n) {
+            kn_t[(size_t)n * p->nlat_pad + i] = knv[(size_t)i * L + n];
+            pmm_t[(size_t)n * p->nlat_pad + i] = pmm[(size_t)i * L + n];
+        }
+    }
+    for (int m = 0; m < L; ++m)
+        for (int n = m + 1; n < L; ++n) {
+            // (a ct) p1 - 0 * p2 at n = m+1 is bit-identical to utilities.py:46
+            rec_a[(size_t)m * p->lpad + (n - m)] = (n == m + 1) ? rc[n] : ra[(size_t)n * L + m];
+            rec_b[(size_t)m * p->lpad + (n - m)] = (n == m + 1) ? 0.0 : rb[(size_t)n * L + m];
+        }
+
     int rc_ = GB_OK;
-    if ((rc_ = upload(&p->d_trig_t, trig_t)) || (p->sym && (rc_ = upload(&p->d_trig_q_t, trig_q_t))) ||
+    if ((rc_ = upload(&p->d_ct_pad, ct_pad)) || (rc_ = upload(&p->d_kn_t, kn_t)) || (rc_ = upload(&p->d_pmm_t, pmm_t)) ||
+        (rc_ = upload(&p->d_rec_a, rec_a)) || (rc_ = upload(&p->d_rec_b, rec_b)) ||
+        (rc_ = upload(&p->d_trig_t, trig_t)) || (p->sym && (rc_ = upload(&p->d_trig_q_t, trig_q_t))) ||
         (rc_ = upload(&p->d_ct, ct)) || (rc_ = upload(&p->d_kn, knv)) || (rc_ = upload(&p->d_pmm, pmm)) ||
         (rc_ = upload(&p->d_ra, ra)) || (rc_ = upload(&p->d_rb, rb)) || (rc_ = upload(&p->d_rc, rc)) ||
         (rc_ = upload(&p->d_trig, trig)) || (rc_ = upload(&p->d_zero, std::vector<double>(512, 0.0))) ||
@@ -214,6 +235,7 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     cudaSetDevice(p->device);
     cudaFree(p->d_ct); cudaFree(p->d_kn); cudaFree(p->d_pmm); cudaFree(p->d_ra); cudaFree(p->d_rb);
     cudaFree(p->d_rc); cudaFree(p->d_trig); cudaFree(p->d_zero);
+    cudaFree(p->d_ct_pad); cudaFree(p->d_kn_t); cudaFree(p->d_pmm_t); cudaFree(p->d_rec_a); cudaFree(p->d_rec_b);
     cudaFree(p->d_krow_id); cudaFree(p->d_krow_sym); cudaFree(p->d_trig_q);
     cudaFree(p->d_trig_t); cudaFree(p->d_trig_q_t); cudaFree(p->d_x); cudaFree(p->d_ab);
     cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);

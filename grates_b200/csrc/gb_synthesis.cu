@@ -128,14 +128,18 @@ gb_legendre_stage1_simple(const double* __restrict__ X, double* __restrict__ AB,
 
 
 // ---------------------------------------------------------------------------------------------
-// stage 1 on the FP64 tensor cores.  One CTA = (order m, 64 parallels, 240 columns (e, cos|sin)):
+// stage 1 on the FP64 tensor cores, persistent.  Work item = (order pair (p, nmax-p), 64 parallels,
+// 240 columns (e, cos|sin)); every item carries L+1 degrees, so items cost the same:
 //   D[i, col] = sum_n Pk[i, n] X_m[n, col],  Pk = kn * P_nm produced ON THE FLY:
 //   two Legendre warps (lane = parallel) advance the recursion 16 degrees at a time and write the
-//   chunk k-major into shared memory; a copy warp streams the matching 16 rows of X_m with bulk
+//   chunk k-major into shared memory; a copy warp streams the matching rows of X_m with bulk
 //   copies; twelve consumer warps (2 x 6, 32 x 40 register tiles) issue DMMA.8x8x4.
-// Degrees beyond nmax in the last chunk are fed from a zero row, parallels beyond nlat are zero.
+// One CTA per SM walks the items with a 4-stage ring that never drains: the Legendre and copy warps
+// run ahead into the next order / item while the consumers store their tile, and all tables they
+// read are global (transposed, zero padded: gb_plan::d_rec_a/b, d_kn_t, d_pmm_t, d_ct_pad), so no
+// per-item prologue exists.  The last chunk of an order is processed in whole 4-degree steps only.
 // ---------------------------------------------------------------------------------------------
-constexpr int T1_TM = 64, T1_TN = 240, T1_KC = 16, T1_STAGES = 4;
+constexpr int T1_TM = GB_T1_TM, T1_TN = 240, T1_KC = GB_T1_KC, T1_STAGES = 4;
 constexpr int T1_LDA = T1_TM + 4;    // 68
 constexpr int T1_LDB = T1_TN + 4;    // 244
 constexpr int T1_CONSUMER_WARPS = 12;
@@ -143,30 +147,27 @@ constexpr int T1_THREADS = 32 * (T1_CONSUMER_WARPS + 3);   // + copy warp + 2 Le
 constexpr int T1_STAGE_DOUBLES = T1_KC * (T1_LDA + T1_LDB);
 constexpr size_t T1_SMEM = (size_t)T1_STAGES * T1_STAGE_DOUBLES * sizeof(double) + 2 * T1_STAGES * sizeof(uint64_t);
 
+struct T1Tables {
+    const double* ct_pad;   // [nlat_pad]
+    const double* kn_t;     // [L + 16][nlat_pad]
+    const double* pmm_t;    // [L][nlat_pad]
+    const double* rec_a;    // [L][lpad]   rec_a[m][n - m]
+    const double* rec_b;    // [L][lpad]
+    const double* zeros;
+    const int* krow;
+    int nlat_pad, lpad;
+};
+
 __global__ void __launch_bounds__(T1_THREADS, 1)
-gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const double* __restrict__ ct,
-                   const double* __restrict__ kn, const double* __restrict__ pmm, const double* __restrict__ ra,
-                   const double* __restrict__ rb, const double* __restrict__ rc, const double* __restrict__ zeros,
-                   const int* __restrict__ krow, int L, int nlat, int E, int ab_rows, int n_coltiles) {
+gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tables tb, int L, int nlat, int E,
+                   int ab_rows, int n_lattiles, int n_coltiles, int n_items) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)T1_STAGES * T1_STAGE_DOUBLES * sizeof(double));
     uint64_t* empty = full + T1_STAGES;
-
-    // one CTA contracts the order pair (p, nmax - p): (L - p) + (p + 1) = L + 1 degrees in total, so
-    // all CTAs carry the same work and the pipeline keeps running across the two orders
-    const int m_first = blockIdx.y;
-    const int m_second = L - 1 - m_first;
-    const int npass = (m_second == m_first) ? 1 : 2;
-    const int it = blockIdx.x / n_coltiles;
-    const int ctile = blockIdx.x % n_coltiles;
-    const int i0 = it * T1_TM;
     const int cols = 2 * E;
-    const int c0 = ctile * T1_TN;
-    const int width = min(T1_TN, cols - c0);       // even
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int lpad = (L + T1_KC - 1) / T1_KC * T1_KC;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T1_STAGES; ++s) {
@@ -175,133 +176,133 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, const 
         }
         gb::fence_mbar_init();
     }
-    // recursion coefficients of both orders, padded to whole chunks.  Entry 1 (n = m+1) uses
-    // a = sqrt(2n+1), b = 0: (a ct) p1 - 0 * 0 is bit-identical to utilities.py:46.
-    double* s_ra = reinterpret_cast<double*>(empty + T1_STAGES);   // [2][lpad]
-    double* s_rb = s_ra + 2 * lpad;                                 // [2][lpad]
-    for (int idx = threadIdx.x; idx < 2 * lpad; idx += blockDim.x) {
-        const int pass = idx / lpad, nn = idx % lpad;
-        const int m = pass ? m_second : m_first;
-        const int n = m + nn;
-        double a = 0.0, b = 0.0;
-        if (nn == 1 && n < L) a = rc[n];
-        else if (nn >= 2 && n < L) { a = ra[(size_t)n * L + m]; b = rb[(size_t)n * L + m]; }
-        s_ra[idx] = a;
-        s_rb[idx] = b;
-    }
     __syncthreads();
 
     int stage = 0;
     uint32_t phase = 0;
-    if (warp == T1_CONSUMER_WARPS) {
-        // ===== copy warp: 16 rows of X_m per chunk =====
-        for (int pass = 0; pass < npass; ++pass) {
-            const int m = pass ? m_second : m_first;
-            const int Kn = L - m;
-            const int n_chunks = (Kn + T1_KC - 1) / T1_KC;
-            const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
-            const double* Xm = X + xo + c0;
-            for (int c = 0; c < n_chunks; ++c) {
-                gb::mbar_wait(&empty[stage], phase ^ 1u);
-                double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA;
-                if (lane == 0) gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(T1_KC * width * sizeof(double)));
-                __syncwarp();
-                if (lane < T1_KC) {
-                    const int nn = c * T1_KC + lane;
-                    const double* src = (nn < Kn) ? Xm + (size_t)nn * cols : zeros;
-                    gb::bulk_g2s(sB + lane * T1_LDB, src, (uint32_t)(width * sizeof(double)), &full[stage]);
+    const int tiles_per_pair = n_lattiles * n_coltiles;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int m_first = item / tiles_per_pair;
+        const int rem = item - m_first * tiles_per_pair;
+        const int i0 = (rem / n_coltiles) * T1_TM;
+        const int c0 = (rem % n_coltiles) * T1_TN;
+        const int m_second = L - 1 - m_first;
+        const int npass = (m_second == m_first) ? 1 : 2;
+        const int width = min(T1_TN, cols - c0);       // even
+
+        if (warp == T1_CONSUMER_WARPS) {
+            // ===== copy warp: the rows of X_m a chunk needs (whole 4-degree steps) =====
+            for (int pass = 0; pass < npass; ++pass) {
+                const int m = pass ? m_second : m_first;
+                const int Kn = L - m;
+                const int n_chunks = (Kn + T1_KC - 1) / T1_KC;
+                const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
+                const double* Xm = X + xo + c0;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int rows = min(T1_KC, (Kn - c * T1_KC + 3) & ~3);
+                    gb::mbar_wait(&empty[stage], phase ^ 1u);
+                    double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA;
+                    if (lane == 0) gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * width * sizeof(double)));
+                    __syncwarp();
+                    if (lane < rows) {
+                        const int nn = c * T1_KC + lane;
+                        const double* src = (nn < Kn) ? Xm + (size_t)nn * cols : tb.zeros;
+                        gb::bulk_g2s(sB + lane * T1_LDB, src, (uint32_t)(width * sizeof(double)), &full[stage]);
+                    }
+                    if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
             }
-        }
-    } else if (warp > T1_CONSUMER_WARPS) {
-        // ===== Legendre warps: lane = parallel, recursion state lives in registers =====
-        const int li = (warp - T1_CONSUMER_WARPS - 1) * 32 + lane;
-        const int i = i0 + li;
-        const bool live = i < nlat;
-        const double cti = live ? ct[i] : 0.0;
-        for (int pass = 0; pass < npass; ++pass) {
-            const int m = pass ? m_second : m_first;
-            const int Kn = L - m;
-            const int n_chunks = (Kn + T1_KC - 1) / T1_KC;
-            const double* kn_i = kn + (size_t)(live ? i : 0) * L + m;
-            const double* c_ra = s_ra + pass * lpad;
-            const double* c_rb = s_rb + pass * lpad;
-            double p1 = 0.0, p2 = 0.0;
-            for (int c = 0; c < n_chunks; ++c) {
-                // factors and recursion coefficients of the chunk first (independent loads in flight
-                // together), then the serial chain: per degree one dependent multiply + subtract
-                double knv[T1_KC], act[T1_KC];
+        } else if (warp > T1_CONSUMER_WARPS) {
+            // ===== Legendre warps: lane = parallel, recursion state lives in registers =====
+            const int li = (warp - T1_CONSUMER_WARPS - 1) * 32 + lane;
+            const int i = i0 + li;                           // < nlat_pad; padded parallels read zeros
+            const double cti = tb.ct_pad[i];
+            for (int pass = 0; pass < npass; ++pass) {
+                const int m = pass ? m_second : m_first;
+                const int n_chunks = (L - m + T1_KC - 1) / T1_KC;
+                const double* kn_i = tb.kn_t + (size_t)m * tb.nlat_pad + i;
+                const double* c_ra = tb.rec_a + (size_t)m * tb.lpad;
+                const double* c_rb = tb.rec_b + (size_t)m * tb.lpad;
+                const double seed = tb.pmm_t[(size_t)m * tb.nlat_pad + i];
+                double p1 = 0.0, p2 = 0.0;
+                for (int c = 0; c < n_chunks; ++c) {
+                    // factors and recursion coefficients of the chunk first (independent loads in flight
+                    // together), then the serial chain: per degree one dependent multiply + subtract
+                    double knv[T1_KC], act[T1_KC], rbv[T1_KC];
 #pragma unroll
-                for (int kk = 0; kk < T1_KC; ++kk) {
-                    const int nn = c * T1_KC + kk;
-                    knv[kk] = (live && nn < Kn) ? __ldg(kn_i + nn) : 0.0;
-                    act[kk] = __dmul_rn(c_ra[nn], cti);
-                }
-                gb::mbar_wait(&empty[stage], phase ^ 1u);
-                double* sA = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + li;
+                    for (int kk = 0; kk < T1_KC; ++kk) {
+                        const int nn = c * T1_KC + kk;
+                        knv[kk] = __ldg(kn_i + (size_t)nn * tb.nlat_pad);     // 0 beyond nmax / nlat
+                        act[kk] = __dmul_rn(__ldg(c_ra + nn), cti);
+                        rbv[kk] = __ldg(c_rb + nn);
+                    }
+                    gb::mbar_wait(&empty[stage], phase ^ 1u);
+                    double* sA = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + li;
 #pragma unroll
-                for (int kk = 0; kk < T1_KC; ++kk) {
-                    const int nn = c * T1_KC + kk;
-                    double pn;
-                    if (nn == 0) pn = live ? pmm[(size_t)i * L + m] : 0.0;
-                    else pn = __dsub_rn(__dmul_rn(act[kk], p1), __dmul_rn(c_rb[nn], p2));
-                    p2 = p1;
-                    p1 = pn;
-                    sA[kk * T1_LDA] = __dmul_rn(pn, knv[kk]);   // knv = 0 beyond nmax / nlat
+                    for (int kk = 0; kk < T1_KC; ++kk) {
+                        double pn;
+                        if (c == 0 && kk == 0) pn = seed;
+                        else pn = __dsub_rn(__dmul_rn(act[kk], p1), __dmul_rn(rbv[kk], p2));
+                        p2 = p1;
+                        p1 = pn;
+                        sA[kk * T1_LDA] = __dmul_rn(pn, knv[kk]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) gb::mbar_arrive(&full[stage]);
+                    if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (lane == 0) gb::mbar_arrive(&full[stage]);
-                if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
             }
-        }
-    } else {
-        // ===== consumer warps =====
-        const int wm = warp / 6;
-        const int wn = warp % 6;
-        const int g = lane >> 2, q = lane & 3;
-        for (int pass = 0; pass < npass; ++pass) {
-            const int m = pass ? m_second : m_first;
-            const int n_chunks = (L - m + T1_KC - 1) / T1_KC;
-            double acc[4][5][2];
+        } else {
+            // ===== consumer warps =====
+            const int wm = warp / 6;
+            const int wn = warp % 6;
+            const int g = lane >> 2, q = lane & 3;
+            for (int pass = 0; pass < npass; ++pass) {
+                const int m = pass ? m_second : m_first;
+                const int Kn = L - m;
+                const int n_chunks = (Kn + T1_KC - 1) / T1_KC;
+                double acc[4][5][2];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            for (int c = 0; c < n_chunks; ++c) {
-                gb::mbar_wait(&full[stage], phase);
-                const double* sA = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + wm * 32 + g;
-                const double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA + wn * 40 + g;
+                    for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int rows = Kn - c * T1_KC;             // degrees left (whole steps are processed)
+                    gb::mbar_wait(&full[stage], phase);
+                    const double* sA = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + wm * 32 + g;
+                    const double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA + wn * 40 + g;
 #pragma unroll
-                for (int kk = 0; kk < T1_KC; kk += 4) {
-                    double a[4], b[5];
+                    for (int kk = 0; kk < T1_KC; kk += 4) {
+                        if (kk >= rows) break;
+                        double a[4], b[5];
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * T1_LDA + mi * 8];
+                        for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * T1_LDA + mi * 8];
 #pragma unroll
-                    for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * T1_LDB + ni * 8];
+                        for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * T1_LDB + ni * 8];
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
+                        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                            for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                    if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (lane == 0) gb::mbar_arrive(&empty[stage]);
-                if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
-            }
-            // epilogue: column pair (2q, 2q+1) of a fragment = (cos, sin) of one epoch
-            const int kc_row = krow[2 * m], ks_row = krow[2 * m + 1];
+                // epilogue: column pair (2q, 2q+1) of a fragment = (cos, sin) of one epoch
+                const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
 #pragma unroll
-            for (int ni = 0; ni < 5; ++ni) {
-                const int col = c0 + wn * 40 + ni * 8 + 2 * q;
-                if (col >= cols) continue;
-                const int e = col >> 1;
+                for (int ni = 0; ni < 5; ++ni) {
+                    const int col = c0 + wn * 40 + ni * 8 + 2 * q;
+                    if (col >= cols) continue;
+                    const int e = col >> 1;
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
-                    const int i = i0 + wm * 32 + mi * 8 + g;
-                    if (i < nlat) {
-                        const long long row = (long long)e * nlat + i;
-                        AB[gb_ab_offset(row, kc_row, ab_rows)] = acc[mi][ni][0];
-                        AB[gb_ab_offset(row, ks_row, ab_rows)] = acc[mi][ni][1];
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const int i = i0 + wm * 32 + mi * 8 + g;
+                        if (i < nlat) {
+                            const long long row = (long long)e * nlat + i;
+                            AB[gb_ab_offset(row, kc_row, ab_rows)] = acc[mi][ni][0];
+                            AB[gb_ab_offset(row, ks_row, ab_rows)] = acc[mi][ni][1];
+                        }
                     }
                 }
             }
@@ -540,12 +541,12 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     } else {
         const int n_coltiles = (2 * E + T1_TN - 1) / T1_TN;
         const int n_lattiles = (p->nlat + T1_TM - 1) / T1_TM;
-        dim3 grid(n_lattiles * n_coltiles, (L + 1) / 2);     // order pairs (p, nmax - p)
-        const size_t smem1 = T1_SMEM + 4 * (size_t)((L + T1_KC - 1) / T1_KC * T1_KC) * sizeof(double);
-        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        gb_legendre_stage1<<<grid, T1_THREADS, smem1, st>>>(p->d_x, p->d_ab, p->d_ct, p->d_kn, p->d_pmm, p->d_ra,
-                                                            p->d_rb, p->d_rc, p->d_zero, d_krow, L, p->nlat, E,
-                                                            p->ab_rows, n_coltiles);
+        const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
+        const int grid = n_items < p->sm_count ? n_items : p->sm_count;
+        T1Tables tb{p->d_ct_pad, p->d_kn_t, p->d_pmm_t, p->d_rec_a, p->d_rec_b, p->d_zero, d_krow, p->nlat_pad, p->lpad};
+        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        gb_legendre_stage1<<<grid, T1_THREADS, T1_SMEM, st>>>(p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows,
+                                                              n_lattiles, n_coltiles, n_items);
         GB_LAUNCH_CHECK();
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[2], st));
