@@ -124,6 +124,13 @@ struct gb_plan {
 };
 
 int gb_plan_ensure_workspace(gb_plan* p, int n_epochs);
+// keep stream-ordered allocations in the device's default pool between calls
+void gb_retain_pool_memory(int device);
+
+// anm [E][L][L] <-> order-wise packed X (gb_pack.cu): block of order m at 2E (m L - m(m-1)/2),
+// X_m[n - m][cs * E + e]
+int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st);
+int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st);
 
 // Recursion coefficients a_nm, b_nm [L][L], sqrt(2n+1) [L] and sectorial seeds P_mm [npts][L],
 // evaluated in IEEE double in the operation order of reference utilities.py:37-54.
@@ -187,6 +194,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 
 __device__ __forceinline__ void st_cs_v2(double* p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_v2(double* p, double a, double b) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 __device__ __forceinline__ void st_cs(double* p, double a) {
     asm volatile("st.global.cs.f64 [%0], %1;\n" ::"l"(p), "d"(a) : "memory");

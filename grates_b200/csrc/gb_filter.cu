@@ -1,66 +1,128 @@
 // Order-wise block filter, batched over epochs (reference filter.py:180-189).
 //
-// One CTA per (block g, epoch tile).  Block g = 0 acts on C_n0; g = 2m-1 / 2m on C_nm / S_nm.
-// The block's top-left k x k corner (k = nmax+1-m) multiplies the coefficient column of every
-// epoch in the tile: y[e][r] = sum_c W[r][c] x[e][c].  A warp owns a row r, its lanes stride over
-// the columns c (coalesced reads of W), per-epoch partial sums are combined with warp shuffles.
-// HBM-bound: the blocks (9.4 MB at N=120) are read once per epoch tile, coefficients once.
+// Block g = 0 acts on C_n0; g = 2m-1 / 2m on C_nm / S_nm.  The block's top-left k x k corner
+// (k = nmax+1-m) multiplies the coefficient column of every epoch: y[r][e] = sum_c W[r][c] x[c][e].
+// In the order-wise packed layout of gb_pack.cu the columns of all epochs of one (order, cos|sin)
+// form a dense k x E matrix with the epochs contiguous, so the filter is one small GEMM per block:
+//
+//   gb_pack_kernel           anm [E][L][L] -> X            (HBM-bound transpose)
+//   gb_filter_blocks_kernel  Y_g = W_g X_g                 one CTA per (block g, 64 epochs): the X tile
+//                            stays in shared memory, W streams through it in 16-column chunks
+//                            (register-staged double buffer), 4 x 4 register tiles of FMAs
+//   gb_pack_kernel<false>    Y -> anm [E][L][L]
+//
+// Bytes: anm in + out once each (2 x 8 E L^2), X/Y once each way, blocks once per epoch tile
+// (L2-resident).  Flops 2 k^2 per block and epoch (2.36 MFLOP per epoch at N = 120).
 #include "gb_common.cuh"
 
 namespace {
 
-constexpr int FE = 8;  // epochs per CTA
+constexpr int FT_E = 64;            // epochs per CTA
+constexpr int FT_R = 64;            // rows per pass
+constexpr int FT_KC = 16;           // columns of W per chunk
+constexpr int FT_LDX = FT_E + 4;    // pitch of the X tile
+constexpr int FT_LDW = FT_R + 4;    // pitch of a (transposed) W chunk
 
 __global__ void __launch_bounds__(256)
-gb_orderwise_filter_kernel(const double* __restrict__ blocks, const long long* __restrict__ offsets, int nf,
-                           const double* __restrict__ in, double* __restrict__ out, int E, int nmax) {
-    extern __shared__ double s_x[];  // [FE][k]
+gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __restrict__ offsets, int nf,
+                        const double* __restrict__ X, double* __restrict__ Y, int E, int nmax) {
+    extern __shared__ __align__(16) double s_f[];
     const int L = nmax + 1;
     const int g = blockIdx.x;                 // 0 .. 2*nmax
     const int m = (g + 1) >> 1;
-    const bool sine = (g > 0) && ((g & 1) == 0);
+    const int cs = (g > 0) && ((g & 1) == 0);
     const int k = L - m;                      // rows/cols used
     const int kf = nf + 1 - m;                // leading dimension of the stored block
+    const int kp = (k + FT_KC - 1) / FT_KC * FT_KC;
     const double* W = blocks + offsets[g];
-    const int e0 = blockIdx.y * FE;
-    const int ne = min(FE, E - e0);
+    const int e0 = blockIdx.y * FT_E;
+    const int ne = min(FT_E, E - e0);
+    const long long xo = 2LL * E * ((long long)m * L - (long long)m * (m - 1) / 2) + (long long)cs * E + e0;
+    const double* Xg = X + xo;                // element (c, e) at Xg[c * 2E + e]
+    double* Yg = Y + xo;
 
-    // element (n = m + c) of the coefficient column: C_nm = anm[n][m], S_nm = anm[m-1][n]
-    auto elem = [&](int c) -> size_t {
-        const int n = m + c;
-        return sine ? (size_t)(m - 1) * L + n : (size_t)n * L + m;
-    };
-    for (int idx = threadIdx.x; idx < FE * k; idx += blockDim.x) {
-        const int e = idx / k, c = idx % k;
-        s_x[idx] = (e < ne) ? in[(size_t)(e0 + e) * L * L + elem(c)] : 0.0;
+    double* s_x = s_f;                        // [kp][FT_LDX]
+    double* s_w = s_f + (size_t)kp * FT_LDX;  // [2][FT_KC][FT_LDW]
+    const int tid = threadIdx.x;
+
+    // coefficient tile: rows beyond k and epochs beyond E are zero
+    for (int idx = tid; idx < kp * FT_E; idx += 256) {
+        const int c = idx / FT_E, e = idx % FT_E;
+        s_x[c * FT_LDX + e] = (c < k && e < ne) ? Xg[(size_t)c * 2 * E + e] : 0.0;
     }
-    __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int r = warp; r < k; r += nwarps) {
-        double acc[FE];
+    const int tr = tid >> 4, te = tid & 15;   // thread tile: rows 4 tr .. +3, epochs 4 te .. +3
+    const int lr = tid >> 2, lc = (tid & 3) * 4;   // W chunk loader: row lr, columns lc .. lc+3
+    const int n_chunks = kp / FT_KC;
+
+    for (int r0 = 0; r0 < k; r0 += FT_R) {
+        double acc[4][4];
 #pragma unroll
-        for (int e = 0; e < FE; ++e) acc[e] = 0.0;
-        const double* wrow = W + (size_t)r * kf;
-        for (int c = lane; c < k; c += 32) {
-            const double w = __ldg(wrow + c);
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int e = 0; e < FE; ++e) acc[e] = fma(w, s_x[e * k + c], acc[e]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        const bool active = r0 + 4 * tr < k;          // warp-uniform up to 8-row granularity
+        double wreg[4];
+        auto load_w = [&](int chunk) {
+            const int r = r0 + lr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = chunk * FT_KC + lc + j;
+                wreg[j] = (r < k && c < k) ? __ldg(W + (size_t)r * kf + c) : 0.0;
+            }
+        };
+        auto store_w = [&](int buf) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s_w[(buf * FT_KC + lc + j) * FT_LDW + lr] = wreg[j];
+        };
+        load_w(0);
+        __syncthreads();                               // previous pass finished with s_w; s_x is complete
+        store_w(0);
+        __syncthreads();
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            if (chunk + 1 < n_chunks) load_w(chunk + 1);
+            if (active) {
+                const double* wp = s_w + (size_t)buf * FT_KC * FT_LDW + 4 * tr;
+                const double* xp = s_x + (size_t)chunk * FT_KC * FT_LDX + 4 * te;
+#pragma unroll
+                for (int cc = 0; cc < FT_KC; ++cc) {
+                    const double2 w01 = *reinterpret_cast<const double2*>(wp + cc * FT_LDW);
+                    const double2 w23 = *reinterpret_cast<const double2*>(wp + cc * FT_LDW + 2);
+                    const double2 x01 = *reinterpret_cast<const double2*>(xp + cc * FT_LDX);
+                    const double2 x23 = *reinterpret_cast<const double2*>(xp + cc * FT_LDX + 2);
+                    const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+                    const double x[4] = {x01.x, x01.y, x23.x, x23.y};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fma(w[i], x[j], acc[i][j]);
+                }
+            }
+            if (chunk + 1 < n_chunks) {
+                store_w(buf ^ 1);                      // the other buffer was last read before the previous barrier
+                __syncthreads();
+            }
         }
+        if (active) {
 #pragma unroll
-        for (int e = 0; e < FE; ++e) {
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + 4 * tr + i;
+                if (r >= k) continue;
+                const bool pass = (m + r) < 2;         // degrees 0 and 1 pass through unchanged (filter.py:189)
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+                for (int j = 0; j < 4; ++j) {
+                    const int e = 4 * te + j;
+                    if (e < ne) Yg[(size_t)r * 2 * E + e] = pass ? s_x[r * FT_LDX + e] : acc[i][j];
+                }
+            }
         }
-        if (lane < ne) {
-            double v = 0.0;
-#pragma unroll
-            for (int e = 0; e < FE; ++e)
-                if (lane == e) v = acc[e];
-            const int n = m + r;
-            const size_t pos = (size_t)(e0 + lane) * L * L + elem(r);
-            // degrees 0 and 1 pass through unchanged (filter.py:189)
-            out[pos] = (n < 2) ? in[pos] : v;
+    }
+    // order 0 has no sine coefficients: keep that plane of Y defined (zero)
+    if (g == 0) {
+        for (int idx = tid; idx < k * FT_E; idx += 256) {
+            const int c = idx / FT_E, e = idx % FT_E;
+            if (e < ne) Y[(size_t)c * 2 * E + E + e0 + e] = 0.0;
         }
     }
 }
@@ -76,16 +138,36 @@ extern "C" int gb_orderwise_filter(const double* d_blocks, const int64_t* block_
     GB_REQUIRE(d_blocks && block_offsets && d_anm_in && d_anm_out, "gb_orderwise_filter: NULL pointer");
     GB_REQUIRE(d_anm_in != d_anm_out, "gb_orderwise_filter: input and output may not alias");
     GB_CUDA(cudaSetDevice(device));
+    gb_retain_pool_memory(device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nblocks = 2 * nf + 1;
-    long long* d_off = nullptr;
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_off), (nblocks + 1) * sizeof(long long), st));
-    GB_CUDA(cudaMemcpyAsync(d_off, block_offsets, (nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     const int L = nmax + 1;
-    dim3 grid(2 * nmax + 1, (n_epochs + FE - 1) / FE);
-    const size_t smem = (size_t)FE * L * sizeof(double);
-    gb_orderwise_filter_kernel<<<grid, 256, smem, st>>>(d_blocks, d_off, nf, d_anm_in, d_anm_out, n_epochs, nmax);
-    GB_LAUNCH_CHECK();
-    GB_CUDA(cudaFreeAsync(d_off, st));
-    return GB_OK;
+    const int E = n_epochs;
+    const size_t x_elems = (size_t)L * (L + 1) * (size_t)E;      // 2E doubles per (order, degree) pair
+    const int kp_max = (L + FT_KC - 1) / FT_KC * FT_KC;
+    const size_t smem = ((size_t)kp_max * FT_LDX + 2 * FT_KC * FT_LDW) * sizeof(double);
+    GB_REQUIRE(smem <= 227 * 1024, "gb_orderwise_filter: max_degree=%d exceeds the shared-memory tile of the filter kernel", nmax);
+    long long* d_off = nullptr;
+    double* d_xy = nullptr;
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_off), (nblocks + 1) * sizeof(long long), st));
+    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_xy), 2 * x_elems * sizeof(double), st));
+    GB_CUDA(cudaMemcpyAsync(d_off, block_offsets, (nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    int rc = gb_launch_pack(d_anm_in, d_xy, L, E, st);
+    if (!rc) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(gb_filter_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) rc = gb_set_error(GB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (!rc) {
+        dim3 grid(2 * nmax + 1, (E + FT_E - 1) / FT_E);
+        gb_filter_blocks_kernel<<<grid, 256, smem, st>>>(d_blocks, d_off, nf, d_xy, d_xy + x_elems, E, nmax);
+        gb_count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = gb_set_error(GB_ERR_CUDA, "gb_filter_blocks_kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = gb_launch_unpack(d_xy + x_elems, d_anm_out, L, E, st);
+    cudaFreeAsync(d_xy, st);
+    cudaFreeAsync(d_off, st);
+    return rc;
 }

@@ -1,0 +1,80 @@
+// Order-wise packing of epoch batches of potential coefficients (HBM-bound transposes).
+//
+//   anm [E][L][L]   reference layout (gravityfield.py:149-159): C_nm = anm[n][m], S_nm = anm[m-1][n]
+//   X               order-wise: the block of order m starts at 2E (m L - m(m-1)/2) and is
+//                   X_m[n - m][cs * E + e], cs = 0 (cos) / 1 (sin), epochs contiguous
+//
+// Row r of anm[e] holds C_{r,0..r} followed by S_{r+1, r+1..nmax}; one CTA moves that row for 32
+// epochs through shared memory, so both sides are touched in full contiguous lines: reads are
+// rows of L doubles, writes are 32 consecutive epochs (256 B).  The sine plane of order 0 does not
+// exist in anm and is kept at zero (stage 1 contracts it like any other column).
+#include "gb_common.cuh"
+
+namespace {
+
+constexpr int PK_E = 32;          // epochs per CTA
+constexpr int PK_LD = PK_E + 1;   // shared-memory pitch
+constexpr int PK_C = 512;         // columns of anm per CTA (bounds shared memory at high degree)
+
+__device__ __forceinline__ long long x_block_offset(int m, int L, int E) {
+    return 2LL * E * ((long long)m * L - (long long)m * (m - 1) / 2);
+}
+
+// X position of element (row r, column c) of anm: (order, degree offset, cos|sin)
+__device__ __forceinline__ long long x_position(int r, int c, int L, int E) {
+    const int m = (c <= r) ? c : r + 1;
+    const int nn = (c <= r) ? r - c : c - r - 1;
+    const int cs = (c <= r) ? 0 : 1;
+    return x_block_offset(m, L, E) + (long long)nn * 2 * E + (long long)cs * E;
+}
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int L,
+                                                      int E) {
+    extern __shared__ double s_t[];   // [min(L, PK_C)][PK_LD]
+    const int r = blockIdx.x;
+    const int cb = blockIdx.z * PK_C;                 // first column of this CTA
+    const int nc = min(PK_C, L - cb);
+    const int e0 = blockIdx.y * PK_E;
+    const int ne = min(PK_E, E - e0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (PACK) {
+        for (int e = warp; e < ne; e += nwarps) {
+            const double* row = src + ((size_t)(e0 + e) * L + r) * L;
+            for (int c = lane; c < nc; c += 32) s_t[c * PK_LD + e] = row[cb + c];
+        }
+        __syncthreads();
+        for (int c = warp; c < nc; c += nwarps)
+            if (lane < ne) dst[x_position(r, cb + c, L, E) + e0 + lane] = s_t[c * PK_LD + lane];
+        // sine plane of order 0, degree r
+        if (blockIdx.z == 0 && warp == 0 && lane < ne) dst[(long long)r * 2 * E + E + e0 + lane] = 0.0;
+    } else {
+        for (int c = warp; c < nc; c += nwarps)
+            if (lane < ne) s_t[c * PK_LD + lane] = src[x_position(r, cb + c, L, E) + e0 + lane];
+        __syncthreads();
+        for (int e = warp; e < ne; e += nwarps) {
+            double* row = dst + ((size_t)(e0 + e) * L + r) * L;
+            for (int c = lane; c < nc; c += 32) row[cb + c] = s_t[c * PK_LD + e];
+        }
+    }
+}
+
+template <bool PACK>
+int launch(const double* src, double* dst, int L, int E, cudaStream_t st) {
+    const size_t smem = (size_t)(L < PK_C ? L : PK_C) * PK_LD * sizeof(double);
+    if (smem > 48 * 1024)
+        GB_CUDA(cudaFuncSetAttribute(gb_pack_kernel<PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(L, (E + PK_E - 1) / PK_E, (L + PK_C - 1) / PK_C);
+    gb_pack_kernel<PACK><<<grid, 256, smem, st>>>(src, dst, L, E);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}
+
+}  // namespace
+
+int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st) {
+    return launch<true>(d_anm, d_x, L, E, st);
+}
+int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st) {
+    return launch<false>(d_x, d_anm, L, E, st);
+}

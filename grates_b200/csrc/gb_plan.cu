@@ -24,6 +24,16 @@ extern "C" int64_t gb_launch_count(int reset) {
     return v;
 }
 
+// The default release threshold (0) returns stream-ordered workspace to the driver at every
+// synchronisation: milliseconds per GB on the next call.
+void gb_retain_pool_memory(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
+
 extern "C" int gb_device_count(int* count) {
     GB_REQUIRE(count != nullptr, "gb_device_count: count is NULL");
     GB_CUDA(cudaGetDeviceCount(count));
@@ -88,14 +98,7 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
         return gb_set_error(GB_ERR_UNSUPPORTED, "gb_plan_create: device %d is sm_%d%d; this library is built for sm_100a",
                             device, prop.major, prop.minor);
 
-    {   // keep stream-ordered workspace allocations in the pool between calls (default threshold 0
-        // returns them to the driver at every synchronisation: milliseconds per GB on the next call)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
+    gb_retain_pool_memory(device);
     gb_plan* p = new gb_plan();
     p->device = device;
     p->nmax = nmax;

@@ -7,14 +7,14 @@
 //
 // HBM layout
 //   anm   [E][L][L]          packed coefficients as the reference stores them
-//   X     order-wise packed  X_m[n-m][2e+cs], block of order m at offset 2E*(m*L - m(m-1)/2)
+//   X     order-wise packed  X_m[n-m][cs*E+e], block of order m at offset 2E*(m*L - m(m-1)/2) (gb_pack.cu)
 //   AB    [row tile][k][132]  spectral intermediate, tiled by 128 grid rows (e*nlat + i), see gb_common.cuh;
 //                            row order k = 2m+cs, or [CE|CO|SE|SO] groups for the symmetric stage 2
 //   trig  [col tile][k][124]  row 2m = cos(m lon_j), row 2m+1 = sin(m lon_j) (first quadrant only when symmetric)
 //   V     [E][nlat][nlon]    output
 //
 // Kernels
-//   gb_pack_orderwise    gathers anm into X (18 MB at N=96, E=240; HBM-bound, negligible)
+//   gb_pack_kernel       transposes anm into X (gb_pack.cu; HBM-bound)
 //   gb_legendre_stage1   per (latitude tile, order m): runs the Legendre recursion on the fly
 //                        (unfused IEEE ops -> bit-identical to utilities.py:37-54), multiplies
 //                        kn[i,n] in, contracts against all epochs, writes AB
@@ -25,28 +25,6 @@
 #include "gb_gemm.cuh"
 
 namespace {
-
-// ---------------------------------------------------------------------------------------------
-// pack: anm[E][L][L] -> X
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gb_pack_orderwise(const double* __restrict__ anm, double* __restrict__ X,
-                                                         int L, int E) {
-    const int m = blockIdx.y;
-    const int cols = 2 * E;
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nn = (int)(j / cols);
-    const int col = (int)(j % cols);
-    if (nn >= L - m) return;
-    const int n = m + nn;
-    const int e = col >> 1;
-    const int cs = col & 1;
-    const double* a = anm + (size_t)e * L * L;
-    double v;
-    if (cs == 0) v = a[(size_t)n * L + m];
-    else v = (m > 0) ? a[(size_t)(m - 1) * L + n] : 0.0;
-    const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
-    X[xo + (long long)nn * cols + col] = v;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Legendre recursion for one (latitude, order): calls f(n - m, P_nm) for n = m..nmax.
@@ -115,7 +93,7 @@ gb_legendre_stage1_simple(const double* __restrict__ X, double* __restrict__ AB,
             a2 = fma(p23.x, x, a2);
             a3 = fma(p23.y, x, a3);
         }
-        const int e = col >> 1, cs = col & 1;
+        const int cs = col >= E, e = col - cs * E;
         const int i = i0 + ig * 4;
         const int k = krow[2 * m + cs];
         const long long row = (long long)e * nlat + i;
@@ -158,6 +136,7 @@ struct T1Tables {
     int nlat_pad, lpad;
 };
 
+template <bool PAIRS>   // nlat even: rows (e, i), (e, i+1) with i even are 16-byte aligned in AB
 __global__ void __launch_bounds__(T1_THREADS, 1)
 gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tables tb, int L, int nlat, int E,
                    int ab_rows, int n_lattiles, int n_coltiles, int n_items) {
@@ -253,7 +232,9 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
                 }
             }
         } else {
-            // ===== consumer warps =====
+            // ===== consumer warps: D[col][i] = sum_n X_m[n][col] Pk[n][i] =====
+            // The columns (e, cos|sin) are the M side of the DMMA tiles and the parallels the N side, so a
+            // thread ends up with two neighbouring parallels of one column: one 16-byte store into AB.
             const int wm = warp / 6;
             const int wn = warp % 6;
             const int g = lane >> 2, q = lane & 3;
@@ -261,47 +242,58 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
                 const int m = pass ? m_second : m_first;
                 const int Kn = L - m;
                 const int n_chunks = (Kn + T1_KC - 1) / T1_KC;
-                double acc[4][5][2];
+                double acc[5][4][2];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 5; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
                 for (int c = 0; c < n_chunks; ++c) {
                     const int rows = Kn - c * T1_KC;             // degrees left (whole steps are processed)
                     gb::mbar_wait(&full[stage], phase);
-                    const double* sA = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + wm * 32 + g;
-                    const double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA + wn * 40 + g;
+                    const double* sP = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + wm * 32 + g;
+                    const double* sX = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA + wn * 40 + g;
 #pragma unroll
                     for (int kk = 0; kk < T1_KC; kk += 4) {
                         if (kk >= rows) break;
-                        double a[4], b[5];
+                        double a[5], b[4];
 #pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * T1_LDA + mi * 8];
+                        for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + q) * T1_LDB + mi * 8];
 #pragma unroll
-                        for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * T1_LDB + ni * 8];
+                        for (int ni = 0; ni < 4; ++ni) b[ni] = sP[(kk + q) * T1_LDA + ni * 8];
 #pragma unroll
-                        for (int mi = 0; mi < 4; ++mi)
+                        for (int mi = 0; mi < 5; ++mi)
 #pragma unroll
-                            for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                            for (int ni = 0; ni < 4; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
                     }
                     __syncwarp();
                     if (lane == 0) gb::mbar_arrive(&empty[stage]);
                     if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                // epilogue: column pair (2q, 2q+1) of a fragment = (cos, sin) of one epoch
+                // epilogue: columns [0, E) are the cosine coefficients of epoch col, [E, 2E) the sines.
+                // The 32 parallels of a warp sit in at most two neighbouring 128-row tiles of AB.
                 const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
+                const int ib = i0 + wm * 32 + 2 * q;
+                const int tile_step = ab_rows * GB_LDA - GB_TM;      // to the same k row of the next row tile
 #pragma unroll
-                for (int ni = 0; ni < 5; ++ni) {
-                    const int col = c0 + wn * 40 + ni * 8 + 2 * q;
+                for (int mi = 0; mi < 5; ++mi) {
+                    const int col = c0 + wn * 40 + mi * 8 + g;
                     if (col >= cols) continue;
-                    const int e = col >> 1;
+                    const int cs = col >= E;
+                    const int e = col - cs * E;
+                    const long long row = (long long)e * nlat + ib;
+                    const int o0 = (int)(row & (GB_TM - 1));
+                    double* base = AB + ((size_t)(row >> 7) * ab_rows + (cs ? ks_row : kc_row)) * GB_LDA + o0;
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {
-                        const int i = i0 + wm * 32 + mi * 8 + g;
-                        if (i < nlat) {
-                            const long long row = (long long)e * nlat + i;
-                            AB[gb_ab_offset(row, kc_row, ab_rows)] = acc[mi][ni][0];
-                            AB[gb_ab_offset(row, ks_row, ab_rows)] = acc[mi][ni][1];
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int i = ib + ni * 8;
+                        if (PAIRS) {
+                            if (i < nlat)
+                                gb::st_v2(base + ni * 8 + ((o0 + ni * 8 >= GB_TM) ? tile_step : 0), acc[mi][ni][0],
+                                          acc[mi][ni][1]);
+                        } else {
+                            if (i < nlat) base[ni * 8 + ((o0 + ni * 8 >= GB_TM) ? tile_step : 0)] = acc[mi][ni][0];
+                            if (i + 1 < nlat)
+                                base[ni * 8 + 1 + ((o0 + ni * 8 + 1 >= GB_TM) ? tile_step : 0)] = acc[mi][ni][1];
                         }
                     }
                 }
@@ -522,9 +514,8 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     cudaEvent_t* prof = (p->prof_ev && p->prof_count < p->prof_capacity) ? p->prof_ev + (size_t)p->prof_count * 4 : nullptr;
     if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
     {
-        dim3 grid((unsigned)(((long long)L * 2 * E + 255) / 256), L);
-        gb_pack_orderwise<<<grid, 256, 0, st>>>(d_anm, p->d_x, L, E);
-        GB_LAUNCH_CHECK();
+        int rc = gb_launch_pack(d_anm, p->d_x, L, E, st);
+        if (rc) return rc;
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[1], st));
     const bool naive2 = env_flag("GB_NAIVE_STAGE2");
@@ -544,9 +535,15 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
         const int grid = n_items < p->sm_count ? n_items : p->sm_count;
         T1Tables tb{p->d_ct_pad, p->d_kn_t, p->d_pmm_t, p->d_rec_a, p->d_rec_b, p->d_zero, d_krow, p->nlat_pad, p->lpad};
-        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
-        gb_legendre_stage1<<<grid, T1_THREADS, T1_SMEM, st>>>(p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows,
-                                                              n_lattiles, n_coltiles, n_items);
+        if (p->nlat % 2 == 0) {
+            GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+            gb_legendre_stage1<true><<<grid, T1_THREADS, T1_SMEM, st>>>(p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows,
+                                                                        n_lattiles, n_coltiles, n_items);
+        } else {
+            GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+            gb_legendre_stage1<false><<<grid, T1_THREADS, T1_SMEM, st>>>(p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows,
+                                                                         n_lattiles, n_coltiles, n_items);
+        }
         GB_LAUNCH_CHECK();
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[2], st));
