@@ -58,6 +58,41 @@ gb_cov_permute(const double* __restrict__ sigma, double* __restrict__ St, const 
     St[gb_ab_offset(a, b, Kp4)] = (pa < 0 || pb < 0) ? 0.0 : sigma[(size_t)pa * K + pb];
 }
 
+// The same permutation, one CTA per (64 rows a', degree n of the columns): the 2n+1 columns of a degree
+// are contiguous in the degree-wise order, so Sigma is read in row segments and St written in 512-byte
+// runs (the element-wise gather above fetches a 32-byte sector per double).
+constexpr int CP_ROWS = 64;
+__global__ void __launch_bounds__(256)
+gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St, const int* __restrict__ perm8,
+                      const int* __restrict__ goff4, int Kp4, long long K, int nmin) {
+    extern __shared__ double s_p[];   // [CP_ROWS][2n+1]
+    const int a0 = blockIdx.x * CP_ROWS;
+    const int n = nmin + blockIdx.y;
+    const int width = 2 * n + 1;      // odd pitch: conflict-free column reads
+    const long long col0 = (long long)n * n - (long long)nmin * nmin;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < CP_ROWS; r += 8) {
+        const int pa = perm8[a0 + r];
+        const double* src = sigma + (size_t)(pa < 0 ? 0 : pa) * K + col0;
+        for (int j = lane; j < width; j += 32) s_p[r * width + j] = pa < 0 ? 0.0 : src[j];
+    }
+    __syncthreads();
+    for (int j = warp; j < width; j += 8) {
+        const int m = (j + 1) >> 1;
+        const int k = (j == 0) ? 0 : 2 * m + ((j & 1) ? 0 : 1);          // j = 2m-1: cos, j = 2m: sin
+        const int b = goff4[k] + n - max(m, nmin);
+        double* dst = St + ((size_t)(a0 >> 7) * Kp4 + b) * GB_LDA + (a0 & (GB_TM - 1));
+        dst[lane] = s_p[lane * width + j];
+        dst[lane + 32] = s_p[(lane + 32) * width + j];
+    }
+}
+
+// rows b of St that pad a group to a multiple of four
+__global__ void __launch_bounds__(128)
+gb_cov_zero_rows(double* __restrict__ St, const int* __restrict__ padrows, int Kp4) {
+    St[((size_t)blockIdx.x * Kp4 + padrows[blockIdx.y]) * GB_LDA + threadIdx.x] = 0.0;
+}
+
 // U as B tiles: Ut[((k * nti + i/120) * Kg + (n - n0)) * 124 + i % 120] = kn[i][n] * P_nm(theta_i)
 __global__ void __launch_bounds__(128)
 gb_cov_legendre(double* __restrict__ Ut, const double* __restrict__ ct, const double* __restrict__ kn,
@@ -80,64 +115,126 @@ gb_cov_legendre(double* __restrict__ Ut, const double* __restrict__ ct, const do
     });
 }
 
-// H[i][k][k'] accumulated in the A-tile layout of stage 4: Ht[((i * hmt + k/128) * kpad + k') * 132 + k%128]
+// sum over the 8 rows of a fragment slab (lanes with equal lane % 4)
+__device__ __forceinline__ double slab_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+// H[i][k][k'] accumulated in the A-tile layout of stage 4: Ht[((i * hmt + k/128) * kpad + k') * 132 + k%128].
+// The four 8-row slabs a thread holds are multiplied by U and summed in the thread as long as they
+// belong to the same group k; only then the slab is reduced across lanes and added to H.
 struct QuadEpilogue {
+    static constexpr bool whole_tile = true;
     const double* Ut;        // B tiles of U (also the source of the row-side factor)
     double* Ht;
     const int* rowgroup;     // [rows_a / 8] group k of each 8-row slab, -1 for padding
     const int* goff8;        // [kpad] first a' of each group
     int nti, Kg, kpad, hmt, nrows;
-    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
-        const int k = rowgroup[row >> 3];                 // uniform over the 8 fragment rows
-        const int nt = col / GB_S2_TN, cc = col % GB_S2_TN;
-        const int kprime = nt / nti, it = nt % nti;
-        const int i = it * GB_S2_TN + cc;
-        double p0 = 0.0, p1 = 0.0;
-        if (k >= 0) {
-            const double* u = Ut + (((size_t)k * nti + it) * Kg + (row - goff8[k])) * GB_S2_LDB + cc;
-            p0 = v0 * u[0];
-            p1 = v1 * u[1];
+    int symmetric;           // only group pairs k <= k' are kept, the off-diagonal ones counted twice
+    __device__ __forceinline__ void flush(int k, int kprime, int i, double s0, double s1) const {
+        if (k < 0) return;                                   // warp-uniform
+        if (symmetric) {
+            if (k > kprime) return;
+            if (k < kprime) { s0 += s0; s1 += s1; }
         }
-        // sum over the 8 rows of the fragment (lanes with equal lane % 4)
-        p0 += __shfl_xor_sync(0xffffffffu, p0, 4);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, 4);
-        p0 += __shfl_xor_sync(0xffffffffu, p0, 8);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, 8);
-        p0 += __shfl_xor_sync(0xffffffffu, p0, 16);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, 16);
-        if ((threadIdx.x & 31) < 4 && k >= 0) {
+        s0 = slab_sum(s0);
+        s1 = slab_sum(s1);
+        if ((threadIdx.x & 31) < 4) {
             double* h = Ht + (((size_t)i * hmt + (k >> 7)) * kpad + kprime) * GB_LDA + (k & 127);
-            if (i < nrows) atomicAdd(h, p0);
-            if (i + 1 < nrows) atomicAdd(h + (size_t)hmt * kpad * GB_LDA, p1);
+            if (i < nrows) atomicAdd(h, s0);
+            if (i + 1 < nrows) atomicAdd(h + (size_t)hmt * kpad * GB_LDA, s1);
+        }
+    }
+    struct Pre {
+        int kslab[4];          // group of each of the thread's four 8-row slabs (uniform over the warp), -1: padding
+        int uoff[4];           // offset of the slab's row inside the U tiles of its group (checked on the host)
+    };
+    __device__ __forceinline__ Pre prepare(long long row_base) const {
+        Pre pr;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const long long row = row_base + mi * 8;
+            const int k = rowgroup[row >> 3];
+            pr.kslab[mi] = k;
+            pr.uoff[mi] = k >= 0 ? (k * nti * Kg + (int)(row - goff8[k])) * GB_S2_LDB : 0;
+        }
+        return pr;
+    }
+    __device__ __forceinline__ void tile(const Pre& pr, long long row_base, int col_base, double (&acc)[4][5][2]) const {
+        // 1. multiply by the row-side factor in place: twenty independent loads in flight, no extra registers
+#pragma unroll
+        for (int ni = 0; ni < 5; ++ni) {
+            const int col = col_base + ni * 8;
+            const int nt = col / GB_S2_TN, cc = col % GB_S2_TN;
+            const double* ucol = Ut + (size_t)(nt % nti) * Kg * GB_S2_LDB + cc;       // cc is even: 16-byte aligned
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                if (pr.kslab[mi] >= 0) {
+                    const double2 u = __ldg(reinterpret_cast<const double2*>(ucol + pr.uoff[mi]));
+                    acc[mi][ni][0] *= u.x;
+                    acc[mi][ni][1] *= u.y;
+                }
+            }
+        }
+        // 2. sum the slabs of one group in the thread, reduce across the slab, add to H
+#pragma unroll
+        for (int ni = 0; ni < 5; ++ni) {
+            const int col = col_base + ni * 8;
+            const int nt = col / GB_S2_TN, cc = col % GB_S2_TN;
+            const int kprime = nt / nti, it = nt % nti;
+            const int i = it * GB_S2_TN + cc;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                if (mi > 0 && pr.kslab[mi] != pr.kslab[mi - 1]) {
+                    flush(pr.kslab[mi - 1], kprime, i, s0, s1);
+                    s0 = s1 = 0.0;
+                }
+                if (pr.kslab[mi] >= 0) {
+                    s0 += acc[mi][ni][0];
+                    s1 += acc[mi][ni][1];
+                }
+            }
+            flush(pr.kslab[3], kprime, i, s0, s1);
         }
     }
 };
 
-// var[i][j] += T[k][j] * W_i[k][j], rows of the GEMM = (i, k)
+// var[i][j] += T[k][j] * W_i[k][j], rows of the GEMM = (i, k); all 128 rows of a tile belong to one
+// parallel, so the thread sums its four rows before the slab reduction
 struct LonEpilogue {
+    static constexpr bool whole_tile = true;
     const double* trig;      // [kpad][nlp]
     double* var;             // [nrows][nlon]
     int hmt, kpad, nlp, nlon;
-    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
-        const int mt = (int)(row >> 7);
+    __device__ __forceinline__ int prepare(long long) const { return 0; }
+    __device__ __forceinline__ void tile(int, long long row_base, int col_base, double (&acc)[4][5][2]) const {
+        const int mt = (int)(row_base >> 7);
         const int i = mt / hmt;
-        const int k = (mt % hmt) * 128 + (int)(row & 127);
-        double p0 = 0.0, p1 = 0.0;
-        if (k < kpad) {
-            const double* t = trig + (size_t)k * nlp + col;
-            if (col < nlp) p0 = v0 * t[0];
-            if (col + 1 < nlp) p1 = v1 * t[1];
-        }
-        p0 += __shfl_xor_sync(0xffffffffu, p0, 4);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, 4);
-        p0 += __shfl_xor_sync(0xffffffffu, p0, 8);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, 8);
-        p0 += __shfl_xor_sync(0xffffffffu, p0, 16);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, 16);
-        if ((threadIdx.x & 31) < 4) {
-            double* o = var + (size_t)i * nlon + col;
-            if (col < nlon) atomicAdd(o, p0);
-            if (col + 1 < nlon) atomicAdd(o + 1, p1);
+        const int kb = (mt % hmt) * 128 + (int)(row_base & 127);
+#pragma unroll
+        for (int ni = 0; ni < 5; ++ni) {
+            const int col = col_base + ni * 8;
+            double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int k = kb + mi * 8;
+                if (k < kpad) {
+                    const double* t = trig + (size_t)k * nlp + col;
+                    if (col < nlp) p0 = fma(acc[mi][ni][0], t[0], p0);
+                    if (col + 1 < nlp) p1 = fma(acc[mi][ni][1], t[1], p1);
+                }
+            }
+            p0 = slab_sum(p0);
+            p1 = slab_sum(p1);
+            if ((threadIdx.x & 31) < 4) {
+                double* o = var + (size_t)i * nlon + col;
+                if (col < nlon) atomicAdd(o, p0);
+                if (col + 1 < nlon) atomicAdd(o + 1, p1);
+            }
         }
     }
 };
@@ -157,7 +254,9 @@ int to_device(T** d, const std::vector<T>& h, cudaStream_t st) {
 }  // namespace
 
 extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
-                                         double* d_out, int take_sqrt, void* stream) {
+                                         double* d_out, int flags, void* stream) {
+    const int take_sqrt = flags & GB_COV_SQRT;
+    const int symmetric = (flags & GB_COV_SYMMETRIC) ? 1 : 0;
     GB_REQUIRE(plan != nullptr, "gb_covariance_propagation: plan is NULL");
     gb_plan* p = plan;
     GB_REQUIRE(nmin >= 0 && nmin <= p->nmax, "gb_covariance_propagation: min_degree=%d outside [0, %d]", nmin, p->nmax);
@@ -208,14 +307,34 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
             nt_klen[k * nti + it] = (gcnt[k] + 3) / 4 * 4;
         }
     const int hmt = (kpad + GB_TM - 1) / GB_TM;                 // row tiles of H_i
+    GB_REQUIRE((long long)n_ct * Kg * GB_S2_LDB < (1LL << 31),
+               "gb_covariance_propagation: %d parallels at degree %d exceed the 32-bit tile index; pass row blocks", nrows, p->nmax);
+
+    std::vector<int> padrows;
+    for (int b = 0; b < Kp4; ++b)
+        if (perm4[b] < 0) padrows.push_back(b);
+    const size_t permute_smem = (size_t)CP_ROWS * (2 * p->nmax + 1) * sizeof(double);
+    const bool by_degree = permute_smem <= 200 * 1024;
+
+    // symmetric Sigma: H_i is symmetric, row tile mt needs the column groups k' >= its first group only
+    std::vector<int> first_nt(n_atiles, 0);
+    for (int t = 0; t < n_atiles; ++t) {
+        int kmin = kpad;
+        for (int sl = t * (GB_TM / 8); sl < (t + 1) * (GB_TM / 8); ++sl)
+            if (rowgroup[sl] >= 0 && rowgroup[sl] < kmin) kmin = rowgroup[sl];
+        first_nt[t] = kmin * nti;
+    }
+    int* d_first_nt = nullptr;
 
     int *d_perm8 = nullptr, *d_perm4 = nullptr, *d_rowgroup = nullptr, *d_goff8 = nullptr, *d_koff = nullptr,
-        *d_klen = nullptr;
+        *d_klen = nullptr, *d_goff4 = nullptr, *d_padrows = nullptr;
     double *d_st = nullptr, *d_ut = nullptr, *d_ht = nullptr;
     int rc = GB_OK;
     if ((rc = to_device(&d_perm8, perm8, st)) || (rc = to_device(&d_perm4, perm4, st)) ||
         (rc = to_device(&d_rowgroup, rowgroup, st)) || (rc = to_device(&d_goff8, goff8, st)) ||
-        (rc = to_device(&d_koff, nt_koff, st)) || (rc = to_device(&d_klen, nt_klen, st)))
+        (rc = to_device(&d_koff, nt_koff, st)) || (rc = to_device(&d_klen, nt_klen, st)) ||
+        (rc = to_device(&d_goff4, goff4, st)) || (rc = to_device(&d_padrows, padrows, st)) ||
+        (rc = to_device(&d_first_nt, first_nt, st)))
         return rc;
     const size_t st_elems = (size_t)n_atiles * Kp4 * GB_LDA;
     const size_t ut_elems = (size_t)n_ct * Kg * GB_S2_LDB;
@@ -223,12 +342,25 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
     GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_st), st_elems * sizeof(double), st));
     GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ut), ut_elems * sizeof(double), st));
     GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ht), ht_elems * sizeof(double), st));
-    GB_CUDA(cudaMemsetAsync(d_st, 0, st_elems * sizeof(double), st));    // pad columns 128..131 of every row
+    if (!by_degree) GB_CUDA(cudaMemsetAsync(d_st, 0, st_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_ut, 0, ut_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_ht, 0, ht_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nrows * p->nlon * sizeof(double), st));
     GB_CUDA(cudaStreamSynchronize(st));   // the host index vectors go out of scope; their copies are tiny
-    {
+    if (by_degree) {
+        // pad columns 128..131 of the St rows stay unwritten: no DMMA fragment reads them
+        if (permute_smem > 48 * 1024)
+            GB_CUDA(cudaFuncSetAttribute(gb_cov_permute_degree, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)permute_smem));
+        dim3 grid(rows_a / CP_ROWS, L - nmin);
+        gb_cov_permute_degree<<<grid, 256, permute_smem, st>>>(d_sigma, d_st, d_perm8, d_goff4, Kp4, K, nmin);
+        GB_LAUNCH_CHECK();
+        if (!padrows.empty()) {
+            dim3 gz(n_atiles, (unsigned)padrows.size());
+            gb_cov_zero_rows<<<gz, GB_TM, 0, st>>>(d_st, d_padrows, Kp4);
+            GB_LAUNCH_CHECK();
+        }
+    } else {
         dim3 grid((rows_a + 255) / 256, Kp4);
         gb_cov_permute<<<grid, 256, 0, st>>>(d_sigma, d_st, d_perm8, d_perm4, rows_a, Kp4, K);
         GB_LAUNCH_CHECK();
@@ -252,7 +384,8 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
         sh.n_ntiles = n_ct;
         sh.nt_koff = d_koff;
         sh.nt_klen = d_klen;
-        QuadEpilogue epi{d_ut, d_ht, d_rowgroup, d_goff8, nti, Kg, kpad, hmt, nrows};
+        sh.mt_first_nt = symmetric ? d_first_nt : nullptr;
+        QuadEpilogue epi{d_ut, d_ht, d_rowgroup, d_goff8, nti, Kg, kpad, hmt, nrows, symmetric};
         if ((rc = gbgemm::launch(sh, epi, p->sm_count, st))) return rc;
     }
     {
@@ -280,6 +413,9 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
     GB_CUDA(cudaFreeAsync(d_goff8, st));
     GB_CUDA(cudaFreeAsync(d_koff, st));
     GB_CUDA(cudaFreeAsync(d_klen, st));
+    GB_CUDA(cudaFreeAsync(d_goff4, st));
+    GB_CUDA(cudaFreeAsync(d_padrows, st));
+    GB_CUDA(cudaFreeAsync(d_first_nt, st));
     GB_CUDA(cudaFreeAsync(d_st, st));
     GB_CUDA(cudaFreeAsync(d_ut, st));
     GB_CUDA(cudaFreeAsync(d_ht, st));

@@ -13,8 +13,14 @@
 // (one elected lane), 3-stage mbarrier pipeline, static round-robin tile schedule over <= #SM CTAs.
 // The column tiles may be partitioned into groups that read different k ranges of A
 // (a_koff = (col tile / tiles_per_group) * a_koff_mul): the analysis uses this for its four folded
-// inputs.  The epilogue functor receives accumulator pairs (row, col, col+1).
+// inputs.  The epilogue functor receives accumulator pairs (row, col, col+1); an epilogue that
+// declares `static constexpr bool whole_tile = true` gets the warp's 32 x 40 register tile at once
+// (`tile(row_base, col_base, acc)`, rows row_base + 8 mi, columns col_base + 8 ni + {0, 1}) so that it
+// can reduce inside the thread before it touches shuffles or atomics; its `prepare(row_base)` runs
+// before the K loop (index look-ups whose latency then hides behind the tile's DMMAs) and its result
+// is handed back to `tile`.
 #pragma once
+#include <type_traits>
 #include "gb_common.cuh"
 
 namespace gbgemm {
@@ -43,7 +49,13 @@ struct Shape {
     int n_mtiles, n_ntiles;
     const int* nt_koff = nullptr;   // optional per-column-tile A k offset and contraction length
     const int* nt_klen = nullptr;   // (overrides a_koff_mul / klen; used by the covariance quadratic form)
+    const int* mt_first_nt = nullptr;   // optional: row tile mt only computes column tiles nt >= mt_first_nt[mt]
 };
+
+template <class E, class = void>
+struct wants_whole_tile { static constexpr bool value = false; };
+template <class E>
+struct wants_whole_tile<E, std::enable_if_t<E::whole_tile>> { static constexpr bool value = true; };
 
 template <class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
@@ -71,6 +83,7 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const long long mt = t / sh.n_ntiles;
                 const int nt = (int)(t % sh.n_ntiles);
+                if (sh.mt_first_nt && nt < sh.mt_first_nt[mt]) continue;
                 const int a_koff = sh.nt_koff ? sh.nt_koff[nt] : (nt / sh.tiles_per_group) * sh.a_koff_mul;
                 const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
                 for (int k0 = 0; k0 < klen; k0 += KC) {
@@ -95,12 +108,19 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const long long mt = t / sh.n_ntiles;
             const int nt = (int)(t % sh.n_ntiles);
+            if (sh.mt_first_nt && nt < sh.mt_first_nt[mt]) continue;
             double acc[4][5][2];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
+            const long long row_base = mt * TM + wm * 32 + g;
+            const int col_base = nt * TN + wn * 40 + 2 * q;
+            auto pre = [&] {
+                if constexpr (wants_whole_tile<Epilogue>::value) return epi.prepare(row_base);
+                else return 0;
+            }();
             for (int k0 = 0; k0 < klen; k0 += KC) {
                 const int kc = min(KC, klen - k0);
                 gb::mbar_wait(&full[stage], phase);
@@ -123,13 +143,16 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
                 if (lane == 0) gb::mbar_arrive(&empty[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            const long long row_base = mt * TM + wm * 32 + g;
-            const int col_base = nt * TN + wn * 40 + 2 * q;
+            if constexpr (wants_whole_tile<Epilogue>::value) {
+                epi.tile(pre, row_base, col_base, acc);
+            } else {
+                (void)pre;
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 5; ++ni)
-                    epi(row_base + mi * 8, col_base + ni * 8, acc[mi][ni][0], acc[mi][ni][1]);
+                    for (int ni = 0; ni < 5; ++ni)
+                        epi(row_base + mi * 8, col_base + ni * 8, acc[mi][ni][0], acc[mi][ni][1]);
+            }
         }
     }
 }

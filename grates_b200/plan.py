@@ -226,9 +226,11 @@ class SHPlan:
         return out
 
     # -- covariance propagation ---------------------------------------------------------
-    def covariance_propagation(self, sigma, min_degree, row0=0, nrows=None, take_sqrt=True, out=None):
+    def covariance_propagation(self, sigma, min_degree, row0=0, nrows=None, take_sqrt=True, out=None, symmetric=None):
         """sigma: CUDA tensor [K', K'] (degree-wise order, offset min_degree^2) ->
-        [nrows, nlon] standard deviations (or variances) for parallels row0..row0+nrows."""
+        [nrows, nlon] standard deviations (or variances) for parallels row0..row0+nrows.
+        symmetric: True lets the kernels contract the order-block pairs k <= k' only (half the work);
+        None (default) decides by comparing sigma with its transpose on a sample of entries."""
         nrows = self.nlat - row0 if nrows is None else nrows
         kp = self.L ** 2 - min_degree ** 2
         if sigma.dim() != 2 or tuple(sigma.shape) != (kp, kp):
@@ -236,13 +238,34 @@ class SHPlan:
         if sigma.dtype != torch.float64 or not sigma.is_cuda or sigma.device.index != self.device:
             raise ValueError("covariance matrix must be a float64 CUDA tensor on device {0}".format(self.device))
         sigma = sigma.contiguous()
+        if symmetric is None:
+            symmetric = _looks_symmetric(sigma)
         if out is None:
             out = torch.empty((nrows, self.nlon), dtype=torch.float64, device=sigma.device)
+        flags = (1 if take_sqrt else 0) | (2 if symmetric else 0)      # GB_COV_SQRT | GB_COV_SYMMETRIC
         _lib.check(self._lib.gb_covariance_propagation(self._handle, ctypes.c_void_p(sigma.data_ptr()),
                                                        int(min_degree), int(row0), int(nrows),
-                                                       ctypes.c_void_p(out.data_ptr()), int(bool(take_sqrt)),
+                                                       ctypes.c_void_p(out.data_ptr()), flags,
                                                        _stream_handle(self.device)))
         return out
+
+
+_SYM_SAMPLES = {}
+
+
+def _looks_symmetric(sigma, samples=16384):
+    """sigma[a, b] == sigma[b, a] to 1e-13 of the largest sampled entry on a fixed pseudo-random sample of
+    index pairs (a full comparison would cost as much memory traffic as the propagation itself)."""
+    k = sigma.shape[0]
+    key = (k, sigma.device.index)
+    if key not in _SYM_SAMPLES:
+        gen = torch.Generator(device="cpu").manual_seed(12345)
+        a = torch.randint(0, k, (samples,), generator=gen)
+        b = torch.randint(0, k, (samples,), generator=gen)
+        _SYM_SAMPLES[key] = (a.to(sigma.device), b.to(sigma.device))
+    a, b = _SYM_SAMPLES[key]
+    u, l = sigma[a, b], sigma[b, a]
+    return bool(((u - l).abs().max() <= 1e-13 * u.abs().max()).item())
 
 
 def separable_weights(areas):

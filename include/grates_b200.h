@@ -134,12 +134,17 @@ int gb_analysis_matrix(gb_plan* plan, double* d_out, void* stream);
 /*
  * Covariance propagation to per-point variances, diag(F Sigma F'), for the parallels
  * [row0, row0 + nrows) of the plan's grid.  Replaces grid.py:833-835 (the reference then takes
- * the square root, grid.py:837-839; pass take_sqrt = 1 for that).
+ * the square root, grid.py:837-839; pass GB_COV_SQRT for that).
  *   d_sigma [K'][K'] row-major, K' = (nmax+1)^2 - nmin^2, degree-wise order
  *   d_out   [nrows][nlon]
+ *   flags   GB_COV_SQRT: return standard deviations.  GB_COV_SYMMETRIC: the caller states that
+ *           Sigma is symmetric (a covariance matrix is); only its order-block pairs k <= k' are
+ *           contracted, which halves the work.  Without the flag the full matrix is used.
  */
+#define GB_COV_SQRT 1
+#define GB_COV_SYMMETRIC 2
 int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
-                              double* d_out, int take_sqrt, void* stream);
+                              double* d_out, int flags, void* stream);
 
 /*
  * Order-wise block filter, batched over epochs.  Replaces OrderWiseFilter.filter,

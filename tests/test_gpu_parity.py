@@ -326,6 +326,31 @@ def test_covariance_vs_oracle_and_row_blocks(gb, orc):
     assert maxnorm_err(v, (P ** 2) @ (T ** 2).T) < TOL
     with pytest.raises(ValueError):
         plan.covariance_propagation(s[:-1, :-1], 0)
+    # both code paths (order-block pairs k <= k' only / full matrix) agree on a symmetric matrix
+    full = plan.covariance_propagation(s, 0, symmetric=False).cpu().numpy().ravel()
+    half = plan.covariance_propagation(s, 0, symmetric=True).cpu().numpy().ravel()
+    assert maxnorm_err(full, ref) < TOL and maxnorm_err(half, ref) < TOL
+
+
+def test_covariance_nonsymmetric_matrix_uses_full_path(gb, orc):
+    """diag(F S F') only sees the symmetric part of S; a visibly non-symmetric S must be detected and
+    propagated with the full matrix (the reference multiplies whatever it is given, grid.py:833-835)."""
+    from grates_b200 import plan as gplan
+    N = 20
+    sigma = orc.synthetic_covariance(N, rank=16)
+    rng = np.random.default_rng(7)
+    skew = np.triu(rng.standard_normal(sigma.shape), 1) * np.abs(sigma).max() * 0.3
+    ns = sigma + skew - skew.T                             # antisymmetric perturbation: variances unchanged
+    s = torch.as_tensor(ns).cuda()
+    assert not gplan._looks_symmetric(s) and gplan._looks_symmetric(torch.as_tensor(sigma).cuda())
+    grid = gb.GeographicGrid(6.0, 6.0)
+    plan = gb.get_plan(grid, N, "ewh")
+    var = plan.covariance_propagation(s, 0, take_sqrt=False).cpu().numpy().ravel()
+    og = orc.geographic_grid(6.0, 6.0)
+    ref = orc.covariance_propagation(sigma, og, 0, N, "ewh") ** 2
+    assert maxnorm_err(var, ref) < 1e-10                   # cancellation of the antisymmetric part (30 % of max|S|)
+    wrong = plan.covariance_propagation(s, 0, take_sqrt=False, symmetric=True).cpu().numpy().ravel()
+    assert maxnorm_err(wrong, ref) > 1e-3                  # the half path really relies on symmetry
 
 
 # ------------------------------------------------------------------------------ irregular point sets
