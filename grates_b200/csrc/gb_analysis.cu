@@ -10,9 +10,16 @@
 // with lon_op = u_j trig(m lon_j) / sum_j u_j trig^2 and lat_op_m = solve(P'WP, P'W), built once
 // per plan on the host (grates_b200/plan.py: analysis_operators).
 //
-// HBM layout:  V [E][nlat][nlon] (input), lonT [nlp][kpad] (lon_op transposed, zero padded),
-//              G [kpad][mpad] (same spectral layout as the synthesis intermediate AB),
-//              lat_ops concatenated [cnt_m][nlat] blocks, anm [E][L][L] packed (output).
+// Both stages run on the persistent DMMA GEMM of gb_gemm.cuh.  The rows of the longitude stage are
+// ordered (parallel i, epoch e) with the epochs fastest, so that its epilogue writes the B operand of
+// the latitude stage, Gt[order m][column tile][parallel i][column (cs, e)], in contiguous 64-byte runs
+// (eight epochs of one fragment slab); the latitude stage then is one GEMM per order (row tiles of the
+// per-order operators, contraction over the parallels) batched into a single launch.
+//
+// HBM layout:  V [E][nlat][nlon] (input), VF folded input tiles [row tile][j'][132],
+//              Gt [L][n_ct][nlat_p4][124], lat operator tiles [row tile][nlat_p4][132],
+//              anm [E][L][L] packed (output).  GB_SIMPLE_ANALYSIS=1 runs plain FMA kernels with
+//              G [kpad][mpad] and lat_ops concatenated [cnt_m][nlat] blocks as a cross-check.
 #include <vector>
 #include <cmath>
 #include "gb_common.cuh"
@@ -27,9 +34,10 @@ namespace {
 //   set 0 (even m, cos) (v1+v3)+(v2+v4)      set 1 (odd m, cos) (v1+v3)-(v2+v4)
 //   set 2 (even m, sin) (v1-v3)+(v4-v2)      set 3 (odd m, sin) (v1-v3)-(v4-v2)
 // so that the contraction runs over one quadrant only (a quarter of the multiply-adds).
+// GEMM row rho = i * E + e  (epochs fastest, see above)
 __global__ void __launch_bounds__(256)
 gb_analysis_fold(const double* __restrict__ V, double* __restrict__ VF, long long M, int nlon, int nsets, int kp,
-                 int kvalid) {
+                 int kvalid, int E, int nlat) {
     __shared__ double s_f[4][32][33];
     const int j0 = blockIdx.x * 32;                 // first k (j or j') of this block
     const long long r0 = (long long)blockIdx.y * 32;
@@ -40,7 +48,8 @@ gb_analysis_fold(const double* __restrict__ V, double* __restrict__ VF, long lon
         const int j = j0 + lane;
         double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
         if (row < M && j < kvalid) {
-            const double* v = V + (size_t)row * nlon;
+            const long long i = row / E, e = row - i * E;
+            const double* v = V + (size_t)(e * nlat + i) * nlon;
             if (nsets == 4) {
                 const double v1 = v[h + j], v2 = v[nlon - 1 - j], v3 = v[h - 1 - j], v4 = v[j];
                 const double p13 = v1 + v3, p24 = v2 + v4, m13 = v1 - v3, m42 = v4 - v2;
@@ -62,15 +71,77 @@ gb_analysis_fold(const double* __restrict__ V, double* __restrict__ VF, long lon
     }
 }
 
-struct SpectralStore {   // epilogue: G[kmap[col]][row]
-    double* G;
-    long long mpad, M;
+// epilogue of the longitude stage: row rho = i * E + e, column -> spectral row k = 2m + cs;
+// Gt[((m * n_ct + c / 120) * nlat_p4 + i) * 124 + c % 120] with c = cs * E + e
+struct LatOperandStore {
+    static constexpr bool whole_tile = true;
+    double* Gt;
+    long long M;
     const int* kmap;
-    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
-        if (row >= M) return;
-        const int k0 = kmap[col], k1 = kmap[col + 1];
-        if (k0 >= 0) G[(size_t)k0 * mpad + row] = v0;
-        if (k1 >= 0) G[(size_t)k1 * mpad + row] = v1;
+    int E, n_ct, nlat_p4;
+    struct Pre { int i[4], e[4]; };
+    __device__ __forceinline__ Pre prepare(long long row_base) const {
+        Pre pr;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const long long row = row_base + mi * 8;
+            pr.i[mi] = row < M ? (int)(row / E) : -1;
+            pr.e[mi] = (int)(row - (long long)pr.i[mi] * E);
+        }
+        return pr;
+    }
+    __device__ __forceinline__ void tile(const Pre& pr, long long, int col_base, double (&acc)[4][5][2]) const {
+#pragma unroll
+        for (int ni = 0; ni < 5; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int k = kmap[col_base + ni * 8 + r];
+                if (k < 0) continue;
+                const int m = k >> 1, cs = k & 1;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    if (pr.i[mi] < 0) continue;
+                    const int c = cs * E + pr.e[mi];
+                    const int ct = c / GB_S2_TN, cc = c - ct * GB_S2_TN;
+                    Gt[(((size_t)m * n_ct + ct) * nlat_p4 + pr.i[mi]) * GB_S2_LDB + cc] = acc[mi][ni][r];
+                }
+            }
+        }
+    }
+};
+
+// epilogue of the latitude stage: row tile -> (order m, first degree), column c = cs * E + e
+struct CoefficientStore {
+    static constexpr bool whole_tile = true;
+    double* anm;
+    const int* tile_m;
+    const int* tile_n;
+    int L, E;
+    struct Pre { int m, n; };
+    __device__ __forceinline__ Pre prepare(long long row_base) const {
+        const int t = (int)(row_base >> 7);
+        return Pre{tile_m[t], tile_n[t] + (int)(row_base & 127)};
+    }
+    __device__ __forceinline__ void tile(const Pre& pr, long long, int col_base, double (&acc)[4][5][2]) const {
+        // columns are local to the order's column tiles: col_base = ct * 120 + ...
+#pragma unroll
+        for (int ni = 0; ni < 5; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int c = col_base + ni * 8 + r;
+                if (c >= 2 * E) continue;
+                const int cs = c >= E, e = c - cs * E;
+                if (cs && pr.m == 0) continue;
+                double* a = anm + (size_t)e * L * L;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int n = pr.n + mi * 8;
+                    if (n >= L) continue;
+                    if (cs) a[(size_t)(pr.m - 1) * L + n] = acc[mi][ni][r];
+                    else a[(size_t)n * L + pr.m] = acc[mi][ni][r];
+                }
+            }
+        }
     }
 };
 
@@ -288,6 +359,39 @@ extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_o
     GB_CUDA(cudaMemcpy(p->d_ana_w_t, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice));
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_kmap), kmap.size() * sizeof(int)));
     GB_CUDA(cudaMemcpy(p->d_ana_kmap, kmap.data(), kmap.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // ---- operator tiles for the tensor-core latitude stage: A[i][r] = lat_op_m[r][i] ----
+    cudaFree(p->d_ana_lat_t); p->d_ana_lat_t = nullptr;
+    cudaFree(p->d_ana_lat_m); p->d_ana_lat_m = nullptr;
+    cudaFree(p->d_ana_lat_n); p->d_ana_lat_n = nullptr;
+    {
+        const int nlat = p->nlat;
+        p->ana_nlat_p4 = (nlat + 3) / 4 * 4;
+        std::vector<int> tile_m, tile_n;
+        for (int m = 0; m < L; ++m) {
+            const int n0 = m > nmin ? m : nmin;
+            for (int r0 = 0; r0 < L - n0; r0 += GB_TM) {
+                tile_m.push_back(m);
+                tile_n.push_back(n0 + r0);
+            }
+        }
+        p->ana_lat_tiles = (int)tile_m.size();
+        std::vector<double> lt((size_t)p->ana_lat_tiles * p->ana_nlat_p4 * GB_LDA, 0.0);
+        for (int t = 0; t < p->ana_lat_tiles; ++t) {
+            const int m = tile_m[t], n0 = m > nmin ? m : nmin;
+            const int r0 = tile_n[t] - n0;
+            const int rows = (L - tile_n[t]) < GB_TM ? (L - tile_n[t]) : GB_TM;
+            const double* op = lat_ops + p->h_lat_off[m];
+            for (int r = 0; r < rows; ++r)
+                for (int i = 0; i < nlat; ++i)
+                    lt[((size_t)t * p->ana_nlat_p4 + i) * GB_LDA + r] = op[(size_t)(r0 + r) * nlat + i];
+        }
+        GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_lat_t), (lt.size() ? lt.size() : 1) * sizeof(double)));
+        GB_CUDA(cudaMemcpy(p->d_ana_lat_t, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_lat_m), (tile_m.size() + 1) * sizeof(int)));
+        GB_CUDA(cudaMemcpy(p->d_ana_lat_m, tile_m.data(), tile_m.size() * sizeof(int), cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_lat_n), (tile_n.size() + 1) * sizeof(int)));
+        GB_CUDA(cudaMemcpy(p->d_ana_lat_n, tile_n.data(), tile_n.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     p->ana_nmin = nmin;
     return GB_OK;
 }
@@ -302,28 +406,50 @@ static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_an
         dim3 grid((unsigned)((M + LT - 1) / LT), (p->kpad + LT - 1) / LT);
         gb_analysis_lon_kernel<<<grid, 256, 0, st>>>(d_grid, p->d_lon_ops, p->d_ab, M, p->nlon, p->kpad, mpad);
         GB_LAUNCH_CHECK();
-    } else {
-        // fold / transpose V into the tiled operand layout, then one persistent DMMA GEMM over all sets
-        const int n_mtiles = (int)((M + GB_TM - 1) / GB_TM);
-        const int a_rows = p->ana_nsets * p->ana_kp;
-        const size_t vf_elems = (size_t)n_mtiles * a_rows * GB_LDA;
-        if (vf_elems > p->ana_vf_elems) {   // grow-only workspace (a fresh 1 GB allocation per call costs milliseconds)
-            GB_CUDA(cudaStreamSynchronize(st));
+        dim3 grid2(L, (E + AE - 1) / AE);
+        const size_t smem = (size_t)2 * AE * p->nlat * sizeof(double);
+        if (smem > 48 * 1024)
+            GB_CUDA(cudaFuncSetAttribute(gb_analysis_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gb_analysis_lat_kernel<<<grid2, 256, smem, st>>>(p->d_ab, p->d_lat_ops, p->d_lat_off, d_anm, L, p->nlat, E,
+                                                         p->ana_nmin, mpad);
+        GB_LAUNCH_CHECK();
+        return GB_OK;
+    }
+    // fold / transpose V into the tiled operand layout (rows (i, e), epochs fastest), then one persistent
+    // DMMA GEMM over all sets whose epilogue writes the B tiles of the latitude stage
+    const int n_mtiles = (int)((M + GB_TM - 1) / GB_TM);
+    const int a_rows = p->ana_nsets * p->ana_kp;
+    const size_t vf_elems = (size_t)n_mtiles * a_rows * GB_LDA;
+    const int n_ct = (2 * E + GB_S2_TN - 1) / GB_S2_TN;
+    const size_t gt_elems = (size_t)L * n_ct * p->ana_nlat_p4 * GB_S2_LDB;
+    if (vf_elems > p->ana_vf_elems || gt_elems > p->ana_gt_elems) {   // grow-only workspaces (a fresh 1 GB allocation per call costs milliseconds)
+        GB_CUDA(cudaStreamSynchronize(st));
+        if (vf_elems > p->ana_vf_elems) {
             cudaFree(p->d_ana_vf);
             p->d_ana_vf = nullptr;
             p->ana_vf_elems = 0;
             GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_vf), vf_elems * sizeof(double)));
             p->ana_vf_elems = vf_elems;
         }
-        double* d_vf = p->d_ana_vf;
-        {
-            dim3 grid((p->ana_kp + 31) / 32, n_mtiles * 4);
-            gb_analysis_fold<<<grid, 256, 0, st>>>(d_grid, d_vf, M, p->nlon, p->ana_nsets, p->ana_kp,
-                                                   p->ana_nsets == 4 ? p->nlon / 4 : p->nlon);
-            GB_LAUNCH_CHECK();
+        if (gt_elems > p->ana_gt_elems) {
+            cudaFree(p->d_ana_gt);
+            p->d_ana_gt = nullptr;
+            p->ana_gt_elems = 0;
+            GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_gt), gt_elems * sizeof(double)));
+            p->ana_gt_elems = gt_elems;
         }
+    }
+    // padding parallels / columns and the sine columns of order 0 are never written: keep them finite
+    GB_CUDA(cudaMemsetAsync(p->d_ana_gt, 0, gt_elems * sizeof(double), st));
+    {
+        dim3 grid((p->ana_kp + 31) / 32, n_mtiles * 4);
+        gb_analysis_fold<<<grid, 256, 0, st>>>(d_grid, p->d_ana_vf, M, p->nlon, p->ana_nsets, p->ana_kp,
+                                               p->ana_nsets == 4 ? p->nlon / 4 : p->nlon, E, p->nlat);
+        GB_LAUNCH_CHECK();
+    }
+    {
         gbgemm::Shape sh;
-        sh.A_t = d_vf;
+        sh.A_t = p->d_ana_vf;
         sh.a_rows = a_rows;
         sh.a_koff_mul = p->ana_kp;
         sh.tiles_per_group = p->ana_tps;
@@ -332,17 +458,23 @@ static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_an
         sh.klen = p->ana_kp;
         sh.n_mtiles = n_mtiles;
         sh.n_ntiles = p->ana_nsets * p->ana_tps;
-        int rc = gbgemm::launch(sh, SpectralStore{p->d_ab, mpad, M, p->d_ana_kmap}, p->sm_count, st);
+        int rc = gbgemm::launch(sh, LatOperandStore{p->d_ana_gt, M, p->d_ana_kmap, E, n_ct, p->ana_nlat_p4}, p->sm_count, st);
         if (rc) return rc;
     }
     {
-        dim3 grid(L, (E + AE - 1) / AE);
-        const size_t smem = (size_t)2 * AE * p->nlat * sizeof(double);
-        if (smem > 48 * 1024)
-            GB_CUDA(cudaFuncSetAttribute(gb_analysis_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gb_analysis_lat_kernel<<<grid, 256, smem, st>>>(p->d_ab, p->d_lat_ops, p->d_lat_off, d_anm, L, p->nlat, E,
-                                                        p->ana_nmin, mpad);
-        GB_LAUNCH_CHECK();
+        gbgemm::Shape sh;
+        sh.A_t = p->d_ana_lat_t;
+        sh.a_rows = p->ana_nlat_p4;
+        sh.a_koff_mul = 0;
+        sh.tiles_per_group = 1;
+        sh.B_t = p->d_ana_gt;
+        sh.b_rows = p->ana_nlat_p4;
+        sh.klen = p->ana_nlat_p4;
+        sh.n_mtiles = p->ana_lat_tiles;
+        sh.n_ntiles = n_ct;
+        sh.mt_bgroup = p->d_ana_lat_m;
+        int rc = gbgemm::launch(sh, CoefficientStore{d_anm, p->d_ana_lat_m, p->d_ana_lat_n, L, E}, p->sm_count, st);
+        if (rc) return rc;
     }
     return GB_OK;
 }

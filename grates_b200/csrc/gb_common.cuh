@@ -116,6 +116,13 @@ struct gb_plan {
     int* d_ana_kmap = nullptr;       // [nsets*tiles_per_set*GB_S2_TN] output column -> spectral row 2m+cs, or -1
     double* d_ana_vf = nullptr;      // folded / transposed input tiles (grow-only workspace)
     size_t ana_vf_elems = 0;
+    // latitude stage on the tensor cores: per-order operators as A tiles [row tile][parallel][GB_LDA]
+    int ana_lat_tiles = 0, ana_nlat_p4 = 0;
+    double* d_ana_lat_t = nullptr;
+    int* d_ana_lat_m = nullptr;      // [ana_lat_tiles] order of each row tile
+    int* d_ana_lat_n = nullptr;      // [ana_lat_tiles] degree of the tile's first row
+    double* d_ana_gt = nullptr;      // longitude-stage output as B tiles [order][column tile][parallel][GB_S2_LDB]
+    size_t ana_gt_elems = 0;
     // optional per-kernel event timing (gb_plan_set_profiling)
     cudaEvent_t* prof_ev = nullptr;  // [capacity][4]
     int prof_capacity = 0, prof_count = 0;

@@ -50,6 +50,8 @@ struct Shape {
     const int* nt_koff = nullptr;   // optional per-column-tile A k offset and contraction length
     const int* nt_klen = nullptr;   // (overrides a_koff_mul / klen; used by the covariance quadratic form)
     const int* mt_first_nt = nullptr;   // optional: row tile mt only computes column tiles nt >= mt_first_nt[mt]
+    const int* mt_bgroup = nullptr;     // optional: row tile mt multiplies B tile mt_bgroup[mt] * n_ntiles + nt
+                                        // (block-diagonal batches: the analysis latitude stage, one group per order)
 };
 
 template <class E, class = void>
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
                     const uint32_t bytes_b = (uint32_t)(kc * LDB * sizeof(double));
                     gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
                     gb::bulk_g2s(sA, sh.A_t + ((size_t)mt * sh.a_rows + a_koff + k0) * LDA, bytes_a, &full[stage]);
-                    gb::bulk_g2s(sB, sh.B_t + ((size_t)nt * sh.b_rows + k0) * LDB, bytes_b, &full[stage]);
+                    const size_t bt = sh.mt_bgroup ? (size_t)sh.mt_bgroup[mt] * sh.n_ntiles + nt : (size_t)nt;
+                    gb::bulk_g2s(sB, sh.B_t + (bt * sh.b_rows + k0) * LDB, bytes_b, &full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
