@@ -6,9 +6,11 @@
 // form a dense k x E matrix with the epochs contiguous, so the filter is one small GEMM per block:
 //
 //   gb_pack_kernel           anm [E][L][L] -> X            (HBM-bound transpose)
-//   gb_filter_blocks_kernel  Y_g = W_g X_g                 one CTA per (block g, 64 epochs): the X tile
+//   gb_filter_blocks_kernel  Y_g = W_g X_g                 one CTA per (block g, 32 epochs): the X tile
 //                            stays in shared memory, W streams through it in 16-column chunks
-//                            (register-staged double buffer), 4 x 4 register tiles of FMAs
+//                            (register-staged double buffer); both tiles are k-major with pitches
+//                            = 4 mod 16, i.e. conflict-free DMMA.8x8x4 operands: 8 warps x (16 rows
+//                            x 32 epochs) of FP64 tensor-core tiles, three CTAs per SM
 //   gb_pack_kernel<false>    Y -> anm [E][L][L]
 //
 // Bytes: anm in + out once each (2 x 8 E L^2), X/Y once each way, blocks once per epoch tile
@@ -17,13 +19,13 @@
 
 namespace {
 
-constexpr int FT_E = 64;            // epochs per CTA
-constexpr int FT_R = 64;            // rows per pass
+constexpr int FT_E = 32;            // epochs per CTA
+constexpr int FT_R = 128;           // rows per pass
 constexpr int FT_KC = 16;           // columns of W per chunk
 constexpr int FT_LDX = FT_E + 4;    // pitch of the X tile
 constexpr int FT_LDW = FT_R + 4;    // pitch of a (transposed) W chunk
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __restrict__ offsets, int nf,
                         const double* __restrict__ X, double* __restrict__ Y, int E, int nmax) {
     extern __shared__ __align__(16) double s_f[];
@@ -51,29 +53,29 @@ gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __re
         s_x[c * FT_LDX + e] = (c < k && e < ne) ? Xg[(size_t)c * 2 * E + e] : 0.0;
     }
 
-    const int tr = tid >> 4, te = tid & 15;   // thread tile: rows 4 tr .. +3, epochs 4 te .. +3
-    const int lr = tid >> 2, lc = (tid & 3) * 4;   // W chunk loader: row lr, columns lc .. lc+3
+    const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, q = lane & 3;   // fragment row / k index
+    const int lr = tid >> 1, lc = (tid & 1) * 8;   // W chunk loader: row lr, columns lc .. lc+7
     const int n_chunks = kp / FT_KC;
 
     for (int r0 = 0; r0 < k; r0 += FT_R) {
-        double acc[4][4];
+        double acc[2][4][2];                           // warp tile: rows 16 warp .. +15, all 32 epochs
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        const bool active = r0 + 4 * tr < k;          // warp-uniform up to 8-row granularity
-        double wreg[4];
+            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const bool active = r0 + 16 * warp < k;        // warp-uniform
+        double wreg[8];
         auto load_w = [&](int chunk) {
             const int r = r0 + lr;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const int c = chunk * FT_KC + lc + j;
                 wreg[j] = (r < k && c < k) ? __ldg(W + (size_t)r * kf + c) : 0.0;
             }
         };
         auto store_w = [&](int buf) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s_w[(buf * FT_KC + lc + j) * FT_LDW + lr] = wreg[j];
+            for (int j = 0; j < 8; ++j) s_w[(buf * FT_KC + lc + j) * FT_LDW + lr] = wreg[j];
         };
         load_w(0);
         __syncthreads();                               // previous pass finished with s_w; s_x is complete
@@ -83,20 +85,19 @@ gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __re
             const int buf = chunk & 1;
             if (chunk + 1 < n_chunks) load_w(chunk + 1);
             if (active) {
-                const double* wp = s_w + (size_t)buf * FT_KC * FT_LDW + 4 * tr;
-                const double* xp = s_x + (size_t)chunk * FT_KC * FT_LDX + 4 * te;
+                const double* wp = s_w + (size_t)buf * FT_KC * FT_LDW + 16 * warp + fg;
+                const double* xp = s_x + (size_t)chunk * FT_KC * FT_LDX + fg;
 #pragma unroll
-                for (int cc = 0; cc < FT_KC; ++cc) {
-                    const double2 w01 = *reinterpret_cast<const double2*>(wp + cc * FT_LDW);
-                    const double2 w23 = *reinterpret_cast<const double2*>(wp + cc * FT_LDW + 2);
-                    const double2 x01 = *reinterpret_cast<const double2*>(xp + cc * FT_LDX);
-                    const double2 x23 = *reinterpret_cast<const double2*>(xp + cc * FT_LDX + 2);
-                    const double w[4] = {w01.x, w01.y, w23.x, w23.y};
-                    const double x[4] = {x01.x, x01.y, x23.x, x23.y};
+                for (int kk = 0; kk < FT_KC; kk += 4) {
+                    double a[2], b[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int mi = 0; mi < 2; ++mi) a[mi] = wp[(kk + q) * FT_LDW + mi * 8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] = fma(w[i], x[j], acc[i][j]);
+                    for (int ni = 0; ni < 4; ++ni) b[ni] = xp[(kk + q) * FT_LDX + ni * 8];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
                 }
             }
             if (chunk + 1 < n_chunks) {
@@ -106,15 +107,17 @@ gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __re
         }
         if (active) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + 4 * tr + i;
+            for (int mi = 0; mi < 2; ++mi) {
+                const int r = r0 + 16 * warp + mi * 8 + fg;
                 if (r >= k) continue;
                 const bool pass = (m + r) < 2;         // degrees 0 and 1 pass through unchanged (filter.py:189)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int e = 4 * te + j;
-                    if (e < ne) Yg[(size_t)r * 2 * E + e] = pass ? s_x[r * FT_LDX + e] : acc[i][j];
-                }
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int e = ni * 8 + 2 * q + j;
+                        if (e < ne) Yg[(size_t)r * 2 * E + e] = pass ? s_x[r * FT_LDX + e] : acc[mi][ni][j];
+                    }
             }
         }
     }
