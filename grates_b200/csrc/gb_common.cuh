@@ -136,7 +136,7 @@ void gb_retain_pool_memory(int device);
 
 // anm [E][L][L] <-> order-wise packed X (gb_pack.cu): block of order m at 2E (m L - m(m-1)/2),
 // X_m[n - m][cs * E + e]
-int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st);
+int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st, const double* d_wn = nullptr);
 int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st);
 
 // Recursion coefficients a_nm, b_nm [L][L], sqrt(2n+1) [L] and sectorial seeds P_mm [npts][L],

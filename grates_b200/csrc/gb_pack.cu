@@ -7,7 +7,9 @@
 // Row r of anm[e] holds C_{r,0..r} followed by S_{r+1, r+1..nmax}; one CTA moves that row for 32
 // epochs through shared memory, so both sides are touched in full contiguous lines: reads are
 // rows of L doubles, writes are 32 consecutive epochs (256 B).  The sine plane of order 0 does not
-// exist in anm and is kept at zero (stage 1 contracts it like any other column).
+// exist in anm and is kept at zero (stage 1 contracts it like any other column).  Optional per-degree
+// weights w[n] (Gaussian / Butterworth filters, reference filter.py:31-130) are multiplied in while
+// packing: element (r, c) of anm has degree max(r, c).
 #include "gb_common.cuh"
 
 namespace {
@@ -30,7 +32,7 @@ __device__ __forceinline__ long long x_position(int r, int c, int L, int E) {
 
 template <bool PACK>
 __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int L,
-                                                      int E) {
+                                                      int E, const double* __restrict__ wn) {
     extern __shared__ double s_t[];   // [min(L, PK_C)][PK_LD]
     const int r = blockIdx.x;
     const int cb = blockIdx.z * PK_C;                 // first column of this CTA
@@ -41,7 +43,11 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
     if (PACK) {
         for (int e = warp; e < ne; e += nwarps) {
             const double* row = src + ((size_t)(e0 + e) * L + r) * L;
-            for (int c = lane; c < nc; c += 32) s_t[c * PK_LD + e] = row[cb + c];
+            if (wn) {
+                for (int c = lane; c < nc; c += 32) s_t[c * PK_LD + e] = __dmul_rn(row[cb + c], wn[max(r, cb + c)]);
+            } else {
+                for (int c = lane; c < nc; c += 32) s_t[c * PK_LD + e] = row[cb + c];
+            }
         }
         __syncthreads();
         for (int c = warp; c < nc; c += nwarps)
@@ -59,22 +65,46 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
     }
 }
 
+// out[e][r][c] = in[e][r][c] * w[max(r, c)]
+__global__ void __launch_bounds__(256) gb_scale_degree_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                              const double* __restrict__ wn, int L, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int rc = (int)(idx % ((long long)L * L));
+    const int r = rc / L, c = rc - r * L;
+    out[idx] = __dmul_rn(in[idx], wn[max(r, c)]);
+}
+
 template <bool PACK>
-int launch(const double* src, double* dst, int L, int E, cudaStream_t st) {
+int launch(const double* src, double* dst, int L, int E, const double* wn, cudaStream_t st) {
     const size_t smem = (size_t)(L < PK_C ? L : PK_C) * PK_LD * sizeof(double);
     if (smem > 48 * 1024)
         GB_CUDA(cudaFuncSetAttribute(gb_pack_kernel<PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L, (E + PK_E - 1) / PK_E, (L + PK_C - 1) / PK_C);
-    gb_pack_kernel<PACK><<<grid, 256, smem, st>>>(src, dst, L, E);
+    gb_pack_kernel<PACK><<<grid, 256, smem, st>>>(src, dst, L, E, wn);
     GB_LAUNCH_CHECK();
     return GB_OK;
 }
 
 }  // namespace
 
-int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st) {
-    return launch<true>(d_anm, d_x, L, E, st);
+int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st, const double* d_wn) {
+    return launch<true>(d_anm, d_x, L, E, d_wn, st);
 }
 int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st) {
-    return launch<false>(d_x, d_anm, L, E, st);
+    return launch<false>(d_x, d_anm, L, E, nullptr, st);
+}
+
+extern "C" int gb_scale_by_degree(const double* d_anm_in, const double* d_wn, int n_epochs, int nmax, double* d_anm_out,
+                                  int device, void* stream) {
+    GB_REQUIRE(n_epochs >= 0 && nmax >= 0, "gb_scale_by_degree: negative size");
+    if (n_epochs == 0) return GB_OK;
+    GB_REQUIRE(d_anm_in && d_wn && d_anm_out, "gb_scale_by_degree: NULL pointer");
+    GB_CUDA(cudaSetDevice(device));
+    const int L = nmax + 1;
+    const long long total = (long long)n_epochs * L * L;
+    gb_scale_degree_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_anm_in, d_anm_out, d_wn, L, total);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
 }

@@ -508,13 +508,14 @@ bool env_flag(const char* name) {
 
 }  // namespace
 
-static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_out, cudaStream_t st) {
+static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_out, cudaStream_t st,
+                            const double* d_wn = nullptr) {
     const int L = p->L;
     const long long M = (long long)E * p->nlat;
     cudaEvent_t* prof = (p->prof_ev && p->prof_count < p->prof_capacity) ? p->prof_ev + (size_t)p->prof_count * 4 : nullptr;
     if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
     {
-        int rc = gb_launch_pack(d_anm, p->d_x, L, E, st);
+        int rc = gb_launch_pack(d_anm, p->d_x, L, E, st, d_wn);
         if (rc) return rc;
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[1], st));
@@ -593,6 +594,18 @@ extern "C" int gb_synthesis(gb_plan* plan, const double* d_anm, int n_epochs, do
     int rc = gb_plan_ensure_workspace(plan, n_epochs);
     if (rc) return rc;
     return launch_synthesis(plan, d_anm, n_epochs, d_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gb_synthesis_weighted(gb_plan* plan, const double* d_anm, const double* d_wn, int n_epochs, double* d_out,
+                                     void* stream) {
+    GB_REQUIRE(plan != nullptr, "gb_synthesis_weighted: plan is NULL");
+    GB_REQUIRE(n_epochs >= 0, "gb_synthesis_weighted: n_epochs=%d is negative", n_epochs);
+    if (n_epochs == 0) return GB_OK;
+    GB_REQUIRE(d_anm && d_out && d_wn, "gb_synthesis_weighted: NULL device pointer");
+    GB_CUDA(cudaSetDevice(plan->device));
+    int rc = gb_plan_ensure_workspace(plan, n_epochs);
+    if (rc) return rc;
+    return launch_synthesis(plan, d_anm, n_epochs, d_out, static_cast<cudaStream_t>(stream), d_wn);
 }
 
 static int ensure_pipeline(gb_plan* p) {

@@ -1,5 +1,6 @@
-"""Order-wise block filters (DDK-style) on the GPU, batched over epochs.  Mirrors
-OrderWiseFilter of grates.filter (reference filter.py:133-222)."""
+"""Spatial filters on the GPU, batched over epochs.  Mirrors grates.filter: Gaussian and Butterworth
+(degree-wise weights, reference filter.py:31-130) and OrderWiseFilter (DDK-style blocks, filter.py:133-222)."""
+import abc
 import ctypes
 
 import numpy as np
@@ -9,7 +10,93 @@ from . import _lib, plan as _plan
 from .gravityfield import PotentialCoefficients
 
 
-class OrderWiseFilter:
+class SpatialFilter(metaclass=abc.ABCMeta):
+    """Interface of the reference (filter.py:15-28): ``filter`` returns a filtered copy of a
+    PotentialCoefficients instance, ``matrix`` the dense filter matrix in degree-wise order."""
+
+    @abc.abstractmethod
+    def filter(self, gravityfield):
+        pass
+
+    @abc.abstractmethod
+    def matrix(self, min_degree, max_degree):
+        pass
+
+
+class _DegreeWiseFilter(SpatialFilter):
+    """Filters that scale every coefficient of degree n by a weight w_n.  The weights are host numpy
+    (a few hundred doubles); batches are scaled on the GPU (gb_scale_by_degree), and a batched
+    synthesis can take them as ``degree_weights`` so that the scaled coefficients are never written."""
+
+    _first_degree = 0      # degrees below are left untouched by ``filter``
+
+    @abc.abstractmethod
+    def _weights(self, max_degree):
+        pass
+
+    def degree_weights(self, max_degree):
+        """w[0..max_degree] as applied by ``filter`` (1 below the first filtered degree)."""
+        w = np.array(self._weights(max_degree), dtype=float)
+        w[0:min(self._first_degree, max_degree + 1)] = 1.0
+        return w
+
+    def filter_batch(self, anm, out=None):
+        """anm: [E, L, L] packed coefficients (numpy or CUDA tensor) -> filtered copy, same type."""
+        on_host = not isinstance(anm, torch.Tensor)
+        dev = _plan._current_device(None if on_host else anm.device)
+        x = torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", dev)) if on_host else anm.contiguous()
+        if x.dim() != 3 or x.shape[1] != x.shape[2] or x.dtype != torch.float64:
+            raise ValueError("coefficients must be a float64 array of shape [epochs, L, L]")
+        nmax = x.shape[-1] - 1
+        w = torch.as_tensor(self.degree_weights(nmax)).to(x.device)
+        y = torch.empty_like(x) if out is None else out
+        lib = _lib.load()
+        _lib.check(lib.gb_scale_by_degree(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()), x.shape[0], nmax,
+                                          ctypes.c_void_p(y.data_ptr()), dev, _plan._stream_handle(dev)))
+        return y.cpu().numpy() if on_host else y
+
+    def filter(self, gravityfield):
+        if not isinstance(gravityfield, PotentialCoefficients):
+            raise TypeError("Filter operation only implemented for instances of 'PotentialCoefficients'")
+        result = gravityfield.copy()
+        result.anm = self.filter_batch(np.ascontiguousarray(gravityfield.anm, dtype=float)[None])[0]
+        return result
+
+    def matrix(self, min_degree, max_degree):
+        """Diagonal filter matrix in degree-wise order (filter.py:72-92, :120-127); unlike ``filter`` it
+        weights every degree from min_degree on."""
+        w = np.asarray(self._weights(max_degree), dtype=float)
+        diag = np.concatenate([np.full(2 * n + 1, w[n]) for n in range(min_degree, max_degree + 1)])
+        return np.diag(diag)
+
+
+class Gaussian(_DegreeWiseFilter):
+    """Gaussian filter of a given radius in kilometres (filter.py:31-92); degrees 0 and 1 pass through."""
+
+    _first_degree = 2
+
+    def __init__(self, radius):
+        self.radius = radius
+
+    def _weights(self, max_degree):
+        from .kernel import Gauss
+        return Gauss(self.radius).coefficients(0, max_degree).ravel()
+
+
+class Butterworth(_DegreeWiseFilter):
+    """Butterworth filter on the sphere (filter.py:95-127)."""
+
+    def __init__(self, order, cutoff_degree):
+        self.order = order
+        self.cutoff_degree = cutoff_degree
+
+    def _weights(self, max_degree):
+        # per degree with Python scalars, in the reference's own expression (filter.py:116): a vectorised
+        # power differs from it in the last bit
+        return np.array([np.power(1 + (n / self.cutoff_degree) ** (2 * self.order), -0.5) for n in range(max_degree + 1)])
+
+
+class OrderWiseFilter(SpatialFilter):
     """Sparse spherical-harmonic filter that only couples coefficients of the same order and
     trigonometric function.  ``orderwise_blocks[0]`` acts on C_n0; blocks ``2m-1`` / ``2m`` act on
     C_nm / S_nm (n = m..nmax), each of shape [(nmax+1-m), (nmax+1-m)]."""

@@ -206,12 +206,23 @@ class TimeSeries:
         return to_grid_batch(self.to_packed(), grid, kernel, first.GM, first.R, device_output=device_output, out=out)
 
 
-def to_grid_batch(anm, grid=None, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT, device_output=False, out=None):
+def to_grid_batch(anm, grid=None, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT, device_output=False, out=None,
+                  degree_weights=None):
     """Batched synthesis.  anm: [E, L, L] packed coefficients (numpy array or CUDA float64
     tensor).  Returns [E, nlat, nlon]; with a CUDA tensor input (or device_output=True) the
-    result stays on the device, otherwise it is copied to the host inside the call."""
+    result stays on the device, otherwise it is copied to the host inside the call.
+    degree_weights: weights of an isotropic filter (``Gaussian(r).degree_weights(nmax)``) fused into
+    the synthesis on regular grids."""
     grid = GeographicGrid() if grid is None else grid
     L = anm.shape[-1]
+    if degree_weights is not None:
+        if not _plan.is_regular(grid):
+            raise ValueError("degree_weights are fused into the regular-grid synthesis only; filter the coefficients first")
+        p = _plan.get_plan(grid, L - 1, kernel, GM, R)
+        on_device = isinstance(anm, torch.Tensor)
+        x = anm if on_device else torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", p.device))
+        vals = p.synthesis(x, out=out if (on_device or device_output) else None, degree_weights=degree_weights)
+        return vals if (on_device or device_output) else vals.cpu().numpy()
     if not _plan.is_regular(grid):
         p = _plan.get_points_plan(grid, L - 1, kernel, GM, R)      # -> [E, points]
         on_device = isinstance(anm, torch.Tensor)

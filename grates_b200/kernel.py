@@ -169,6 +169,47 @@ class IsotropicKernel(metaclass=abc.ABCMeta):
         return np.zeros(kn.shape) if np.allclose(kn, 0.0) else 1.0 / kn
 
 
+class Gauss(IsotropicKernel):
+    """Gauss kernel (reference kernel.py:464-506): degree weights by the three-term recursion in
+    b = ln 2 / (1 - cos(radius / R)), stopped (remaining weights zero) once a weight falls below 1e-7.
+    The reference's own quirk is kept: the table is built with R = 6378.1366 km, an extension beyond
+    degree 1024 uses R = 6378.1363 km."""
+
+    def __init__(self, radius):
+        if radius < 0:
+            raise ValueError('Gaussian filter radius must be positive (got {0:f})'.format(radius))
+        nmax = 1024
+        self._radius = radius
+        if self._radius > 0:
+            b = np.log(2.0) / (1 - np.cos(radius / 6378.1366))
+            self._wn = np.zeros(nmax + 1)
+            self._wn[0] = 1.0
+            self._wn[1] = (1 + np.exp(-2 * b)) / (1 - np.exp(-2 * b)) - 1 / b
+            for n in range(2, nmax + 1):
+                self._wn[n] = -(2 * n - 1) / b * self._wn[n - 1] + self._wn[n - 2]
+                if self._wn[n] < 1e-7:
+                    break
+        else:
+            self._wn = np.ones(nmax + 1)
+
+    def _coefficients(self, min_degree, max_degree, r=6378136.3, colat=0):
+        local_nmax = self._wn.size - 1
+        if max_degree > local_nmax:
+            if self._radius > 0:
+                wn = self._wn.copy()
+                self._wn = np.zeros(max_degree + 1)   # np.empty in the reference: weights behind the cut-off are undefined there
+                self._wn[0:local_nmax + 1] = wn
+                b = np.log(2.0) / (1 - np.cos(self._radius / 6378.1363))
+                for d in range(local_nmax + 1, max_degree + 1):
+                    self._wn[d] = -(2 * d - 1) / b * self._wn[d - 1] + self._wn[d - 2]
+                    if self._wn[d] < 1e-7:
+                        break
+            else:
+                self._wn = np.ones(max_degree + 1)
+        count = max(np.asarray(r).size, np.asarray(colat).size)
+        return np.tile(self._wn[min_degree:max_degree + 1], (count, 1))
+
+
 def _degrees(min_degree, max_degree):
     return np.arange(min_degree, max_degree + 1, dtype=float)
 

@@ -116,8 +116,10 @@ class SHPlan:
             raise ValueError("coefficients must be a float64 CUDA tensor on device {0}".format(self.device))
 
     # -- synthesis ----------------------------------------------------------------------
-    def synthesis(self, anm, out=None):
-        """anm: CUDA float64 tensor [E, L, L] (packed) -> CUDA tensor [E, nlat, nlon]."""
+    def synthesis(self, anm, out=None, degree_weights=None):
+        """anm: CUDA float64 tensor [E, L, L] (packed) -> CUDA tensor [E, nlat, nlon].
+        degree_weights: optional [L] weights w_n of an isotropic filter (Gaussian, Butterworth),
+        multiplied into the coefficients while they are packed (gb_synthesis_weighted)."""
         self._check_anm(anm)
         anm = anm.contiguous()
         E = anm.shape[0]
@@ -125,6 +127,14 @@ class SHPlan:
             out = torch.empty((E, self.nlat, self.nlon), dtype=torch.float64, device=anm.device)
         elif tuple(out.shape) != (E, self.nlat, self.nlon) or out.dtype != torch.float64 or not out.is_contiguous():
             raise ValueError("out must be a contiguous float64 tensor of shape [E, nlat, nlon]")
+        if degree_weights is not None:
+            w = torch.as_tensor(np.ascontiguousarray(degree_weights, dtype=np.float64)).to(anm.device)
+            if w.numel() != self.L:
+                raise ValueError("degree_weights must have {0} entries (got {1})".format(self.L, w.numel()))
+            _lib.check(self._lib.gb_synthesis_weighted(self._handle, ctypes.c_void_p(anm.data_ptr()),
+                                                       ctypes.c_void_p(w.data_ptr()), E,
+                                                       ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+            return out
         _lib.check(self._lib.gb_synthesis(self._handle, ctypes.c_void_p(anm.data_ptr()), E,
                                           ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out

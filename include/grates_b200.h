@@ -147,6 +147,19 @@ int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, in
                               double* d_out, int flags, void* stream);
 
 /*
+ * Isotropic (degree-wise) filters: Gaussian and Butterworth, filter.py:31-130, scale every
+ * coefficient of degree n by a weight w_n.
+ *   gb_scale_by_degree      d_anm_out[e][r][c] = d_anm_in[e][r][c] * d_wn[max(r, c)]   (may alias)
+ *   gb_synthesis_weighted   gb_synthesis of the scaled coefficients without materialising them: the
+ *                           weights are multiplied in while the coefficients are packed order-wise
+ *   d_wn [nmax+1] device array (the reference leaves degrees 0, 1 unscaled for the Gaussian: w = 1)
+ */
+int gb_scale_by_degree(const double* d_anm_in, const double* d_wn, int n_epochs, int nmax,
+                       double* d_anm_out, int device, void* stream);
+int gb_synthesis_weighted(gb_plan* plan, const double* d_anm, const double* d_wn, int n_epochs,
+                          double* d_out, void* stream);
+
+/*
  * Order-wise block filter, batched over epochs.  Replaces OrderWiseFilter.filter,
  * filter.py:180-189: order 0 block on C_n0, blocks 2m-1 / 2m on C_nm / S_nm, each block
  * truncated to its top-left (nmax+1-m)^2 corner; degrees 0 and 1 pass through unchanged.

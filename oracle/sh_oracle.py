@@ -567,6 +567,50 @@ def orderwise_filter_matrix(blocks, nmin, nmax):
 # --------------------------------------------------------------------------------------
 # Synthetic inputs shared by tests and bench
 # --------------------------------------------------------------------------------------
+def gauss_weights(radius, nmax):
+    """Degree weights of the Gauss kernel (kernel.py:468-506): recursion in b = ln2 / (1 - cos(radius/R)),
+    stopped at the first weight below 1e-7 (the rest stays zero); the table is built to degree 1024 with
+    R = 6378.1366 km, degrees beyond are appended with R = 6378.1363 km."""
+    table = max(nmax, 1024)
+    if radius <= 0:
+        return np.ones(nmax + 1)
+    wn = np.zeros(1025)
+    b = np.log(2.0) / (1 - np.cos(radius / 6378.1366))
+    wn[0] = 1.0
+    wn[1] = (1 + np.exp(-2 * b)) / (1 - np.exp(-2 * b)) - 1 / b
+    for n in range(2, 1025):
+        wn[n] = -(2 * n - 1) / b * wn[n - 1] + wn[n - 2]
+        if wn[n] < 1e-7:
+            break
+    if table > 1024:
+        ext = np.empty(table + 1)       # np.empty in the reference: entries after the break are undefined there
+        ext[:] = 0.0
+        ext[0:1025] = wn
+        b = np.log(2.0) / (1 - np.cos(radius / 6378.1363))
+        for d in range(1025, table + 1):
+            ext[d] = -(2 * d - 1) / b * ext[d - 1] + ext[d - 2]
+            if ext[d] < 1e-7:
+                break
+        wn = ext
+    return wn[0:nmax + 1].copy()
+
+
+def butterworth_weights(order, cutoff_degree, nmax):
+    """filter.py:113-118: (1 + (n / n_c)^(2 order))^(-1/2)."""
+    # per degree with Python scalars, as the reference does (a vectorised power differs in the last bit)
+    return np.array([np.power(1 + (n / cutoff_degree) ** (2 * order), -0.5) for n in range(nmax + 1)])
+
+
+def degreewise_filter(anm, wn, first_degree=0):
+    """Scale every coefficient of degree n >= first_degree by wn[n] (filter.py:66-68 uses first_degree = 2
+    for the Gaussian, filter.py:115-116 first_degree = 0 for the Butterworth filter)."""
+    out = np.array(anm, dtype=float, copy=True)
+    L = out.shape[-1]
+    deg = np.maximum(np.arange(L)[:, None], np.arange(L)[None, :])
+    w = np.where(deg >= first_degree, np.asarray(wn, dtype=float)[deg], 1.0)
+    return out * w
+
+
 def synthetic_coefficients(nmax, epoch=0):
     """Kaula-like random coefficients, seed 1000 + epoch; degrees 0-1 zero."""
     rng = np.random.default_rng(1000 + epoch)

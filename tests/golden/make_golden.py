@@ -249,7 +249,32 @@ def filters():
     save("filters", **out)
 
 
+def degreewise_filters():
+    """Gaussian / Butterworth filters and the Gauss kernel (filter.py:31-130, kernel.py:464-506)."""
+    out = {}
+    pc = coeffs(40, 1002)
+    pc.anm[0:2, 0:2] = np.random.default_rng(9).standard_normal((2, 2))
+    out["in_40"] = pc.anm
+    for radius in (0.0, 150.0, 500.0):
+        tag = "%d" % radius
+        out["gauss_w_" + tag] = grates.kernel.Gauss(radius).coefficients(0, 200).ravel()
+        out["gauss_out_" + tag] = grates.filter.Gaussian(radius).filter(pc).anm
+    out["gauss_matrix_300_2_9"] = np.diag(grates.filter.Gaussian(300.0).matrix(2, 9))
+    out["gauss_w_300_ext"] = grates.kernel.Gauss(300.0).coefficients(1020, 1030).ravel()
+    for order, cutoff in ((2, 30), (5, 12)):
+        tag = "%d_%d" % (order, cutoff)
+        out["butter_out_" + tag] = grates.filter.Butterworth(order, cutoff).filter(pc).anm
+        out["butter_matrix_" + tag] = np.diag(grates.filter.Butterworth(order, cutoff).matrix(1, 12))
+    out["ewh_gauss300_in40"] = grates.filter.Gaussian(300.0).filter(pc).to_grid(
+        grates.grid.GeographicGrid(dlon=6.0, dlat=6.0), kernel='ewh').value_array
+    save("degreewise_filters", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     l1_numerics()
     kernels()
     grids()
@@ -257,3 +282,4 @@ if __name__ == "__main__":
     analysis()
     covariance()
     filters()
+    degreewise_filters()

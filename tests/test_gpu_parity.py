@@ -408,6 +408,33 @@ def test_orderwise_filter_golden(gb, golden):
         flt.filter(np.zeros((5, 5)))
 
 
+def test_degreewise_filters_golden_and_fused_synthesis(gb, orc, golden):
+    """Gaussian / Butterworth filters (filter.py:31-130): filtered coefficients are bit-identical to the
+    reference (one multiplication per coefficient), and weights fused into the synthesis give the same
+    grid as filtering first."""
+    g = golden("degreewise_filters")
+    pc = _pc(gb, g["in_40"])
+    for radius in (0.0, 150.0, 500.0):
+        np.testing.assert_array_equal(gb.Gaussian(radius).filter(pc).anm, g["gauss_out_%d" % radius])
+    for order, cutoff in ((2, 30), (5, 12)):
+        np.testing.assert_array_equal(gb.Butterworth(order, cutoff).filter(pc).anm, g["butter_out_%d_%d" % (order, cutoff)])
+    np.testing.assert_array_equal(pc.anm, g["in_40"])                      # input untouched
+    grid = gb.GeographicGrid(6.0, 6.0)
+    flt = gb.Gaussian(300.0)
+    vals = flt.filter(pc).to_grid(grid, "ewh").value_array
+    assert maxnorm_err(vals, g["ewh_gauss300_in40"]) < TOL
+    batch = np.stack([g["in_40"], 2.0 * g["in_40"], g["gauss_out_150"]])
+    fused = gb.to_grid_batch(batch, grid, "ewh", degree_weights=flt.degree_weights(40))
+    plain = gb.to_grid_batch(flt.filter_batch(batch), grid, "ewh")
+    np.testing.assert_array_equal(fused, plain)                            # same products, same kernels
+    assert maxnorm_err(fused[0], g["ewh_gauss300_in40"]) < TOL
+    dev = flt.filter_batch(torch.as_tensor(batch).cuda())
+    assert dev.is_cuda
+    np.testing.assert_array_equal(dev.cpu().numpy()[0], orc.degreewise_filter(g["in_40"], orc.gauss_weights(300.0, 40), 2))
+    with pytest.raises(ValueError):
+        gb.to_grid_batch(batch, grid, "ewh", degree_weights=np.ones(7))
+
+
 def test_orderwise_filter_batch_then_synthesis(gb, orc):
     """BASELINE config 5 in small: block filter over an epoch batch feeding the synthesis."""
     nf, N, E = 40, 36, 11

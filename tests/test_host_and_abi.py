@@ -194,3 +194,24 @@ def test_analysis_operator_host_construction(golden):
     assert np.max(np.abs(full - ref)) / np.max(np.abs(ref)) < 1e-13
     with pytest.raises(ValueError):
         gplan.separable_weights(np.random.default_rng(0).uniform(1, 2, (4, 5)))
+
+
+def test_gauss_kernel_and_filter_matrices_host(golden):
+    """Host side of the degree-wise filters: Gauss kernel table and the diagonal filter matrices
+    (no GPU involved)."""
+    import grates_b200 as gb
+    from grates_b200 import kernel as gk
+    g = golden("degreewise_filters")
+    for radius in (0.0, 150.0, 500.0):
+        np.testing.assert_array_equal(gk.Gauss(radius).coefficients(0, 200).ravel(), g["gauss_w_%d" % radius])
+    np.testing.assert_array_equal(gk.Gauss(300.0).coefficients(1020, 1030).ravel()[0:5], g["gauss_w_300_ext"][0:5])
+    with pytest.raises(ValueError):
+        gk.Gauss(-1.0)
+    np.testing.assert_array_equal(np.diag(gb.Gaussian(300.0).matrix(2, 9)), g["gauss_matrix_300_2_9"])
+    m = gb.Butterworth(5, 12).matrix(1, 12)
+    np.testing.assert_array_equal(np.diag(m), g["butter_matrix_5_12"])
+    assert np.count_nonzero(m - np.diag(np.diag(m))) == 0
+    w = gb.Gaussian(500.0).degree_weights(40)
+    assert w[0] == 1.0 and w[1] == 1.0 and w[2] == g["gauss_w_500"][2]
+    with pytest.raises(TypeError):
+        gb.Gaussian(300.0).filter(np.zeros((5, 5)))
