@@ -4,10 +4,12 @@ path: same packed ``anm`` layout, same ``to_grid(grid, kernel)`` signature and r
 plus the batched entry points the reference lacks (its users loop over epochs,
 gravityfield.py:1143-1172).
 """
+import ctypes
+
 import numpy as np
 import torch
 
-from . import plan as _plan, utilities
+from . import _lib, plan as _plan, utilities
 from .grid import GeographicGrid
 
 GM_DEFAULT = 3.9860044150e+14
@@ -251,7 +253,44 @@ def gridded_rms(temporal_gravityfield, epochs, kernel='ewh', base_grid=None):
     for k, f in enumerate(fields):
         packed[k, :f.anm.shape[0], :f.anm.shape[1]] = f.anm
     values = to_grid_batch(packed, base_grid, kernel, fields[0].GM, fields[0].R, device_output=True)
-    rms = torch.sqrt(torch.sum(values * values, dim=0) / len(fields))
+    values = values.reshape(len(fields), -1)
+    rms = torch.empty(values.shape[1], dtype=torch.float64, device=values.device)
+    dev = values.device.index
+    _lib.check(_lib.load().gb_temporal_rms(ctypes.c_void_p(values.data_ptr()), values.shape[0], values.shape[1],
+                                           ctypes.c_void_p(rms.data_ptr()), dev, _plan._stream_handle(dev)))
     grid = base_grid.copy()
     grid.values = rms.cpu().numpy().reshape(-1)
     return grid
+
+
+def grid_statistics(values, grid, mask=None):
+    """Area-weighted mean, RMS and standard deviation of every epoch of a gridded batch, optionally
+    inside a mask (Grid.mean / rms / std of the reference, grid.py:174-260, for [E, ...] values at once).
+    values: CUDA tensor or numpy array [E, nlat, nlon] or [E, points]; mask: boolean [points] or None.
+    Returns a dict of numpy arrays [E]; the grids stay on the device."""
+    on_host = not isinstance(values, torch.Tensor)
+    dev = _plan._current_device(None if on_host else values.device)
+    v = torch.as_tensor(np.ascontiguousarray(values, dtype=float)).to(torch.device("cuda", dev)) if on_host else values.contiguous()
+    v = v.reshape(v.shape[0], -1)
+    if v.dtype != torch.float64 or v.shape[1] != grid.point_count:
+        raise ValueError("values must be float64 with {0} points per epoch (got {1})".format(grid.point_count, tuple(v.shape)))
+    w = np.array(grid.area, dtype=float).reshape(-1) if grid.area is not None else np.ones(grid.point_count)
+    if mask is not None:
+        mask = np.asarray(mask, dtype=bool).reshape(-1)
+        if mask.size != grid.point_count:
+            raise ValueError("mask must have one entry per grid point")
+        w = np.where(mask, w, 0.0)
+    s0 = float(np.sum(w[mask])) if mask is not None else float(np.sum(w))
+    wd = torch.as_tensor(w).to(v.device)
+    lib, st = _lib.load(), _plan._stream_handle(dev)
+    E = v.shape[0]
+    m1 = torch.empty((E, 2), dtype=torch.float64, device=v.device)
+    _lib.check(lib.gb_weighted_moments(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(wd.data_ptr()), None, E, v.shape[1],
+                                       ctypes.c_void_p(m1.data_ptr()), dev, st))
+    mean = m1[:, 0] / s0
+    m2 = torch.empty((E, 2), dtype=torch.float64, device=v.device)
+    _lib.check(lib.gb_weighted_moments(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(wd.data_ptr()),
+                                       ctypes.c_void_p(mean.contiguous().data_ptr()), E, v.shape[1],
+                                       ctypes.c_void_p(m2.data_ptr()), dev, st))
+    m1, m2, mean = m1.cpu().numpy(), m2.cpu().numpy(), mean.cpu().numpy()
+    return {"mean": mean, "rms": np.sqrt(m1[:, 1] / s0), "std": np.sqrt(m2[:, 1] / s0)}

@@ -188,6 +188,20 @@ int gb_points_synthesis(gb_points* points, const double* d_anm, int n_epochs, do
 int gb_points_covariance(gb_points* points, const double* d_sigma, int nmin, double* d_out, int take_sqrt,
                          void* stream);
 
+/*
+ * Consumers of gridded epoch batches that keep the grids on the device.
+ *   gb_temporal_rms       d_out[p] = sqrt(sum_e v[e][p]^2 / n_epochs); replaces the accumulation loop of
+ *                         gridded_rms, gravityfield.py:1165-1170 (same summation order, bit-identical)
+ *   gb_weighted_moments   d_out[e][0] = sum_p w[p] (v[e][p] - c[e]),  d_out[e][1] = sum_p w[p] (v[e][p] - c[e])^2
+ *                         with w = area element * mask and c = d_shift (NULL: 0): the sums behind
+ *                         Grid.mean / rms / std, grid.py:174-260, for a whole batch
+ *   d_values [n_epochs][n_points], d_weights [n_points], d_shift [n_epochs] or NULL
+ */
+int gb_temporal_rms(const double* d_values, int n_epochs, int64_t n_points, double* d_out, int device,
+                    void* stream);
+int gb_weighted_moments(const double* d_values, const double* d_weights, const double* d_shift,
+                        int n_epochs, int64_t n_points, double* d_out, int device, void* stream);
+
 /* Pinned host memory for the *_host entry points. */
 int gb_host_alloc(void** ptr, uint64_t bytes);
 int gb_host_free(void* ptr);

@@ -435,6 +435,42 @@ def test_degreewise_filters_golden_and_fused_synthesis(gb, orc, golden):
         gb.to_grid_batch(batch, grid, "ewh", degree_weights=np.ones(7))
 
 
+def test_device_reductions_gridded_rms_and_statistics(gb, orc):
+    """Consumers that keep the grids on the device: gridded_rms (gravityfield.py:1143-1172) and the
+    area-weighted statistics of Grid.mean / rms / std (grid.py:174-260) for a whole batch."""
+    import datetime
+    N, E = 20, 5
+    grid = gb.GeographicGrid(6.0, 6.0)
+    og = orc.geographic_grid(6.0, 6.0)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    ref = np.stack([orc.synthesis(a, og, "ewh") for a in anm])
+    data = []
+    for e in range(E):
+        pc = _pc(gb, anm[e])
+        pc.epoch = datetime.datetime(2002, 4, 15) + datetime.timedelta(days=30.4375 * e)
+        data.append(pc)
+    ts = gb.TimeSeries(data)
+    rms = gb.gridded_rms(ts, ts.epochs(), "ewh", grid)
+    assert maxnorm_err(rms.values, np.sqrt(np.sum(ref ** 2, axis=0) / E).ravel()) < TOL
+    vals = gb.to_grid_batch(torch.as_tensor(anm).cuda(), grid, "ewh")
+    rng = np.random.default_rng(3)
+    for mask in (None, rng.uniform(size=grid.point_count) < 0.3):
+        st = gb.grid_statistics(vals, grid, mask)
+        for e in range(E):
+            g1 = grid.copy()
+            g1.values = ref[e].ravel()
+            assert abs(st["mean"][e] - g1.mean(mask)) < 1e-12 * np.abs(ref[e]).max()
+            assert abs(st["rms"][e] - g1.rms(mask)) < 1e-12 * np.abs(ref[e]).max()
+            assert abs(st["std"][e] - g1.std(mask)) < 1e-12 * np.abs(ref[e]).max()
+    host = gb.grid_statistics(ref, grid)                     # numpy input, same numbers
+    np.testing.assert_allclose(host["rms"], st_all_rms(ref, grid), rtol=1e-12)
+
+
+def st_all_rms(ref, grid):
+    w = np.asarray(grid.area).ravel()
+    return np.sqrt((ref.reshape(ref.shape[0], -1) ** 2 @ w) / w.sum())
+
+
 def test_orderwise_filter_batch_then_synthesis(gb, orc):
     """BASELINE config 5 in small: block filter over an epoch batch feeding the synthesis."""
     nf, N, E = 40, 36, 11
