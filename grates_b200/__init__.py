@@ -11,6 +11,7 @@ from .gravityfield import PotentialCoefficients, TimeSeries, to_grid_batch, grid
 from .grid import RegularGrid, IrregularGrid, GeographicGrid, GaussGrid, analysis_batch  # noqa: F401
 from .filter import OrderWiseFilter, Gaussian, Butterworth, SpatialFilter  # noqa: F401
 from .kernel import get_kernel  # noqa: F401
+from .install import install, uninstall, installed  # noqa: F401
 from .plan import SHPlan, PointsPlan, get_plan, get_points_plan, clear_plan_cache, PinnedArray  # noqa: F401
 
 __version__ = "0.1.0"

@@ -471,6 +471,82 @@ def st_all_rms(ref, grid):
     return np.sqrt((ref.reshape(ref.shape[0], -1) ** 2 @ w) / w.sum())
 
 
+def test_install_wrappers_on_gpu(gb, orc, golden):
+    """The wrappers of grates_b200.install() on the GPU.  The reference package cannot travel to the GPU box,
+    so a stand-in with the reference's class layout (subclasses of the mirror classes, private block list
+    under the reference's mangled name) is patched; the CPU suite patches the real package."""
+    import types
+
+    class PC(gb.PotentialCoefficients):
+        def copy(self):
+            new = PC(self.GM, self.R)
+            new.anm = self.anm.copy()
+            new.epoch = self.epoch
+            return new
+
+    class RG(gb.RegularGrid):
+        def copy(self):
+            g2 = RG.__new__(type(self))
+            RG.__init__(g2, self.meridians.copy(), self.parallels.copy(), self._areas.copy(), self._a, self._f)
+            g2.epoch = self.epoch
+            return g2
+
+    class GG(RG):
+        def __init__(self, dlon=0.5, dlat=0.5):
+            base = gb.GeographicGrid(dlon, dlat)
+            RG.__init__(self, base.meridians, base.parallels, base._areas, base._a, base._f)
+
+    class IG(gb.IrregularGrid):
+        pass
+
+    class OWF:
+        def __init__(self, blocks):
+            self._OrderWiseFilter__array = blocks
+
+        def filter(self, gravityfield):
+            raise AssertionError("not rebound")
+
+    class GA(OWF):
+        def __init__(self, radius):
+            self.radius = radius
+
+    class BW(OWF):
+        def __init__(self, order, cutoff_degree):
+            self.order, self.cutoff_degree = order, cutoff_degree
+
+    ref = types.SimpleNamespace(
+        gravityfield=types.SimpleNamespace(PotentialCoefficients=PC, gridded_rms=None),
+        grid=types.SimpleNamespace(RegularGrid=RG, IrregularGrid=IG, GeographicGrid=GG),
+        filter=types.SimpleNamespace(OrderWiseFilter=OWF, Gaussian=GA, Butterworth=BW))
+    g = golden("degreewise_filters")
+    try:
+        gb.install(ref)
+        pc = PC()
+        pc.anm = g["in_40"].copy()
+        grid = GG(6.0, 6.0)
+        out = pc.to_grid(grid, "ewh")
+        assert type(out) is GG and out is not grid
+        og = orc.geographic_grid(6.0, 6.0)
+        assert maxnorm_err(out.value_array, orc.synthesis(g["in_40"], og, "ewh")) < TOL
+        back = out.to_potential_coefficients(2, 20, "ewh")          # 60 meridians resolve up to degree 29
+        assert type(back) is PC
+        assert maxnorm_err(back.anm, orc.analysis_separable(out.value_array[None], og, 2, 20, "ewh")[0]) < TOL
+        filt = GA(500.0).filter(pc)
+        assert type(filt) is PC
+        np.testing.assert_array_equal(filt.anm, g["gauss_out_500"])
+        np.testing.assert_array_equal(BW(2, 30).filter(pc).anm, g["butter_out_2_30"])
+        with pytest.raises(TypeError):
+            GA(500.0).filter(np.zeros((3, 3)))
+        sigma = orc.synthetic_covariance(8, rank=8)
+        cg = GG(15.0, 15.0)
+        std = cg.covariance_propagation(sigma, 0, 8, "ewh")
+        assert maxnorm_err(std, orc.covariance_propagation(sigma, orc.geographic_grid(15.0, 15.0), 0, 8, "ewh")) < TOL
+        np.testing.assert_array_equal(cg.values, std)
+    finally:
+        gb.uninstall()
+    assert not gb.installed()
+
+
 def test_orderwise_filter_batch_then_synthesis(gb, orc):
     """BASELINE config 5 in small: block filter over an epoch batch feeding the synthesis."""
     nf, N, E = 40, 36, 11

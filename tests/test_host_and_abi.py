@@ -3,11 +3,12 @@ Python mirror agrees with the golden reference outputs, nothing computes without
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, maxnorm_err
 
 gb = pytest.importorskip("grates_b200")
 
@@ -215,3 +216,40 @@ def test_gauss_kernel_and_filter_matrices_host(golden):
     assert w[0] == 1.0 and w[1] == 1.0 and w[2] == g["gauss_w_500"][2]
     with pytest.raises(TypeError):
         gb.Gaussian(300.0).filter(np.zeros((5, 5)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/grates"), reason="reference checkout not present on this box")
+def test_install_rebinds_reference_methods_and_has_no_cpu_fallback():
+    """grates_b200.install() rebinds the hot methods of the reference's own classes; without a
+    CUDA device the rebound methods raise instead of computing on the CPU; uninstall() restores grates."""
+    import types
+    import torch
+    nc = types.ModuleType("netCDF4")
+    nc.Dataset = object
+    sys.modules.setdefault("netCDF4", nc)
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import grates
+    import grates_b200 as gb
+    original = grates.gravityfield.PotentialCoefficients.to_grid
+    pc = grates.gravityfield.PotentialCoefficients()
+    pc.anm = np.random.default_rng(0).standard_normal((5, 5)) * 1e-6
+    grid = grates.grid.GeographicGrid(dlon=30.0, dlat=30.0)
+    expected = pc.to_grid(grid, "ewh").values.copy()
+    try:
+        gb.install(grates)
+        assert grates.gravityfield.PotentialCoefficients.to_grid is not original
+        assert len(gb.installed()) == 8
+        if not torch.cuda.is_available():
+            with pytest.raises(Exception) as err:
+                pc.to_grid(grid, "ewh")
+            assert "CUDA" in str(err.value) or "cuda" in str(err.value)
+        else:
+            out = pc.to_grid(grid, "ewh")
+            assert type(out) is type(grid)
+            assert maxnorm_err(out.values, expected) < 1e-12
+    finally:
+        gb.uninstall()
+    assert grates.gravityfield.PotentialCoefficients.to_grid is original and not gb.installed()
+    np.testing.assert_array_equal(pc.to_grid(grid, "ewh").values, expected)
