@@ -104,6 +104,23 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the host cores NVML lists as local to GPU `index`, so that first-touch places the
+    pinned buffers on that NUMA node (8 ranks copying 0.5 GB per step each otherwise meet on one socket)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def cpu_reference_rate(epochs_sample, warm=1):
     """Oracle port of the reference's to_grid (same numpy work per call: Legendre table, factor
     scaling, trig table, L dgemms) on the host cores.  Returns (grid-pts*epochs/s, seconds, threads)."""
@@ -189,6 +206,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
+    full_affinity = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(local_rank)          # pinned host buffers of the e2e loop land next to the GPU
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -320,6 +339,7 @@ def main():
         if args.no_cpu_baseline or world > 1:
             cpu = None
         else:
+            os.sched_setaffinity(0, full_affinity)     # the CPU arm gets every host core
             rate, dt, threads = cpu_reference_rate(24)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "24 of 240 epochs after 1 warm-up call, %.1f s; oracle port of to_grid "
