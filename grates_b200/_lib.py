@@ -33,6 +33,8 @@ SIGNATURES = {
     "gb_analysis_matrix": (ctypes.c_int, [_vp, _vp, _vp]),
     "gb_covariance_propagation": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                                  ctypes.c_int, _vp]),
+    "gb_covariance_propagation_filtered": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                                          ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp]),
     "gb_scale_by_degree": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     "gb_synthesis_weighted": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, _vp]),
     "gb_orderwise_filter": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp,

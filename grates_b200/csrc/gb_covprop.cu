@@ -97,7 +97,8 @@ gb_cov_zero_rows(double* __restrict__ St, const int* __restrict__ padrows, int K
 __global__ void __launch_bounds__(128)
 gb_cov_legendre(double* __restrict__ Ut, const double* __restrict__ ct, const double* __restrict__ kn,
                 const double* __restrict__ pmm, const double* __restrict__ ra, const double* __restrict__ rb,
-                const double* __restrict__ rc, int L, int nmin, int row0, int nrows, int nti, int Kg) {
+                const double* __restrict__ rc, int L, int nmin, int row0, int nrows, int nti, int Kg,
+                const double* __restrict__ wn) {
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y;
     if (il >= nrows) return;
@@ -109,10 +110,49 @@ gb_cov_legendre(double* __restrict__ Ut, const double* __restrict__ ct, const do
     double* us = Ut + ((size_t)(2 * m + 1) * nti + it) * Kg * GB_S2_LDB + ic;
     legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int n, double p) {
         if (n < n0) return;
-        const double v = __dmul_rn(p, kn_i[n]);
+        double v = __dmul_rn(p, kn_i[n]);
+        if (wn) v *= wn[n];                       // isotropic filter: F = diag(w_n)
         uc[(size_t)(n - n0) * GB_S2_LDB] = v;
         if (m > 0) us[(size_t)(n - n0) * GB_S2_LDB] = v;
     });
+}
+
+// Filtered covariances: diag(A F Sigma F' A') = diag((A F) Sigma (A F)').  An order-wise filter F only mixes
+// coefficients of one (order, cos|sin) group, so A F keeps the product structure of A with
+//   U'[b][i] = sum_{a in group} W_g[a][b] U[a][i]          (W_g: the group's block of F, reference filter.py:193-222)
+// One thread per parallel, eight output degrees per CTA; the U tile of the group is re-read from L2.
+constexpr int CF_B = 8;
+__global__ void __launch_bounds__(128)
+gb_cov_apply_blocks(const double* __restrict__ Ut, double* __restrict__ Ut2, const double* __restrict__ blocks,
+                    const long long* __restrict__ offsets, int nf, int L, int nmin, int nti, int Kg) {
+    const int k = blockIdx.x;                 // group 2m + cs
+    const int it = blockIdx.y;
+    const int b0 = blockIdx.z * CF_B;
+    const int m = k >> 1, cs = k & 1;
+    if (m >= L || (m == 0 && cs == 1)) return;
+    const int n0 = max(m, nmin);
+    const int cnt = L - n0;
+    if (b0 >= cnt) return;
+    const int g = (m == 0) ? 0 : 2 * m - 1 + cs;          // block index of the filter (filter.py:180-187)
+    const int kf = nf + 1 - m;
+    const double* W = blocks + offsets[g] + (size_t)(n0 - m) * kf + (n0 - m);   // rows / columns of degree >= n0
+    const size_t tile = ((size_t)k * nti + it) * Kg * GB_S2_LDB;
+    const double* u = Ut + tile + threadIdx.x;
+    double acc[CF_B];
+#pragma unroll
+    for (int j = 0; j < CF_B; ++j) acc[j] = 0.0;
+    if (threadIdx.x < GB_S2_LDB) {
+        for (int a = 0; a < cnt; ++a) {
+            const double ua = u[(size_t)a * GB_S2_LDB];
+            const double* wrow = W + (size_t)a * kf + b0;
+#pragma unroll
+            for (int j = 0; j < CF_B; ++j)
+                if (b0 + j < cnt) acc[j] = fma(__ldg(wrow + j), ua, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < CF_B; ++j)
+            if (b0 + j < cnt) Ut2[tile + (size_t)(b0 + j) * GB_S2_LDB + threadIdx.x] = acc[j];
+    }
 }
 
 // sum over the 8 rows of a fragment slab (lanes with equal lane % 4)
@@ -255,6 +295,13 @@ int to_device(T** d, const std::vector<T>& h, cudaStream_t st) {
 
 extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
                                          double* d_out, int flags, void* stream) {
+    return gb_covariance_propagation_filtered(plan, d_sigma, nmin, row0, nrows, d_out, flags, nullptr, nullptr, 0, nullptr,
+                                              stream);
+}
+
+extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
+                                                  double* d_out, int flags, const double* d_blocks,
+                                                  const int64_t* block_offsets, int nf, const double* d_wn, void* stream) {
     const int take_sqrt = flags & GB_COV_SQRT;
     const int symmetric = (flags & GB_COV_SYMMETRIC) ? 1 : 0;
     GB_REQUIRE(plan != nullptr, "gb_covariance_propagation: plan is NULL");
@@ -264,6 +311,8 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
                "gb_covariance_propagation: parallels [%d, %d) outside the grid (%d parallels)", row0, row0 + nrows, p->nlat);
     if (nrows == 0) return GB_OK;
     GB_REQUIRE(d_sigma && d_out, "gb_covariance_propagation: NULL device pointer");
+    GB_REQUIRE(!d_blocks || (block_offsets && nf >= p->nmax),
+               "gb_covariance_propagation_filtered: the order-wise filter (degree %d) does not reach degree %d", nf, p->nmax);
     GB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int L = p->L, kpad = p->kpad;
@@ -368,8 +417,24 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
     {
         dim3 grid((nrows + 127) / 128, L);
         gb_cov_legendre<<<grid, 128, 0, st>>>(d_ut, p->d_ct, p->d_kn, p->d_pmm, p->d_ra, p->d_rb, p->d_rc, L, nmin,
-                                              row0, nrows, nti, Kg);
+                                              row0, nrows, nti, Kg, d_wn);
         GB_LAUNCH_CHECK();
+    }
+    double* d_ut_unfiltered = nullptr;
+    long long* d_boff = nullptr;
+    if (d_blocks) {
+        // U <- F' U group by group (see gb_cov_apply_blocks); the GEMMs below then run on A F
+        const int nblocks = 2 * nf + 1;
+        GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_boff), (nblocks + 1) * sizeof(long long), st));
+        GB_CUDA(cudaMemcpyAsync(d_boff, block_offsets, (nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        double* d_ut2 = nullptr;
+        GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ut2), ut_elems * sizeof(double), st));
+        GB_CUDA(cudaMemsetAsync(d_ut2, 0, ut_elems * sizeof(double), st));
+        dim3 grid(kpad, nti, (Kg + CF_B - 1) / CF_B);
+        gb_cov_apply_blocks<<<grid, 128, 0, st>>>(d_ut, d_ut2, d_blocks, d_boff, nf, L, nmin, nti, Kg);
+        GB_LAUNCH_CHECK();
+        d_ut_unfiltered = d_ut;
+        d_ut = d_ut2;
     }
     {
         gbgemm::Shape sh;
@@ -418,6 +483,8 @@ extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, i
     GB_CUDA(cudaFreeAsync(d_first_nt, st));
     GB_CUDA(cudaFreeAsync(d_st, st));
     GB_CUDA(cudaFreeAsync(d_ut, st));
+    if (d_ut_unfiltered) GB_CUDA(cudaFreeAsync(d_ut_unfiltered, st));
+    if (d_boff) GB_CUDA(cudaFreeAsync(d_boff, st));
     GB_CUDA(cudaFreeAsync(d_ht, st));
     return GB_OK;
 }

@@ -147,13 +147,16 @@ class RegularGrid:
         p.set_analysis(min_degree, self.area.reshape(p.nlat, p.nlon))
         return p.analysis_matrix().cpu().numpy()
 
-    def covariance_propagation(self, covariance_matrix, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+    def covariance_propagation(self, covariance_matrix, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT,
+                               spatial_filter=None):
         """Propagate a degree-wise ordered coefficient covariance matrix to grid-point standard
         deviations, sqrt(diag(A Sigma A')), on the GPU.  Like the reference (grid.py:792-839)
-        this also stores the result in ``self.values`` and returns a 1-d array."""
+        this also stores the result in ``self.values`` and returns a 1-d array.
+        spatial_filter (extension): propagate F Sigma F' for an OrderWiseFilter / Gaussian / Butterworth F
+        without forming the filtered matrix."""
         p = _plan.get_plan(self, max_degree, kernel, GM, R)
         sigma = torch.as_tensor(np.ascontiguousarray(covariance_matrix, dtype=np.float64)).to(torch.device("cuda", p.device))
-        std = p.covariance_propagation(sigma, min_degree).cpu().numpy().ravel()
+        std = p.covariance_propagation(sigma, min_degree, spatial_filter=spatial_filter).cpu().numpy().ravel()
         self.values = std
         return std.copy()
 

@@ -236,11 +236,14 @@ class SHPlan:
         return out
 
     # -- covariance propagation ---------------------------------------------------------
-    def covariance_propagation(self, sigma, min_degree, row0=0, nrows=None, take_sqrt=True, out=None, symmetric=None):
+    def covariance_propagation(self, sigma, min_degree, row0=0, nrows=None, take_sqrt=True, out=None, symmetric=None,
+                               spatial_filter=None):
         """sigma: CUDA tensor [K', K'] (degree-wise order, offset min_degree^2) ->
         [nrows, nlon] standard deviations (or variances) for parallels row0..row0+nrows.
         symmetric: True lets the kernels contract the order-block pairs k <= k' only (half the work);
-        None (default) decides by comparing sigma with its transpose on a sample of entries."""
+        None (default) decides by comparing sigma with its transpose on a sample of entries.
+        spatial_filter: an OrderWiseFilter, Gaussian or Butterworth instance F; the result then is the propagation
+        of F sigma F' (F = spatial_filter.matrix(min_degree, max_degree)) without forming that product."""
         nrows = self.nlat - row0 if nrows is None else nrows
         kp = self.L ** 2 - min_degree ** 2
         if sigma.dim() != 2 or tuple(sigma.shape) != (kp, kp):
@@ -253,10 +256,28 @@ class SHPlan:
         if out is None:
             out = torch.empty((nrows, self.nlon), dtype=torch.float64, device=sigma.device)
         flags = (1 if take_sqrt else 0) | (2 if symmetric else 0)      # GB_COV_SQRT | GB_COV_SYMMETRIC
-        _lib.check(self._lib.gb_covariance_propagation(self._handle, ctypes.c_void_p(sigma.data_ptr()),
-                                                       int(min_degree), int(row0), int(nrows),
-                                                       ctypes.c_void_p(out.data_ptr()), flags,
-                                                       _stream_handle(self.device)))
+        if spatial_filter is None:
+            _lib.check(self._lib.gb_covariance_propagation(self._handle, ctypes.c_void_p(sigma.data_ptr()),
+                                                           int(min_degree), int(row0), int(nrows),
+                                                           ctypes.c_void_p(out.data_ptr()), flags,
+                                                           _stream_handle(self.device)))
+            return out
+        blocks = offsets = wn = None
+        nf = 0
+        if hasattr(spatial_filter, "_blocks_on"):                       # order-wise blocks
+            if spatial_filter.max_degree < self.max_degree:
+                raise ValueError("filter of degree {0} does not reach degree {1}".format(spatial_filter.max_degree, self.max_degree))
+            blocks, offsets, nf = spatial_filter._blocks_on(self.device), spatial_filter._offsets, spatial_filter.max_degree
+        elif hasattr(spatial_filter, "_weights"):                       # isotropic: F = diag(w_n), every degree weighted
+            wn = torch.as_tensor(np.ascontiguousarray(spatial_filter._weights(self.max_degree), dtype=np.float64)).to(sigma.device)
+        else:
+            raise TypeError("spatial_filter must be an OrderWiseFilter, Gaussian or Butterworth instance")
+        _lib.check(self._lib.gb_covariance_propagation_filtered(
+            self._handle, ctypes.c_void_p(sigma.data_ptr()), int(min_degree), int(row0), int(nrows),
+            ctypes.c_void_p(out.data_ptr()), flags,
+            ctypes.c_void_p(blocks.data_ptr()) if blocks is not None else None,
+            offsets.ctypes.data_as(ctypes.c_void_p) if offsets is not None else None, int(nf),
+            ctypes.c_void_p(wn.data_ptr()) if wn is not None else None, _stream_handle(self.device)))
         return out
 
 

@@ -145,6 +145,18 @@ int gb_analysis_matrix(gb_plan* plan, double* d_out, void* stream);
 #define GB_COV_SYMMETRIC 2
 int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
                               double* d_out, int flags, void* stream);
+/*
+ * Propagation of a FILTERED covariance, diag(A F Sigma F' A'), without forming F Sigma F' (the reference
+ * multiplies the dense matrices, F = SpatialFilter.matrix(nmin, nmax), filter.py:72-92, :120-127, :193-222):
+ * a degree-wise or order-wise F keeps the product structure of A, so the filter is applied to the small
+ * Legendre factor instead (K^2-sized products disappear).
+ *   d_blocks / block_offsets / nf   order-wise blocks as for gb_orderwise_filter, or NULL
+ *   d_wn [nmax+1]                   degree weights of an isotropic filter, or NULL
+ * Both may be given (F = diag(w) * F_blocks: the blocks act first).
+ */
+int gb_covariance_propagation_filtered(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
+                                       double* d_out, int flags, const double* d_blocks,
+                                       const int64_t* block_offsets, int nf, const double* d_wn, void* stream);
 
 /*
  * Isotropic (degree-wise) filters: Gaussian and Butterworth, filter.py:31-130, scale every

@@ -332,6 +332,33 @@ def test_covariance_vs_oracle_and_row_blocks(gb, orc):
     assert maxnorm_err(full, ref) < TOL and maxnorm_err(half, ref) < TOL
 
 
+def test_filtered_covariance_propagation(gb, orc):
+    """diag(A F S F' A') with the filter applied to the Legendre factor must equal the reference's way:
+    F = filter.matrix(nmin, nmax) (filter.py:72-92, :193-222), S_f = F S F', then grid.py:792-839."""
+    N = 18
+    sigma = orc.synthetic_covariance(N, rank=16)
+    grid = gb.GeographicGrid(6.0, 6.0)
+    og = orc.geographic_grid(6.0, 6.0)
+    blocks = orc.synthetic_filter_blocks(24)                    # filter reaches beyond the field's degree
+    flt = gb.OrderWiseFilter(blocks)
+    for nmin in (0, 2):
+        F = orc.orderwise_filter_matrix(blocks, nmin, N)
+        np.testing.assert_array_equal(F, flt.matrix(nmin, N))
+        s = sigma[nmin * nmin:, nmin * nmin:]
+        ref = orc.covariance_propagation(F @ s @ F.T, og, nmin, N, "ewh")
+        std = gb.GeographicGrid(6.0, 6.0).covariance_propagation(s, nmin, N, "ewh", spatial_filter=flt)
+        assert maxnorm_err(std, ref) < TOL
+    for iso in (gb.Gaussian(400.0), gb.Butterworth(3, 10)):
+        D = iso.matrix(0, N)
+        ref = orc.covariance_propagation(D @ sigma @ D.T, og, 0, N, "ewh")
+        std = grid.covariance_propagation(sigma, 0, N, "ewh", spatial_filter=iso)
+        assert maxnorm_err(std, ref) < TOL
+    with pytest.raises(ValueError):
+        grid.covariance_propagation(sigma, 0, N, "ewh", spatial_filter=gb.OrderWiseFilter(orc.synthetic_filter_blocks(10)))
+    with pytest.raises(TypeError):
+        grid.covariance_propagation(sigma, 0, N, "ewh", spatial_filter=object())
+
+
 def test_covariance_nonsymmetric_matrix_uses_full_path(gb, orc):
     """diag(F S F') only sees the symmetric part of S; a visibly non-symmetric S must be detected and
     propagated with the full matrix (the reference multiplies whatever it is given, grid.py:833-835)."""
