@@ -104,3 +104,105 @@ extern "C" int gb_weighted_moments(const double* d_values, const double* d_weigh
     GB_CUDA(cudaFreeAsync(d_partial, st));
     return GB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Basin (functional) variances  var_b = a_b' Sigma a_b  for a handful of coefficient-space functionals
+// a_b (the area-weighted basin mean of a synthesised field is a linear functional of the coefficients,
+// a_b = A' w_b; the adjoint synthesis A' w runs through the analysis kernels with adjoint operators).
+//   gb_ravel_coefficients   packed [B][L][L] -> degree-wise vectors [B][K'] (reference utilities.py:310-360)
+//   gb_quadratic_forms      var_b = sum_r a_b[r] (sum_c Sigma[r][c] a_b[c]): one warp per row of Sigma,
+//                           Sigma is read once (HBM-bound: 708 MB at degree 96), the vectors stay in L2
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256)
+gb_ravel_kernel(const double* __restrict__ anm, double* __restrict__ vec, int L, int nmin, long long K, int B) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * B) return;
+    const int b = (int)(idx / K);
+    const long long c = idx - (long long)b * K + (long long)nmin * nmin;     // degree-wise index from degree 0
+    const int n = (int)floor(sqrt((double)c));
+    int nn = n;
+    if ((long long)nn * nn > c) --nn;
+    if ((long long)(nn + 1) * (nn + 1) <= c) ++nn;
+    const int j = (int)(c - (long long)nn * nn);                              // 0: C_n0, 2m-1: C_nm, 2m: S_nm
+    const int m = (j + 1) >> 1;
+    const bool sine = j > 0 && (j & 1) == 0;
+    const double* a = anm + (size_t)b * L * L;
+    vec[idx] = sine ? a[(size_t)(m - 1) * L + nn] : a[(size_t)nn * L + m];
+}
+
+constexpr int QF_B = 8;    // functionals per pass
+
+__global__ void __launch_bounds__(256)
+gb_quadratic_forms_kernel(const double* __restrict__ sigma, const double* __restrict__ vec, long long K, int b0, int nb,
+                          double* __restrict__ out) {
+    __shared__ double s_part[8][QF_B];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double tot[QF_B];
+#pragma unroll
+    for (int b = 0; b < QF_B; ++b) tot[b] = 0.0;
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < K; r += (long long)gridDim.x * 8) {
+        const double* row = sigma + (size_t)r * K;
+        double acc[QF_B];
+#pragma unroll
+        for (int b = 0; b < QF_B; ++b) acc[b] = 0.0;
+        for (long long c = lane; c < K; c += 32) {
+            const double s = row[c];
+#pragma unroll
+            for (int b = 0; b < QF_B; ++b)
+                if (b < nb) acc[b] = fma(s, __ldg(vec + (size_t)(b0 + b) * K + c), acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < QF_B; ++b) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], off);
+            if (b < nb) tot[b] = fma(acc[b], vec[(size_t)(b0 + b) * K + r], tot[b]);
+        }
+    }
+    if (lane == 0)
+        for (int b = 0; b < QF_B; ++b) s_part[warp][b] = tot[b];
+    __syncthreads();
+    if (threadIdx.x < nb) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+        atomicAdd(out + b0 + threadIdx.x, t);
+    }
+}
+
+}  // namespace
+
+extern "C" int gb_ravel_coefficients(const double* d_anm, int n_sets, int nmax, int nmin, double* d_vec, int device,
+                                     void* stream) {
+    GB_REQUIRE(n_sets >= 0 && nmax >= 0 && nmin >= 0 && nmin <= nmax, "gb_ravel_coefficients: bad degree range");
+    if (n_sets == 0) return GB_OK;
+    GB_REQUIRE(d_anm && d_vec, "gb_ravel_coefficients: NULL pointer");
+    GB_CUDA(cudaSetDevice(device));
+    const int L = nmax + 1;
+    const long long K = (long long)L * L - (long long)nmin * nmin;
+    const long long total = K * n_sets;
+    gb_ravel_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_anm, d_vec, L, nmin,
+                                                                                                   K, n_sets);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}
+
+extern "C" int gb_quadratic_forms(const double* d_sigma, int64_t k, const double* d_vec, int n_vec, double* d_out,
+                                  int device, void* stream) {
+    GB_REQUIRE(k >= 0 && n_vec >= 0, "gb_quadratic_forms: negative size");
+    if (n_vec == 0) return GB_OK;
+    GB_REQUIRE(d_sigma && d_vec && d_out, "gb_quadratic_forms: NULL pointer");
+    GB_CUDA(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_vec * sizeof(double), st));
+    if (k == 0) return GB_OK;
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int grid = (int)((k + 7) / 8 < (long long)prop.multiProcessorCount * 8 ? (k + 7) / 8 : prop.multiProcessorCount * 8);
+    for (int b0 = 0; b0 < n_vec; b0 += QF_B) {
+        const int nb = n_vec - b0 < QF_B ? n_vec - b0 : QF_B;
+        gb_quadratic_forms_kernel<<<grid, 256, 0, st>>>(d_sigma, d_vec, k, b0, nb, d_out);
+        GB_LAUNCH_CHECK();
+    }
+    return GB_OK;
+}

@@ -256,6 +256,46 @@ class GaussGrid(RegularGrid):
         return grid
 
 
+def basin_variances(covariance_matrix, grid, masks, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT,
+                    R=R_DEFAULT, take_sqrt=True):
+    """Standard deviations of the area-weighted basin means of a field with coefficient covariance Sigma:
+    sqrt(w_b' A Sigma A' w_b), w_b = area * mask_b / sum(area * mask_b), A the synthesis operator of the grid
+    (reference: Grid.mean, grid.py:174-201, of fields synthesised with grid.py:412-443).  The adjoint synthesis
+    A' w_b and the quadratic forms run on the GPU; A is never formed.
+    masks: boolean (or weight) array [B, points] or [B, nlat, nlon]; returns [B]."""
+    import ctypes
+    from . import _lib
+    p = _plan.get_plan(grid, max_degree, kernel, GM, R, variant='adjoint')
+    p.set_adjoint(min_degree)
+    masks = np.asarray(masks)
+    masks = masks.reshape(masks.shape[0], -1) if masks.ndim > 1 else masks.reshape(1, -1)
+    if masks.shape[1] != grid.point_count:
+        raise ValueError("masks must have one entry per grid point")
+    w = masks.astype(float) * np.asarray(grid.area, dtype=float).reshape(1, -1)
+    norm = w.sum(axis=1, keepdims=True)
+    if np.any(norm == 0):
+        raise ValueError("empty basin mask")
+    w = np.ascontiguousarray(w / norm).reshape(masks.shape[0], p.nlat, p.nlon)
+    dev = torch.device("cuda", p.device)
+    functionals = p.analysis(torch.as_tensor(w).to(dev))                      # [B, L, L] packed A' w_b
+    sigma = covariance_matrix if isinstance(covariance_matrix, torch.Tensor) else \
+        torch.as_tensor(np.ascontiguousarray(covariance_matrix, dtype=np.float64)).to(dev)
+    k = (max_degree + 1) ** 2 - min_degree ** 2
+    if tuple(sigma.shape) != (k, k):
+        raise ValueError("covariance matrix must have shape [{0}, {0}] (got {1})".format(k, tuple(sigma.shape)))
+    sigma = sigma.contiguous()
+    B = masks.shape[0]
+    vec = torch.empty((B, k), dtype=torch.float64, device=dev)
+    var = torch.empty(B, dtype=torch.float64, device=dev)
+    lib, st = _lib.load(), _plan._stream_handle(p.device)
+    _lib.check(lib.gb_ravel_coefficients(ctypes.c_void_p(functionals.data_ptr()), B, max_degree, min_degree,
+                                         ctypes.c_void_p(vec.data_ptr()), p.device, st))
+    _lib.check(lib.gb_quadratic_forms(ctypes.c_void_p(sigma.data_ptr()), k, ctypes.c_void_p(vec.data_ptr()), B,
+                                      ctypes.c_void_p(var.data_ptr()), p.device, st))
+    var = var.cpu().numpy()
+    return np.sqrt(var) if take_sqrt else var
+
+
 def analysis_batch(values, grid, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT, device_output=False):
     """Batched analysis: values [E, nlat, nlon] (numpy or CUDA tensor) -> packed anm [E, L, L].
     New entry point (the reference loops over epochs and rebuilds its operators every call)."""

@@ -189,6 +189,20 @@ class SHPlan:
         self._analysis_nmin = key
         self.analysis_min_degree = int(min_degree)
 
+    def set_adjoint(self, min_degree):
+        """Load the ADJOINT of the synthesis operator into the analysis slots of this plan: afterwards
+        ``analysis(w)`` returns A' w (packed), A being the synthesis matrix of reference grid.py:412-443.
+        Longitude operator = the trig table itself, latitude operator of order m = (kn * P_nm)'.  Used for
+        functionals of gridded fields (basin means); keep such a plan separate from one used for analysis."""
+        key = ("adjoint", int(min_degree))
+        if self._analysis_nmin == key:
+            return
+        lon_ops, lat_ops, offsets = adjoint_operators(self, int(min_degree))
+        _lib.check(self._lib.gb_plan_set_analysis(self._handle, int(min_degree), _ptr(lon_ops), _ptr(lat_ops),
+                                                  _ptr(offsets)))
+        self._analysis_nmin = key
+        self.analysis_min_degree = int(min_degree)
+
     def analysis(self, values, out=None):
         """values: CUDA tensor [E, nlat, nlon] -> packed coefficients [E, L, L] (CUDA)."""
         if self._analysis_nmin is None:
@@ -343,6 +357,25 @@ def _legendre_per_order_host(nmax, m, colat):
     return out
 
 
+def adjoint_operators(plan, min_degree):
+    """Operators that make the analysis kernels compute A' w (see SHPlan.set_adjoint)."""
+    L, nlon, nlat = plan.L, plan.nlon, plan.nlat
+    lam = plan.meridians
+    lon_ops = np.zeros((2 * L, nlon))
+    for m in range(L):
+        lon_ops[2 * m] = np.cos(m * lam)
+        if m > 0:
+            lon_ops[2 * m + 1] = np.sin(m * lam)
+    blocks, offsets = [], np.zeros(L + 1, dtype=np.int64)
+    for m in range(L):
+        P = (_legendre_per_order_host(plan.max_degree, m, plan.colat) * plan.kn[:, m:])[:, max(min_degree - m, 0):]
+        op = np.ascontiguousarray(P.T) if P.shape[1] else np.zeros((0, nlat))
+        blocks.append(op.ravel())
+        offsets[m + 1] = offsets[m] + op.size
+    lat_ops = np.concatenate(blocks) if offsets[-1] > 0 else np.zeros(1)
+    return np.ascontiguousarray(lon_ops), np.ascontiguousarray(lat_ops), offsets
+
+
 def analysis_operators(plan, min_degree, w_lat, u_lon):
     """Host construction of the separable analysis operators (see gb_plan_set_analysis)."""
     L, nlon, nlat = plan.L, plan.nlon, plan.nlat
@@ -461,8 +494,9 @@ def is_regular(grid):
     return hasattr(grid, "parallels") and hasattr(grid, "meridians")
 
 
-def get_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
-    """Cached plan for a regular grid object exposing .meridians/.parallels/.semimajor_axis/.flattening."""
+def get_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000e+06, device=None, variant=''):
+    """Cached plan for a regular grid object exposing .meridians/.parallels/.semimajor_axis/.flattening.
+    variant: extra cache key for plans whose analysis slots hold other operators (the adjoint)."""
     try:
         meridians, parallels = grid.meridians, grid.parallels
     except AttributeError:
@@ -470,7 +504,8 @@ def get_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000
                                   "entry points for irregular grids -- there is no CPU fallback") from None
     dev = _current_device(device)
     key = (np.asarray(meridians, dtype=float).tobytes(), np.asarray(parallels, dtype=float).tobytes(),
-           float(grid.semimajor_axis), float(grid.flattening), int(max_degree), kernel.lower(), float(GM), float(R), dev)
+           float(grid.semimajor_axis), float(grid.flattening), int(max_degree), kernel.lower(), float(GM), float(R), dev,
+           variant)
     with _cache_lock:
         plan = _cache.get(key)
         if plan is None:

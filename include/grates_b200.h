@@ -214,6 +214,20 @@ int gb_temporal_rms(const double* d_values, int n_epochs, int64_t n_points, doub
 int gb_weighted_moments(const double* d_values, const double* d_weights, const double* d_shift,
                         int n_epochs, int64_t n_points, double* d_out, int device, void* stream);
 
+/*
+ * Variances of linear functionals of the coefficients (basin means): var_b = a_b' Sigma a_b.
+ *   gb_ravel_coefficients   packed d_anm [n_sets][L][L] -> degree-wise vectors d_vec [n_sets][K'],
+ *                           K' = (nmax+1)^2 - nmin^2 (reference utilities.py:310-360)
+ *   gb_quadratic_forms      d_out[b] = d_vec[b]' * d_sigma * d_vec[b]  for n_vec vectors of length k;
+ *                           d_sigma [k][k] row-major is read once per eight vectors
+ * The functional of an area-weighted basin mean is a_b = A' w_b (A: synthesis operator of
+ * grid.py:412-443); A' runs through gb_analysis with adjoint operators (grates_b200/plan.py: set_adjoint).
+ */
+int gb_ravel_coefficients(const double* d_anm, int n_sets, int nmax, int nmin, double* d_vec, int device,
+                          void* stream);
+int gb_quadratic_forms(const double* d_sigma, int64_t k, const double* d_vec, int n_vec, double* d_out,
+                       int device, void* stream);
+
 /* Pinned host memory for the *_host entry points. */
 int gb_host_alloc(void** ptr, uint64_t bytes);
 int gb_host_free(void* ptr);

@@ -532,6 +532,23 @@ def covariance_propagation_points(sigma, lon, lat, nmin, nmax, kernel='potential
 # --------------------------------------------------------------------------------------
 # Order-wise block filter
 # --------------------------------------------------------------------------------------
+def basin_variances(sigma, grid, masks, nmin, nmax, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+    """Variances of area-weighted basin means (Grid.mean, grid.py:174-201) of a field with coefficient covariance
+    sigma: w' A sigma A' w with the synthesis operator A built column by column from unit coefficient sets
+    (Grid.synthesis_matrix, grid.py:412-443, degree-wise columns from nmin)."""
+    K = (nmax + 1) ** 2 - nmin ** 2
+    A = np.empty((grid.shape[0] * grid.shape[1], K))
+    for c in range(K):
+        unit = np.zeros(K)
+        unit[c] = 1.0
+        A[:, c] = synthesis(unravel_coefficients(unit, nmin, nmax), grid, kernel, GM, R).ravel()
+    masks = np.asarray(masks, dtype=float).reshape(len(masks), -1)
+    w = masks * np.asarray(grid.areas).reshape(1, -1)
+    w = w / w.sum(axis=1, keepdims=True)
+    f = w @ A
+    return np.einsum('bi,ij,bj->b', f, sigma, f)
+
+
 def orderwise_filter(blocks, anm):
     """OrderWiseFilter.filter on a packed array (filter.py:175-191).  blocks[0]: order 0;
     blocks[2m-1], blocks[2m]: cosine / sine block of order m, each [(Nf+1-m), (Nf+1-m)]."""

@@ -332,6 +332,31 @@ def test_covariance_vs_oracle_and_row_blocks(gb, orc):
     assert maxnorm_err(full, ref) < TOL and maxnorm_err(half, ref) < TOL
 
 
+def test_basin_variances(gb, orc):
+    """Variance of area-weighted basin means, w' A S A' w: adjoint synthesis through the analysis kernels,
+    device ravel, batched quadratic forms; against the dense oracle."""
+    N = 12
+    sigma = orc.synthetic_covariance(N, rank=12)
+    grid, og = gb.GeographicGrid(10.0, 10.0), orc.geographic_grid(10.0, 10.0)
+    rng = np.random.default_rng(21)
+    masks = rng.uniform(size=(11, grid.point_count)) < 0.25        # more than eight: two passes over Sigma
+    masks[0, :] = True
+    for nmin in (0, 2):
+        s = sigma[nmin * nmin:, nmin * nmin:]
+        ref = orc.basin_variances(s, og, masks, nmin, N, "ewh")
+        var = gb.basin_variances(s, grid, masks, nmin, N, "ewh", take_sqrt=False)
+        assert maxnorm_err(var, ref) < TOL
+        std = gb.basin_variances(torch.as_tensor(s).cuda(), grid, masks.reshape(11, 18, 36), nmin, N, "ewh")
+        assert maxnorm_err(std, np.sqrt(ref)) < TOL
+    # the functional of the global mean is the degree-0 term only (up to the ellipsoidal factors)
+    vec = gb.utilities.ravel_coefficients(np.arange(169.0).reshape(13, 13))
+    with pytest.raises(ValueError):
+        gb.basin_variances(sigma, grid, np.zeros((1, grid.point_count), dtype=bool), 0, N, "ewh")
+    with pytest.raises(ValueError):
+        gb.basin_variances(sigma[:-1, :-1], grid, masks, 0, N, "ewh")
+    assert vec.shape == (169,)
+
+
 def test_filtered_covariance_propagation(gb, orc):
     """diag(A F S F' A') with the filter applied to the Legendre factor must equal the reference's way:
     F = filter.matrix(nmin, nmax) (filter.py:72-92, :193-222), S_f = F S F', then grid.py:792-839."""
