@@ -80,7 +80,7 @@ struct LatOperandStore {
     const int* kmap;
     int E, n_ct, nlat_p4;
     struct Pre { int i[4], e[4]; };
-    __device__ __forceinline__ Pre prepare(long long row_base) const {
+    __device__ __forceinline__ Pre prepare(long long row_base, int, int) const {
         Pre pr;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
@@ -118,7 +118,7 @@ struct CoefficientStore {
     const int* tile_n;
     int L, E;
     struct Pre { int m, n; };
-    __device__ __forceinline__ Pre prepare(long long row_base) const {
+    __device__ __forceinline__ Pre prepare(long long row_base, int, int) const {
         const int t = (int)(row_base >> 7);
         return Pre{tile_m[t], tile_n[t] + (int)(row_base & 127)};
     }

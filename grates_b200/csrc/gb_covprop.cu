@@ -174,71 +174,73 @@ struct QuadEpilogue {
     const int* goff8;        // [kpad] first a' of each group
     int nti, Kg, kpad, hmt, nrows;
     int symmetric;           // only group pairs k <= k' are kept, the off-diagonal ones counted twice
-    __device__ __forceinline__ void flush(int k, int kprime, int i, double s0, double s1) const {
-        if (k < 0) return;                                   // warp-uniform
-        if (symmetric) {
-            if (k > kprime) return;
-            if (k < kprime) { s0 += s0; s1 += s1; }
-        }
-        s0 = slab_sum(s0);
-        s1 = slab_sum(s1);
-        if ((threadIdx.x & 31) < 4) {
-            double* h = Ht + (((size_t)i * hmt + (k >> 7)) * kpad + kprime) * GB_LDA + (k & 127);
-            if (i < nrows) atomicAdd(h, s0);
-            if (i + 1 < nrows) atomicAdd(h + (size_t)hmt * kpad * GB_LDA, s1);
-        }
-    }
     struct Pre {
         int kslab[4];          // group of each of the thread's four 8-row slabs (uniform over the warp), -1: padding
         int uoff[4];           // offset of the slab's row inside the U tiles of its group (checked on the host)
+        int kprime, i0;        // column group of the tile, first parallel of this thread (column pair i0, i0 + 1)
     };
-    __device__ __forceinline__ Pre prepare(long long row_base) const {
+    __device__ __forceinline__ Pre prepare(long long row_base, int nt, int col_base) const {
         Pre pr;
+        const int it = nt % nti;
+        pr.kprime = nt / nti;
+        const int cc = col_base - nt * GB_S2_TN;              // column of the thread inside the tile (even)
+        pr.i0 = it * GB_S2_TN + cc;
+        const int ubase = it * Kg * GB_S2_LDB + cc;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             const long long row = row_base + mi * 8;
             const int k = rowgroup[row >> 3];
             pr.kslab[mi] = k;
-            pr.uoff[mi] = k >= 0 ? (k * nti * Kg + (int)(row - goff8[k])) * GB_S2_LDB : 0;
+            pr.uoff[mi] = k >= 0 ? ubase + (k * nti * Kg + (int)(row - goff8[k])) * GB_S2_LDB : 0;
         }
+        // the row-side factors are needed after the K loop: start pulling them into L1 now
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+            if (pr.kslab[mi] >= 0) {
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(Ut + pr.uoff[mi] + ni * 8));
+            }
         return pr;
     }
-    __device__ __forceinline__ void tile(const Pre& pr, long long row_base, int col_base, double (&acc)[4][5][2]) const {
+    __device__ __forceinline__ void tile(const Pre& pr, long long, int, double (&acc)[4][5][2]) const {
         // 1. multiply by the row-side factor in place: twenty independent loads in flight, no extra registers
 #pragma unroll
-        for (int ni = 0; ni < 5; ++ni) {
-            const int col = col_base + ni * 8;
-            const int nt = col / GB_S2_TN, cc = col % GB_S2_TN;
-            const double* ucol = Ut + (size_t)(nt % nti) * Kg * GB_S2_LDB + cc;       // cc is even: 16-byte aligned
+        for (int mi = 0; mi < 4; ++mi) {
+            if (pr.kslab[mi] < 0) continue;                    // warp-uniform
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                if (pr.kslab[mi] >= 0) {
-                    const double2 u = __ldg(reinterpret_cast<const double2*>(ucol + pr.uoff[mi]));
-                    acc[mi][ni][0] *= u.x;
-                    acc[mi][ni][1] *= u.y;
-                }
+            for (int ni = 0; ni < 5; ++ni) {
+                const double2 u = __ldg(reinterpret_cast<const double2*>(Ut + pr.uoff[mi] + ni * 8));   // 16-byte aligned
+                acc[mi][ni][0] *= u.x;
+                acc[mi][ni][1] *= u.y;
             }
         }
-        // 2. sum the slabs of one group in the thread, reduce across the slab, add to H
+        // 2. every run of slabs with one group: sum in the thread, reduce across the slab, add to H
 #pragma unroll
-        for (int ni = 0; ni < 5; ++ni) {
-            const int col = col_base + ni * 8;
-            const int nt = col / GB_S2_TN, cc = col % GB_S2_TN;
-            const int kprime = nt / nti, it = nt % nti;
-            const int i = it * GB_S2_TN + cc;
-            double s0 = 0.0, s1 = 0.0;
+        for (int head = 0; head < 4; ++head) {
+            const int k = pr.kslab[head];
+            if (k < 0 || (head > 0 && k == pr.kslab[head - 1])) continue;     // padding, or not the first slab of its run
+            if (symmetric && k > pr.kprime) continue;
+            const double scale = (symmetric && k < pr.kprime) ? 2.0 : 1.0;
+            double* h = Ht + (((size_t)pr.i0 * hmt + (k >> 7)) * kpad + pr.kprime) * GB_LDA + (k & 127);
+            const size_t hstep = (size_t)hmt * kpad * GB_LDA;                 // to the next parallel
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                if (mi > 0 && pr.kslab[mi] != pr.kslab[mi - 1]) {
-                    flush(pr.kslab[mi - 1], kprime, i, s0, s1);
-                    s0 = s1 = 0.0;
-                }
-                if (pr.kslab[mi] >= 0) {
-                    s0 += acc[mi][ni][0];
-                    s1 += acc[mi][ni][1];
+            for (int ni = 0; ni < 5; ++ni) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int mi = head; mi < 4; ++mi)
+                    if (pr.kslab[mi] == k) {
+                        s0 += acc[mi][ni][0];
+                        s1 += acc[mi][ni][1];
+                    }
+                s0 = slab_sum(s0) * scale;
+                s1 = slab_sum(s1) * scale;
+                if ((threadIdx.x & 31) < 4) {
+                    const int i = pr.i0 + ni * 8;
+                    if (i < nrows) atomicAdd(h + (size_t)(ni * 8) * hstep, s0);
+                    if (i + 1 < nrows) atomicAdd(h + (size_t)(ni * 8 + 1) * hstep, s1);
                 }
             }
-            flush(pr.kslab[3], kprime, i, s0, s1);
         }
     }
 };
@@ -250,7 +252,7 @@ struct LonEpilogue {
     const double* trig;      // [kpad][nlp]
     double* var;             // [nrows][nlon]
     int hmt, kpad, nlp, nlon;
-    __device__ __forceinline__ int prepare(long long) const { return 0; }
+    __device__ __forceinline__ int prepare(long long, int, int) const { return 0; }
     __device__ __forceinline__ void tile(int, long long row_base, int col_base, double (&acc)[4][5][2]) const {
         const int mt = (int)(row_base >> 7);
         const int i = mt / hmt;

@@ -16,9 +16,9 @@
 // inputs.  The epilogue functor receives accumulator pairs (row, col, col+1); an epilogue that
 // declares `static constexpr bool whole_tile = true` gets the warp's 32 x 40 register tile at once
 // (`tile(row_base, col_base, acc)`, rows row_base + 8 mi, columns col_base + 8 ni + {0, 1}) so that it
-// can reduce inside the thread before it touches shuffles or atomics; its `prepare(row_base)` runs
-// before the K loop (index look-ups whose latency then hides behind the tile's DMMAs) and its result
-// is handed back to `tile`.
+// can reduce inside the thread before it touches shuffles or atomics; its `prepare(row_base, nt, col_base)`
+// runs before the K loop (index look-ups and prefetches whose latency then hides behind the tile's DMMAs)
+// and its result is handed back to `tile`.
 #pragma once
 #include <type_traits>
 #include "gb_common.cuh"
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
             const long long row_base = mt * TM + wm * 32 + g;
             const int col_base = nt * TN + wn * 40 + 2 * q;
             auto pre = [&] {
-                if constexpr (wants_whole_tile<Epilogue>::value) return epi.prepare(row_base);
+                if constexpr (wants_whole_tile<Epilogue>::value) return epi.prepare(row_base, nt, col_base);
                 else return 0;
             }();
             for (int k0 = 0; k0 < klen; k0 += KC) {
