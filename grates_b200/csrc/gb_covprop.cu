@@ -58,10 +58,10 @@ gb_cov_permute(const double* __restrict__ sigma, double* __restrict__ St, const 
     St[gb_ab_offset(a, b, Kp4)] = (pa < 0 || pb < 0) ? 0.0 : sigma[(size_t)pa * K + pb];
 }
 
-// The same permutation, one CTA per (64 rows a', degree n of the columns): the 2n+1 columns of a degree
-// are contiguous in the degree-wise order, so Sigma is read in row segments and St written in 512-byte
+// The same permutation, one CTA per (32 rows a', degree n of the columns): the 2n+1 columns of a degree
+// are contiguous in the degree-wise order, so Sigma is read in row segments and St written in 256-byte
 // runs (the element-wise gather above fetches a 32-byte sector per double).
-constexpr int CP_ROWS = 64;
+constexpr int CP_ROWS = 32;
 __global__ void __launch_bounds__(256)
 gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St, const int* __restrict__ perm8,
                       const int* __restrict__ goff4, int Kp4, long long K, int nmin) {
@@ -82,8 +82,8 @@ gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St,
         const int k = (j == 0) ? 0 : 2 * m + ((j & 1) ? 0 : 1);          // j = 2m-1: cos, j = 2m: sin
         const int b = goff4[k] + n - max(m, nmin);
         double* dst = St + ((size_t)(a0 >> 7) * Kp4 + b) * GB_LDA + (a0 & (GB_TM - 1));
-        dst[lane] = s_p[lane * width + j];
-        dst[lane + 32] = s_p[(lane + 32) * width + j];
+#pragma unroll
+        for (int r = lane; r < CP_ROWS; r += 32) dst[r] = s_p[r * width + j];
     }
 }
 
