@@ -203,11 +203,80 @@ def config5(pk):
                              "sample": "2 of 500 epochs (filter + to_grid, cost linear in epochs)"}}
 
 
+def widened(pk):
+    """Rows of SURVEY 8(f) built so far, at config-2 / config-4 sizes: isotropic filter fused into the synthesis,
+    device-resident consumers, filtered covariance propagation, basin variances."""
+    N, d, E = 96, 0.5, 240
+    grid, og = gb.GeographicGrid(d, d), orc.geographic_grid(d, d)
+    plan = gb.get_plan(grid, N, "ewh")
+    P = plan.nlat * plan.nlon
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    x = torch.as_tensor(anm).cuda()
+    v = torch.empty((E, plan.nlat, plan.nlon), dtype=torch.float64, device="cuda")
+    flt = gb.Gaussian(300.0)
+    w = torch.as_tensor(flt.degree_weights(N)).cuda()
+    ms_plain = ev_time(lambda: plan.synthesis(x, out=v))
+    ms_fused = ev_time(lambda: plan.synthesis(x, out=v, degree_weights=w))
+    t0 = time.perf_counter()
+    ref = orc.synthesis(orc.degreewise_filter(anm[3], orc.gauss_weights(300.0, N), 2), og, "ewh")
+    cpu_syn = time.perf_counter() - t0
+    par_fused = err(v[3].cpu().numpy(), ref)
+    # consumers on the device
+    mask = np.random.default_rng(2).uniform(size=P) < 0.2
+    mask_d = torch.as_tensor(mask).cuda()
+    ms_stats = ev_time(lambda: gb.grid_statistics(v, grid, mask_d), reps=3, warm=1)
+    st = gb.grid_statistics(v, grid, mask)
+    g1 = grid.copy()
+    g1.values = v[5].cpu().numpy().ravel()
+    t0 = time.perf_counter()
+    cpu_stats = (g1.mean(mask), g1.rms(mask), g1.std(mask))
+    cpu_stats_s = time.perf_counter() - t0
+    par_stats = max(abs(st["mean"][5] - cpu_stats[0]), abs(st["rms"][5] - cpu_stats[1]), abs(st["std"][5] - cpu_stats[2])) / abs(cpu_stats[1])
+    rms = torch.empty(P, dtype=torch.float64, device="cuda")
+    import ctypes
+    lib = gb._lib.load()
+    vv = v.reshape(E, -1)
+    ms_rms = ev_time(lambda: gb._lib.check(lib.gb_temporal_rms(ctypes.c_void_p(vv.data_ptr()), E, P, ctypes.c_void_p(rms.data_ptr()),
+                                                               0, gb.plan._stream_handle(0))))
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+    # covariance side
+    sig_h = orc.synthetic_covariance(N)
+    sigma = torch.as_tensor(sig_h).cuda()
+    out = torch.empty((plan.nlat, plan.nlon), dtype=torch.float64, device="cuda")
+    blocks = orc.synthetic_filter_blocks(N)
+    of = gb.OrderWiseFilter(blocks)
+    ms_cov = ev_time(lambda: plan.covariance_propagation(sigma, 0, out=out), reps=3, warm=1)
+    ms_cov_f = ev_time(lambda: plan.covariance_propagation(sigma, 0, out=out, spatial_filter=of), reps=3, warm=1)
+    masks = np.random.default_rng(3).uniform(size=(16, P)) < 0.05
+    t0 = time.perf_counter()
+    gb.basin_variances(sigma, grid, masks, 0, N, "ewh")           # builds the adjoint operators (host, once)
+    first_call = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    std = gb.basin_variances(sigma, grid, masks, 0, N, "ewh")
+    basin_s = time.perf_counter() - t0
+    K = (N + 1) ** 2
+    return {"config": "f-rows at config-2/4 sizes (N=96, 0.5deg, 240 epochs / K=9409)",
+            "synthesis_ms": ms_plain, "synthesis_with_fused_gaussian_ms": ms_fused,
+            "parity_fused_gaussian": par_fused,
+            "grid_statistics_ms_3_moments_240_epochs": ms_stats,
+            "grid_statistics_gbs": 2.0 * E * P * 8 / ms_stats / 1e6,
+            "grid_statistics_parity_vs_host_formulas": par_stats,
+            "temporal_rms_ms": ms_rms, "temporal_rms_gbs": E * P * 8 / ms_rms / 1e6,
+            "temporal_rms_frac_hbm_peak": (E * P * 8 / ms_rms / 1e6 / hbm) if hbm else None,
+            "covprop_ms": ms_cov, "covprop_with_orderwise_filter_ms": ms_cov_f,
+            "reference_way_for_filtered_covprop": "F Sigma F' dense: 2 * 2 K^3 = %.1f TFLOP before the propagation" % (4.0 * K ** 3 / 1e12),
+            "basin_variances_16_basins_s": basin_s, "basin_variances_first_call_s_incl_operator_build": first_call,
+            "basin_std_range": [float(std.min()), float(std.max())],
+            "cpu_baseline": {"synthesis_one_epoch_s": cpu_syn, "grid_statistics_one_epoch_s": cpu_stats_s,
+                             "cores": blas_threads(), "kind": "port"}}
+
+
 def main():
     torch.cuda.set_device(0)
     pk = peak()
-    which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
-    fns = {"c1": config1, "c3": config3, "c4": config4, "c5": config5}
+    which = sys.argv[1:] or ["c1", "c3", "c4", "c5", "f"]
+    fns = {"c1": config1, "c3": config3, "c4": config4, "c5": config5, "f": widened}
     for name in which:
         line = fns[name](pk)
         line["fp64_peak_tflops_measured_live"] = pk

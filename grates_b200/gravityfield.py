@@ -274,14 +274,18 @@ def grid_statistics(values, grid, mask=None):
     v = v.reshape(v.shape[0], -1)
     if v.dtype != torch.float64 or v.shape[1] != grid.point_count:
         raise ValueError("values must be float64 with {0} points per epoch (got {1})".format(grid.point_count, tuple(v.shape)))
-    w = np.array(grid.area, dtype=float).reshape(-1) if grid.area is not None else np.ones(grid.point_count)
+    # weights = area element * mask, formed on the device (the area table is cached per grid object and device)
+    cache = grid.__dict__.setdefault("_gb_area_on_device", {})
+    if dev not in cache:
+        area = np.array(grid.area, dtype=float).reshape(-1) if grid.area is not None else np.ones(grid.point_count)
+        cache[dev] = torch.as_tensor(area).to(v.device)
+    wd = cache[dev]
     if mask is not None:
-        mask = np.asarray(mask, dtype=bool).reshape(-1)
-        if mask.size != grid.point_count:
+        mask = mask if isinstance(mask, torch.Tensor) else torch.as_tensor(np.asarray(mask, dtype=bool).reshape(-1))
+        if mask.numel() != grid.point_count:
             raise ValueError("mask must have one entry per grid point")
-        w = np.where(mask, w, 0.0)
-    s0 = float(np.sum(w[mask])) if mask is not None else float(np.sum(w))
-    wd = torch.as_tensor(w).to(v.device)
+        wd = wd * mask.reshape(-1).to(device=v.device, dtype=torch.float64)
+    s0 = float(wd.sum().item())
     lib, st = _lib.load(), _plan._stream_handle(dev)
     E = v.shape[0]
     m1 = torch.empty((E, 2), dtype=torch.float64, device=v.device)

@@ -128,7 +128,10 @@ class SHPlan:
         elif tuple(out.shape) != (E, self.nlat, self.nlon) or out.dtype != torch.float64 or not out.is_contiguous():
             raise ValueError("out must be a contiguous float64 tensor of shape [E, nlat, nlon]")
         if degree_weights is not None:
-            w = torch.as_tensor(np.ascontiguousarray(degree_weights, dtype=np.float64)).to(anm.device)
+            if isinstance(degree_weights, torch.Tensor):        # already on the device: no copy in the call
+                w = degree_weights.to(device=anm.device, dtype=torch.float64).contiguous()
+            else:
+                w = torch.as_tensor(np.ascontiguousarray(degree_weights, dtype=np.float64)).to(anm.device)
             if w.numel() != self.L:
                 raise ValueError("degree_weights must have {0} entries (got {1})".format(self.L, w.numel()))
             _lib.check(self._lib.gb_synthesis_weighted(self._handle, ctypes.c_void_p(anm.data_ptr()),
