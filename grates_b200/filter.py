@@ -166,3 +166,85 @@ class OrderWiseFilter(SpatialFilter):
             F[np.ix_(idx[m:] + 2 * m - 1, idx[m:] + 2 * m - 1)] = self._blocks[2 * m - 1][0:k, 0:k]
             F[np.ix_(idx[m:] + 2 * m, idx[m:] + 2 * m)] = self._blocks[2 * m][0:k, 0:k]
         return F[min_degree * min_degree:, min_degree * min_degree:]
+
+
+class GeneralMatrix(SpatialFilter):
+    """Spherical-harmonic filter defined by an arbitrary square matrix in degree-wise coefficient order
+    (reference filter.py:430-510).  Batches are filtered with ONE tensor-core GEMM (gb_dense_filter); the matrix is
+    re-tiled for it once per device."""
+
+    def __init__(self, matrix, min_degree, max_degree):
+        matrix = np.asarray(matrix)
+        if matrix.ndim > 2 or matrix.shape[0] != matrix.shape[1]:
+            raise ValueError('filter matrix must be square (got {0})'.format(str(matrix.shape)))
+        if (max_degree + 1) * (max_degree + 1) - min_degree * min_degree != matrix.shape[0]:
+            raise ValueError('filter matrix dimensions do not correspond to min_degree and max_degree (got {0}, {1:d}, {2:d})'
+                             .format(str(matrix.shape), min_degree, max_degree))
+        self._W = np.ascontiguousarray(matrix, dtype=float)
+        self._nmin = min_degree
+        self._nmax = max_degree
+        self._tiles = {}
+
+    def _tiles_on(self, device):
+        if device not in self._tiles:
+            lib = _lib.load()
+            k = self._W.shape[0]
+            dev = torch.device("cuda", device)
+            w = torch.as_tensor(self._W).to(dev)
+            tiles = torch.empty(int(lib.gb_dense_filter_tile_elements(k)), dtype=torch.float64, device=dev)
+            _lib.check(lib.gb_dense_filter_prepare(ctypes.c_void_p(w.data_ptr()), k, ctypes.c_void_p(tiles.data_ptr()),
+                                                   device, _plan._stream_handle(device)))
+            torch.cuda.current_stream(device).synchronize()       # w may be freed now
+            self._tiles[device] = tiles
+        return self._tiles[device]
+
+    def filter_batch(self, anm, out=None):
+        """anm: [E, L, L] packed coefficients (numpy or CUDA tensor) -> [E, L', L'] with L' - 1 = min(L - 1, max_degree)."""
+        on_host = not isinstance(anm, torch.Tensor)
+        dev = _plan._current_device(None if on_host else anm.device)
+        x = torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", dev)) if on_host else anm.contiguous()
+        if x.dim() != 3 or x.shape[1] != x.shape[2] or x.dtype != torch.float64:
+            raise ValueError("coefficients must be a float64 array of shape [epochs, L, L]")
+        nmax_in = x.shape[-1] - 1
+        lout = min(nmax_in, self._nmax) + 1
+        y = torch.empty((x.shape[0], lout, lout), dtype=torch.float64, device=x.device) if out is None else out
+        if tuple(y.shape) != (x.shape[0], lout, lout):
+            raise ValueError("out must have shape [{0}, {1}, {1}]".format(x.shape[0], lout))
+        _lib.check(_lib.load().gb_dense_filter(ctypes.c_void_p(self._tiles_on(dev).data_ptr()), self._nmin, self._nmax,
+                                               ctypes.c_void_p(x.data_ptr()), x.shape[0], nmax_in,
+                                               ctypes.c_void_p(y.data_ptr()), dev, _plan._stream_handle(dev)))
+        return y.cpu().numpy() if on_host else y
+
+    def filter(self, gravityfield):
+        """Filtered copy of a PotentialCoefficients instance (filter.py:456-479)."""
+        result = gravityfield.copy()
+        result.anm = self.filter_batch(np.ascontiguousarray(gravityfield.anm, dtype=float)[None])[0]
+        return result
+
+    def matrix(self, min_degree, max_degree):
+        """Dense filter matrix for another degree range (filter.py:481-509): coefficients common to both ranges keep
+        their entries, everything else is zero.  Degree-wise orders share contiguous runs of degrees."""
+        if self._nmin == min_degree and self._nmax == max_degree:
+            return self._W.copy()
+        k = (max_degree + 1) ** 2 - min_degree ** 2
+        W = np.zeros((k, k))
+        lo, hi = max(min_degree, self._nmin), min(max_degree, self._nmax)
+        if lo <= hi:
+            n = (hi + 1) ** 2 - lo ** 2
+            s, t = lo ** 2 - self._nmin ** 2, lo ** 2 - min_degree ** 2
+            W[t:t + n, t:t + n] = self._W[s:s + n, s:s + n]
+        return W
+
+
+class VDK(GeneralMatrix):
+    """VDK filter (reference filter.py:512-546): W = (N + diag(kaula weights))^-1 N from a normal-equation matrix in
+    degree-wise order.  The solve is plan-time host work (numpy); the reference's own ``VDK.filter`` reads a
+    name-mangled attribute that does not exist, so ``filter`` follows ``GeneralMatrix.filter``."""
+
+    def __init__(self, normal_equation_matrix, min_degree, max_degree, kaula_scale, kaula_power):
+        normal_equation_matrix = np.asarray(normal_equation_matrix, dtype=float)
+        weights = np.concatenate([np.full(2 * n + 1, kaula_scale * float(n) ** kaula_power)
+                                  for n in range(min_degree, max_degree + 1)])
+        NP = normal_equation_matrix.copy()
+        NP.flat[::NP.shape[0] + 1] = np.diag(normal_equation_matrix) + weights
+        super(VDK, self).__init__(np.linalg.solve(NP, normal_equation_matrix), min_degree, max_degree)

@@ -190,6 +190,12 @@ class TimeSeries:
         width = self._data[0].values.size
         return np.stack([d.values[0:width] for d in self._data])
 
+    def to_array_device(self, min_degree=0):
+        """Same matrix as ``to_array`` (from ``min_degree`` on) as a CUDA tensor [epochs, K']: the packed batch is
+        uploaded once and ravelled on the GPU (gb_ravel_coefficients), the form the covariance / filter-matrix
+        entry points consume."""
+        return ravel_batch(self.to_packed(), min_degree)
+
     def to_packed(self):
         """[epochs, L, L] packed coefficient array (zero-padded to the largest degree)."""
         L = max(d.anm.shape[0] for d in self._data)
@@ -206,6 +212,23 @@ class TimeSeries:
             if d.GM != first.GM or d.R != first.R:
                 raise ValueError("all epochs of a batched synthesis must share GM and R")
         return to_grid_batch(self.to_packed(), grid, kernel, first.GM, first.R, device_output=device_output, out=out)
+
+
+def ravel_batch(anm, min_degree=0):
+    """Packed [E, L, L] coefficients (numpy or CUDA tensor) -> degree-wise vectors [E, (N+1)^2 - min_degree^2] on the
+    device (reference utilities.py:310-360 for a whole batch)."""
+    on_host = not isinstance(anm, torch.Tensor)
+    dev = _plan._current_device(None if on_host else anm.device)
+    x = torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", dev)) if on_host else anm.contiguous()
+    if x.dim() != 3 or x.shape[1] != x.shape[2] or x.dtype != torch.float64:
+        raise ValueError("coefficients must be a float64 array of shape [epochs, L, L]")
+    nmax = x.shape[-1] - 1
+    if not 0 <= min_degree <= nmax:
+        raise ValueError("min_degree must lie in [0, {0}]".format(nmax))
+    out = torch.empty((x.shape[0], (nmax + 1) ** 2 - min_degree ** 2), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().gb_ravel_coefficients(ctypes.c_void_p(x.data_ptr()), x.shape[0], nmax, int(min_degree),
+                                                 ctypes.c_void_p(out.data_ptr()), dev, _plan._stream_handle(dev)))
+    return out
 
 
 def to_grid_batch(anm, grid=None, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT, device_output=False, out=None,

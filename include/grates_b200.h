@@ -172,6 +172,18 @@ int gb_synthesis_weighted(gb_plan* plan, const double* d_anm, const double* d_wn
                           double* d_out, void* stream);
 
 /*
+ * Dense filter matrices (GeneralMatrix / VDK, filter.py:430-572), batched over epochs: x_e = ravel(anm_e, nmin,
+ * nmax_filter), y_e = W x_e, unravel up to min(nmax_in, nmax_filter), degrees below nmin copied through.
+ *   gb_dense_filter_tile_elements   doubles needed for the operand tiles of a k x k matrix
+ *   gb_dense_filter_prepare         d_matrix [k][k] row-major (degree-wise order) -> d_tiles, once per filter
+ *   gb_dense_filter                 d_anm_in [n_epochs][nmax_in+1]^2 -> d_anm_out [n_epochs][min(nmax_in, nmax_filter)+1]^2
+ */
+int64_t gb_dense_filter_tile_elements(int64_t k);
+int gb_dense_filter_prepare(const double* d_matrix, int64_t k, double* d_tiles, int device, void* stream);
+int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter, const double* d_anm_in, int n_epochs,
+                    int nmax_in, double* d_anm_out, int device, void* stream);
+
+/*
  * Order-wise block filter, batched over epochs.  Replaces OrderWiseFilter.filter,
  * filter.py:180-189: order 0 block on C_n0, blocks 2m-1 / 2m on C_nm / S_nm, each block
  * truncated to its top-left (nmax+1-m)^2 corner; degrees 0 and 1 pass through unchanged.

@@ -628,6 +628,25 @@ def degreewise_filter(anm, wn, first_degree=0):
     return out * w
 
 
+def dense_filter(W, nmin, nmax, anm):
+    """GeneralMatrix.filter (filter.py:456-479): x = ravel(anm, nmin, nmax), y = W x, unravel up to
+    min(degree of anm, nmax); the top-left nmin x nmin corner of the packed array is copied through."""
+    anm = np.asarray(anm, dtype=float)
+    max_degree = min(anm.shape[0] - 1, nmax)
+    x = ravel_coefficients(anm, nmin, nmax)
+    out = unravel_coefficients(W @ x, nmin, max_degree)
+    out[0:nmin, 0:nmin] = anm[0:nmin, 0:nmin]
+    return out
+
+
+def vdk_matrix(normals, nmin, nmax, kaula_scale, kaula_power):
+    """VDK filter matrix (filter.py:536-546): (N + diag(kaula_scale * n^kaula_power))^-1 N."""
+    weights = np.concatenate([np.full(2 * n + 1, kaula_scale * float(n) ** kaula_power) for n in range(nmin, nmax + 1)])
+    NP = normals.copy()
+    NP.flat[::NP.shape[0] + 1] = np.diag(normals) + weights
+    return np.linalg.solve(NP, normals)
+
+
 def synthetic_coefficients(nmax, epoch=0):
     """Kaula-like random coefficients, seed 1000 + epoch; degrees 0-1 zero."""
     rng = np.random.default_rng(1000 + epoch)

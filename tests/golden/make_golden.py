@@ -270,6 +270,30 @@ def degreewise_filters():
     save("degreewise_filters", **out)
 
 
+def dense_filters():
+    """GeneralMatrix and VDK (filter.py:430-546)."""
+    out = {}
+    rng = np.random.default_rng(17)
+    nmin, nmax = 2, 10
+    k = (nmax + 1) ** 2 - nmin ** 2
+    W = 0.6 * np.eye(k) + 0.02 * rng.standard_normal((k, k))
+    out["W_2_10"] = W
+    flt = grates.filter.GeneralMatrix(W, nmin, nmax)
+    for N, seed in ((10, 1003), (7, 1004), (14, 1005)):
+        pc = coeffs(N, seed)
+        pc.anm[0:2, 0:2] = rng.standard_normal((2, 2))
+        out["in_%d" % N] = pc.anm
+        out["out_%d" % N] = flt.filter(pc).anm
+    out["matrix_0_12"] = flt.matrix(0, 12)
+    out["matrix_4_8"] = flt.matrix(4, 8)
+    A = rng.standard_normal((2 * k, k))
+    Nmat = A.T @ A
+    out["normals_2_10"] = Nmat
+    vdk = grates.filter.VDK(Nmat, nmin, nmax, 1e2, 2.0)
+    out["vdk_matrix"] = vdk.matrix(nmin, nmax)
+    save("dense_filters", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -283,3 +307,4 @@ if __name__ == "__main__":
     covariance()
     filters()
     degreewise_filters()
+    dense_filters()

@@ -332,6 +332,19 @@ def test_covariance_vs_oracle_and_row_blocks(gb, orc):
     assert maxnorm_err(full, ref) < TOL and maxnorm_err(half, ref) < TOL
 
 
+def test_ravel_batch_matches_reference_ordering(gb, orc, golden):
+    """Device ravel (utilities.py:310-360) against the reference's TimeSeries.to_array ordering."""
+    g = golden("filters")
+    out = gb.ravel_batch(g["ts_anm_sorted"]).cpu().numpy()
+    np.testing.assert_array_equal(out, g["ts_array"])
+    x = np.stack([orc.synthetic_coefficients(31, e) for e in range(3)])
+    for nmin in (0, 2, 31):
+        np.testing.assert_array_equal(gb.ravel_batch(torch.as_tensor(x).cuda(), nmin).cpu().numpy(),
+                                      orc.ravel_coefficients(x, nmin, 31))
+    with pytest.raises(ValueError):
+        gb.ravel_batch(x, 40)
+
+
 def test_basin_variances(gb, orc):
     """Variance of area-weighted basin means, w' A S A' w: adjoint synthesis through the analysis kernels,
     device ravel, batched quadratic forms; against the dense oracle."""
@@ -597,6 +610,31 @@ def test_install_wrappers_on_gpu(gb, orc, golden):
     finally:
         gb.uninstall()
     assert not gb.installed()
+
+
+def test_dense_matrix_filter_golden_and_batch(gb, orc, golden):
+    """GeneralMatrix (filter.py:430-510) as one GEMM over the epoch batch: golden outputs for inputs of equal, lower
+    and higher degree than the filter; a larger random case against the oracle."""
+    g = golden("dense_filters")
+    flt = gb.GeneralMatrix(g["W_2_10"], 2, 10)
+    for N in (10, 7, 14):
+        pc = _pc(gb, g["in_%d" % N])
+        out = flt.filter(pc).anm
+        assert out.shape == g["out_%d" % N].shape
+        assert maxnorm_err(out, g["out_%d" % N]) < TOL
+        np.testing.assert_array_equal(pc.anm, g["in_%d" % N])
+    rng = np.random.default_rng(5)
+    nmin, nmax, E = 0, 30, 130                                    # K = 961: eight row tiles, two epoch tiles
+    k = (nmax + 1) ** 2 - nmin ** 2
+    W = 0.5 * np.eye(k) + rng.standard_normal((k, k)) / k
+    big = gb.GeneralMatrix(W, nmin, nmax)
+    x = np.stack([orc.synthetic_coefficients(nmax, e) for e in range(E)])
+    y = big.filter_batch(torch.as_tensor(x).cuda()).cpu().numpy()
+    ref = np.stack([orc.dense_filter(W, nmin, nmax, a) for a in x[[0, 64, 129]]])
+    assert maxnorm_err(y[[0, 64, 129]], ref) < TOL
+    vdk = gb.VDK(g["normals_2_10"], 2, 10, 1e2, 2.0)
+    out = vdk.filter(_pc(gb, g["in_10"])).anm
+    assert maxnorm_err(out, orc.dense_filter(g["vdk_matrix"], 2, 10, g["in_10"])) < 1e-11
 
 
 def test_orderwise_filter_batch_then_synthesis(gb, orc):

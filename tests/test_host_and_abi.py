@@ -253,3 +253,19 @@ def test_install_rebinds_reference_methods_and_has_no_cpu_fallback():
         gb.uninstall()
     assert grates.gravityfield.PotentialCoefficients.to_grid is original and not gb.installed()
     np.testing.assert_array_equal(pc.to_grid(grid, "ewh").values, expected)
+
+
+def test_general_matrix_host_logic(golden):
+    """GeneralMatrix: constructor checks and the degree-range remapping of matrix() (filter.py:445-509), VDK matrix."""
+    import grates_b200 as gb
+    g = golden("dense_filters")
+    flt = gb.GeneralMatrix(g["W_2_10"], 2, 10)
+    np.testing.assert_array_equal(flt.matrix(2, 10), g["W_2_10"])
+    np.testing.assert_array_equal(flt.matrix(0, 12), g["matrix_0_12"])
+    np.testing.assert_array_equal(flt.matrix(4, 8), g["matrix_4_8"])
+    with pytest.raises(ValueError):
+        gb.GeneralMatrix(np.zeros((3, 4)), 0, 1)
+    with pytest.raises(ValueError):
+        gb.GeneralMatrix(np.zeros((5, 5)), 0, 1)
+    vdk = gb.VDK(g["normals_2_10"], 2, 10, 1e2, 2.0)
+    np.testing.assert_allclose(vdk.matrix(2, 10), g["vdk_matrix"], rtol=1e-12, atol=1e-15)
