@@ -18,6 +18,7 @@ Rebound (reference file:line):
     RegularGrid.covariance_propagation            grid.py:792-839
     IrregularGrid.covariance_propagation          grid.py:1071-1120
     OrderWiseFilter.filter / Gaussian.filter / Butterworth.filter      filter.py:43-70, 108-118, 153-191
+    GeneralMatrix.filter / VDK.filter             filter.py:456-479, 548-572
     gravityfield.gridded_rms                      gravityfield.py:1143-1172
 """
 import numpy as np
@@ -94,6 +95,17 @@ def install(reference=None):
             return out
         return filter
 
+    def dense_filter(self, gravityfield):
+        # GeneralMatrix / VDK keep their matrix under name-mangled attributes; the tiled copy is cached on the object
+        mine = self.__dict__.get("_gb_mirror")
+        if mine is None:
+            mine = _filter.GeneralMatrix(self._GeneralMatrix__W, self._GeneralMatrix__nmin, self._GeneralMatrix__nmax)
+            self.__dict__["_gb_mirror"] = mine
+        res = mine.filter(_mirror_coefficients(gravityfield))
+        out = gravityfield.copy()
+        out.anm = res.anm
+        return out
+
     def gridded_rms(temporal_gravityfield, epochs, kernel='ewh', base_grid=None):
         base_grid = ref.grid.GeographicGrid() if base_grid is None else base_grid
 
@@ -114,6 +126,9 @@ def install(reference=None):
                 _filter_with(lambda f: _filter.OrderWiseFilter(f._OrderWiseFilter__array)))
         _rebind(ref.filter.Gaussian, "filter", _filter_with(lambda f: _filter.Gaussian(f.radius)))
         _rebind(ref.filter.Butterworth, "filter", _filter_with(lambda f: _filter.Butterworth(f.order, f.cutoff_degree)))
+        if hasattr(ref.filter, "GeneralMatrix"):
+            _rebind(ref.filter.GeneralMatrix, "filter", dense_filter)
+            _rebind(ref.filter.VDK, "filter", dense_filter)      # the reference's own VDK.filter raises AttributeError
         _rebind(ref.gravityfield, "gridded_rms", gridded_rms)
     except Exception:
         uninstall()
