@@ -76,15 +76,17 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
     }
     __syncthreads();
 
-    const long long n_tiles = (long long)sh.n_mtiles * sh.n_ntiles;
+    // tiles t = mt * n_ntiles + nt are walked with stride gridDim.x; (mt, nt) advance incrementally (a 64-bit
+    // division per tile costs the single producer thread, and every consumer warp, hundreds of dependent cycles)
+    const int step_m = (int)(gridDim.x / sh.n_ntiles), step_n = (int)(gridDim.x % sh.n_ntiles);
+    int mt = (int)(blockIdx.x / sh.n_ntiles), nt = (int)(blockIdx.x % sh.n_ntiles);
     int stage = 0;
     uint32_t phase = 0;
 
     if (warp == CONSUMER_WARPS) {
         if (lane == 0) {
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const long long mt = t / sh.n_ntiles;
-                const int nt = (int)(t % sh.n_ntiles);
+            for (; mt < sh.n_mtiles; mt += step_m, nt += step_n) {
+                if (nt >= sh.n_ntiles) { nt -= sh.n_ntiles; ++mt; if (mt >= sh.n_mtiles) break; }
                 if (sh.mt_first_nt && nt < sh.mt_first_nt[mt]) continue;
                 const int a_koff = sh.nt_koff ? sh.nt_koff[nt] : (nt / sh.tiles_per_group) * sh.a_koff_mul;
                 const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
@@ -108,9 +110,8 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
         const int wn = warp % WN;
         const int g = lane >> 2;
         const int q = lane & 3;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const long long mt = t / sh.n_ntiles;
-            const int nt = (int)(t % sh.n_ntiles);
+        for (; mt < sh.n_mtiles; mt += step_m, nt += step_n) {
+            if (nt >= sh.n_ntiles) { nt -= sh.n_ntiles; ++mt; if (mt >= sh.n_mtiles) break; }
             if (sh.mt_first_nt && nt < sh.mt_first_nt[mt]) continue;
             double acc[4][5][2];
 #pragma unroll
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
 #pragma unroll
                 for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
-            const long long row_base = mt * TM + wm * 32 + g;
+            const long long row_base = (long long)mt * TM + wm * 32 + g;
             const int col_base = nt * TN + wn * 40 + 2 * q;
             auto pre = [&] {
                 if constexpr (wants_whole_tile<Epilogue>::value) return epi.prepare(row_base, nt, col_base);
