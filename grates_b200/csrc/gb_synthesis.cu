@@ -238,6 +238,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
             const int wm = warp / 6;
             const int wn = warp % 6;
             const int g = lane >> 2, q = lane & 3;
+            const bool has_columns = wn * 40 < width;      // narrow batches (few epochs): the other warps only keep the ring moving
             for (int pass = 0; pass < npass; ++pass) {
                 const int m = pass ? m_second : m_first;
                 const int Kn = L - m;
@@ -254,7 +255,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
                     const double* sX = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA + wn * 40 + g;
 #pragma unroll
                     for (int kk = 0; kk < T1_KC; kk += 4) {
-                        if (kk >= rows) break;
+                        if (kk >= rows || !has_columns) break;
                         double a[5], b[4];
 #pragma unroll
                         for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + q) * T1_LDB + mi * 8];
