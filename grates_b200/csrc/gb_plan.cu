@@ -181,10 +181,17 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
     if (p->sym) {
         p->n_qtiles = (p->nqp + GB_Q_TN - 1) / GB_Q_TN;
         trig_q_t.assign((size_t)p->n_qtiles * p->kpad_s * GB_Q_LDB, 0.0);
+        // Inside every 16-column slab of a warp the columns are interleaved so that a lane's two DMMA fragments
+        // (tile columns 2q, 2q+1 and 8+2q, 9+2q) are FOUR CONSECUTIVE meridians 4q .. 4q+3: one 32-byte store per
+        // output row and lane (gb_fourier_stage2_sym)
         for (int t = 0; t < p->n_qtiles; ++t)
             for (int k = 0; k < p->kpad_s; ++k)
-                for (int c = 0; c < GB_Q_TN && t * GB_Q_TN + c < p->nqp; ++c)
-                    trig_q_t[((size_t)t * p->kpad_s + k) * GB_Q_LDB + c] = trig_q[(size_t)k * p->nqp + t * GB_Q_TN + c];
+                for (int c = 0; c < GB_Q_TN; ++c) {
+                    const int slab = c / 16, tc = c % 16;
+                    const int src = t * GB_Q_TN + slab * 16 + 4 * ((tc % 8) / 2) + 2 * (tc / 8) + (tc % 2);
+                    if (src < p->nqp)
+                        trig_q_t[((size_t)t * p->kpad_s + k) * GB_Q_LDB + c] = trig_q[(size_t)k * p->nqp + src];
+                }
     }
 
     // stage-1 tables (see gb_common.cuh)

@@ -352,7 +352,7 @@ struct QGroups { int off[5]; };
 __global__ void __launch_bounds__(Q_THREADS, 1)
 gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig_q_t, int kpad_s,
                       QGroups grp, double* __restrict__ out, long long M, int nlon, int nq, int n_mtiles,
-                      int n_ntiles) {
+                      int n_ntiles, int wide) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)Q_STAGES * Q_STAGE_DOUBLES * sizeof(double));
@@ -439,32 +439,43 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
                     k0 += kc;
                 }
             }
-            // butterfly epilogue: four output columns per first-quadrant column
+            // butterfly epilogue: four output columns per first-quadrant column.  The trig tiles interleave the
+            // columns of a warp's slab (gb_plan.cu), so this lane's two fragments are the four consecutive meridians
+            // jq .. jq+3: every output row gets one 32-byte store per lane, eight full 128-byte lines per warp store.
             const long long row_base = mt * Q_TM + wm * 32 + g;
+            const int jq = nt * Q_TN + wn * 16 + 4 * q;
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const long long row = row_base + mi * 8;
-                if (row >= M) continue;
+                if (row >= M || jq >= nq) continue;
                 double* orow = out + (size_t)row * nlon;
+                double v1[4], v2[4], v3[4], v4[4];
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {
-                    const int jq = nt * Q_TN + wn * 16 + ni * 8 + 2 * q;   // even; nq is even too
-                    if (jq >= nq) continue;
-                    double v1[2], v2[2], v3[2], v4[2];
+                for (int c = 0; c < 4; ++c) {
+                    const int ni = c >> 1, r = c & 1;
+                    const double ce = acc[0][mi][ni][r], co = acc[1][mi][ni][r];
+                    const double se = acc[2][mi][ni][r], so = acc[3][mi][ni][r];
+                    const double cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
+                    v1[c] = cp + sp;   // mu
+                    v2[c] = cm - sm;   // pi - mu
+                    v3[c] = cp - sp;   // -mu
+                    v4[c] = cm + sm;   // mu - pi
+                }
+                if (wide && jq + 4 <= nq) {
+                    gb::st_cs_v4(orow + h + jq, v1[0], v1[1], v1[2], v1[3]);
+                    gb::st_cs_v4(orow + nlon - 4 - jq, v2[3], v2[2], v2[1], v2[0]);
+                    gb::st_cs_v4(orow + h - 4 - jq, v3[3], v3[2], v3[1], v3[0]);
+                    gb::st_cs_v4(orow + jq, v4[0], v4[1], v4[2], v4[3]);
+                } else {
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const double ce = acc[0][mi][ni][r], co = acc[1][mi][ni][r];
-                        const double se = acc[2][mi][ni][r], so = acc[3][mi][ni][r];
-                        const double cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
-                        v1[r] = cp + sp;   // mu
-                        v2[r] = cm - sm;   // pi - mu
-                        v3[r] = cp - sp;   // -mu
-                        v4[r] = cm + sm;   // mu - pi
+                    for (int c = 0; c < 4; c += 2) {          // nq is even: pairs are all in or all out
+                        const int j = jq + c;
+                        if (j >= nq) continue;
+                        gb::st_cs_v2(orow + h + j, v1[c], v1[c + 1]);
+                        gb::st_cs_v2(orow + nlon - 2 - j, v2[c + 1], v2[c]);
+                        gb::st_cs_v2(orow + h - 2 - j, v3[c + 1], v3[c]);
+                        gb::st_cs_v2(orow + j, v4[c], v4[c + 1]);
                     }
-                    gb::st_cs_v2(orow + h + jq, v1[0], v1[1]);
-                    gb::st_cs_v2(orow + nlon - 2 - jq, v2[1], v2[0]);
-                    gb::st_cs_v2(orow + h - 2 - jq, v3[1], v3[0]);
-                    gb::st_cs_v2(orow + jq, v4[0], v4[1]);
                 }
             }
         }
@@ -562,8 +573,10 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         QGroups grp;
         for (int g = 0; g < 5; ++g) grp.off[g] = p->grp_off[g];
         GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+        // 32-byte stores need 32-byte aligned rows: nlon is a multiple of 8 here, so only the base pointer matters
+        const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 8 == 0) ? 1 : 0;
         gb_fourier_stage2_sym<<<grid, Q_THREADS, Q_SMEM, st>>>(p->d_ab, p->ab_rows, p->d_trig_q_t, p->kpad_s, grp, d_out, M,
-                                                               p->nlon, p->nq, n_mtiles, n_ntiles);
+                                                               p->nlon, p->nq, n_mtiles, n_ntiles, wide);
         GB_LAUNCH_CHECK();
     } else {
         gbgemm::Shape sh;
