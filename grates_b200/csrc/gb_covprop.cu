@@ -466,6 +466,10 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
         sh.klen = kpad;
         sh.n_mtiles = nrows * hmt;
         sh.n_ntiles = p->n_ntiles;
+        if (symmetric) {            // H is upper triangular then: spectral rows k >= 128 j only meet columns k' >= 128 j
+            sh.mt_kstart_mod = hmt;
+            sh.mt_kstart_mul = GB_TM;
+        }
         LonEpilogue epi{p->d_trig, d_out, hmt, kpad, p->nlp, p->nlon};
         if ((rc = gbgemm::launch(sh, epi, p->sm_count, st))) return rc;
     }

@@ -50,6 +50,8 @@ struct Shape {
     const int* nt_koff = nullptr;   // optional per-column-tile A k offset and contraction length
     const int* nt_klen = nullptr;   // (overrides a_koff_mul / klen; used by the covariance quadratic form)
     const int* mt_first_nt = nullptr;   // optional: row tile mt only computes column tiles nt >= mt_first_nt[mt]
+    int mt_kstart_mod = 0, mt_kstart_mul = 0;   // optional: row tile mt starts its contraction at k = (mt % mod) * mul
+                                        // (operand rows below are known zeros: upper-triangular A blocks)
     const int* mt_bgroup = nullptr;     // optional: row tile mt multiplies B tile mt_bgroup[mt] * n_ntiles + nt
                                         // (block-diagonal batches: the analysis latitude stage, one group per order)
 };
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
                 if (sh.mt_first_nt && nt < sh.mt_first_nt[mt]) continue;
                 const int a_koff = sh.nt_koff ? sh.nt_koff[nt] : (nt / sh.tiles_per_group) * sh.a_koff_mul;
                 const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
-                for (int k0 = 0; k0 < klen; k0 += KC) {
+                const int kstart = sh.mt_kstart_mod ? (mt % sh.mt_kstart_mod) * sh.mt_kstart_mul : 0;
+                for (int k0 = kstart; k0 < klen; k0 += KC) {
                     const int kc = min(KC, klen - k0);
                     gb::mbar_wait(&empty[stage], phase ^ 1u);
                     double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES;
@@ -125,7 +128,8 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
                 if constexpr (wants_whole_tile<Epilogue>::value) return epi.prepare(row_base, nt, col_base);
                 else return 0;
             }();
-            for (int k0 = 0; k0 < klen; k0 += KC) {
+            const int kstart = sh.mt_kstart_mod ? (mt % sh.mt_kstart_mod) * sh.mt_kstart_mul : 0;
+            for (int k0 = kstart; k0 < klen; k0 += KC) {
                 const int kc = min(KC, klen - k0);
                 gb::mbar_wait(&full[stage], phase);
                 const double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 32 + g;
