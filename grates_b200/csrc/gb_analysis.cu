@@ -437,10 +437,15 @@ static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_an
             p->ana_gt_elems = 0;
             GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_gt), gt_elems * sizeof(double)));
             p->ana_gt_elems = gt_elems;
+            p->ana_gt_epochs = -1;
         }
     }
-    // padding parallels / columns and the sine columns of order 0 are never written: keep them finite
-    GB_CUDA(cudaMemsetAsync(p->d_ana_gt, 0, gt_elems * sizeof(double), st));
+    // padding parallels / columns and the sine columns of order 0 are never written: they must be finite (zero).
+    // Everything else is overwritten by every call, so the buffer is cleared only when its layout changes.
+    if (p->ana_gt_epochs != E) {
+        GB_CUDA(cudaMemsetAsync(p->d_ana_gt, 0, p->ana_gt_elems * sizeof(double), st));
+        p->ana_gt_epochs = E;
+    }
     {
         dim3 grid((p->ana_kp + 31) / 32, n_mtiles * 4);
         gb_analysis_fold<<<grid, 256, 0, st>>>(d_grid, p->d_ana_vf, M, p->nlon, p->ana_nsets, p->ana_kp,

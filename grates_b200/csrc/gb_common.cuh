@@ -123,6 +123,7 @@ struct gb_plan {
     int* d_ana_lat_n = nullptr;      // [ana_lat_tiles] degree of the tile's first row
     double* d_ana_gt = nullptr;      // longitude-stage output as B tiles [order][column tile][parallel][GB_S2_LDB]
     size_t ana_gt_elems = 0;
+    int ana_gt_epochs = -1;          // epoch count the buffer was last cleared for (its tiling depends on it)
     // optional per-kernel event timing (gb_plan_set_profiling)
     cudaEvent_t* prof_ev = nullptr;  // [capacity][4]
     int prof_capacity = 0, prof_count = 0;
