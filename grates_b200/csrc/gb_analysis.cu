@@ -90,9 +90,10 @@ struct LatOperandStore {
         }
         return pr;
     }
-    __device__ __forceinline__ void tile(const Pre& pr, long long, int col_base, double (&acc)[4][5][2]) const {
+    template <int NI>
+    __device__ __forceinline__ void tile(const Pre& pr, long long, int col_base, double (&acc)[4][NI][2]) const {
 #pragma unroll
-        for (int ni = 0; ni < 5; ++ni) {
+        for (int ni = 0; ni < NI; ++ni) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int k = kmap[col_base + ni * 8 + r];
@@ -338,22 +339,32 @@ extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_o
         p->ana_nsets = 1;
         p->ana_kp = (nlon + 3) / 4 * 4;
     }
-    size_t widest = 0;
+    size_t widest = 1;
     for (auto& c : cols) widest = c.size() > widest ? c.size() : widest;
-    p->ana_tps = (int)((widest + GB_S2_TN - 1) / GB_S2_TN);
-    if (p->ana_tps < 1) p->ana_tps = 1;
+    // column tile width of the longitude GEMM: 24 NI columns with NI = 2..5 fragments per warp; every set gets whole
+    // tiles, so the width that wastes the fewest padded columns wins (91 columns per set at degree 180: 96, not 120)
+    int best_ni = 5;
+    size_t best_cols = ~(size_t)0;
+    for (int ni = 2; ni <= 5; ++ni) {
+        const size_t tn = (size_t)gbgemm::tile_n(ni);
+        const size_t padded = (widest + tn - 1) / tn * tn;
+        if (padded < best_cols) { best_cols = padded; best_ni = ni; }
+    }
+    p->ana_ni = best_ni;
+    const int tn = gbgemm::tile_n(best_ni), ldb = gbgemm::tile_ldb(best_ni);
+    p->ana_tps = (int)((widest + tn - 1) / tn);
     const int ntiles = p->ana_nsets * p->ana_tps;
-    std::vector<double> wt((size_t)ntiles * p->ana_kp * GB_S2_LDB, 0.0);
-    std::vector<int> kmap((size_t)ntiles * GB_S2_TN, -1);
+    std::vector<double> wt((size_t)ntiles * p->ana_kp * ldb, 0.0);
+    std::vector<int> kmap((size_t)ntiles * tn, -1);
     const int kvalid = sym ? q : nlon;
     for (int s = 0; s < p->ana_nsets; ++s)
         for (size_t c = 0; c < cols[s].size(); ++c) {
-            const int tile = s * p->ana_tps + (int)(c / GB_S2_TN), cc = (int)(c % GB_S2_TN);
+            const int tile = s * p->ana_tps + (int)(c / tn), cc = (int)(c % tn);
             const int k = cols[s][c];
-            kmap[(size_t)tile * GB_S2_TN + cc] = k;
+            kmap[(size_t)tile * tn + cc] = k;
             const double* row = lon_ops + (size_t)k * nlon;
             for (int j = 0; j < kvalid; ++j)
-                wt[((size_t)tile * p->ana_kp + j) * GB_S2_LDB + cc] = sym ? row[h + j] : row[j];
+                wt[((size_t)tile * p->ana_kp + j) * ldb + cc] = sym ? row[h + j] : row[j];
         }
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_w_t), wt.size() * sizeof(double)));
     GB_CUDA(cudaMemcpy(p->d_ana_w_t, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -463,7 +474,14 @@ static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_an
         sh.klen = p->ana_kp;
         sh.n_mtiles = n_mtiles;
         sh.n_ntiles = p->ana_nsets * p->ana_tps;
-        int rc = gbgemm::launch(sh, LatOperandStore{p->d_ana_gt, M, p->d_ana_kmap, E, n_ct, p->ana_nlat_p4}, p->sm_count, st);
+        const LatOperandStore epi{p->d_ana_gt, M, p->d_ana_kmap, E, n_ct, p->ana_nlat_p4};
+        int rc;
+        switch (p->ana_ni) {
+            case 2: rc = gbgemm::launch<LatOperandStore, 2>(sh, epi, p->sm_count, st); break;
+            case 3: rc = gbgemm::launch<LatOperandStore, 3>(sh, epi, p->sm_count, st); break;
+            case 4: rc = gbgemm::launch<LatOperandStore, 4>(sh, epi, p->sm_count, st); break;
+            default: rc = gbgemm::launch<LatOperandStore, 5>(sh, epi, p->sm_count, st); break;
+        }
         if (rc) return rc;
     }
     {

@@ -112,6 +112,7 @@ struct gb_plan {
     // longitude stage on the tensor cores: nsets = 4 folded inputs (four-fold symmetric meridians and
     // weights) or 1 (plain transpose); operator tiles [nsets*tiles_per_set][ana_kp][GB_S2_LDB]
     int ana_nsets = 0, ana_kp = 0, ana_tps = 0;
+    int ana_ni = 5;                  // 8-column fragments per warp in the longitude GEMM (column tile = 24 * ana_ni)
     double* d_ana_w_t = nullptr;
     int* d_ana_kmap = nullptr;       // [nsets*tiles_per_set*GB_S2_TN] output column -> spectral row 2m+cs, or -1
     double* d_ana_vf = nullptr;      // folded / transposed input tiles (grow-only workspace)

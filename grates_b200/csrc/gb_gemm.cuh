@@ -27,16 +27,20 @@ namespace gbgemm {
 
 constexpr int WM = 4, WN = 3;
 constexpr int TM = 32 * WM;   // 128
-constexpr int TN = 40 * WN;   // 120
+constexpr int TN = 40 * WN;   // 120 (default column tile; narrower tiles: NI < 5 fragments per warp, TN = 24 NI)
 constexpr int KC = 28;
 constexpr int STAGES = 3;
 constexpr int LDA = GB_LDA;
 constexpr int LDB = GB_S2_LDB;
 constexpr int CONSUMER_WARPS = WM * WN;
 constexpr int THREADS = 32 * (CONSUMER_WARPS + 1);
-constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
-constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 static_assert(TM == GB_TM && TN == GB_S2_TN, "tile shape must match the tiled HBM layouts");
+// column tile of NI 8-column fragments per warp: width, pitch (= 4 mod 16 for every NI), stage size
+__host__ __device__ constexpr int tile_n(int ni) { return 8 * ni * WN; }
+__host__ __device__ constexpr int tile_ldb(int ni) { return tile_n(ni) + 4; }
+__host__ __device__ constexpr size_t smem_bytes(int ni) {
+    return (size_t)STAGES * KC * (LDA + tile_ldb(ni)) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+}
 
 struct Shape {
     const double* A_t;      // [n_mtiles][a_rows][LDA]
@@ -61,8 +65,9 @@ struct wants_whole_tile { static constexpr bool value = false; };
 template <class E>
 struct wants_whole_tile<E, std::enable_if_t<E::whole_tile>> { static constexpr bool value = true; };
 
-template <class Epilogue>
+template <class Epilogue, int NI = 5>
 __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
+    constexpr int TN = tile_n(NI), LDB = tile_ldb(NI), STAGE_DOUBLES = KC * (LDA + LDB);
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)STAGES * STAGE_DOUBLES * sizeof(double));
@@ -116,14 +121,14 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
         for (; mt < sh.n_mtiles; mt += step_m, nt += step_n) {
             if (nt >= sh.n_ntiles) { nt -= sh.n_ntiles; ++mt; if (mt >= sh.n_mtiles) break; }
             if (sh.mt_first_nt && nt < sh.mt_first_nt[mt]) continue;
-            double acc[4][5][2];
+            double acc[4][NI][2];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             const int klen = sh.nt_klen ? sh.nt_klen[nt] : sh.klen;
             const long long row_base = (long long)mt * TM + wm * 32 + g;
-            const int col_base = nt * TN + wn * 40 + 2 * q;
+            const int col_base = nt * TN + wn * (8 * NI) + 2 * q;
             auto pre = [&] {
                 if constexpr (wants_whole_tile<Epilogue>::value) return epi.prepare(row_base, nt, col_base);
                 else return 0;
@@ -133,19 +138,19 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
                 const int kc = min(KC, klen - k0);
                 gb::mbar_wait(&full[stage], phase);
                 const double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 32 + g;
-                const double* sB = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
+                const double* sB = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * (8 * NI) + g;
 #pragma unroll
                 for (int kk = 0; kk < KC; kk += 4) {
                     if (kk >= kc) break;
-                    double a[4], b[5];
+                    double a[4], b[NI];
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * LDA + mi * 8];
 #pragma unroll
-                    for (int ni = 0; ni < 5; ++ni) b[ni] = sB[(kk + q) * LDB + ni * 8];
+                    for (int ni = 0; ni < NI; ++ni) b[ni] = sB[(kk + q) * LDB + ni * 8];
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < 5; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                        for (int ni = 0; ni < NI; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
                 }
                 __syncwarp();
                 if (lane == 0) gb::mbar_arrive(&empty[stage]);
@@ -158,20 +163,21 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(Shape sh, Epilogue epi) {
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 5; ++ni)
+                    for (int ni = 0; ni < NI; ++ni)
                         epi(row_base + mi * 8, col_base + ni * 8, acc[mi][ni][0], acc[mi][ni][1]);
             }
         }
     }
 }
 
-template <class Epilogue>
+template <class Epilogue, int NI = 5>
 inline int launch(const Shape& sh, const Epilogue& epi, int sm_count, cudaStream_t st) {
     const long long n_tiles = (long long)sh.n_mtiles * sh.n_ntiles;
     if (n_tiles == 0) return GB_OK;
     const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
-    GB_CUDA(cudaFuncSetAttribute(kernel<Epilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    kernel<Epilogue><<<grid, THREADS, SMEM, st>>>(sh, epi);
+    constexpr size_t SMEM = smem_bytes(NI);
+    GB_CUDA(cudaFuncSetAttribute(kernel<Epilogue, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    kernel<Epilogue, NI><<<grid, THREADS, SMEM, st>>>(sh, epi);
     GB_LAUNCH_CHECK();
     return GB_OK;
 }
