@@ -141,6 +141,32 @@ void gb_retain_pool_memory(int device);
 int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st, const double* d_wn = nullptr);
 int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st);
 
+// Stream-ordered scratch memory of one C-ABI call: everything allocated through it is returned to the pool
+// (cudaFreeAsync on the same stream) when the call leaves, on every path including the error returns.
+struct gb_scratch {
+    cudaStream_t st;
+    void* ptrs[24];
+    int n = 0;
+    explicit gb_scratch(cudaStream_t s) : st(s) {}
+    gb_scratch(const gb_scratch&) = delete;
+    gb_scratch& operator=(const gb_scratch&) = delete;
+    ~gb_scratch() {
+        for (int i = n - 1; i >= 0; --i) cudaFreeAsync(ptrs[i], st);
+    }
+    template <typename T>
+    cudaError_t alloc(T** out, size_t count) {
+        *out = nullptr;
+        if (n >= 24) return cudaErrorMemoryAllocation;
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st);
+        if (e == cudaSuccess) {
+            ptrs[n++] = p;
+            *out = static_cast<T*>(p);
+        }
+        return e;
+    }
+};
+
 // Recursion coefficients a_nm, b_nm [L][L], sqrt(2n+1) [L] and sectorial seeds P_mm [npts][L],
 // evaluated in IEEE double in the operation order of reference utilities.py:37-54.
 #include <vector>

@@ -287,9 +287,9 @@ __global__ void gb_cov_finish(double* v, long long n) {
 }
 
 template <typename T>
-int to_device(T** d, const std::vector<T>& h, cudaStream_t st) {
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(d), (h.size() ? h.size() : 1) * sizeof(T), st));
-    GB_CUDA(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+int to_device(gb_scratch& scratch, T** d, const std::vector<T>& h) {
+    GB_CUDA(scratch.alloc(d, h.size()));
+    GB_CUDA(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, scratch.st));
     return GB_OK;
 }
 
@@ -317,6 +317,7 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
                "gb_covariance_propagation_filtered: the order-wise filter (degree %d) does not reach degree %d", nf, p->nmax);
     GB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    gb_scratch scratch(st);           // frees every temporary of this call on all return paths
     const int L = p->L, kpad = p->kpad;
     const long long K = (long long)L * L - (long long)nmin * nmin;
 
@@ -381,18 +382,18 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
         *d_klen = nullptr, *d_goff4 = nullptr, *d_padrows = nullptr;
     double *d_st = nullptr, *d_ut = nullptr, *d_ht = nullptr;
     int rc = GB_OK;
-    if ((rc = to_device(&d_perm8, perm8, st)) || (rc = to_device(&d_perm4, perm4, st)) ||
-        (rc = to_device(&d_rowgroup, rowgroup, st)) || (rc = to_device(&d_goff8, goff8, st)) ||
-        (rc = to_device(&d_koff, nt_koff, st)) || (rc = to_device(&d_klen, nt_klen, st)) ||
-        (rc = to_device(&d_goff4, goff4, st)) || (rc = to_device(&d_padrows, padrows, st)) ||
-        (rc = to_device(&d_first_nt, first_nt, st)))
+    if ((rc = to_device(scratch, &d_perm8, perm8)) || (rc = to_device(scratch, &d_perm4, perm4)) ||
+        (rc = to_device(scratch, &d_rowgroup, rowgroup)) || (rc = to_device(scratch, &d_goff8, goff8)) ||
+        (rc = to_device(scratch, &d_koff, nt_koff)) || (rc = to_device(scratch, &d_klen, nt_klen)) ||
+        (rc = to_device(scratch, &d_goff4, goff4)) || (rc = to_device(scratch, &d_padrows, padrows)) ||
+        (rc = to_device(scratch, &d_first_nt, first_nt)))
         return rc;
     const size_t st_elems = (size_t)n_atiles * Kp4 * GB_LDA;
     const size_t ut_elems = (size_t)n_ct * Kg * GB_S2_LDB;
     const size_t ht_elems = (size_t)nrows * hmt * kpad * GB_LDA;
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_st), st_elems * sizeof(double), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ut), ut_elems * sizeof(double), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ht), ht_elems * sizeof(double), st));
+    GB_CUDA(scratch.alloc(&d_st, st_elems));
+    GB_CUDA(scratch.alloc(&d_ut, ut_elems));
+    GB_CUDA(scratch.alloc(&d_ht, ht_elems));
     if (!by_degree) GB_CUDA(cudaMemsetAsync(d_st, 0, st_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_ut, 0, ut_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_ht, 0, ht_elems * sizeof(double), st));
@@ -422,20 +423,18 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
                                               row0, nrows, nti, Kg, d_wn);
         GB_LAUNCH_CHECK();
     }
-    double* d_ut_unfiltered = nullptr;
     long long* d_boff = nullptr;
     if (d_blocks) {
         // U <- F' U group by group (see gb_cov_apply_blocks); the GEMMs below then run on A F
         const int nblocks = 2 * nf + 1;
-        GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_boff), (nblocks + 1) * sizeof(long long), st));
+        GB_CUDA(scratch.alloc(&d_boff, (size_t)nblocks + 1));
         GB_CUDA(cudaMemcpyAsync(d_boff, block_offsets, (nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
         double* d_ut2 = nullptr;
-        GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ut2), ut_elems * sizeof(double), st));
+        GB_CUDA(scratch.alloc(&d_ut2, ut_elems));
         GB_CUDA(cudaMemsetAsync(d_ut2, 0, ut_elems * sizeof(double), st));
         dim3 grid(kpad, nti, (Kg + CF_B - 1) / CF_B);
         gb_cov_apply_blocks<<<grid, 128, 0, st>>>(d_ut, d_ut2, d_blocks, d_boff, nf, L, nmin, nti, Kg);
         GB_LAUNCH_CHECK();
-        d_ut_unfiltered = d_ut;
         d_ut = d_ut2;
     }
     {
@@ -478,19 +477,5 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
         gb_cov_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_out, n);
         GB_LAUNCH_CHECK();
     }
-    GB_CUDA(cudaFreeAsync(d_perm8, st));
-    GB_CUDA(cudaFreeAsync(d_perm4, st));
-    GB_CUDA(cudaFreeAsync(d_rowgroup, st));
-    GB_CUDA(cudaFreeAsync(d_goff8, st));
-    GB_CUDA(cudaFreeAsync(d_koff, st));
-    GB_CUDA(cudaFreeAsync(d_klen, st));
-    GB_CUDA(cudaFreeAsync(d_goff4, st));
-    GB_CUDA(cudaFreeAsync(d_padrows, st));
-    GB_CUDA(cudaFreeAsync(d_first_nt, st));
-    GB_CUDA(cudaFreeAsync(d_st, st));
-    GB_CUDA(cudaFreeAsync(d_ut, st));
-    if (d_ut_unfiltered) GB_CUDA(cudaFreeAsync(d_ut_unfiltered, st));
-    if (d_boff) GB_CUDA(cudaFreeAsync(d_boff, st));
-    GB_CUDA(cudaFreeAsync(d_ht, st));
     return GB_OK;
 }

@@ -138,7 +138,8 @@ extern "C" int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter,
     GB_CUDA(cudaGetDeviceProperties(&prop, device));
     double* d_bt = nullptr;
     const size_t bt_elems = (size_t)n_ct * kp4 * GB_S2_LDB;
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_bt), bt_elems * sizeof(double), st));
+    gb_scratch scratch(st);
+    GB_CUDA(scratch.alloc(&d_bt, bt_elems));
     GB_CUDA(cudaMemsetAsync(d_bt, 0, bt_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_anm_out, 0, (size_t)E * Lout * Lout * sizeof(double), st));
     {
@@ -158,7 +159,7 @@ extern "C" int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter,
         sh.n_mtiles = (int)((K + GB_TM - 1) / GB_TM);
         sh.n_ntiles = n_ct;
         int rc = gbgemm::launch(sh, UnravelStore{d_anm_out, K, nmin, Lout, E}, prop.multiProcessorCount, st);
-        if (rc) { cudaFreeAsync(d_bt, st); return rc; }
+        if (rc) return rc;
     }
     const int nm = nmin < Lout ? nmin : Lout;
     if (nm > 0) {
@@ -167,6 +168,5 @@ extern "C" int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter,
         gb_dense_passthrough<<<(total + 255) / 256, 256, 0, st>>>(d_anm_in, d_anm_out, Lin, Lout, nm, E);
         GB_LAUNCH_CHECK();
     }
-    GB_CUDA(cudaFreeAsync(d_bt, st));
     return GB_OK;
 }

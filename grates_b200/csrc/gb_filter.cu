@@ -152,8 +152,9 @@ extern "C" int gb_orderwise_filter(const double* d_blocks, const int64_t* block_
     GB_REQUIRE(smem <= 227 * 1024, "gb_orderwise_filter: max_degree=%d exceeds the shared-memory tile of the filter kernel", nmax);
     long long* d_off = nullptr;
     double* d_xy = nullptr;
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_off), (nblocks + 1) * sizeof(long long), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_xy), 2 * x_elems * sizeof(double), st));
+    gb_scratch scratch(st);
+    GB_CUDA(scratch.alloc(&d_off, (size_t)nblocks + 1));
+    GB_CUDA(scratch.alloc(&d_xy, 2 * x_elems));
     GB_CUDA(cudaMemcpyAsync(d_off, block_offsets, (nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     int rc = gb_launch_pack(d_anm_in, d_xy, L, E, st);
     if (!rc) {
@@ -170,7 +171,5 @@ extern "C" int gb_orderwise_filter(const double* d_blocks, const int64_t* block_
         if (e != cudaSuccess) rc = gb_set_error(GB_ERR_CUDA, "gb_filter_blocks_kernel launch failed: %s", cudaGetErrorString(e));
     }
     if (!rc) rc = gb_launch_unpack(d_xy + x_elems, d_anm_out, L, E, st);
-    cudaFreeAsync(d_xy, st);
-    cudaFreeAsync(d_off, st);
     return rc;
 }

@@ -333,8 +333,9 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
     const int n_ntiles = (int)((Kc + C_TN - 1) / C_TN);
     double *d_ft = nullptr, *d_sig = nullptr;
     const size_t ft_elems = (size_t)n_mtiles * Kp * C_LDA;
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ft), ft_elems * sizeof(double), st));
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_sig), (size_t)Kp * lds * sizeof(double), st));
+    gb_scratch scratch(st);
+    GB_CUDA(scratch.alloc(&d_ft, ft_elems));
+    GB_CUDA(scratch.alloc(&d_sig, (size_t)Kp * lds));
     GB_CUDA(cudaMemsetAsync(d_ft, 0, ft_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_sig, 0, (size_t)Kp * lds * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->npts * sizeof(double), st));
@@ -359,7 +360,5 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
         gb_points_sqrt<<<(p->npts + 255) / 256, 256, 0, st>>>(d_out, p->npts);
         GB_LAUNCH_CHECK();
     }
-    GB_CUDA(cudaFreeAsync(d_ft, st));
-    GB_CUDA(cudaFreeAsync(d_sig, st));
     return GB_OK;
 }

@@ -95,13 +95,13 @@ extern "C" int gb_weighted_moments(const double* d_values, const double* d_weigh
     gb_retain_pool_memory(device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* d_partial = nullptr;
-    GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_partial), (size_t)n_epochs * RB * 2 * sizeof(double), st));
+    gb_scratch scratch(st);
+    GB_CUDA(scratch.alloc(&d_partial, (size_t)n_epochs * RB * 2));
     dim3 grid(RB, n_epochs);
     gb_moments_partial<<<grid, 256, 0, st>>>(d_values, d_weights, d_shift, n_points, d_partial);
     GB_LAUNCH_CHECK();
     gb_moments_finish<<<n_epochs, 32, 0, st>>>(d_partial, RB, d_out);
     GB_LAUNCH_CHECK();
-    GB_CUDA(cudaFreeAsync(d_partial, st));
     return GB_OK;
 }
 
