@@ -134,8 +134,8 @@ extern "C" int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter,
     const long long K = (long long)(nmax_filter + 1) * (nmax_filter + 1) - (long long)nmin * nmin;
     const int kp4 = (int)((K + 3) / 4 * 4);
     const int n_ct = (E + GB_S2_TN - 1) / GB_S2_TN;
-    cudaDeviceProp prop;
-    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    int sm_count = 0;       // cudaGetDeviceProperties would cost milliseconds per call
+    GB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     double* d_bt = nullptr;
     const size_t bt_elems = (size_t)n_ct * kp4 * GB_S2_LDB;
     gb_scratch scratch(st);
@@ -158,7 +158,7 @@ extern "C" int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter,
         sh.klen = kp4;
         sh.n_mtiles = (int)((K + GB_TM - 1) / GB_TM);
         sh.n_ntiles = n_ct;
-        int rc = gbgemm::launch(sh, UnravelStore{d_anm_out, K, nmin, Lout, E}, prop.multiProcessorCount, st);
+        int rc = gbgemm::launch(sh, UnravelStore{d_anm_out, K, nmin, Lout, E}, sm_count, st);
         if (rc) return rc;
     }
     const int nm = nmin < Lout ? nmin : Lout;

@@ -196,9 +196,9 @@ extern "C" int gb_quadratic_forms(const double* d_sigma, int64_t k, const double
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_vec * sizeof(double), st));
     if (k == 0) return GB_OK;
-    cudaDeviceProp prop;
-    GB_CUDA(cudaGetDeviceProperties(&prop, device));
-    const int grid = (int)((k + 7) / 8 < (long long)prop.multiProcessorCount * 8 ? (k + 7) / 8 : prop.multiProcessorCount * 8);
+    int sm_count = 0;       // cudaGetDeviceProperties would cost milliseconds per call
+    GB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    const int grid = (int)((k + 7) / 8 < (long long)sm_count * 8 ? (k + 7) / 8 : sm_count * 8);
     for (int b0 = 0; b0 < n_vec; b0 += QF_B) {
         const int nb = n_vec - b0 < QF_B ? n_vec - b0 : QF_B;
         gb_quadratic_forms_kernel<<<grid, 256, 0, st>>>(d_sigma, d_vec, k, b0, nb, d_out);
