@@ -667,12 +667,14 @@ extern "C" int gb_synthesis_host(gb_plan* plan, const double* h_anm, int n_epoch
     if (chunk < 1) chunk = 1;
     if ((rc = ensure_io(p, (size_t)n_epochs * coef * sizeof(double), (size_t)chunk * pts * sizeof(double)))) return rc;
     if ((rc = gb_plan_ensure_workspace(p, chunk))) return rc;
-    GB_CUDA(cudaMemcpyAsync(p->d_io_in, h_anm, (size_t)n_epochs * coef * sizeof(double), cudaMemcpyHostToDevice,
-                            p->s_compute));
+    // the coefficients go up chunk by chunk in front of their kernels (1 MB each at config 2): only the first
+    // chunk's upload is exposed, the rest hides behind the result copies of the previous chunks
     int c = 0;
     for (int e0 = 0; e0 < n_epochs; e0 += chunk, ++c) {
         const int ne = (n_epochs - e0 < chunk) ? (n_epochs - e0) : chunk;
         const int b = c & 1;
+        GB_CUDA(cudaMemcpyAsync(p->d_io_in + (size_t)e0 * coef, h_anm + (size_t)e0 * coef, (size_t)ne * coef * sizeof(double),
+                                cudaMemcpyHostToDevice, p->s_compute));
         if (c >= 2) GB_CUDA(cudaStreamWaitEvent(p->s_compute, p->ev[2 + b], 0));  // buffer b drained
         if ((rc = launch_synthesis(p, p->d_io_in + (size_t)e0 * coef, ne, p->d_io_out[b], p->s_compute))) return rc;
         GB_CUDA(cudaEventRecord(p->ev[b], p->s_compute));
