@@ -140,6 +140,9 @@ void gb_retain_pool_memory(int device);
 // X_m[n - m][cs * E + e]
 int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st, const double* d_wn = nullptr);
 int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st);
+// packed batch -> degree-wise vectors as GEMM B tiles [epoch tile of 120][c][124] (gb_densefilter.cu); K = number of
+// coefficients from degree nmin on, kp4 = K padded to 4, degrees above Lin - 1 read as zero
+int gb_launch_ravel_tiles(const double* d_anm, double* d_bt, int Lin, int nmin, long long K, int kp4, int E, cudaStream_t st);
 
 // Stream-ordered scratch memory of one C-ABI call: everything allocated through it is returned to the pool
 // (cudaFreeAsync on the same stream) when the call leaves, on every path including the error returns.

@@ -100,6 +100,14 @@ __global__ void gb_dense_passthrough(const double* __restrict__ in, double* __re
 
 }  // namespace
 
+// shared with the point-set synthesis (gb_points.cu): a batch ravelled into GEMM B tiles [epoch tile][c][124]
+int gb_launch_ravel_tiles(const double* d_anm, double* d_bt, int Lin, int nmin, long long K, int kp4, int E, cudaStream_t st) {
+    dim3 grid((unsigned)K, (E + 255) / 256);
+    gb_dense_ravel_tiles<<<grid, 256, 0, st>>>(d_anm, d_bt, Lin, nmin, K, kp4, E);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}
+
 extern "C" int64_t gb_dense_filter_tile_elements(int64_t k) {
     const long long kp4 = (k + 3) / 4 * 4;
     return (int64_t)((k + GB_TM - 1) / GB_TM) * kp4 * GB_LDA;
@@ -143,9 +151,8 @@ extern "C" int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter,
     GB_CUDA(cudaMemsetAsync(d_bt, 0, bt_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_anm_out, 0, (size_t)E * Lout * Lout * sizeof(double), st));
     {
-        dim3 grid((unsigned)K, (E + 255) / 256);
-        gb_dense_ravel_tiles<<<grid, 256, 0, st>>>(d_anm_in, d_bt, Lin, nmin, K, kp4, E);
-        GB_LAUNCH_CHECK();
+        int rc = gb_launch_ravel_tiles(d_anm_in, d_bt, Lin, nmin, K, kp4, E, st);
+        if (rc) return rc;
     }
     {
         gbgemm::Shape sh;

@@ -14,6 +14,7 @@
 #include <vector>
 #include <cmath>
 #include "gb_common.cuh"
+#include "gb_gemm.cuh"
 
 struct gb_points {
     int device = 0, nmax = 0, L = 0, npts = 0, sm_count = 0;
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(128)
 gb_points_design(double* __restrict__ FT, const double* __restrict__ ct, const double* __restrict__ kn,
                  const double* __restrict__ pmm, const double* __restrict__ cml, const double* __restrict__ sml,
                  const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc, int L,
-                 int nmin, int npts, int rows) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+                 int nmin, int npts, int rows, int p0) {
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;      // tiles are numbered from point p0
     const int m = blockIdx.y;
     if (p >= npts) return;
     const double* kn_p = kn + (size_t)p * L;
@@ -118,8 +119,8 @@ gb_points_design(double* __restrict__ FT, const double* __restrict__ ct, const d
         if (n < nmin) return;
         const double pk = __dmul_rn(pn, kn_p[n]);
         const int a = n * n + (m == 0 ? 0 : 2 * m - 1) - off;
-        FT[gb_ab_offset(p, a, rows)] = __dmul_rn(pk, cm);
-        if (m > 0) FT[gb_ab_offset(p, a + 1, rows)] = __dmul_rn(pk, sm);
+        FT[gb_ab_offset(p - p0, a, rows)] = __dmul_rn(pk, cm);
+        if (m > 0) FT[gb_ab_offset(p - p0, a + 1, rows)] = __dmul_rn(pk, sm);
     });
 }
 
@@ -301,12 +302,74 @@ extern "C" int gb_points_destroy(gb_points* p) {
     return GB_OK;
 }
 
+// epilogue of the batched point synthesis: out[e][p0 + row]
+struct PointStore {
+    double* out;
+    long long npts;
+    int p0, count, E;
+    __device__ __forceinline__ void operator()(long long row, int col, double v0, double v1) const {
+        if (row >= count) return;
+        double* o = out + (size_t)col * npts + p0 + row;
+        if (col < E) *o = v0;
+        if (col + 1 < E) o[npts] = v1;
+    }
+};
+
+// Epoch batches at arbitrary points as a GEMM: the design tiles F^T of a block of points are generated once (on-the-fly
+// recursion, gb_points_design) and multiplied with ALL epochs on the DMMA GEMM, instead of re-running the recursion for
+// every eight epochs.  2 P K E flops; the design matrix only ever exists for one block of points.
+static int points_synthesis_gemm(gb_points* p, const double* d_anm, int E, double* d_out, cudaStream_t st) {
+    const int L = p->L;
+    const long long K = (long long)L * L;
+    const int Kp = (int)((K + 3) / 4 * 4);
+    const int n_ct = (E + GB_S2_TN - 1) / GB_S2_TN;
+    int tiles_per_block = 2 * p->sm_count / n_ct;                 // about two waves of GEMM tiles per block
+    if (tiles_per_block < 8) tiles_per_block = 8;
+    const int n_mtiles_all = (p->npts + GB_TM - 1) / GB_TM;
+    if (tiles_per_block > n_mtiles_all) tiles_per_block = n_mtiles_all;
+    gb_scratch scratch(st);
+    double *d_ft = nullptr, *d_bt = nullptr;
+    const size_t ft_elems = (size_t)tiles_per_block * Kp * GB_LDA;
+    const size_t bt_elems = (size_t)n_ct * Kp * GB_S2_LDB;
+    GB_CUDA(scratch.alloc(&d_ft, ft_elems));
+    GB_CUDA(scratch.alloc(&d_bt, bt_elems));
+    GB_CUDA(cudaMemsetAsync(d_bt, 0, bt_elems * sizeof(double), st));
+    int rc = gb_launch_ravel_tiles(d_anm, d_bt, L, 0, K, Kp, E, st);
+    if (rc) return rc;
+    for (int t0 = 0; t0 < n_mtiles_all; t0 += tiles_per_block) {
+        const int nt = (n_mtiles_all - t0 < tiles_per_block) ? (n_mtiles_all - t0) : tiles_per_block;
+        const int p0 = t0 * GB_TM;
+        const int count = (p->npts - p0 < nt * GB_TM) ? (p->npts - p0) : nt * GB_TM;
+        GB_CUDA(cudaMemsetAsync(d_ft, 0, (size_t)nt * Kp * GB_LDA * sizeof(double), st));   // padding rows / points
+        dim3 grid((count + 127) / 128, L);
+        gb_points_design<<<grid, 128, 0, st>>>(d_ft, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra, p->d_rb,
+                                              p->d_rc, L, 0, p0 + count, Kp, p0);
+        GB_LAUNCH_CHECK();
+        gbgemm::Shape sh;
+        sh.A_t = d_ft;
+        sh.a_rows = Kp;
+        sh.a_koff_mul = 0;
+        sh.tiles_per_group = 1;
+        sh.B_t = d_bt;
+        sh.b_rows = Kp;
+        sh.klen = Kp;
+        sh.n_mtiles = nt;
+        sh.n_ntiles = n_ct;
+        if ((rc = gbgemm::launch(sh, PointStore{d_out, p->npts, p0, count, E}, p->sm_count, st))) return rc;
+    }
+    return GB_OK;
+}
+
 extern "C" int gb_points_synthesis(gb_points* p, const double* d_anm, int n_epochs, double* d_out, void* stream) {
     GB_REQUIRE(p != nullptr, "gb_points_synthesis: point set is NULL");
     GB_REQUIRE(n_epochs >= 0, "gb_points_synthesis: n_epochs=%d is negative", n_epochs);
     if (n_epochs == 0) return GB_OK;
     GB_REQUIRE(d_anm && d_out, "gb_points_synthesis: NULL device pointer");
     GB_CUDA(cudaSetDevice(p->device));
+    if (n_epochs >= 16 && !(getenv("GB_POINTS_SIMPLE") && getenv("GB_POINTS_SIMPLE")[0] == '1')) {
+        gb_retain_pool_memory(p->device);
+        return points_synthesis_gemm(p, d_anm, n_epochs, d_out, static_cast<cudaStream_t>(stream));
+    }
     dim3 grid((p->npts + 127) / 128, (n_epochs + PE - 1) / PE);
     const size_t smem = (size_t)2 * PE * p->L * sizeof(double);
     if (smem > 48 * 1024)
@@ -345,7 +408,7 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
     {
         dim3 grid((p->npts + 127) / 128, L);
         gb_points_design<<<grid, 128, 0, st>>>(d_ft, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra, p->d_rb,
-                                              p->d_rc, L, nmin, p->npts, Kp);
+                                              p->d_rc, L, nmin, p->npts, Kp, 0);
         GB_LAUNCH_CHECK();
     }
     {

@@ -434,6 +434,24 @@ def test_irregular_synthesis_golden(gb, golden, orc):
     assert vals.shape == (11, 1111) and maxnorm_err(vals, ref) < TOL
 
 
+def test_irregular_synthesis_epoch_batch_on_gemm(gb, orc, monkeypatch):
+    """Sixteen or more epochs at arbitrary points run as design tiles x DMMA GEMM (gb_points.cu); point count not a
+    multiple of the tile, more than one epoch tile; against the oracle and against the per-point kernel."""
+    rng = np.random.default_rng(31)
+    npts, N, E = 1500, 33, 131
+    lon, lat = rng.uniform(-np.pi, np.pi, npts), rng.uniform(-1.57, 1.57, npts)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    grid = gb.IrregularGrid(lon, lat)
+    vals = gb.to_grid_batch(anm, grid, "ewh")
+    assert vals.shape == (E, npts)
+    for e in (0, 64, 130):
+        assert maxnorm_err(vals[e], orc.synthesis_points(anm[e], lon, lat, "ewh")) < TOL
+    monkeypatch.setenv("GB_POINTS_SIMPLE", "1")
+    simple = gb.to_grid_batch(anm, grid, "ewh")
+    monkeypatch.delenv("GB_POINTS_SIMPLE")
+    assert maxnorm_err(vals, simple) < 1e-13
+
+
 def test_irregular_covariance_golden(gb, golden, orc):
     g = golden("covariance")
     ig = gb.IrregularGrid(g["irr_lon"], g["irr_lat"])

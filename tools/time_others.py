@@ -57,8 +57,24 @@ def filt(N=120, E=500, d=0.25):
     best, med = ev_time(lambda: plan.synthesis(flt.filter_batch(x, out=y), out=out), reps=3, warm=1)
     print(f"filter+synthesis N={N} E={E} d={d}: {best:.3f} ms -> {E*plan.nlat*plan.nlon/best/1e6:.2f} Gpt.ep/s")
 
+def points(N=96, E=240, npts=41000):
+    rng = np.random.default_rng(1)
+    lon, lat = rng.uniform(-np.pi, np.pi, npts), np.arcsin(rng.uniform(-1, 1, npts))
+    pp = gb.get_points_plan(gb.IrregularGrid(lon, lat), N, "ewh")
+    x = torch.as_tensor(np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])).cuda()
+    out = torch.empty((E, npts), dtype=torch.float64, device="cuda")
+    fl = 2.0 * npts * (N + 1) ** 2 * E
+    best, _ = ev_time(lambda: pp.synthesis(x, out=out), reps=3, warm=1)
+    print(f"points synthesis (GEMM) N={N} E={E} points={npts}: {best:.3f} ms, {fl/best/1e9:.2f} TF")
+    os.environ["GB_POINTS_SIMPLE"] = "1"
+    best2, _ = ev_time(lambda: pp.synthesis(x, out=out), reps=2, warm=1)
+    del os.environ["GB_POINTS_SIMPLE"]
+    print(f"points synthesis (per-point kernel): {best2:.3f} ms, {fl/best2/1e9:.2f} TF")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["analysis", "covprop", "filter"]
     if "analysis" in which: analysis()
     if "covprop" in which: covprop()
     if "filter" in which: filt()
+    if "points" in which: points()
