@@ -392,31 +392,37 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
     const long long Kc = (long long)L * L - (long long)nmin * nmin;   // coefficients
     const int Kp = (int)((Kc + 3) / 4 * 4);                            // padded to whole k4 steps
     const long long lds = (Kc + 1) / 2 * 2 + 2;                        // even leading dimension, room for the tail
-    const int n_mtiles = (p->npts + C_TM - 1) / C_TM;
+    const int n_mtiles_all = (p->npts + C_TM - 1) / C_TM;
     const int n_ntiles = (int)((Kc + C_TN - 1) / C_TN);
+    // the design matrix only ever exists for one block of points (about four waves of GEMM tiles): 75 KB per point at
+    // degree 96 would otherwise be 12 GB for a 0.5-degree Reuter grid
+    int tiles_per_block = 4 * p->sm_count / (n_ntiles > 0 ? n_ntiles : 1);
+    if (tiles_per_block < 16) tiles_per_block = 16;
+    if (tiles_per_block > n_mtiles_all) tiles_per_block = n_mtiles_all;
     double *d_ft = nullptr, *d_sig = nullptr;
-    const size_t ft_elems = (size_t)n_mtiles * Kp * C_LDA;
+    const size_t ft_elems = (size_t)tiles_per_block * Kp * C_LDA;
     gb_scratch scratch(st);
     GB_CUDA(scratch.alloc(&d_ft, ft_elems));
     GB_CUDA(scratch.alloc(&d_sig, (size_t)Kp * lds));
-    GB_CUDA(cudaMemsetAsync(d_ft, 0, ft_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_sig, 0, (size_t)Kp * lds * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->npts * sizeof(double), st));
     // covariance rows re-pitched to an even leading dimension (16-byte aligned rows for the bulk copies)
     GB_CUDA(cudaMemcpy2DAsync(d_sig, lds * sizeof(double), d_sigma, Kc * sizeof(double), Kc * sizeof(double), Kc,
                               cudaMemcpyDeviceToDevice, st));
-    {
-        dim3 grid((p->npts + 127) / 128, L);
+    GB_CUDA(cudaFuncSetAttribute(gb_points_quadform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM));
+    for (int t0 = 0; t0 < n_mtiles_all; t0 += tiles_per_block) {
+        const int n_mtiles = (n_mtiles_all - t0 < tiles_per_block) ? (n_mtiles_all - t0) : tiles_per_block;
+        const int p0 = t0 * C_TM;
+        const int count = (p->npts - p0 < n_mtiles * C_TM) ? (p->npts - p0) : n_mtiles * C_TM;
+        GB_CUDA(cudaMemsetAsync(d_ft, 0, (size_t)n_mtiles * Kp * C_LDA * sizeof(double), st));
+        dim3 grid((count + 127) / 128, L);
         gb_points_design<<<grid, 128, 0, st>>>(d_ft, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra, p->d_rb,
-                                              p->d_rc, L, nmin, p->npts, Kp, 0);
+                                              p->d_rc, L, nmin, p0 + count, Kp, p0);
         GB_LAUNCH_CHECK();
-    }
-    {
         const long long n_tiles = (long long)n_mtiles * n_ntiles;
-        const int grid = (int)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
-        GB_CUDA(cudaFuncSetAttribute(gb_points_quadform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM));
-        gb_points_quadform<<<grid, C_THREADS, C_SMEM, st>>>(d_ft, Kp, d_sig, lds, Kp, Kc, d_out, p->npts, n_mtiles,
-                                                            n_ntiles);
+        const int gridq = (int)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
+        gb_points_quadform<<<gridq, C_THREADS, C_SMEM, st>>>(d_ft, Kp, d_sig, lds, Kp, Kc, d_out + p0, count, n_mtiles,
+                                                             n_ntiles);
         GB_LAUNCH_CHECK();
     }
     if (take_sqrt) {
