@@ -136,7 +136,7 @@ constexpr size_t C_SMEM = (size_t)C_STAGES * C_STAGE_DOUBLES * sizeof(double) + 
 
 __global__ void __launch_bounds__(C_THREADS, 1)
 gb_points_quadform(const double* __restrict__ FT, int rows, const double* __restrict__ sig, long long lds, int Kp,
-                   long long Kc, double* __restrict__ var, int npts, int n_mtiles, int n_ntiles) {
+                   long long Kc, double* __restrict__ var, int npts, int n_mtiles, int n_ntiles, int upper) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)C_STAGES * C_STAGE_DOUBLES * sizeof(double));
@@ -161,8 +161,11 @@ gb_points_quadform(const double* __restrict__ FT, int rows, const double* __rest
             long long w = Kc - n0;
             if (w > C_TN) w = C_TN;
             const int width = (int)((w + 1) & ~1LL);     // even number of doubles (16-byte granules)
-            for (int k0 = 0; k0 < Kp; k0 += C_KC) {
-                const int kc = min(C_KC, Kp - k0);
+            // upper-triangular operand (symmetric Sigma, off-diagonal entries doubled): rows a beyond the tile's last
+            // column are zero
+            const int kend = upper ? min(Kp, (n0 + C_TN + 3) & ~3) : Kp;
+            for (int k0 = 0; k0 < kend; k0 += C_KC) {
+                const int kc = min(C_KC, kend - k0);
                 gb::mbar_wait(&empty[stage], phase ^ 1u);
                 double* sA = s_tiles + (size_t)stage * C_STAGE_DOUBLES;
                 double* sB = sA + C_KC * C_LDA;
@@ -189,8 +192,9 @@ gb_points_quadform(const double* __restrict__ FT, int rows, const double* __rest
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 5; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            for (int k0 = 0; k0 < Kp; k0 += C_KC) {
-                const int kc = min(C_KC, Kp - k0);
+            const int kend = upper ? min(Kp, (n0 + C_TN + 3) & ~3) : Kp;
+            for (int k0 = 0; k0 < kend; k0 += C_KC) {
+                const int kc = min(C_KC, kend - k0);
                 gb::mbar_wait(&full[stage], phase);
                 const double* sA = s_tiles + (size_t)stage * C_STAGE_DOUBLES + wm * 32 + g;
                 const double* sB = s_tiles + (size_t)stage * C_STAGE_DOUBLES + C_KC * C_LDA + wn * 40 + g;
@@ -381,8 +385,22 @@ extern "C" int gb_points_synthesis(gb_points* p, const double* d_anm, int n_epoc
     return GB_OK;
 }
 
-extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmin, double* d_out, int take_sqrt,
+// Sigma re-pitched to an even leading dimension; for a symmetric Sigma only its upper triangle is kept, the
+// off-diagonal entries doubled:  x' S x = sum_a S_aa x_a^2 + 2 sum_{a<b} S_ab x_a x_b
+__global__ void __launch_bounds__(256)
+gb_points_sigma_operand(const double* __restrict__ sigma, double* __restrict__ sig, long long Kc, long long lds, int upper) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long a = blockIdx.y;
+    if (b >= Kc) return;
+    double v = sigma[(size_t)a * Kc + b];
+    if (upper) v = (a < b) ? v + v : (a == b ? v : 0.0);
+    sig[(size_t)a * lds + b] = v;
+}
+
+extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmin, double* d_out, int flags,
                                     void* stream) {
+    const int take_sqrt = flags & GB_COV_SQRT;
+    const int upper = (flags & GB_COV_SYMMETRIC) ? 1 : 0;
     GB_REQUIRE(p != nullptr, "gb_points_covariance: point set is NULL");
     GB_REQUIRE(nmin >= 0 && nmin <= p->nmax, "gb_points_covariance: min_degree=%d outside [0, %d]", nmin, p->nmax);
     GB_REQUIRE(d_sigma && d_out, "gb_points_covariance: NULL device pointer");
@@ -406,9 +424,11 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
     GB_CUDA(scratch.alloc(&d_sig, (size_t)Kp * lds));
     GB_CUDA(cudaMemsetAsync(d_sig, 0, (size_t)Kp * lds * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->npts * sizeof(double), st));
-    // covariance rows re-pitched to an even leading dimension (16-byte aligned rows for the bulk copies)
-    GB_CUDA(cudaMemcpy2DAsync(d_sig, lds * sizeof(double), d_sigma, Kc * sizeof(double), Kc * sizeof(double), Kc,
-                              cudaMemcpyDeviceToDevice, st));
+    {   // covariance rows re-pitched to an even leading dimension (16-byte aligned rows for the bulk copies)
+        dim3 grid((unsigned)((Kc + 255) / 256), (unsigned)Kc);
+        gb_points_sigma_operand<<<grid, 256, 0, st>>>(d_sigma, d_sig, Kc, lds, upper);
+        GB_LAUNCH_CHECK();
+    }
     GB_CUDA(cudaFuncSetAttribute(gb_points_quadform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM));
     for (int t0 = 0; t0 < n_mtiles_all; t0 += tiles_per_block) {
         const int n_mtiles = (n_mtiles_all - t0 < tiles_per_block) ? (n_mtiles_all - t0) : tiles_per_block;
@@ -422,7 +442,7 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
         const long long n_tiles = (long long)n_mtiles * n_ntiles;
         const int gridq = (int)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
         gb_points_quadform<<<gridq, C_THREADS, C_SMEM, st>>>(d_ft, Kp, d_sig, lds, Kp, Kc, d_out + p0, count, n_mtiles,
-                                                             n_ntiles);
+                                                             n_ntiles, upper);
         GB_LAUNCH_CHECK();
     }
     if (take_sqrt) {

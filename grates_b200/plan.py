@@ -461,17 +461,21 @@ class PointsPlan:
                                                  ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
 
-    def covariance_propagation(self, sigma, min_degree, take_sqrt=True):
-        """sigma: CUDA tensor [K', K'] in degree-wise order -> [npts] standard deviations / variances."""
+    def covariance_propagation(self, sigma, min_degree, take_sqrt=True, symmetric=None):
+        """sigma: CUDA tensor [K', K'] in degree-wise order -> [npts] standard deviations / variances.
+        symmetric: contract only the upper triangle of sigma (half the flops); None decides on sampled entries."""
         kp = self.L ** 2 - min_degree ** 2
         if sigma.dim() != 2 or tuple(sigma.shape) != (kp, kp):
             raise ValueError("covariance matrix must have shape [{0}, {0}] (got {1})".format(kp, tuple(sigma.shape)))
         if sigma.dtype != torch.float64 or not sigma.is_cuda or sigma.device.index != self.device:
             raise ValueError("covariance matrix must be a float64 CUDA tensor on device {0}".format(self.device))
         sigma = sigma.contiguous()
+        if symmetric is None:
+            symmetric = _looks_symmetric(sigma)
         out = torch.empty((self.npts,), dtype=torch.float64, device=sigma.device)
+        flags = (1 if take_sqrt else 0) | (2 if symmetric else 0)      # GB_COV_SQRT | GB_COV_SYMMETRIC
         _lib.check(self._lib.gb_points_covariance(self._handle, ctypes.c_void_p(sigma.data_ptr()), int(min_degree),
-                                                  ctypes.c_void_p(out.data_ptr()), int(bool(take_sqrt)),
+                                                  ctypes.c_void_p(out.data_ptr()), flags,
                                                   _stream_handle(self.device)))
         return out
 

@@ -202,14 +202,15 @@ int gb_orderwise_filter(const double* d_blocks, const int64_t* block_offsets, in
  *   (cos(m*lon_p), sin(m*lon_p), utilities.py:303-304).
  * gb_points_synthesis replaces gravityfield.py:376-388: d_anm [n_epochs][L][L] -> d_out [n_epochs][npts].
  * gb_points_covariance replaces grid.py:1103-1116: direct blocked diag(F Sigma F') with Sigma
- *   [K'][K'] (degree-wise order, offset nmin^2) -> d_out [npts] variances (std-devs if take_sqrt).
+ *   [K'][K'] (degree-wise order, offset nmin^2) -> d_out [npts] variances; flags as for gb_covariance_propagation
+ *   (GB_COV_SQRT: std-devs; GB_COV_SYMMETRIC: only the upper triangle of Sigma is contracted, half the flops).
  */
 typedef struct gb_points gb_points;
 int gb_points_create(gb_points** points, int nmax, int npts, const double* cos_theta, const double* sin_theta,
                      const double* kn, const double* cos_mlon, const double* sin_mlon, int device);
 int gb_points_destroy(gb_points* points);
 int gb_points_synthesis(gb_points* points, const double* d_anm, int n_epochs, double* d_out, void* stream);
-int gb_points_covariance(gb_points* points, const double* d_sigma, int nmin, double* d_out, int take_sqrt,
+int gb_points_covariance(gb_points* points, const double* d_sigma, int nmin, double* d_out, int flags,
                          void* stream);
 
 /*

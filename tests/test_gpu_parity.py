@@ -466,6 +466,15 @@ def test_irregular_covariance_golden(gb, golden, orc):
     std = gb.IrregularGrid(lon, lat).covariance_propagation(sigma, nmin, N, "potential")
     ref = orc.covariance_propagation_points(sigma, lon, lat, nmin, N, "potential")
     assert maxnorm_err(std, ref) < TOL
+    # upper-triangle path (symmetric Sigma) and full path agree; an antisymmetric perturbation needs the full path
+    pp = gb.get_points_plan(gb.IrregularGrid(lon, lat), N, "potential")
+    sd = torch.as_tensor(sigma).cuda()
+    half = pp.covariance_propagation(sd, nmin, symmetric=True).cpu().numpy()
+    full = pp.covariance_propagation(sd, nmin, symmetric=False).cpu().numpy()
+    assert maxnorm_err(half, ref) < TOL and maxnorm_err(full, ref) < TOL
+    skew = np.triu(rng.standard_normal(sigma.shape), 1) * np.abs(sigma).max() * 0.2
+    auto = pp.covariance_propagation(torch.as_tensor(sigma + skew - skew.T).cuda(), nmin).cpu().numpy()
+    assert maxnorm_err(auto, ref) < 1e-10
     # the direct point kernel and the structured regular-grid kernel agree on a regular grid
     grid = gb.GeographicGrid(12.0, 9.0)
     reg = grid.covariance_propagation(sigma, nmin, N, "potential")
