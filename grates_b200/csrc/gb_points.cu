@@ -156,8 +156,10 @@ gb_points_quadform(const double* __restrict__ FT, int rows, const double* __rest
     if (warp == C_CONSUMER_WARPS) {
         // producer: one bulk copy for the F^T chunk, one per covariance row
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const long long mt = t / n_ntiles;
-            const int n0 = (int)(t % n_ntiles) * C_TN;
+            // upper-triangular operand: the work of a tile grows with its column tile, so the heaviest column tiles
+            // go first (and the CTAs of one wave share the same covariance columns in L2)
+            const long long mt = upper ? t % n_mtiles : t / n_ntiles;
+            const int n0 = (int)(upper ? n_ntiles - 1 - t / n_mtiles : t % n_ntiles) * C_TN;
             long long w = Kc - n0;
             if (w > C_TN) w = C_TN;
             const int width = (int)((w + 1) & ~1LL);     // even number of doubles (16-byte granules)
@@ -185,8 +187,8 @@ gb_points_quadform(const double* __restrict__ FT, int rows, const double* __rest
         const int wm = warp / C_WN, wn = warp % C_WN;
         const int g = lane >> 2, q = lane & 3;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const long long mt = t / n_ntiles;
-            const int n0 = (int)(t % n_ntiles) * C_TN;
+            const long long mt = upper ? t % n_mtiles : t / n_ntiles;
+            const int n0 = (int)(upper ? n_ntiles - 1 - t / n_mtiles : t % n_ntiles) * C_TN;
             double acc[4][5][2];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
