@@ -117,13 +117,16 @@ gb_legendre_stage1_simple(const double* __restrict__ X, double* __restrict__ AB,
 // read are global (transposed, zero padded: gb_plan::d_rec_a/b, d_kn_t, d_pmm_t, d_ct_pad), so no
 // per-item prologue exists.  The last chunk of an order is processed in whole 4-degree steps only.
 // ---------------------------------------------------------------------------------------------
-constexpr int T1_TM = GB_T1_TM, T1_TN = 240, T1_KC = GB_T1_KC, T1_STAGES = 4;
+// NWN = warps along the columns: 6 (240-column items, one CTA per SM) for epoch batches, 2 (80-column items, two
+// CTAs per SM) for narrow batches, where an item is paced by the Legendre warps' dependent recursion and twice as many
+// resident items double the recursion throughput.
+constexpr int T1_TM = GB_T1_TM, T1_KC = GB_T1_KC, T1_STAGES = 4;
 constexpr int T1_LDA = T1_TM + 4;    // 68
-constexpr int T1_LDB = T1_TN + 4;    // 244
-constexpr int T1_CONSUMER_WARPS = 12;
-constexpr int T1_THREADS = 32 * (T1_CONSUMER_WARPS + 3);   // + copy warp + 2 Legendre warps
-constexpr int T1_STAGE_DOUBLES = T1_KC * (T1_LDA + T1_LDB);
-constexpr size_t T1_SMEM = (size_t)T1_STAGES * T1_STAGE_DOUBLES * sizeof(double) + 2 * T1_STAGES * sizeof(uint64_t);
+__host__ __device__ constexpr int t1_tn(int nwn) { return 40 * nwn; }
+__host__ __device__ constexpr int t1_threads(int nwn) { return 32 * (2 * nwn + 3); }   // + copy warp + 2 Legendre warps
+__host__ __device__ constexpr size_t t1_smem(int nwn) {
+    return (size_t)T1_STAGES * T1_KC * (T1_LDA + t1_tn(nwn) + 4) * sizeof(double) + 2 * T1_STAGES * sizeof(uint64_t);
+}
 
 struct T1Tables {
     const double* ct_pad;   // [nlat_pad]
@@ -136,10 +139,12 @@ struct T1Tables {
     int nlat_pad, lpad;
 };
 
-template <bool PAIRS>   // nlat even: rows (e, i), (e, i+1) with i even are 16-byte aligned in AB
-__global__ void __launch_bounds__(T1_THREADS, 1)
+template <bool PAIRS, int NWN>   // PAIRS: nlat even, rows (e, i), (e, i+1) with i even are 16-byte aligned in AB
+__global__ void __launch_bounds__(t1_threads(NWN), NWN <= 2 ? 2 : 1)
 gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tables tb, int L, int nlat, int E,
                    int ab_rows, int n_lattiles, int n_coltiles, int n_items) {
+    constexpr int T1_TN = t1_tn(NWN), T1_LDB = T1_TN + 4, T1_CONSUMER_WARPS = 2 * NWN;
+    constexpr int T1_STAGE_DOUBLES = T1_KC * (T1_LDA + T1_LDB);
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)T1_STAGES * T1_STAGE_DOUBLES * sizeof(double));
@@ -235,8 +240,8 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
             // ===== consumer warps: D[col][i] = sum_n X_m[n][col] Pk[n][i] =====
             // The columns (e, cos|sin) are the M side of the DMMA tiles and the parallels the N side, so a
             // thread ends up with two neighbouring parallels of one column: one 16-byte store into AB.
-            const int wm = warp / 6;
-            const int wn = warp % 6;
+            const int wm = warp / NWN;
+            const int wn = warp % NWN;
             const int g = lane >> 2, q = lane & 3;
             const bool has_columns = wn * 40 < width;      // narrow batches (few epochs): the other warps only keep the ring moving
             for (int pass = 0; pass < npass; ++pass) {
@@ -543,20 +548,29 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
                                                            p->d_rb, p->d_rc, d_krow, L, p->nlat, E, p->ab_rows);
         GB_LAUNCH_CHECK();
     } else {
-        const int n_coltiles = (2 * E + T1_TN - 1) / T1_TN;
+        // narrow batches (at most 80 epochs): 80-column items, two CTAs per SM
+        const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
+        const int tn = narrow ? t1_tn(2) : t1_tn(6);
+        const int n_coltiles = (2 * E + tn - 1) / tn;
         const int n_lattiles = (p->nlat + T1_TM - 1) / T1_TM;
         const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
-        const int grid = n_items < p->sm_count ? n_items : p->sm_count;
+        const int max_ctas = narrow ? 2 * p->sm_count : p->sm_count;
+        const int grid = n_items < max_ctas ? n_items : max_ctas;
         T1Tables tb{p->d_ct_pad, p->d_kn_t, p->d_pmm_t, p->d_rec_a, p->d_rec_b, p->d_zero, d_krow, p->nlat_pad, p->lpad};
-        if (p->nlat % 2 == 0) {
-            GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
-            gb_legendre_stage1<true><<<grid, T1_THREADS, T1_SMEM, st>>>(p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows,
-                                                                        n_lattiles, n_coltiles, n_items);
+#define GB_S1_LAUNCH(PAIRS, NWN)                                                                                     \
+    do {                                                                                                             \
+        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<PAIRS, NWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                     (int)t1_smem(NWN)));                                                            \
+        gb_legendre_stage1<PAIRS, NWN><<<grid, t1_threads(NWN), t1_smem(NWN), st>>>(                                  \
+            p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows, n_lattiles, n_coltiles, n_items);                        \
+    } while (0)
+        const bool pairs = p->nlat % 2 == 0;
+        if (narrow) {
+            if (pairs) GB_S1_LAUNCH(true, 2); else GB_S1_LAUNCH(false, 2);
         } else {
-            GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
-            gb_legendre_stage1<false><<<grid, T1_THREADS, T1_SMEM, st>>>(p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows,
-                                                                         n_lattiles, n_coltiles, n_items);
+            if (pairs) GB_S1_LAUNCH(true, 6); else GB_S1_LAUNCH(false, 6);
         }
+#undef GB_S1_LAUNCH
         GB_LAUNCH_CHECK();
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[2], st));
