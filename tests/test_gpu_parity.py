@@ -758,3 +758,20 @@ def test_config5_filter_then_synthesis_full_degree(gb, orc):
     lin = 2.0 * vals[3] - 0.5 * vals[9]
     got = gb.to_grid_batch(flt.filter_batch(mix), grid, "ewh")[0]
     assert maxnorm_err(got.cpu().numpy(), lin.cpu().numpy()) < 1e-13
+
+
+def test_degree_360(gb, orc):
+    """Degree 360 (tolerance 1e-10 at degree >= 180, north star): synthesis to 0.5 deg against the oracle, block filter,
+    analysis round trip on a 0.25 deg grid."""
+    N, E = 360, 6
+    grid, og = gb.GeographicGrid(0.5, 0.5), orc.geographic_grid(0.5, 0.5)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    out = gb.to_grid_batch(torch.as_tensor(anm).cuda(), grid, "ewh")
+    assert maxnorm_err(out[3].cpu().numpy(), orc.synthesis(anm[3], og, "ewh")) < 1e-10
+    blocks = orc.synthetic_filter_blocks(N)
+    f = gb.OrderWiseFilter(blocks).filter_batch(torch.as_tensor(anm[:2]).cuda())
+    assert maxnorm_err(f[1].cpu().numpy(), orc.orderwise_filter(blocks, anm[1])) < 1e-13
+    grid2 = gb.GeographicGrid(0.25, 0.25)
+    v = gb.to_grid_batch(torch.as_tensor(anm[:2]).cuda(), grid2, "ewh")
+    back = gb.analysis_batch(v, grid2, 0, N, "ewh", device_output=True)
+    assert maxnorm_err(back.cpu().numpy(), anm[:2]) < 1e-10
