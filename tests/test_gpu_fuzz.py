@@ -28,7 +28,7 @@ def orc():
     return sh_oracle
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("GB_FUZZ_SEEDS", "10"))))
 def test_random_synthesis_analysis_filter(gb, orc, seed):
     rng = np.random.default_rng(100 + seed)
     dlon, dlat = float(rng.choice(STEPS)), float(rng.choice(STEPS))
@@ -59,7 +59,7 @@ def test_random_synthesis_analysis_filter(gb, orc, seed):
         assert maxnorm_err(back, want) < 1e-10, (dlon, dlat, N, nmin, kernel)
 
 
-@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("seed", range(max(5, int(__import__("os").environ.get("GB_FUZZ_SEEDS", "10")) // 2)))
 def test_random_covariance_and_statistics(gb, orc, seed):
     rng = np.random.default_rng(300 + seed)
     dlon, dlat = float(rng.choice(STEPS[3:])), float(rng.choice(STEPS[3:]))
