@@ -588,7 +588,7 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         for (int g = 0; g < 5; ++g) grp.off[g] = p->grp_off[g];
         GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
         // 32-byte stores need 32-byte aligned rows: nlon is a multiple of 8 here, so only the base pointer matters
-        const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 8 == 0) ? 1 : 0;
+        const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 8 == 0 && !env_flag("GB_S2_NARROW_STORES")) ? 1 : 0;
         gb_fourier_stage2_sym<<<grid, Q_THREADS, Q_SMEM, st>>>(p->d_ab, p->ab_rows, p->d_trig_q_t, p->kpad_s, grp, d_out, M,
                                                                p->nlon, p->nq, n_mtiles, n_ntiles, wide);
         GB_LAUNCH_CHECK();

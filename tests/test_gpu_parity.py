@@ -134,6 +134,9 @@ def test_synthesis_symmetric_vs_general_path(gb, orc, monkeypatch, nmax, dlon, E
     if nmax >= 1:
         anm[:, 1, 0], anm[:, 1, 1], anm[:, 0, 1] = 2e-6, -3e-6, 4e-6
     sym = gb.to_grid_batch(anm, grid, "ewh")
+    monkeypatch.setenv("GB_S2_NARROW_STORES", "1")       # 16-byte store path (output rows not 32-byte aligned)
+    np.testing.assert_array_equal(gb.to_grid_batch(anm, grid, "ewh"), sym)
+    monkeypatch.delenv("GB_S2_NARROW_STORES")
     monkeypatch.setenv("GB_NO_SYMMETRY", "1")
     gen = gb.to_grid_batch(anm, grid, "ewh")
     monkeypatch.delenv("GB_NO_SYMMETRY")
