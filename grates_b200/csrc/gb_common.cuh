@@ -230,6 +230,26 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// Fully normalised Legendre functions of one (point, order): calls f(n, P_nm) for n = m..L-1.
+// Forward column recursion of reference utilities.py:37-54 with unfused multiplies / subtract in numpy's evaluation
+// order, so that the values are bit-identical to the reference table (seed P_mm from the plan, a/b/sqrt(2n+1) tables).
+template <typename F>
+__device__ __forceinline__ void legendre_column(int m, int L, double ct, double pmm, const double* __restrict__ ra,
+                                                const double* __restrict__ rb, const double* __restrict__ rc, F&& f) {
+    double p2 = pmm;  // P_mm
+    f(m, p2);
+    if (m + 1 >= L) return;
+    double p1 = __dmul_rn(__dmul_rn(rc[m + 1], ct), p2);  // P_{m+1,m} = sqrt(2n+1) * cos * P_mm
+    f(m + 1, p1);
+    for (int n = m + 2; n < L; ++n) {
+        const double p = __dsub_rn(__dmul_rn(__dmul_rn(ra[(size_t)n * L + m], ct), p1),
+                                   __dmul_rn(rb[(size_t)n * L + m], p2));
+        f(n, p);
+        p2 = p1;
+        p1 = p;
+    }
+}
+
 __device__ __forceinline__ void st_cs_v2(double* p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(a), "d"(b) : "memory");
 }

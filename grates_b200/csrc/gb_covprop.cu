@@ -30,22 +30,7 @@
 
 namespace {
 
-template <typename F>
-__device__ __forceinline__ void legendre_column(int m, int L, double ct, double pmm, const double* __restrict__ ra,
-                                                const double* __restrict__ rb, const double* __restrict__ rc, F&& f) {
-    double p2 = pmm;
-    f(m, p2);
-    if (m + 1 >= L) return;
-    double p1 = __dmul_rn(__dmul_rn(rc[m + 1], ct), p2);
-    f(m + 1, p1);
-    for (int n = m + 2; n < L; ++n) {
-        const double p = __dsub_rn(__dmul_rn(__dmul_rn(ra[(size_t)n * L + m], ct), p1),
-                                   __dmul_rn(rb[(size_t)n * L + m], p2));
-        f(n, p);
-        p2 = p1;
-        p1 = p;
-    }
-}
+using gb::legendre_column;
 
 // St[gb_ab_offset(a', b, Kp4)] = Sigma[perm8[a']][perm4[b]]  (0 where either index is padding)
 __global__ void __launch_bounds__(256)

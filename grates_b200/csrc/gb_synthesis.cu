@@ -26,27 +26,7 @@
 
 namespace {
 
-// ---------------------------------------------------------------------------------------------
-// Legendre recursion for one (latitude, order): calls f(n - m, P_nm) for n = m..nmax.
-// Unfused multiplies / subtract reproduce numpy's evaluation order of utilities.py:46,52-54.
-// ---------------------------------------------------------------------------------------------
-template <typename F>
-__device__ __forceinline__ void legendre_column(int m, int L, double ct, double pmm, const double* __restrict__ ra,
-                                                const double* __restrict__ rb, const double* __restrict__ rc, F&& f) {
-    double p2 = pmm;  // P_mm
-    f(0, p2);
-    if (m + 1 >= L) return;
-    double p1 = __dmul_rn(__dmul_rn(rc[m + 1], ct), p2);  // P_{m+1,m} = sqrt(2n+1) * cos * P_mm
-    f(1, p1);
-    for (int n = m + 2; n < L; ++n) {
-        const double a = ra[(size_t)n * L + m];
-        const double b = rb[(size_t)n * L + m];
-        const double p = __dsub_rn(__dmul_rn(__dmul_rn(a, ct), p1), __dmul_rn(b, p2));
-        f(n - m, p);
-        p2 = p1;
-        p1 = p;
-    }
-}
+using gb::legendre_column;   // f(n, P_nm), n = m..L-1 (gb_common.cuh)
 
 constexpr int S1_TI = 32;  // latitudes per CTA
 
@@ -65,7 +45,7 @@ gb_legendre_stage1_simple(const double* __restrict__ X, double* __restrict__ AB,
         if (i < nlat) {
             const double* kn_i = kn + (size_t)i * L + m;
             legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc,
-                            [&](int nn, double p) { s_pk[nn * S1_TI + tid] = __dmul_rn(p, kn_i[nn]); });
+                            [&](int n, double p) { s_pk[(n - m) * S1_TI + tid] = __dmul_rn(p, kn_i[n - m]); });
         } else {
             for (int nn = 0; nn < Kn; ++nn) s_pk[nn * S1_TI + tid] = 0.0;
         }
@@ -510,8 +490,7 @@ gb_legendre_table_kernel(double* __restrict__ out, const double* __restrict__ ct
     const int i = idx / L, m = idx % L;
     double* o = out + (size_t)i * L * L;
     const double* kn_i = kn + (size_t)i * L;
-    legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int nn, double p) {
-        const int n = m + nn;
+    legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int n, double p) {
         const double v = scaled ? __dmul_rn(p, kn_i[n]) : p;
         o[(size_t)n * L + m] = v;
         if (m > 0) o[(size_t)(m - 1) * L + n] = v;
