@@ -492,7 +492,7 @@ def get_points_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.378
         if plan is None:
             plan = PointsPlan(lon, lat, grid.semimajor_axis, grid.flattening, max_degree, kernel, GM, R, dev)
             if len(_cache) >= _MAX_CACHED_PLANS:
-                _cache.pop(next(iter(_cache))).close()
+                _cache.pop(next(iter(_cache)))       # destroyed by __del__ once no caller holds it any more
             _cache[key] = plan
         return plan
 
@@ -518,7 +518,7 @@ def get_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000
         if plan is None:
             plan = SHPlan(meridians, parallels, grid.semimajor_axis, grid.flattening, max_degree, kernel, GM, R, dev)
             if len(_cache) >= _MAX_CACHED_PLANS:
-                _cache.pop(next(iter(_cache))).close()
+                _cache.pop(next(iter(_cache)))       # destroyed by __del__ once no caller holds it any more
             _cache[key] = plan
         return plan
 
