@@ -4,7 +4,7 @@
  * The reference (pure Python/numpy) has no FFI; the boundary it offers is its Python method
  * signatures.  Each entry point below replaces the numpy/BLAS body of one of those methods
  * (citations are relative to /root/reference/grates/).  The Python host side
- * (grates_b200/*.py) builds the small epoch-independent tables with the reference's exact
+ * (the grates_b200 Python package) builds the small epoch-independent tables with the reference's exact
  * numpy expressions and calls these functions through ctypes; see INTEGRATION.md for the
  * binding a maintainer of the reference would add.
  *
