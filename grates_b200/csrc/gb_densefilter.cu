@@ -10,18 +10,7 @@
 
 namespace {
 
-// degree-wise index c (counted from degree 0) -> position in the packed [L][L] array
-__device__ __forceinline__ void degreewise_position(long long c, int& row, int& col, int& degree) {
-    int n = (int)floor(sqrt((double)c));
-    if ((long long)n * n > c) --n;
-    if ((long long)(n + 1) * (n + 1) <= c) ++n;
-    const int j = (int)(c - (long long)n * n);             // 0: C_n0, 2m-1: C_nm, 2m: S_nm
-    const int m = (j + 1) >> 1;
-    const bool sine = j > 0 && (j & 1) == 0;
-    row = sine ? m - 1 : n;
-    col = sine ? n : m;
-    degree = n;
-}
+using gbgemm::degreewise_position;
 
 // 32 x 32 transposing tiles: reads rows of W, writes runs of 32 rows r per column c
 __global__ void __launch_bounds__(256)
@@ -54,41 +43,6 @@ gb_dense_ravel_tiles(const double* __restrict__ anm, double* __restrict__ Bt, in
     }
     Bt[((size_t)(e / GB_S2_TN) * kp4 + c) * GB_S2_LDB + e % GB_S2_TN] = v;
 }
-
-struct UnravelStore {
-    static constexpr bool whole_tile = true;
-    double* out;
-    long long K;
-    int nmin, Lout, E;
-    struct Pre { int pos[4]; };          // packed position of the thread's four rows, -1: not stored
-    __device__ __forceinline__ Pre prepare(long long row_base, int, int) const {
-        Pre pr;
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            const long long r = row_base + mi * 8;
-            pr.pos[mi] = -1;
-            if (r < K) {
-                int row, col, n;
-                degreewise_position(r + (long long)nmin * nmin, row, col, n);
-                if (n < Lout) pr.pos[mi] = row * Lout + col;
-            }
-        }
-        return pr;
-    }
-    __device__ __forceinline__ void tile(const Pre& pr, long long, int col_base, double (&acc)[4][5][2]) const {
-#pragma unroll
-        for (int ni = 0; ni < 5; ++ni)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int e = col_base + ni * 8 + r;
-                if (e >= E) continue;
-                double* o = out + (size_t)e * Lout * Lout;
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-                    if (pr.pos[mi] >= 0) o[pr.pos[mi]] = acc[mi][ni][r];
-            }
-    }
-};
 
 // degrees below nmin pass through: the top-left nmin x nmin corner of the packed array (filter.py:477)
 __global__ void gb_dense_passthrough(const double* __restrict__ in, double* __restrict__ out, int Lin, int Lout, int nmin, int E) {
@@ -165,7 +119,7 @@ extern "C" int gb_dense_filter(const double* d_tiles, int nmin, int nmax_filter,
         sh.klen = kp4;
         sh.n_mtiles = (int)((K + GB_TM - 1) / GB_TM);
         sh.n_ntiles = n_ct;
-        int rc = gbgemm::launch(sh, UnravelStore{d_anm_out, K, nmin, Lout, E}, sm_count, st);
+        int rc = gbgemm::launch(sh, gbgemm::UnravelStore<false>{d_anm_out, K, nmin, Lout, E}, sm_count, st);
         if (rc) return rc;
     }
     const int nm = nmin < Lout ? nmin : Lout;

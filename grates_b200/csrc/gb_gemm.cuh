@@ -182,4 +182,60 @@ inline int launch(const Shape& sh, const Epilogue& epi, int sm_count, cudaStream
     return GB_OK;
 }
 
+// degree-wise index c (counted from degree 0; reference utilities.py:310-360) -> position in the packed [L][L] array
+__device__ __forceinline__ void degreewise_position(long long c, int& row, int& col, int& degree) {
+    int n = (int)floor(sqrt((double)c));
+    if ((long long)n * n > c) --n;
+    if ((long long)(n + 1) * (n + 1) <= c) ++n;
+    const int j = (int)(c - (long long)n * n);             // 0: C_n0, 2m-1: C_nm, 2m: S_nm
+    const int m = (j + 1) >> 1;
+    const bool sine = j > 0 && (j & 1) == 0;
+    row = sine ? m - 1 : n;
+    col = sine ? n : m;
+    degree = n;
+}
+
+// Epilogue: GEMM rows are degree-wise coefficient indices (from nmin^2), columns epochs; scatter into packed
+// out[e][Lout][Lout].  ACCUMULATE adds to what is there (K loop split over several launches on one stream).
+template <bool ACCUMULATE>
+struct UnravelStore {
+    static constexpr bool whole_tile = true;
+    double* out;
+    long long K;
+    int nmin, Lout, E;
+    struct Pre { int pos[4]; };          // packed position of the thread's four rows, -1: not stored
+    __device__ __forceinline__ Pre prepare(long long row_base, int, int) const {
+        Pre pr;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const long long r = row_base + mi * 8;
+            pr.pos[mi] = -1;
+            if (r < K) {
+                int row, col, n;
+                degreewise_position(r + (long long)nmin * nmin, row, col, n);
+                if (n < Lout) pr.pos[mi] = row * Lout + col;
+            }
+        }
+        return pr;
+    }
+    template <int NI>
+    __device__ __forceinline__ void tile(const Pre& pr, long long, int col_base, double (&acc)[4][NI][2]) const {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int e = col_base + ni * 8 + r;
+                if (e >= E) continue;
+                double* o = out + (size_t)e * Lout * Lout;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+                    if (pr.pos[mi] >= 0) {
+                        if (ACCUMULATE) o[pr.pos[mi]] += acc[mi][ni][r];
+                        else o[pr.pos[mi]] = acc[mi][ni][r];
+                    }
+            }
+    }
+};
+
 }  // namespace gbgemm
+

@@ -110,6 +110,56 @@ gb_points_design(double* __restrict__ FT, const double* __restrict__ ct, const d
 }
 
 // ---------------------------------------------------------------------------------------------
+// adjoint: design matrix as the GEMM A operand, F[a][p] in tiles [coefficient tile][p][GB_LDA] (K loop over points),
+// and the point values as B tiles [epoch tile][p][GB_S2_LDB]
+// ---------------------------------------------------------------------------------------------
+// CTA = one point, thread = order m, all threads walk the degrees n together: for a fixed n the entries
+// a = n^2 .. (n+1)^2 - 1 of the point's row are contiguous, so the stores coalesce.  The recursion is
+// gb::legendre_column's, step for step (bit-identical values).  Rows beyond the last point (K-loop padding) are zeroed.
+__global__ void __launch_bounds__(1024)
+gb_points_design_adjoint(double* __restrict__ AT, const double* __restrict__ ct, const double* __restrict__ kn,
+                         const double* __restrict__ pmm, const double* __restrict__ cml, const double* __restrict__ sml,
+                         const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc, int L,
+                         int npts, int rows, int p0) {
+    const int pp = blockIdx.x;
+    const int p = p0 + pp;
+    if (p >= npts) {
+        for (long long a = threadIdx.x; a < (long long)L * L; a += blockDim.x) AT[gb_ab_offset(a, pp, rows)] = 0.0;
+        return;
+    }
+    const double ctp = ct[p];
+    const double* kn_p = kn + (size_t)p * L;
+    for (int m0 = threadIdx.x & ~31; m0 < L; m0 += blockDim.x) {        // the warp's orders m0 .. m0 + 31
+        const int m = m0 + (threadIdx.x & 31);
+        if (m >= L) continue;
+        const double cm = cml[(size_t)p * L + m], sm = sml[(size_t)p * L + m];
+        double p1 = 0.0, p2 = 0.0;
+        for (int n = m0; n < L; ++n) {                                  // same n across the warp at every step
+            if (n < m) continue;
+            double v;
+            if (n == m) v = pmm[(size_t)p * L + m];
+            else if (n == m + 1) v = __dmul_rn(__dmul_rn(rc[n], ctp), p1);
+            else v = __dsub_rn(__dmul_rn(__dmul_rn(ra[(size_t)n * L + m], ctp), p1), __dmul_rn(rb[(size_t)n * L + m], p2));
+            p2 = p1;
+            p1 = v;
+            const double pk = __dmul_rn(v, kn_p[n]);
+            const long long a = (long long)n * n + (m == 0 ? 0 : 2 * m - 1);
+            AT[gb_ab_offset(a, pp, rows)] = __dmul_rn(pk, cm);
+            if (m > 0) AT[gb_ab_offset(a + 1, pp, rows)] = __dmul_rn(pk, sm);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gb_points_value_tiles(const double* __restrict__ values, double* __restrict__ Bt, int npts, int p0, int count, int rows, int E,
+                      int tn, int ldb) {
+    const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.y;
+    if (pp >= count) return;
+    Bt[((size_t)(e / tn) * rows + pp) * ldb + e % tn] = values[(size_t)e * npts + p0 + pp];
+}
+
+// ---------------------------------------------------------------------------------------------
 // blocked diag(F Sigma F'): tile = 128 points x 120 columns b; K loop over a in chunks of 28
 // ---------------------------------------------------------------------------------------------
 constexpr int C_WM = 4, C_WN = 3, C_TM = 128, C_TN = 120, C_KC = 28, C_STAGES = 3;
@@ -370,6 +420,70 @@ extern "C" int gb_points_synthesis(gb_points* p, const double* d_anm, int n_epoc
         n_epochs);
     GB_LAUNCH_CHECK();
     return GB_OK;
+}
+
+// Adjoint of the point synthesis: anm_e[n, m] = sum_p F[p, (n, m)] v_e[p]  (the sum over nodal points of
+// RadialBasisFunctions.to_potential_coefficients, reference gravityfield.py:707-724, with the plan's per-point
+// degree factors as the upward continuation).  One GEMM per block of points on the DMMA kernel, K loop over the
+// points of the block; blocks accumulate in launch order, so the result is deterministic.  NI: column fragments per
+// warp (epoch tile of 24 NI columns) -- a single value set does not pay for a 120-column tile.
+template <int NI>
+static int points_adjoint_blocks(gb_points* p, const double* d_values, int E, double* d_anm, cudaStream_t st) {
+    constexpr int TN = gbgemm::tile_n(NI), LDB = gbgemm::tile_ldb(NI);
+    const int L = p->L;
+    const long long K = (long long)L * L;
+    const int n_mtiles = (int)((K + GB_TM - 1) / GB_TM);
+    const int n_ct = (E + TN - 1) / TN;
+    // points per block: A operand of about 512 MB, at least one k chunk
+    long long pb = (512LL << 20) / ((long long)n_mtiles * GB_LDA * sizeof(double));
+    pb = pb / 128 * 128;
+    if (pb < 128) pb = 128;
+    if (pb > 16384) pb = 16384;
+    if (pb > (p->npts + 3) / 4 * 4) pb = (p->npts + 3) / 4 * 4;
+    gb_scratch scratch(st);
+    double *d_at = nullptr, *d_bt = nullptr;
+    GB_CUDA(scratch.alloc(&d_at, (size_t)n_mtiles * pb * GB_LDA));
+    GB_CUDA(scratch.alloc(&d_bt, (size_t)n_ct * pb * LDB));
+    GB_CUDA(cudaMemsetAsync(d_anm, 0, (size_t)E * K * sizeof(double), st));
+    for (int p0 = 0; p0 < p->npts; p0 += (int)pb) {
+        const int count = (p->npts - p0 < pb) ? (p->npts - p0) : (int)pb;
+        const int rows = (count + 3) / 4 * 4;
+        GB_CUDA(cudaMemsetAsync(d_bt, 0, (size_t)n_ct * rows * LDB * sizeof(double), st));
+        const int threads = L >= 1024 ? 1024 : (L + 31) / 32 * 32;
+        gb_points_design_adjoint<<<rows, threads, 0, st>>>(d_at, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra,
+                                                          p->d_rb, p->d_rc, L, p0 + count, rows, p0);
+        GB_LAUNCH_CHECK();
+        dim3 vgrid((count + 255) / 256, E);
+        gb_points_value_tiles<<<vgrid, 256, 0, st>>>(d_values, d_bt, p->npts, p0, count, rows, E, TN, LDB);
+        GB_LAUNCH_CHECK();
+        gbgemm::Shape sh;
+        sh.A_t = d_at;
+        sh.a_rows = rows;
+        sh.a_koff_mul = 0;
+        sh.tiles_per_group = 1;
+        sh.B_t = d_bt;
+        sh.b_rows = rows;
+        sh.klen = rows;
+        sh.n_mtiles = n_mtiles;
+        sh.n_ntiles = n_ct;
+        int rc = gbgemm::launch<gbgemm::UnravelStore<true>, NI>(sh, gbgemm::UnravelStore<true>{d_anm, K, 0, L, E},
+                                                               p->sm_count, st);
+        if (rc) return rc;
+    }
+    return GB_OK;
+}
+
+extern "C" int gb_points_adjoint(gb_points* p, const double* d_values, int n_epochs, double* d_anm, void* stream) {
+    GB_REQUIRE(p != nullptr, "gb_points_adjoint: point set is NULL");
+    GB_REQUIRE(n_epochs >= 0, "gb_points_adjoint: n_epochs=%d is negative", n_epochs);
+    if (n_epochs == 0) return GB_OK;
+    GB_REQUIRE(d_values && d_anm, "gb_points_adjoint: NULL device pointer");
+    GB_CUDA(cudaSetDevice(p->device));
+    gb_retain_pool_memory(p->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_epochs <= gbgemm::tile_n(1)) return points_adjoint_blocks<1>(p, d_values, n_epochs, d_anm, st);
+    if (n_epochs <= gbgemm::tile_n(2)) return points_adjoint_blocks<2>(p, d_values, n_epochs, d_anm, st);
+    return points_adjoint_blocks<5>(p, d_values, n_epochs, d_anm, st);
 }
 
 // Sigma re-pitched to an even leading dimension; for a symmetric Sigma only its upper triangle is kept, the

@@ -135,6 +135,74 @@ class PotentialCoefficients:
         return output_grid
 
 
+class RadialBasisFunctions:
+    """Gravity field represented by radial basis functions at nodal points (reference gravityfield.py:645-781).
+
+    Constructor, ``values``, ``copy`` and ``to_grid`` as in the reference.  ``to_potential_coefficients`` runs the sum
+    over the nodal points as one GEMM against the on-the-fly design matrix (``gb_points_adjoint``); ``blocking_factor``
+    is accepted for signature compatibility and ignored (the device code blocks by itself).
+    """
+
+    def __init__(self, point_distribution, K, min_degree, max_degree, GM=GM_DEFAULT, R=R_DEFAULT):
+        self._K = np.array(K, dtype=float, copy=True)
+        self.point_distribution = point_distribution.copy()
+        self._min_degree = min_degree
+        self._max_degree = max_degree
+        self.GM = GM
+        self.R = R
+        self.epoch = None
+        self.values = np.zeros((self.point_distribution.size))
+
+    def copy(self):
+        rbf = RadialBasisFunctions(self.point_distribution.copy(), self._K, self._min_degree, self._max_degree, self.GM, self.R)
+        rbf.epoch = self.epoch
+        rbf.values = self.values.copy()
+        return rbf
+
+    @property
+    def values(self):
+        return self.point_distribution.values
+
+    @values.setter
+    def values(self, val):
+        self.point_distribution.values = val
+
+    def is_compatible(self, other):
+        return self.point_distribution.is_compatible(other.point_distribution)
+
+    def _points_plan(self):
+        """Point-set plan whose degree factors are the upward continuation (R / r_p)^(n + 1), gravityfield.py:713."""
+        grid = self.point_distribution
+        lon = np.asarray(grid.longitude, dtype=float)
+        lat = np.asarray(grid.latitude, dtype=float)
+        key = (lon.tobytes(), lat.tobytes(), float(grid.semimajor_axis), float(grid.flattening), self._max_degree, float(self.R))
+        cached = getattr(self, "_plan_cache", None)
+        if cached is None or cached[0] != key:
+            radius = utilities.geocentric_radius(lat, grid.semimajor_axis, grid.flattening)
+            kn = np.power((self.R / radius)[:, np.newaxis], np.arange(self._max_degree + 1, dtype=int) + 1)
+            cached = (key, _plan.PointsPlan(lon, lat, grid.semimajor_axis, grid.flattening, self._max_degree,
+                                            degree_factors=kn))
+            self._plan_cache = cached
+        return cached[1]
+
+    def to_potential_coefficients_batch(self, values):
+        """values [E, points] (numpy or CUDA tensor) -> CUDA tensor [E, L, L] of packed coefficients."""
+        p = self._points_plan()
+        dev = torch.device("cuda", p.device)
+        v = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(values, dtype=float))
+        anm = p.adjoint(v.to(dev))
+        return anm.mul_(torch.as_tensor(self._K).to(dev))
+
+    def to_potential_coefficients(self, blocking_factor=256):
+        coefficients = PotentialCoefficients(self.GM, self.R)
+        coefficients.anm = self.to_potential_coefficients_batch(np.asarray(self.values, dtype=float)[None])[0].cpu().numpy()
+        coefficients.epoch = self.epoch
+        return coefficients
+
+    def to_grid(self, grid=None, kernel='ewh'):
+        return self.to_potential_coefficients().to_grid(GeographicGrid() if grid is None else grid, kernel)
+
+
 class TimeSeries:
     """Epoch-sorted list of gravity fields (reference gravityfield.py:815-1052)."""
 

@@ -20,6 +20,7 @@ Rebound (reference file:line):
     OrderWiseFilter.filter / Gaussian.filter / Butterworth.filter      filter.py:43-70, 108-118, 153-191
     GeneralMatrix.filter / VDK.filter             filter.py:456-479, 548-572
     gravityfield.gridded_rms                      gravityfield.py:1143-1172
+    RadialBasisFunctions.to_potential_coefficients      gravityfield.py:692-727
 """
 import numpy as np
 
@@ -106,6 +107,21 @@ def install(reference=None):
         out.anm = res.anm
         return out
 
+    def rbf_to_potential_coefficients(self, blocking_factor=256):
+        mine = self.__dict__.get("_gb_mirror")
+        if mine is None:
+            mine = _gf.RadialBasisFunctions(_mirror_grid(self.point_distribution), self._RadialBasisFunctions__K,
+                                            self._RadialBasisFunctions__min_degree,
+                                            self._RadialBasisFunctions__max_degree, self.GM, self.R)
+            self.__dict__["_gb_mirror"] = mine
+        mine.GM, mine.R, mine.epoch = self.GM, self.R, self.epoch
+        mine.values = np.ascontiguousarray(self.values, dtype=float)
+        res = mine.to_potential_coefficients()
+        out = ref.gravityfield.PotentialCoefficients(self.GM, self.R)
+        out.anm = res.anm
+        out.epoch = self.epoch
+        return out
+
     def gridded_rms(temporal_gravityfield, epochs, kernel='ewh', base_grid=None):
         base_grid = ref.grid.GeographicGrid() if base_grid is None else base_grid
 
@@ -130,6 +146,8 @@ def install(reference=None):
             _rebind(ref.filter.GeneralMatrix, "filter", dense_filter)
             _rebind(ref.filter.VDK, "filter", dense_filter)      # the reference's own VDK.filter raises AttributeError
         _rebind(ref.gravityfield, "gridded_rms", gridded_rms)
+        if hasattr(ref.gravityfield, "RadialBasisFunctions"):
+            _rebind(ref.gravityfield.RadialBasisFunctions, "to_potential_coefficients", rbf_to_potential_coefficients)
     except Exception:
         uninstall()
         raise

@@ -408,7 +408,8 @@ class PointsPlan:
     """Device tables for an arbitrary point set (reference IrregularGrid path); wraps ``gb_points``."""
 
     def __init__(self, longitude, latitude, a, f, max_degree, kernel='ewh',
-                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
+                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None, degree_factors=None):
+        """degree_factors: [npts, L] array used instead of the kernel's factors (None: from ``kernel``)."""
         self._lib = _lib.load()
         self.device = _current_device(device)
         self.max_degree = int(max_degree)
@@ -417,7 +418,13 @@ class PointsPlan:
         if self.longitude.shape != self.latitude.shape or self.longitude.ndim != 1:
             raise ValueError("longitude and latitude must be 1-d arrays of equal length")
         self.npts = self.longitude.size
-        colat, kn = _kernel.degree_factors(kernel, self.max_degree, self.latitude, a, f, GM, R)
+        if degree_factors is None:
+            colat, kn = _kernel.degree_factors(kernel, self.max_degree, self.latitude, a, f, GM, R)
+        else:
+            colat = utilities.colatitude(self.latitude, a, f)
+            kn = np.ascontiguousarray(degree_factors, dtype=float)
+            if kn.shape != (self.npts, self.max_degree + 1):
+                raise ValueError("degree_factors must have shape [{0}, {1}]".format(self.npts, self.max_degree + 1))
         if not np.all(np.isfinite(kn)):
             raise ValueError("kernel '{0}' has non-finite degree factors on this point set".format(kernel))
         self.colat, self.kn = colat, kn
@@ -459,6 +466,21 @@ class PointsPlan:
             out = torch.empty((E, self.npts), dtype=torch.float64, device=anm.device)
         _lib.check(self._lib.gb_points_synthesis(self._handle, ctypes.c_void_p(anm.data_ptr()), E,
                                                  ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+        return out
+
+    def adjoint(self, values, out=None):
+        """values: CUDA float64 [E, npts] -> CUDA tensor [E, L, L]: the transposed synthesis operator applied to
+        point values (sum over points of kn * Y_nm * value, reference gravityfield.py:707-724)."""
+        if values.dim() != 2 or values.shape[1] != self.npts:
+            raise ValueError("values must have shape [epochs, {0}] (got {1})".format(self.npts, tuple(values.shape)))
+        if values.dtype != torch.float64 or not values.is_cuda or values.device.index != self.device:
+            raise ValueError("values must be a float64 CUDA tensor on device {0}".format(self.device))
+        values = values.contiguous()
+        E = values.shape[0]
+        if out is None:
+            out = torch.empty((E, self.L, self.L), dtype=torch.float64, device=values.device)
+        _lib.check(self._lib.gb_points_adjoint(self._handle, ctypes.c_void_p(values.data_ptr()), E,
+                                               ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
 
     def covariance_propagation(self, sigma, min_degree, take_sqrt=True, symmetric=None):

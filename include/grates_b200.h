@@ -204,6 +204,9 @@ int gb_orderwise_filter(const double* d_blocks, const int64_t* block_offsets, in
  * gb_points_covariance replaces grid.py:1103-1116: direct blocked diag(F Sigma F') with Sigma
  *   [K'][K'] (degree-wise order, offset nmin^2) -> d_out [npts] variances; flags as for gb_covariance_propagation
  *   (GB_COV_SQRT: std-devs; GB_COV_SYMMETRIC: only the upper triangle of Sigma is contracted, half the flops).
+ * gb_points_adjoint replaces the sum over nodal points of RadialBasisFunctions.to_potential_coefficients,
+ *   gravityfield.py:707-724 (the transposed design matrix): d_values [n_epochs][npts] -> d_anm [n_epochs][L][L],
+ *   anm[n, m] = sum_p kn[p][n] Y_nm(p) v[p]; the shape factors K[n, m] are applied by the caller.
  */
 typedef struct gb_points gb_points;
 int gb_points_create(gb_points** points, int nmax, int npts, const double* cos_theta, const double* sin_theta,
@@ -212,6 +215,7 @@ int gb_points_destroy(gb_points* points);
 int gb_points_synthesis(gb_points* points, const double* d_anm, int n_epochs, double* d_out, void* stream);
 int gb_points_covariance(gb_points* points, const double* d_sigma, int nmin, double* d_out, int flags,
                          void* stream);
+int gb_points_adjoint(gb_points* points, const double* d_values, int n_epochs, double* d_anm, void* stream);
 
 /*
  * Consumers of gridded epoch batches that keep the grids on the device.

@@ -647,6 +647,27 @@ def vdk_matrix(normals, nmin, nmax, kaula_scale, kaula_power):
     return np.linalg.solve(NP, normals)
 
 
+def radial_basis_to_coefficients(K, values, lon, lat, nmax, R=R_DEFAULT, a=A_GRS80, f=F_GRS80, blocking_factor=256):
+    """RadialBasisFunctions.to_potential_coefficients (reference gravityfield.py:692-727): per block of nodal points the
+    spherical harmonics, scaled by the upward continuation (R/r)^(n+1) and the shape factors K, times the point
+    values, summed over the points."""
+    anm = np.zeros((nmax + 1, nmax + 1))
+    values = np.asarray(values, dtype=float)
+    for start in range(0, values.size, blocking_factor):
+        sl = slice(start, min(start + blocking_factor, values.size))
+        colat = colatitude(lat[sl], a, f)
+        radius = geocentric_radius(lat[sl], a, f)
+        Ynm = spherical_harmonics(nmax, colat, lon[sl])
+        kn = np.power((R / radius)[:, np.newaxis], np.arange(nmax + 1, dtype=int) + 1)
+        Ynm[:, :, 0] *= kn
+        for m in range(1, nmax + 1):
+            Ynm[:, m:, m] *= kn[:, m:]
+            Ynm[:, m - 1, m:] *= kn[:, m:]
+        Ynm *= K[np.newaxis, :, :]
+        anm += np.sum(Ynm * values[sl, np.newaxis, np.newaxis], axis=0)
+    return anm
+
+
 def synthetic_coefficients(nmax, epoch=0):
     """Kaula-like random coefficients, seed 1000 + epoch; degrees 0-1 zero."""
     rng = np.random.default_rng(1000 + epoch)

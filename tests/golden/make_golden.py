@@ -294,6 +294,28 @@ def dense_filters():
     save("dense_filters", **out)
 
 
+def radial_basis():
+    """RadialBasisFunctions.to_potential_coefficients / to_grid (gravityfield.py:645-781) on a seeded point set."""
+    out = {}
+    rng = np.random.default_rng(23)
+    N, P = 20, 700           # three 256-point blocks of the reference, the last one ragged
+    lon = rng.uniform(-np.pi, np.pi, P)
+    lat = np.arcsin(rng.uniform(-1, 1, P))
+    K = np.zeros((N + 1, N + 1))
+    shape = 1.0 / (1.0 + 0.1 * np.arange(N + 1)) ** 2          # isotropic shape factors sigma_n
+    for n in range(2, N + 1):
+        K[n, 0:n + 1] = shape[n]
+        K[0:n, n] = shape[n]
+    pts = grates.grid.IrregularGrid(lon, lat)
+    rbf = grates.gravityfield.RadialBasisFunctions(pts, K, 2, N)
+    rbf.values = rng.standard_normal(P) * 1e-9
+    out["lon"], out["lat"], out["K"], out["values"] = lon, lat, K, rbf.values
+    out["anm"] = rbf.to_potential_coefficients().anm
+    g = grates.grid.GeographicGrid(6.0, 6.0)
+    out["grid_ewh"] = rbf.to_grid(g, "ewh").value_array
+    save("radial_basis", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -308,3 +330,4 @@ if __name__ == "__main__":
     filters()
     degreewise_filters()
     dense_filters()
+    radial_basis()

@@ -609,8 +609,18 @@ def test_install_wrappers_on_gpu(gb, orc, golden):
         def __init__(self, order, cutoff_degree):
             self.order, self.cutoff_degree = order, cutoff_degree
 
+    class RBF:
+        def __init__(self, point_distribution, K, min_degree, max_degree):
+            self._RadialBasisFunctions__K = K
+            self._RadialBasisFunctions__min_degree, self._RadialBasisFunctions__max_degree = min_degree, max_degree
+            self.point_distribution, self.GM, self.R, self.epoch = point_distribution, PC().GM, PC().R, None
+            self.values = None
+
+        def to_potential_coefficients(self, blocking_factor=256):
+            raise AssertionError("not rebound")
+
     ref = types.SimpleNamespace(
-        gravityfield=types.SimpleNamespace(PotentialCoefficients=PC, gridded_rms=None),
+        gravityfield=types.SimpleNamespace(PotentialCoefficients=PC, gridded_rms=None, RadialBasisFunctions=RBF),
         grid=types.SimpleNamespace(RegularGrid=RG, IrregularGrid=IG, GeographicGrid=GG),
         filter=types.SimpleNamespace(OrderWiseFilter=OWF, Gaussian=GA, Butterworth=BW))
     g = golden("degreewise_filters")
@@ -637,9 +647,50 @@ def test_install_wrappers_on_gpu(gb, orc, golden):
         std = cg.covariance_propagation(sigma, 0, 8, "ewh")
         assert maxnorm_err(std, orc.covariance_propagation(sigma, orc.geographic_grid(15.0, 15.0), 0, 8, "ewh")) < TOL
         np.testing.assert_array_equal(cg.values, std)
+        rb = golden("radial_basis")
+        rbf = RBF(IG(rb["lon"], rb["lat"]), rb["K"], 2, 20)
+        rbf.values = rb["values"]
+        conv = rbf.to_potential_coefficients()
+        assert type(conv) is PC and maxnorm_err(conv.anm, rb["anm"]) < TOL
     finally:
         gb.uninstall()
     assert not gb.installed()
+
+
+def test_radial_basis_functions_golden_and_batch(gb, orc, golden):
+    """RadialBasisFunctions (gravityfield.py:645-781): the sum over nodal points as a GEMM against the on-the-fly design
+    matrix.  Golden vectors of the reference; a batch of value sets over several point blocks against the oracle."""
+    g = golden("radial_basis")
+    pts = gb.IrregularGrid(g["lon"], g["lat"])
+    rbf = gb.RadialBasisFunctions(pts, g["K"], 2, 20)
+    rbf.values = g["values"]
+    pc = rbf.to_potential_coefficients()
+    assert pc.anm.shape == (21, 21) and maxnorm_err(pc.anm, g["anm"]) < TOL
+    out = rbf.to_grid(gb.GeographicGrid(6.0, 6.0), "ewh")
+    assert maxnorm_err(out.value_array, g["grid_ewh"]) < TOL
+    twin = rbf.copy()
+    np.testing.assert_array_equal(twin.values, rbf.values)
+    rng = np.random.default_rng(8)
+    N, P, E = 45, 5000, 130                     # 17 coefficient tiles, two epoch tiles, ragged last point block
+    lon = rng.uniform(-np.pi, np.pi, P)
+    lat = np.arcsin(rng.uniform(-1, 1, P))
+    K = rng.uniform(0.5, 1.5, (N + 1, N + 1))
+    big = gb.RadialBasisFunctions(gb.IrregularGrid(lon, lat), K, 0, N)
+    v = rng.standard_normal((E, P))
+    anm = big.to_potential_coefficients_batch(v).cpu().numpy()
+    assert anm.shape == (E, N + 1, N + 1)
+    for e in (0, 119, 129):
+        assert maxnorm_err(anm[e], orc.radial_basis_to_coefficients(K, v[e], lon, lat, N)) < TOL
+    for sub in (7, 30):                         # narrower epoch tiles of the GEMM (24 and 48 columns)
+        part = big.to_potential_coefficients_batch(v[:sub]).cpu().numpy()
+        assert maxnorm_err(part, anm[:sub]) < 1e-14
+    # the adjoint identity <A x, v> = <x, A' v> ties it to the point synthesis
+    plan = big._points_plan()
+    x = torch.as_tensor(rng.standard_normal((3, N + 1, N + 1))).cuda()
+    vv = torch.as_tensor(v[:3]).cuda()
+    lhs = (plan.synthesis(x) * vv).sum(dim=1)
+    rhs = (x * plan.adjoint(vv)).sum(dim=(1, 2))
+    np.testing.assert_allclose(lhs.cpu().numpy(), rhs.cpu().numpy(), rtol=1e-11)
 
 
 def test_dense_matrix_filter_golden_and_batch(gb, orc, golden):

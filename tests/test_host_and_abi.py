@@ -240,7 +240,7 @@ def test_install_rebinds_reference_methods_and_has_no_cpu_fallback():
     try:
         gb.install(grates)
         assert grates.gravityfield.PotentialCoefficients.to_grid is not original
-        assert len(gb.installed()) == 10
+        assert len(gb.installed()) == 11
         if not torch.cuda.is_available():
             with pytest.raises(Exception) as err:
                 pc.to_grid(grid, "ewh")
