@@ -7,7 +7,7 @@ torch.distributed); all arithmetic on the path runs in hand-written CUDA kernels
 C ABI of ``include/grates_b200.h``.  There is no CPU fallback.
 """
 from . import _lib, utilities, kernel, plan, grid, gravityfield, filter  # noqa: F401
-from .gravityfield import PotentialCoefficients, RadialBasisFunctions, TimeSeries, to_grid_batch, gridded_rms, grid_statistics, ravel_batch  # noqa: F401
+from .gravityfield import PotentialCoefficients, RadialBasisFunctions, AnisotropicBasisFunctions, TimeSeries, to_grid_batch, gridded_rms, grid_statistics, ravel_batch  # noqa: F401
 from .grid import RegularGrid, IrregularGrid, GeographicGrid, GaussGrid, analysis_batch, basin_variances  # noqa: F401
 from .filter import OrderWiseFilter, Gaussian, Butterworth, GeneralMatrix, VDK, SpatialFilter  # noqa: F401
 from .kernel import get_kernel  # noqa: F401

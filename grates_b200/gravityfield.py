@@ -135,6 +135,66 @@ class PotentialCoefficients:
         return output_grid
 
 
+class AnisotropicBasisFunctions:
+    """Gravity field represented by anisotropic kernel basis functions (reference gravityfield.py:573-642).
+
+    ``to_grid`` in the reference is ``K @ (Y' v)`` accumulated over 512-point blocks, followed by a synthesis that loops
+    over the meridians.  Here: the point-set adjoint (``gb_points_adjoint``, unit degree factors), the dense matrix on the
+    filter GEMM (``gb_dense_filter``), and the regular-grid synthesis -- three device calls, no table ever on the host.
+    """
+
+    def __init__(self, point_distribution, K, min_degree, max_degree, GM=GM_DEFAULT, R=R_DEFAULT):
+        self._K = np.array(K, dtype=float, copy=True)
+        self.point_distribution = point_distribution
+        self._min_degree = min_degree
+        self._max_degree = max_degree
+        self.GM = GM
+        self.R = R
+        self.epoch = None
+        self.values = np.zeros((self.point_distribution.size))
+        self._operator = None
+        self._plan_cache = None
+
+    @property
+    def values(self):
+        return self.point_distribution.values
+
+    @values.setter
+    def values(self, val):
+        self.point_distribution.values = val
+
+    def is_compatible(self, other):
+        return self.point_distribution.is_compatible(other.point_distribution)
+
+    def to_potential_coefficients_batch(self, values):
+        """values [E, points] (numpy or CUDA tensor) -> CUDA tensor [E, L, L]: unravel(K @ ravel(Y' v)), degrees below
+        the minimum degree zero."""
+        from .filter import GeneralMatrix
+        grid = self.point_distribution
+        lon = np.asarray(grid.longitude, dtype=float)
+        lat = np.asarray(grid.latitude, dtype=float)
+        key = (lon.tobytes(), lat.tobytes(), float(grid.semimajor_axis), float(grid.flattening))
+        if self._plan_cache is None or self._plan_cache[0] != key:
+            ones = np.ones((lon.size, self._max_degree + 1))
+            self._plan_cache = (key, _plan.PointsPlan(lon, lat, grid.semimajor_axis, grid.flattening, self._max_degree,
+                                                      degree_factors=ones))
+        p = self._plan_cache[1]
+        if self._operator is None:
+            self._operator = GeneralMatrix(self._K, self._min_degree, self._max_degree)
+        dev = torch.device("cuda", p.device)
+        v = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(values, dtype=float))
+        anm = self._operator.filter_batch(p.adjoint(v.to(dev)))
+        anm[:, 0:self._min_degree, 0:self._min_degree] = 0.0        # the dense operator passes lower degrees through
+        return anm
+
+    def to_grid(self, grid=None, kernel='ewh'):
+        grid = GeographicGrid() if grid is None else grid
+        anm = self.to_potential_coefficients_batch(np.asarray(self.values, dtype=float)[None])
+        output_grid = grid.copy()
+        output_grid.values = to_grid_batch(anm, grid, kernel, self.GM, self.R)[0].cpu().numpy().reshape(-1)
+        return output_grid
+
+
 class RadialBasisFunctions:
     """Gravity field represented by radial basis functions at nodal points (reference gravityfield.py:645-781).
 

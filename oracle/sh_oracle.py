@@ -668,6 +668,31 @@ def radial_basis_to_coefficients(K, values, lon, lat, nmax, R=R_DEFAULT, a=A_GRS
     return anm
 
 
+def anisotropic_basis_to_grid(K, values, lon, lat, nmin, nmax, grid, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT,
+                              a=A_GRS80, f=F_GRS80):
+    """AnisotropicBasisFunctions.to_grid (reference gravityfield.py:600-642): K @ (Y' v) accumulated over 512-point
+    blocks, then per meridian the ravelled, continued Legendre table times that vector."""
+    radius = geocentric_radius(grid.parallels, grid.a, grid.f)
+    colat = colatitude(grid.parallels, grid.a, grid.f)
+    kn = inverse_kernel_coefficients(kernel, 0, nmax, radius, colat)
+    continuation = np.power(R / radius[:, np.newaxis], np.arange(0, nmax + 1, dtype=float) + 1) * kn
+    Pnm = legendre_functions(nmax, colat)
+    for n in range(nmin, nmax + 1):
+        rows = np.concatenate((np.full(n + 1, n, dtype=int), np.arange(n, dtype=int)))
+        cols = np.concatenate((np.arange(n + 1, dtype=int), np.full(n, n, dtype=int)))
+        Pnm[:, rows, cols] *= continuation[:, n:n + 1]
+    values = np.asarray(values, dtype=float)
+    out = np.zeros((grid.parallels.size, grid.meridians.size))
+    for start in range(0, values.size, 512):
+        sl = slice(start, min(start + 512, values.size))
+        Ynm = ravel_coefficients(spherical_harmonics(nmax, colatitude(lat[sl], a, f), lon[sl]), nmin, nmax).T
+        K_tmp = K @ (Ynm @ values[sl])
+        for k in range(grid.meridians.size):
+            cs = trigonometric_functions(nmax, grid.meridians[k])
+            out[:, k] += ravel_coefficients(Pnm * cs, nmin, nmax) @ K_tmp * GM / R
+    return out
+
+
 def synthetic_coefficients(nmax, epoch=0):
     """Kaula-like random coefficients, seed 1000 + epoch; degrees 0-1 zero."""
     rng = np.random.default_rng(1000 + epoch)

@@ -313,6 +313,15 @@ def radial_basis():
     out["anm"] = rbf.to_potential_coefficients().anm
     g = grates.grid.GeographicGrid(6.0, 6.0)
     out["grid_ewh"] = rbf.to_grid(g, "ewh").value_array
+    # anisotropic basis functions (gravityfield.py:573-642): dense operator between the point adjoint and the synthesis
+    N2, nmin2, P2 = 10, 2, 300
+    k = (N2 + 1) ** 2 - nmin2 ** 2
+    Ka = 0.5 * np.eye(k) + 0.05 * rng.standard_normal((k, k))
+    lon2, lat2 = lon[:P2], lat[:P2]
+    abf = grates.gravityfield.AnisotropicBasisFunctions(grates.grid.IrregularGrid(lon2, lat2), Ka, nmin2, N2)
+    abf.values = rng.standard_normal(P2) * 1e-9
+    out["aniso_K"], out["aniso_values"] = Ka, abf.values
+    out["aniso_grid_ewh"] = abf.to_grid(grates.grid.GeographicGrid(10.0, 10.0), "ewh").value_array
     save("radial_basis", **out)
 
 

@@ -670,6 +670,11 @@ def test_radial_basis_functions_golden_and_batch(gb, orc, golden):
     assert maxnorm_err(out.value_array, g["grid_ewh"]) < TOL
     twin = rbf.copy()
     np.testing.assert_array_equal(twin.values, rbf.values)
+    # anisotropic basis functions (gravityfield.py:573-642): point adjoint -> dense operator -> synthesis
+    abf = gb.AnisotropicBasisFunctions(gb.IrregularGrid(g["lon"][:300], g["lat"][:300]), g["aniso_K"], 2, 10)
+    abf.values = g["aniso_values"]
+    aout = abf.to_grid(gb.GeographicGrid(10.0, 10.0), "ewh")
+    assert maxnorm_err(aout.value_array, g["aniso_grid_ewh"]) < TOL
     rng = np.random.default_rng(8)
     N, P, E = 45, 5000, 130                     # 17 coefficient tiles, two epoch tiles, ragged last point block
     lon = rng.uniform(-np.pi, np.pi, P)
