@@ -48,6 +48,7 @@ SIGNATURES = {
     "gb_points_synthesis": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
     "gb_points_covariance": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     "gb_points_adjoint": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    "gb_points_synthesis_matrix": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
     "gb_temporal_rms": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, _vp, ctypes.c_int, _vp]),
     "gb_weighted_moments": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int64, _vp, ctypes.c_int, _vp]),
     "gb_ravel_coefficients": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp]),

@@ -115,16 +115,31 @@ gb_points_design(double* __restrict__ FT, const double* __restrict__ ct, const d
 // ---------------------------------------------------------------------------------------------
 // CTA = one point, thread = order m, all threads walk the degrees n together: for a fixed n the entries
 // a = n^2 .. (n+1)^2 - 1 of the point's row are contiguous, so the stores coalesce.  The recursion is
-// gb::legendre_column's, step for step (bit-identical values).  Rows beyond the last point (K-loop padding) are zeroed.
+// gb::legendre_column's, step for step (bit-identical values).  Where the row goes is the layout's business:
+struct AdjointTiles {      // GEMM A operand [coefficient tile][point][GB_LDA]; rows beyond the last point are zeroed
+    double* at;
+    int rows;
+    static constexpr bool pad_rows = true;
+    __device__ __forceinline__ double* operator()(long long a, int pp) const { return at + gb_ab_offset(a, pp, rows); }
+};
+struct DenseRows {         // row-major [point][K'], K' = L^2 - nmin^2 (Grid.synthesis_matrix, reference grid.py:412-443)
+    double* out;
+    long long kc, off;
+    static constexpr bool pad_rows = false;
+    __device__ __forceinline__ double* operator()(long long a, int pp) const { return out + (size_t)pp * kc + (a - off); }
+};
+
+template <class Layout>
 __global__ void __launch_bounds__(1024)
-gb_points_design_adjoint(double* __restrict__ AT, const double* __restrict__ ct, const double* __restrict__ kn,
-                         const double* __restrict__ pmm, const double* __restrict__ cml, const double* __restrict__ sml,
-                         const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc, int L,
-                         int npts, int rows, int p0) {
+gb_points_design_rows(Layout row, const double* __restrict__ ct, const double* __restrict__ kn,
+                      const double* __restrict__ pmm, const double* __restrict__ cml, const double* __restrict__ sml,
+                      const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc, int L,
+                      int nmin, int npts, int p0) {
     const int pp = blockIdx.x;
     const int p = p0 + pp;
     if (p >= npts) {
-        for (long long a = threadIdx.x; a < (long long)L * L; a += blockDim.x) AT[gb_ab_offset(a, pp, rows)] = 0.0;
+        if (Layout::pad_rows)
+            for (long long a = threadIdx.x; a < (long long)L * L; a += blockDim.x) *row(a, pp) = 0.0;
         return;
     }
     const double ctp = ct[p];
@@ -142,10 +157,11 @@ gb_points_design_adjoint(double* __restrict__ AT, const double* __restrict__ ct,
             else v = __dsub_rn(__dmul_rn(__dmul_rn(ra[(size_t)n * L + m], ctp), p1), __dmul_rn(rb[(size_t)n * L + m], p2));
             p2 = p1;
             p1 = v;
+            if (n < nmin) continue;
             const double pk = __dmul_rn(v, kn_p[n]);
             const long long a = (long long)n * n + (m == 0 ? 0 : 2 * m - 1);
-            AT[gb_ab_offset(a, pp, rows)] = __dmul_rn(pk, cm);
-            if (m > 0) AT[gb_ab_offset(a + 1, pp, rows)] = __dmul_rn(pk, sm);
+            *row(a, pp) = __dmul_rn(pk, cm);
+            if (m > 0) *row(a + 1, pp) = __dmul_rn(pk, sm);
         }
     }
 }
@@ -450,8 +466,8 @@ static int points_adjoint_blocks(gb_points* p, const double* d_values, int E, do
         const int rows = (count + 3) / 4 * 4;
         GB_CUDA(cudaMemsetAsync(d_bt, 0, (size_t)n_ct * rows * LDB * sizeof(double), st));
         const int threads = L >= 1024 ? 1024 : (L + 31) / 32 * 32;
-        gb_points_design_adjoint<<<rows, threads, 0, st>>>(d_at, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra,
-                                                          p->d_rb, p->d_rc, L, p0 + count, rows, p0);
+        gb_points_design_rows<<<rows, threads, 0, st>>>(AdjointTiles{d_at, rows}, p->d_ct, p->d_kn, p->d_pmm, p->d_cml,
+                                                       p->d_sml, p->d_ra, p->d_rb, p->d_rc, L, 0, p0 + count, p0);
         GB_LAUNCH_CHECK();
         dim3 vgrid((count + 255) / 256, E);
         gb_points_value_tiles<<<vgrid, 256, 0, st>>>(d_values, d_bt, p->npts, p0, count, rows, E, TN, LDB);
@@ -484,6 +500,23 @@ extern "C" int gb_points_adjoint(gb_points* p, const double* d_values, int n_epo
     if (n_epochs <= gbgemm::tile_n(1)) return points_adjoint_blocks<1>(p, d_values, n_epochs, d_anm, st);
     if (n_epochs <= gbgemm::tile_n(2)) return points_adjoint_blocks<2>(p, d_values, n_epochs, d_anm, st);
     return points_adjoint_blocks<5>(p, d_values, n_epochs, d_anm, st);
+}
+
+// Dense synthesis operator of the point set, [npts][K'] row-major in degree-wise order (reference grid.py:412-443 with
+// IrregularGrid.synthesis_matrix_per_order, grid.py:957-991).
+extern "C" int gb_points_synthesis_matrix(gb_points* p, int nmin, double* d_out, void* stream) {
+    GB_REQUIRE(p != nullptr, "gb_points_synthesis_matrix: point set is NULL");
+    GB_REQUIRE(nmin >= 0 && nmin <= p->nmax, "gb_points_synthesis_matrix: nmin=%d out of range [0, %d]", nmin, p->nmax);
+    GB_REQUIRE(d_out != nullptr, "gb_points_synthesis_matrix: NULL device pointer");
+    GB_CUDA(cudaSetDevice(p->device));
+    const int L = p->L;
+    const long long off = (long long)nmin * nmin;
+    const int threads = L >= 1024 ? 1024 : (L + 31) / 32 * 32;
+    gb_points_design_rows<<<p->npts, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        DenseRows{d_out, (long long)L * L - off, off}, p->d_ct, p->d_kn, p->d_pmm, p->d_cml, p->d_sml, p->d_ra, p->d_rb,
+        p->d_rc, L, nmin, p->npts, 0);
+    GB_LAUNCH_CHECK();
+    return GB_OK;
 }
 
 // Sigma re-pitched to an even leading dimension; for a symmetric Sigma only its upper triangle is kept, the

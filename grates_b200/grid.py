@@ -8,7 +8,7 @@ this path and raise instead of falling back to the CPU.
 import numpy as np
 import torch
 
-from . import plan as _plan
+from . import plan as _plan, utilities
 
 GM_DEFAULT = 3.9860044150e+14
 R_DEFAULT = 6.3781363000e+06
@@ -204,6 +204,49 @@ class IrregularGrid:
             self._values = val
         else:
             raise ValueError("grid values must be either None or " + str(np.ndarray))
+
+    def synthesis_matrix(self, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+        """Dense operator A [points, K'] mapping coefficients in degree-wise order to point values
+        (reference grid.py:412-443 over :957-991), generated on the GPU."""
+        p = _plan.get_points_plan(self, max_degree, kernel, GM, R)
+        return p.synthesis_matrix(min_degree).cpu().numpy()
+
+    def synthesis_matrix_per_order(self, m, min_degree, max_degree, kernel, GM, R):
+        """Columns of the synthesis operator for one order: [points, n_m] for m = 0, else the tuple
+        (cosine part, sine part) (reference grid.py:957-991)."""
+        if m > max_degree:
+            raise ValueError('order exceeds maximum degree ({0:d} vs. {1:d})'.format(m, max_degree))
+        A = self.synthesis_matrix(min_degree, max_degree, kernel, GM, R)
+        n = np.arange(max(m, min_degree), max_degree + 1)
+        base = n * n - min_degree * min_degree
+        if m == 0:
+            return np.ascontiguousarray(A[:, base])
+        return np.ascontiguousarray(A[:, base + 2 * m - 1]), np.ascontiguousarray(A[:, base + 2 * m])
+
+    def _analysis_operator(self, min_degree, max_degree, kernel, GM, R):
+        """Area-weighted least-squares operator solve(A'WA, A'W) on the device (reference grid.py:993-1017).  The design
+        matrix comes from the point-set kernels; the dense normal-equation product and solve are cuBLAS / cuSOLVER through
+        torch, where the reference calls BLAS / LAPACK through numpy."""
+        p = _plan.get_points_plan(self, max_degree, kernel, GM, R)
+        A = p.synthesis_matrix(min_degree)
+        sw = torch.as_tensor(np.sqrt(np.asarray(self.area, dtype=float))).to(A.device)
+        A = A * sw[:, None]
+        return torch.linalg.solve(A.T @ A, A.T * sw)
+
+    def analysis_matrix(self, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+        """Dense analysis operator [K', points] (reference grid.py:993-1017)."""
+        return self._analysis_operator(min_degree, max_degree, kernel, GM, R).cpu().numpy()
+
+    def to_potential_coefficients(self, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
+        """Least-squares spherical-harmonic analysis of the point values (reference grid.py:477-507)."""
+        from .gravityfield import PotentialCoefficients
+        if self.values is None:
+            raise ValueError('grid has no values to propagate to potential coefficients')
+        F = self._analysis_operator(min_degree, max_degree, kernel, GM, R)
+        x = F @ torch.as_tensor(np.ascontiguousarray(self.values, dtype=float)).to(F.device)
+        coeffs = PotentialCoefficients(GM, R)
+        coeffs.anm = utilities.unravel_coefficients(x.cpu().numpy(), min_degree, max_degree)
+        return coeffs
 
     def covariance_propagation(self, covariance_matrix, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
         """sqrt(diag(F Sigma F')) at every point on the GPU (reference grid.py:1071-1120: 256-point

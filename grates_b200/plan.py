@@ -468,6 +468,14 @@ class PointsPlan:
                                                  ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
 
+    def synthesis_matrix(self, min_degree):
+        """Dense synthesis operator of the point set: CUDA tensor [npts, K'] in degree-wise order."""
+        k = self.L ** 2 - int(min_degree) ** 2
+        out = torch.empty((self.npts, k), dtype=torch.float64, device=torch.device("cuda", self.device))
+        _lib.check(self._lib.gb_points_synthesis_matrix(self._handle, int(min_degree), ctypes.c_void_p(out.data_ptr()),
+                                                        _stream_handle(self.device)))
+        return out
+
     def adjoint(self, values, out=None):
         """values: CUDA float64 [E, npts] -> CUDA tensor [E, L, L]: the transposed synthesis operator applied to
         point values (sum over points of kn * Y_nm * value, reference gravityfield.py:707-724)."""

@@ -216,6 +216,9 @@ int gb_points_synthesis(gb_points* points, const double* d_anm, int n_epochs, do
 int gb_points_covariance(gb_points* points, const double* d_sigma, int nmin, double* d_out, int flags,
                          void* stream);
 int gb_points_adjoint(gb_points* points, const double* d_values, int n_epochs, double* d_anm, void* stream);
+/* Dense synthesis operator of the point set: d_out [npts][K'], K' = (nmax+1)^2 - nmin^2, degree-wise order
+ * (Grid.synthesis_matrix, grid.py:412-443, with IrregularGrid.synthesis_matrix_per_order, grid.py:957-991). */
+int gb_points_synthesis_matrix(gb_points* points, int nmin, double* d_out, void* stream);
 
 /*
  * Consumers of gridded epoch batches that keep the grids on the device.

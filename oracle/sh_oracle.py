@@ -693,6 +693,32 @@ def anisotropic_basis_to_grid(K, values, lon, lat, nmin, nmax, grid, kernel='ewh
     return out
 
 
+def synthesis_matrix_points(lon, lat, nmin, nmax, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT, a=A_GRS80, f=F_GRS80):
+    """Grid.synthesis_matrix over IrregularGrid.synthesis_matrix_per_order (reference grid.py:412-443, 957-991):
+    [points, K'] in degree-wise order, from the per-order Legendre recursion."""
+    colat = colatitude(lat, a, f)
+    r = geocentric_radius(lat, a, f)
+    kn = inverse_kernel_coefficients(kernel, 0, nmax, r, colat) * \
+        np.power((R / r)[:, np.newaxis], np.arange(nmax + 1, dtype=int) + 1) * GM / R
+    A = np.empty((lon.size, (nmax + 1) ** 2 - nmin ** 2))
+    for m in range(nmax + 1):
+        Pnm = (legendre_functions_per_order(nmax, m, colat) * kn[:, m:])[:, max(nmin - m, 0):]
+        n = np.arange(max(m, nmin), nmax + 1)
+        base = n * n - nmin * nmin
+        if m == 0:
+            A[:, base] = Pnm
+        else:
+            A[:, base + 2 * m - 1] = Pnm * np.cos(m * lon[:, np.newaxis])
+            A[:, base + 2 * m] = Pnm * np.sin(m * lon[:, np.newaxis])
+    return A
+
+
+def analysis_matrix_points(lon, lat, area, nmin, nmax, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT, a=A_GRS80, f=F_GRS80):
+    """IrregularGrid.analysis_matrix (reference grid.py:993-1017): area-weighted least squares."""
+    A = synthesis_matrix_points(lon, lat, nmin, nmax, kernel, GM, R, a, f) * np.sqrt(area)[:, np.newaxis]
+    return np.linalg.solve(A.T @ A, A.T * np.sqrt(area))
+
+
 def synthetic_coefficients(nmax, epoch=0):
     """Kaula-like random coefficients, seed 1000 + epoch; degrees 0-1 zero."""
     rng = np.random.default_rng(1000 + epoch)

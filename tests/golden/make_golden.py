@@ -325,6 +325,29 @@ def radial_basis():
     save("radial_basis", **out)
 
 
+def irregular_operators():
+    """IrregularGrid.synthesis_matrix(_per_order) / analysis_matrix / to_potential_coefficients
+    (grid.py:412-443, 477-507, 957-1017)."""
+    out = {}
+    rng = np.random.default_rng(29)
+    P, N = 240, 6
+    lon = rng.uniform(-np.pi, np.pi, P)
+    lat = np.arcsin(rng.uniform(-1, 1, P))
+    area = rng.uniform(0.5, 1.5, P) * 4 * np.pi / P
+    g = grates.grid.IrregularGrid(lon, lat, area)
+    out["lon"], out["lat"], out["area"] = lon, lat, area
+    out["A_2_N_ewh"] = g.synthesis_matrix(2, N, "ewh")
+    c3, s3 = g.synthesis_matrix_per_order(3, 2, N, "ewh", GM, R)
+    out["A_m3_cos"], out["A_m3_sin"] = c3, s3
+    out["F_0_N_potential"] = g.analysis_matrix(0, N, "potential")
+    pc = coeffs(N, 1006)
+    vals = g.synthesis_matrix(0, N, "ewh") @ grates.utilities.ravel_coefficients(pc.anm) + 1e-4 * rng.standard_normal(P)
+    g.values = vals
+    out["values"] = vals
+    out["anm_2_N_ewh"] = g.to_potential_coefficients(2, N, "ewh").anm
+    save("irregular_operators", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -340,3 +363,4 @@ if __name__ == "__main__":
     degreewise_filters()
     dense_filters()
     radial_basis()
+    irregular_operators()

@@ -657,6 +657,34 @@ def test_install_wrappers_on_gpu(gb, orc, golden):
     assert not gb.installed()
 
 
+def test_irregular_operators_golden(gb, orc, golden):
+    """IrregularGrid.synthesis_matrix(_per_order) from the point-set design kernel, the least-squares analysis operator and
+    to_potential_coefficients (reference grid.py:412-443, 477-507, 957-1017) against the reference's outputs."""
+    g = golden("irregular_operators")
+    grid = gb.IrregularGrid(g["lon"], g["lat"], g["area"])
+    A = grid.synthesis_matrix(2, 6, "ewh")
+    assert A.shape == (240, 45) and maxnorm_err(A, g["A_2_N_ewh"]) < TOL
+    c3, s3 = grid.synthesis_matrix_per_order(3, 2, 6, "ewh", 3.9860044150e+14, 6.3781363000e+06)
+    assert maxnorm_err(c3, g["A_m3_cos"]) < TOL and maxnorm_err(s3, g["A_m3_sin"]) < TOL
+    F = grid.analysis_matrix(0, 6, "potential")
+    assert F.shape == (49, 240) and maxnorm_err(F, g["F_0_N_potential"]) < 1e-10
+    grid.values = g["values"]
+    back = grid.to_potential_coefficients(2, 6, "ewh")
+    assert maxnorm_err(back.anm, g["anm_2_N_ewh"]) < 1e-10
+    with pytest.raises(ValueError):
+        gb.IrregularGrid(g["lon"], g["lat"]).to_potential_coefficients(0, 4)
+    # the dense operator is the point synthesis: A x == to_grid at the points, for a larger, ragged case
+    rng = np.random.default_rng(3)
+    P, N = 1500, 33
+    big = gb.IrregularGrid(rng.uniform(-np.pi, np.pi, P), np.arcsin(rng.uniform(-1, 1, P)))
+    anm = orc.synthetic_coefficients(N, 2)
+    A = big.synthesis_matrix(0, N, "ewh")
+    pc = gb.PotentialCoefficients()
+    pc.anm = anm
+    np.testing.assert_allclose(A @ orc.ravel_coefficients(anm), pc.to_grid(big, "ewh").values, rtol=0, atol=1e-13 * np.abs(A).max())
+    assert maxnorm_err(A[::97], orc.synthesis_matrix_points(big.longitude[::97], big.latitude[::97], 0, N, "ewh")) < TOL
+
+
 def test_radial_basis_functions_golden_and_batch(gb, orc, golden):
     """RadialBasisFunctions (gravityfield.py:645-781): the sum over nodal points as a GEMM against the on-the-fly design
     matrix.  Golden vectors of the reference; a batch of value sets over several point blocks against the oracle."""
