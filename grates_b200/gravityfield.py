@@ -259,6 +259,13 @@ class RadialBasisFunctions:
         coefficients.epoch = self.epoch
         return coefficients
 
+    def to_potential_coefficients_matrix(self, blocking_factor=256):
+        """Matrix [K', points] from the radial basis function coefficients to degree-wise ordered spherical harmonics
+        (reference gravityfield.py:729-763): the transposed point-set design matrix scaled by the shape factors."""
+        A = self._points_plan().synthesis_matrix(self._min_degree)
+        k = torch.as_tensor(utilities.ravel_coefficients(self._K, self._min_degree, self._max_degree)).to(A.device)
+        return (A * k[None, :]).T.contiguous().cpu().numpy()
+
     def to_grid(self, grid=None, kernel='ewh'):
         return self.to_potential_coefficients().to_grid(GeographicGrid() if grid is None else grid, kernel)
 

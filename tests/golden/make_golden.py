@@ -311,6 +311,7 @@ def radial_basis():
     rbf.values = rng.standard_normal(P) * 1e-9
     out["lon"], out["lat"], out["K"], out["values"] = lon, lat, K, rbf.values
     out["anm"] = rbf.to_potential_coefficients().anm
+    out["matrix_cols"] = rbf.to_potential_coefficients_matrix()[:, ::50]       # [K', 14] of the [K', 700] matrix
     g = grates.grid.GeographicGrid(6.0, 6.0)
     out["grid_ewh"] = rbf.to_grid(g, "ewh").value_array
     # anisotropic basis functions (gravityfield.py:573-642): dense operator between the point adjoint and the synthesis

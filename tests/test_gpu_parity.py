@@ -698,6 +698,9 @@ def test_radial_basis_functions_golden_and_batch(gb, orc, golden):
     assert maxnorm_err(out.value_array, g["grid_ewh"]) < TOL
     twin = rbf.copy()
     np.testing.assert_array_equal(twin.values, rbf.values)
+    M = rbf.to_potential_coefficients_matrix()
+    assert M.shape == (21 ** 2 - 4, 700) and maxnorm_err(M[:, ::50], g["matrix_cols"]) < TOL
+    np.testing.assert_allclose(orc.unravel_coefficients(M @ g["values"], 2, 20), g["anm"], rtol=0, atol=1e-13 * np.abs(g["anm"]).max())
     # anisotropic basis functions (gravityfield.py:573-642): point adjoint -> dense operator -> synthesis
     abf = gb.AnisotropicBasisFunctions(gb.IrregularGrid(g["lon"][:300], g["lat"][:300]), g["aniso_K"], 2, 10)
     abf.values = g["aniso_values"]
