@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib, plan as _plan
+from . import _lib, kernel as _kernel, plan as _plan, utilities
 from .gravityfield import PotentialCoefficients
 
 
@@ -248,3 +248,18 @@ class VDK(GeneralMatrix):
         NP = normal_equation_matrix.copy()
         NP.flat[::NP.shape[0] + 1] = np.diag(normal_equation_matrix) + weights
         super(VDK, self).__init__(np.linalg.solve(NP, normal_equation_matrix), min_degree, max_degree)
+
+class FilterKernel(_kernel.AnisotropicKernel):
+    """Space-domain kernel of a (possibly anisotropic) filter (reference filter.py:575-598): the filter matrix between
+    the kernel's functional, K2 = diag(kn') F diag(kn)."""
+
+    def __init__(self, spatial_filter, min_degree, max_degree, input_kernel='potential'):
+        K = spatial_filter.matrix(min_degree, max_degree) if isinstance(spatial_filter, SpatialFilter) else spatial_filter
+        generator = _kernel.get_kernel(input_kernel)
+        kn = generator.coefficient_array(min_degree, max_degree)
+        kn_prime = generator.inverse_coefficient_array(min_degree, max_degree)
+        # the reference's expression with its broadcasting: both ravelled factor arrays are [1, K'], so both scale the
+        # COLUMNS of K and the product carries a leading axis of one (filter.py:596)
+        K2 = (K * utilities.ravel_coefficients(kn, min_degree, max_degree)[np.newaxis, :]) * \
+            utilities.ravel_coefficients(kn_prime, min_degree, max_degree)[:, np.newaxis]
+        super(FilterKernel, self).__init__(K2.reshape(K2.shape[-2:]), min_degree, max_degree)

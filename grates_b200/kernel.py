@@ -161,6 +161,22 @@ class IsotropicKernel(metaclass=abc.ABCMeta):
                        for j in range(kn.shape[1])]
         return np.vstack(columns).T
 
+    def _as_array(self, kn, min_degree, max_degree, count):
+        """Per-degree factors spread over the packed [L, L] layout (reference kernel.py:210-218)."""
+        out = np.zeros((count, max_degree + 1, max_degree + 1))
+        for n in range(min_degree, max_degree + 1):
+            out[:, n, 0:n + 1] = kn[:, n - min_degree, np.newaxis]
+            out[:, 0:n, n] = kn[:, n - min_degree, np.newaxis]
+        return out
+
+    def coefficient_array(self, min_degree, max_degree, r=6378136.3, colat=0):
+        count = max(np.asarray(r).size, np.asarray(colat).size)
+        return self._as_array(self.coefficients(min_degree, max_degree, r, colat), min_degree, max_degree, count)
+
+    def inverse_coefficient_array(self, min_degree, max_degree, r=6378136.3, colat=0):
+        count = max(np.asarray(r).size, np.asarray(colat).size)
+        return self._as_array(self.inverse_coefficients(min_degree, max_degree, r, colat), min_degree, max_degree, count)
+
     def coefficient(self, n, r=6378136.3, colat=0):
         return self.coefficients(n, n, r, colat).squeeze(axis=1)
 
@@ -303,6 +319,74 @@ _KERNELS = {
     'deformation': VerticalDeformation, 'vertical_derformation': VerticalDeformation,
     'uplift': Uplift,
 }
+
+
+class AnisotropicKernel:
+    """Possibly anisotropic kernel in the space domain, given as a matrix K between degree-wise ordered spherical
+    harmonics (reference kernel.py:576-658).  ``evaluate`` / ``evaluate_grid`` give the kernel of one source point as the
+    reference does; the ``*_batch`` forms take many source points at once -- footprints of a filter over a region are one
+    design-matrix kernel, one dense GEMM and one batched synthesis on the device:
+
+        Y(sources) [E, K']  --  V = Y K  --  values = synthesis(V) on the evaluation points / grid (unit sphere)
+    """
+
+    def __init__(self, K, min_degree, max_degree):
+        self._matrix = np.array(K, dtype=float, copy=True)
+        self._min_degree = min_degree
+        self._max_degree = max_degree
+        self._operator = None
+        self._plans = {}
+
+    def _source_vectors(self, source_longitude, source_latitude):
+        """V = ravel(Y(source)) @ K for every source point, as packed coefficients [E, L, L] on the device
+        (reference kernel.py:615-616)."""
+        import torch
+        from . import plan as _plan, utilities
+        from .filter import GeneralMatrix
+        lon = np.atleast_1d(np.asarray(source_longitude, dtype=float))
+        lat = np.atleast_1d(np.asarray(source_latitude, dtype=float))
+        L = self._max_degree + 1
+        src = _plan.PointsPlan(lon, lat, 1.0, 0.0, self._max_degree, degree_factors=np.ones((lon.size, L)),
+                               colatitude=np.pi * 0.5 - lat)
+        Y = src.synthesis_matrix(0)                                          # [E, L^2], degree-wise order
+        rows, cols = utilities.degreewise_index(0, self._max_degree)
+        packed = torch.zeros((lon.size, L, L), dtype=torch.float64, device=Y.device)
+        packed[:, torch.as_tensor(rows).to(Y.device), torch.as_tensor(cols).to(Y.device)] = Y
+        if self._operator is None:                                           # v K == K' v
+            self._operator = GeneralMatrix(np.ascontiguousarray(self._matrix.T), self._min_degree, self._max_degree)
+        V = self._operator.filter_batch(packed)
+        V[:, 0:self._min_degree, 0:self._min_degree] = 0.0                   # degrees below the band do not enter
+        return V
+
+    def evaluate_batch(self, source_longitude, source_latitude, eval_longitude, eval_latitude):
+        """Kernels of E source points at m evaluation points: CUDA tensor [E, m]."""
+        from . import plan as _plan
+        lon = np.atleast_1d(np.asarray(eval_longitude, dtype=float))
+        lat = np.atleast_1d(np.asarray(eval_latitude, dtype=float))
+        pts = _plan.PointsPlan(lon, lat, 1.0, 0.0, self._max_degree,
+                               degree_factors=np.ones((lon.size, self._max_degree + 1)), colatitude=np.pi * 0.5 - lat)
+        return pts.synthesis(self._source_vectors(source_longitude, source_latitude))
+
+    def evaluate_grid_batch(self, source_longitude, source_latitude, eval_longitude, eval_latitude):
+        """Kernels of E source points on the grid of eval_latitude x eval_longitude: CUDA tensor [E, nlat, nlon]."""
+        from . import plan as _plan
+        lon = np.atleast_1d(np.asarray(eval_longitude, dtype=float))
+        lat = np.atleast_1d(np.asarray(eval_latitude, dtype=float))
+        key = (lon.tobytes(), lat.tobytes())
+        if key not in self._plans:
+            self._plans.clear()
+            self._plans[key] = _plan.SHPlan(lon, lat, 1.0, 0.0, self._max_degree,
+                                            degree_factors=np.ones((lat.size, self._max_degree + 1)),
+                                            colatitude=np.pi * 0.5 - lat)
+        return self._plans[key].synthesis(self._source_vectors(source_longitude, source_latitude))
+
+    def evaluate(self, source_longitude, source_latitude, eval_longitude, eval_latitude):
+        """Kernel of one source point at the evaluation points, ndarray(m,) (reference kernel.py:595-620)."""
+        return self.evaluate_batch(source_longitude, source_latitude, eval_longitude, eval_latitude)[0].cpu().numpy()
+
+    def evaluate_grid(self, source_longitude, source_latitude, eval_longitude, eval_latitude):
+        """Kernel of one source point on a longitude / latitude grid, ndarray(nlat, nlon) (reference kernel.py:622-658)."""
+        return self.evaluate_grid_batch(source_longitude, source_latitude, eval_longitude, eval_latitude)[0].cpu().numpy()
 
 
 def get_kernel(kernel_name):

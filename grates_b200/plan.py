@@ -62,7 +62,9 @@ class SHPlan:
     """
 
     def __init__(self, meridians, parallels, a, f, max_degree, kernel='ewh',
-                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None):
+                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None, degree_factors=None, colatitude=None):
+        """degree_factors [nlat, L] / colatitude [nlat]: used instead of the kernel's factors and the ellipsoidal
+        colatitudes (space-domain kernels on the unit sphere, reference kernel.py:622-658)."""
         self._lib = _lib.load()
         self.device = _current_device(device)
         self.max_degree = int(max_degree)
@@ -71,7 +73,17 @@ class SHPlan:
         self.a, self.f = a, f
         self.kernel, self.GM, self.R = kernel, GM, R
         self.nlat, self.nlon = self.parallels.size, self.meridians.size
-        colat, kn = _kernel.degree_factors(kernel, self.max_degree, self.parallels, a, f, GM, R)
+        if degree_factors is None:
+            colat, kn = _kernel.degree_factors(kernel, self.max_degree, self.parallels, a, f, GM, R)
+        else:
+            colat = utilities.colatitude(self.parallels, a, f)
+            kn = np.ascontiguousarray(degree_factors, dtype=float)
+            if kn.shape != (self.nlat, self.max_degree + 1):
+                raise ValueError("degree_factors must have shape [{0}, {1}]".format(self.nlat, self.max_degree + 1))
+        if colatitude is not None:
+            colat = np.ascontiguousarray(colatitude, dtype=float)
+            if colat.shape != (self.nlat,):
+                raise ValueError("colatitude must have shape [{0}]".format(self.nlat))
         if not np.all(np.isfinite(kn)):
             raise ValueError("kernel '{0}' has non-finite degree factors on this grid".format(kernel))
         self.colat, self.kn = colat, kn
@@ -408,8 +420,9 @@ class PointsPlan:
     """Device tables for an arbitrary point set (reference IrregularGrid path); wraps ``gb_points``."""
 
     def __init__(self, longitude, latitude, a, f, max_degree, kernel='ewh',
-                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None, degree_factors=None):
-        """degree_factors: [npts, L] array used instead of the kernel's factors (None: from ``kernel``)."""
+                 GM=3.9860044150e+14, R=6.3781363000e+06, device=None, degree_factors=None, colatitude=None):
+        """degree_factors [npts, L] / colatitude [npts]: used instead of the kernel's factors and the ellipsoidal
+        colatitudes (None: from ``kernel`` and the ellipsoid)."""
         self._lib = _lib.load()
         self.device = _current_device(device)
         self.max_degree = int(max_degree)
@@ -425,6 +438,10 @@ class PointsPlan:
             kn = np.ascontiguousarray(degree_factors, dtype=float)
             if kn.shape != (self.npts, self.max_degree + 1):
                 raise ValueError("degree_factors must have shape [{0}, {1}]".format(self.npts, self.max_degree + 1))
+        if colatitude is not None:
+            colat = np.ascontiguousarray(colatitude, dtype=float)
+            if colat.shape != (self.npts,):
+                raise ValueError("colatitude must have shape [{0}]".format(self.npts))
         if not np.all(np.isfinite(kn)):
             raise ValueError("kernel '{0}' has non-finite degree factors on this point set".format(kernel))
         self.colat, self.kn = colat, kn

@@ -719,6 +719,40 @@ def analysis_matrix_points(lon, lat, area, nmin, nmax, kernel='potential', GM=GM
     return np.linalg.solve(A.T @ A, A.T * np.sqrt(area))
 
 
+def anisotropic_kernel_evaluate(K, nmin, nmax, source_lon, source_lat, eval_lon, eval_lat):
+    """AnisotropicKernel.evaluate (reference kernel.py:595-620)."""
+    v1 = ravel_coefficients(spherical_harmonics(nmax, np.pi * 0.5 - source_lat, source_lon), nmin, nmax) @ K
+    Y = spherical_harmonics(nmax, np.pi * 0.5 - eval_lat, eval_lon)
+    return np.atleast_1d((v1 @ ravel_coefficients(Y, nmin, nmax).T).squeeze())
+
+
+def anisotropic_kernel_evaluate_grid(K, nmin, nmax, source_lon, source_lat, eval_lon, eval_lat):
+    """AnisotropicKernel.evaluate_grid (reference kernel.py:622-658): [nlat, nlon]."""
+    v1 = ravel_coefficients(spherical_harmonics(nmax, np.pi * 0.5 - source_lat, source_lon), nmin, nmax) @ K
+    pnm = legendre_functions(nmax, np.pi * 0.5 - eval_lat)
+    cs = trigonometric_functions(nmax, eval_lon)
+    grid = np.empty((eval_lat.size, eval_lon.size))
+    for k in range(eval_lat.size):
+        grid[k, :] = (ravel_coefficients(cs * pnm[k], nmin, nmax) @ v1.T).squeeze()
+    return grid
+
+
+def filter_kernel_matrix(F, nmin, nmax, kernel='potential'):
+    """Matrix of FilterKernel (reference filter.py:588-598) with the reference's broadcasting: both ravelled factor
+    arrays have shape [1, K'], so both scale the columns of F."""
+    def as_array(kn):
+        out = np.zeros((1, nmax + 1, nmax + 1))
+        for n in range(nmin, nmax + 1):
+            out[:, n, 0:n + 1] = kn[:, n - nmin, np.newaxis]
+            out[:, 0:n, n] = kn[:, n - nmin, np.newaxis]
+        return out
+    r, colat = np.full(1, 6378136.3), np.zeros(1)
+    kn = as_array(kernel_coefficients(kernel, nmin, nmax, r, colat))
+    kn_prime = as_array(inverse_kernel_coefficients(kernel, nmin, nmax, r, colat))
+    K2 = (F * ravel_coefficients(kn, nmin, nmax)[np.newaxis, :]) * ravel_coefficients(kn_prime, nmin, nmax)[:, np.newaxis]
+    return K2.reshape(K2.shape[-2:])
+
+
 def synthetic_coefficients(nmax, epoch=0):
     """Kaula-like random coefficients, seed 1000 + epoch; degrees 0-1 zero."""
     rng = np.random.default_rng(1000 + epoch)

@@ -349,6 +349,36 @@ def irregular_operators():
     save("irregular_operators", **out)
 
 
+def space_kernels():
+    """AnisotropicKernel.evaluate / evaluate_grid and FilterKernel (kernel.py:576-658, filter.py:575-598)."""
+    out = {}
+    rng = np.random.default_rng(37)
+    nmin, nmax = 2, 12
+    k = (nmax + 1) ** 2 - nmin ** 2
+    K = 0.3 * np.eye(k) + 0.02 * rng.standard_normal((k, k))
+    ker = grates.kernel.AnisotropicKernel(K, nmin, nmax)
+    elon = rng.uniform(-np.pi, np.pi, 50)
+    elat = np.arcsin(rng.uniform(-1, 1, 50))
+    glon = np.linspace(-np.pi, np.pi, 24, endpoint=False) + 0.1
+    glat = np.linspace(1.4, -1.4, 13)
+    out["K"], out["eval_lon"], out["eval_lat"], out["grid_lon"], out["grid_lat"] = K, elon, elat, glon, glat
+    out["sources"] = np.array([[0.3, 0.7], [-2.0, -0.4]])
+    for i, (slon, slat) in enumerate(out["sources"]):
+        out["points_%d" % i] = ker.evaluate(slon, slat, elon, elat)
+        out["grid_%d" % i] = ker.evaluate_grid(slon, slat, glon, glat)
+    fk = grates.filter.FilterKernel(grates.filter.Gaussian(400.0), nmin, nmax, "ewh")
+    out["gauss_points"] = fk.evaluate(0.3, 0.7, elon, elat)       # (evaluate_grid raises on FilterKernel's 3-d matrix)
+    blocks = [0.7 * np.eye(nmax + 1) + 0.03 * rng.standard_normal((nmax + 1, nmax + 1))]
+    for m in range(1, nmax + 1):
+        for _ in range(2):
+            blocks.append(0.7 * np.eye(nmax + 1 - m) + 0.03 * rng.standard_normal((nmax + 1 - m, nmax + 1 - m)))
+    for i, b in enumerate(blocks):
+        out["block_%d" % i] = b
+    fo = grates.filter.FilterKernel(grates.filter.OrderWiseFilter(blocks), nmin, nmax, "potential")
+    out["orderwise_points"] = fo.evaluate(-2.0, -0.4, elon, elat)
+    save("space_kernels", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -365,3 +395,4 @@ if __name__ == "__main__":
     dense_filters()
     radial_basis()
     irregular_operators()
+    space_kernels()

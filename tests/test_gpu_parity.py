@@ -685,6 +685,34 @@ def test_irregular_operators_golden(gb, orc, golden):
     assert maxnorm_err(A[::97], orc.synthesis_matrix_points(big.longitude[::97], big.latitude[::97], 0, N, "ewh")) < TOL
 
 
+def test_space_kernels_golden_and_batch(gb, orc, golden):
+    """AnisotropicKernel.evaluate / evaluate_grid and FilterKernel (kernel.py:576-658, filter.py:575-598): design rows of
+    the source points, the dense operator on the filter GEMM, synthesis on the unit sphere."""
+    from grates_b200.kernel import AnisotropicKernel
+    from grates_b200.filter import FilterKernel
+    g = golden("space_kernels")
+    ker = AnisotropicKernel(g["K"], 2, 12)
+    for i, (slon, slat) in enumerate(g["sources"]):
+        pts = ker.evaluate(slon, slat, g["eval_lon"], g["eval_lat"])
+        assert pts.shape == (50,) and maxnorm_err(pts, g["points_%d" % i]) < TOL
+        grid = ker.evaluate_grid(slon, slat, g["grid_lon"], g["grid_lat"])
+        assert grid.shape == (13, 24) and maxnorm_err(grid, g["grid_%d" % i]) < TOL
+    both = ker.evaluate_grid_batch(g["sources"][:, 0], g["sources"][:, 1], g["grid_lon"], g["grid_lat"]).cpu().numpy()
+    assert maxnorm_err(both, np.stack([g["grid_0"], g["grid_1"]])) < TOL
+    fk = FilterKernel(gb.Gaussian(400.0), 2, 12, "ewh")
+    assert maxnorm_err(fk.evaluate(0.3, 0.7, g["eval_lon"], g["eval_lat"]), g["gauss_points"]) < TOL
+    fo = FilterKernel(gb.OrderWiseFilter([g["block_%d" % i] for i in range(25)]), 2, 12, "potential")
+    assert maxnorm_err(fo.evaluate(-2.0, -0.4, g["eval_lon"], g["eval_lat"]), g["orderwise_points"]) < TOL
+    # footprints of 40 source points on a grid in one call, against the oracle (where the reference's FilterKernel
+    # cannot evaluate grids at all)
+    rng = np.random.default_rng(12)
+    slon, slat = rng.uniform(-np.pi, np.pi, 40), np.arcsin(rng.uniform(-1, 1, 40))
+    many = fo.evaluate_grid_batch(slon, slat, g["grid_lon"], g["grid_lat"]).cpu().numpy()
+    K3 = orc.filter_kernel_matrix(orc.orderwise_filter_matrix([g["block_%d" % i] for i in range(25)], 2, 12), 2, 12)
+    for e in (0, 17, 39):
+        assert maxnorm_err(many[e], orc.anisotropic_kernel_evaluate_grid(K3, 2, 12, slon[e], slat[e], g["grid_lon"], g["grid_lat"])) < TOL
+
+
 def test_radial_basis_functions_golden_and_batch(gb, orc, golden):
     """RadialBasisFunctions (gravityfield.py:645-781): the sum over nodal points as a GEMM against the on-the-fly design
     matrix.  Golden vectors of the reference; a batch of value sets over several point blocks against the oracle."""
