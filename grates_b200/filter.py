@@ -249,6 +249,36 @@ class VDK(GeneralMatrix):
         NP.flat[::NP.shape[0] + 1] = np.diag(normal_equation_matrix) + weights
         super(VDK, self).__init__(np.linalg.solve(NP, normal_equation_matrix), min_degree, max_degree)
 
+class BlockedNormalsVDK(OrderWiseFilter):
+    """Blocked VDK filter (reference filter.py:352-427): the order-wise (DDK-structured) blocks of a normal-equation
+    matrix in degree-wise order, each regularised with Kaula weights and solved -- plan-time host work (numpy), the
+    resulting blocks run on the order-wise filter kernel."""
+
+    def __init__(self, normal_equation_matrix, min_degree, max_degree, kaula_scale, kaula_power):
+        normals_in = np.asarray(normal_equation_matrix, dtype=float)
+        weights = kaula_scale * np.arange(max_degree + 1, dtype=float) ** kaula_power
+        weights[0] = 1
+        off = min_degree * min_degree
+
+        def block(m, sine):
+            n = np.arange(max(m, min_degree), max_degree + 1)
+            idx = n * n - off + (0 if m == 0 else (2 * m if sine else 2 * m - 1))
+            full = np.zeros((max_degree + 1 - m, max_degree + 1 - m))
+            lead = max(min_degree - m, 0)
+            full[lead:, lead:] = normals_in[np.ix_(idx, idx)]
+            return full
+
+        normals = [block(0, False)]
+        for m in range(1, max_degree + 1):
+            normals.append(block(m, False))
+            normals.append(block(m, True))
+        array = []
+        for normals_block in normals:
+            m = max_degree + 1 - normals_block.shape[0]
+            array.append(np.linalg.solve(normals_block + np.diag(weights[m:]), normals_block))
+        super(BlockedNormalsVDK, self).__init__(array)
+
+
 class FilterKernel(_kernel.AnisotropicKernel):
     """Space-domain kernel of a (possibly anisotropic) filter (reference filter.py:575-598): the filter matrix between
     the kernel's functional, K2 = diag(kn') F diag(kn)."""

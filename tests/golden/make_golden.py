@@ -291,6 +291,11 @@ def dense_filters():
     out["normals_2_10"] = Nmat
     vdk = grates.filter.VDK(Nmat, nmin, nmax, 1e2, 2.0)
     out["vdk_matrix"] = vdk.matrix(nmin, nmax)
+    bvdk = grates.filter.BlockedNormalsVDK(Nmat, nmin, nmax, 1e2, 2.0)
+    out["blocked_vdk_matrix"] = bvdk.matrix(0, nmax)
+    pc10 = coeffs(10, 1003)
+    pc10.anm = out["in_10"].copy()
+    out["blocked_vdk_out_10"] = bvdk.filter(pc10).anm
     save("dense_filters", **out)
 
 

@@ -777,6 +777,8 @@ def test_dense_matrix_filter_golden_and_batch(gb, orc, golden):
     y = big.filter_batch(torch.as_tensor(x).cuda()).cpu().numpy()
     ref = np.stack([orc.dense_filter(W, nmin, nmax, a) for a in x[[0, 64, 129]]])
     assert maxnorm_err(y[[0, 64, 129]], ref) < TOL
+    bvdk = gb.filter.BlockedNormalsVDK(g["normals_2_10"], 2, 10, 1e2, 2.0)          # filter.py:352-427
+    assert maxnorm_err(bvdk.filter(_pc(gb, g["in_10"])).anm, g["blocked_vdk_out_10"]) < TOL
     vdk = gb.VDK(g["normals_2_10"], 2, 10, 1e2, 2.0)
     out = vdk.filter(_pc(gb, g["in_10"])).anm
     assert maxnorm_err(out, orc.dense_filter(g["vdk_matrix"], 2, 10, g["in_10"])) < 1e-11

@@ -269,3 +269,12 @@ def test_general_matrix_host_logic(golden):
         gb.GeneralMatrix(np.zeros((5, 5)), 0, 1)
     vdk = gb.VDK(g["normals_2_10"], 2, 10, 1e2, 2.0)
     np.testing.assert_allclose(vdk.matrix(2, 10), g["vdk_matrix"], rtol=1e-12, atol=1e-15)
+
+
+def test_blocked_normals_vdk_blocks_match_reference(golden):
+    """BlockedNormalsVDK (reference filter.py:352-427): block extraction and regularised solves are host work;
+    the assembled filter matrix equals the reference's bit for bit."""
+    import grates_b200 as gb
+    g = golden("dense_filters")
+    flt = gb.filter.BlockedNormalsVDK(g["normals_2_10"], 2, 10, 1e2, 2.0)
+    np.testing.assert_array_equal(flt.matrix(0, 10), g["blocked_vdk_matrix"])
