@@ -8,7 +8,8 @@ C ABI of ``include/grates_b200.h``.  There is no CPU fallback.
 """
 from . import _lib, utilities, kernel, plan, grid, gravityfield, filter  # noqa: F401
 from .gravityfield import PotentialCoefficients, RadialBasisFunctions, AnisotropicBasisFunctions, TimeSeries, to_grid_batch, gridded_rms, grid_statistics, ravel_batch  # noqa: F401
-from .grid import RegularGrid, IrregularGrid, GeographicGrid, GaussGrid, analysis_batch, basin_variances  # noqa: F401
+from .grid import (RegularGrid, IrregularGrid, GeographicGrid, GaussGrid, analysis_batch, basin_variances,  # noqa: F401
+                   covariance_from_normals)
 from .filter import OrderWiseFilter, Gaussian, Butterworth, GeneralMatrix, VDK, SpatialFilter  # noqa: F401
 from .kernel import get_kernel  # noqa: F401
 from .install import install, uninstall, installed  # noqa: F401

@@ -155,7 +155,7 @@ class RegularGrid:
         spatial_filter (extension): propagate F Sigma F' for an OrderWiseFilter / Gaussian / Butterworth F
         without forming the filtered matrix."""
         p = _plan.get_plan(self, max_degree, kernel, GM, R)
-        sigma = torch.as_tensor(np.ascontiguousarray(covariance_matrix, dtype=np.float64)).to(torch.device("cuda", p.device))
+        sigma = _device_matrix(covariance_matrix, p.device)
         std = p.covariance_propagation(sigma, min_degree, spatial_filter=spatial_filter).cpu().numpy().ravel()
         self.values = std
         return std.copy()
@@ -252,7 +252,7 @@ class IrregularGrid:
         """sqrt(diag(F Sigma F')) at every point on the GPU (reference grid.py:1071-1120: 256-point
         blocks of dense products); stores the standard deviations in ``self.values`` as the reference does."""
         p = _plan.get_points_plan(self, max_degree, kernel, GM, R)
-        sigma = torch.as_tensor(np.ascontiguousarray(covariance_matrix, dtype=np.float64)).to(torch.device("cuda", p.device))
+        sigma = _device_matrix(covariance_matrix, p.device)
         std = p.covariance_propagation(sigma, min_degree).cpu().numpy()
         self.values = std
         return std.copy()
@@ -297,6 +297,25 @@ class GaussGrid(RegularGrid):
             grid.values = self.values.copy()
         grid.epoch = self.epoch
         return grid
+
+
+def _device_matrix(matrix, device):
+    """A covariance matrix on the plan's device: CUDA tensors pass through (no 0.7 GB host round trip at degree 96)."""
+    if isinstance(matrix, torch.Tensor):
+        return matrix.to(device=torch.device("cuda", device), dtype=torch.float64)
+    return torch.as_tensor(np.ascontiguousarray(matrix, dtype=np.float64)).to(torch.device("cuda", device))
+
+
+def covariance_from_normals(normal_equation_matrix, device_output=True):
+    """Covariance matrix Sigma = N^-1 of a dense, symmetric positive definite normal-equation matrix, kept on the device
+    for ``covariance_propagation`` / ``basin_variances`` (the dense case of NormalEquations.compute_covariance, reference
+    lstsq.py:1026-1043: Cholesky factor, then W^-1 W^-T).  The factorisation is cuSOLVER through torch -- where the
+    reference calls LAPACK -- and is not part of the measured path."""
+    dev = torch.device("cuda", _plan._current_device(None))
+    n = normal_equation_matrix if isinstance(normal_equation_matrix, torch.Tensor) else \
+        torch.as_tensor(np.ascontiguousarray(normal_equation_matrix, dtype=np.float64))
+    sigma = torch.cholesky_inverse(torch.linalg.cholesky(n.to(device=dev, dtype=torch.float64), upper=True), upper=True)
+    return sigma if device_output else sigma.cpu().numpy()
 
 
 def basin_variances(covariance_matrix, grid, masks, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT,

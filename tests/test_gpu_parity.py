@@ -713,6 +713,26 @@ def test_space_kernels_golden_and_batch(gb, orc, golden):
         assert maxnorm_err(many[e], orc.anisotropic_kernel_evaluate_grid(K3, 2, 12, slon[e], slat[e], g["grid_lon"], g["grid_lat"])) < TOL
 
 
+def test_covariance_from_normals_feeds_propagation_on_device(gb, orc):
+    """Normal-equation matrix -> Sigma = N^-1 on the device -> grid standard deviations, no host round trip of Sigma
+    (the dense case of NormalEquations.compute_covariance, lstsq.py:1026-1043, in front of grid.py:792-839)."""
+    N = 12
+    k = (N + 1) ** 2
+    rng = np.random.default_rng(21)
+    J = rng.standard_normal((3 * k, k))
+    normals = J.T @ J + 1e-3 * np.eye(k)
+    sigma = gb.covariance_from_normals(normals)
+    assert sigma.is_cuda and tuple(sigma.shape) == (k, k)
+    ref_sigma = np.linalg.inv(normals)
+    assert maxnorm_err(sigma.cpu().numpy(), ref_sigma) < 1e-10
+    grid = gb.GeographicGrid(10.0, 10.0)
+    std = grid.covariance_propagation(sigma, 0, N, "ewh")                      # CUDA tensor accepted as is
+    assert maxnorm_err(std, orc.covariance_propagation(ref_sigma, orc.geographic_grid(10.0, 10.0), 0, N, "ewh").ravel()) < 1e-9
+    pts = gb.IrregularGrid(rng.uniform(-np.pi, np.pi, 300), np.arcsin(rng.uniform(-1, 1, 300)))
+    std_p = pts.covariance_propagation(sigma, 0, N, "ewh")
+    assert maxnorm_err(std_p, orc.covariance_propagation_points(ref_sigma, pts.longitude, pts.latitude, 0, N, "ewh")) < 1e-9
+
+
 def test_radial_basis_functions_golden_and_batch(gb, orc, golden):
     """RadialBasisFunctions (gravityfield.py:645-781): the sum over nodal points as a GEMM against the on-the-fly design
     matrix.  Golden vectors of the reference; a batch of value sets over several point blocks against the oracle."""
