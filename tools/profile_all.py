@@ -32,4 +32,15 @@ if "c5" in which:
     y = torch.empty_like(x)
     for _ in range(reps): flt.filter_batch(x, out=y)
     torch.cuda.synchronize()
+if "pts" in which:
+    rng = np.random.default_rng(0)
+    P = 41000
+    pg = gb.IrregularGrid(rng.uniform(-np.pi, np.pi, P), np.arcsin(rng.uniform(-1, 1, P)))
+    pp = gb.get_points_plan(pg, 96, "ewh")
+    sigma = torch.as_tensor(orc.synthetic_covariance(96)).cuda()
+    x = torch.randn(240, 97, 97, dtype=torch.float64, device="cuda") * 1e-6
+    for _ in range(reps):
+        pp.covariance_propagation(sigma, 0)
+        pp.synthesis(x)
+    torch.cuda.synchronize()
 print("done")
