@@ -275,11 +275,67 @@ def widened(pk):
                              "cores": blas_threads(), "kind": "port"}}
 
 
+def point_sets(pk):
+    """Rows a6 / a13 / f1 of SURVEY 8 at degree 96 on 40 962 scattered points: batched synthesis, the direct
+    diag(F Sigma F'), and the adjoint (RadialBasisFunctions.to_potential_coefficients)."""
+    N, P, E = 96, 40962, 240
+    rng = np.random.default_rng(7)
+    lon, lat = rng.uniform(-np.pi, np.pi, P), np.arcsin(rng.uniform(-1, 1, P))
+    pts = gb.IrregularGrid(lon, lat)
+    pp = gb.get_points_plan(pts, N, "ewh")
+    K = (N + 1) ** 2
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    x = torch.as_tensor(anm).cuda()
+    out = torch.empty((E, P), dtype=torch.float64, device="cuda")
+    ms_syn = ev_time(lambda: pp.synthesis(x, out=out), reps=3, warm=1)
+    sub = slice(0, 512)
+    t0 = time.perf_counter()
+    ref = orc.synthesis_points(anm[7], lon[sub], lat[sub], "ewh")
+    cpu_syn = (time.perf_counter() - t0) * P / 512
+    par_syn = err(out[7, sub].cpu().numpy(), ref)
+    sig_h = orc.synthetic_covariance(N)
+    sigma = torch.as_tensor(sig_h).cuda()
+    ms_cov = ev_time(lambda: pp.covariance_propagation(sigma, 0, symmetric=True), reps=2, warm=1)
+    ms_cov_full = ev_time(lambda: pp.covariance_propagation(sigma, 0, symmetric=False), reps=2, warm=1)
+    std = pp.covariance_propagation(sigma, 0).cpu().numpy()
+    t0 = time.perf_counter()
+    ref_std = orc.covariance_propagation_points(sig_h, lon[sub], lat[sub], 0, N, "ewh")
+    cpu_cov = (time.perf_counter() - t0) * P / 512
+    par_cov = err(std[sub], ref_std)
+    Kf = np.ones((N + 1, N + 1))
+    rbf = gb.RadialBasisFunctions(pts, Kf, 0, N)
+    v1 = torch.as_tensor(rng.standard_normal((1, P))).cuda()
+    vE = torch.as_tensor(rng.standard_normal((E, P))).cuda()
+    plan = rbf._points_plan()
+    ms_adj1 = ev_time(lambda: plan.adjoint(v1), reps=3, warm=1)
+    ms_adjE = ev_time(lambda: plan.adjoint(vE), reps=3, warm=1)
+    got = rbf.to_potential_coefficients_batch(v1)[0].cpu().numpy()
+    n_cpu = 2048
+    t0 = time.perf_counter()
+    part = orc.radial_basis_to_coefficients(Kf, v1[0, :n_cpu].cpu().numpy(), lon[:n_cpu], lat[:n_cpu], N)
+    cpu_adj = (time.perf_counter() - t0) * P / n_cpu
+    small = gb.RadialBasisFunctions(gb.IrregularGrid(lon[:n_cpu], lat[:n_cpu]), Kf, 0, N)
+    par_adj = err(small.to_potential_coefficients_batch(v1[:, :n_cpu].contiguous())[0].cpu().numpy(), part)
+    del got
+    return {"config": "point sets: N=96, 40962 scattered points, 240 epochs / K=9409",
+            "synthesis_ms": ms_syn, "synthesis_tflops": 2.0 * P * K * E / ms_syn / 1e9, "synthesis_parity": par_syn,
+            "covariance_symmetric_ms": ms_cov, "covariance_general_ms": ms_cov_full,
+            "covariance_general_tflops": 2.0 * P * K * K / ms_cov_full / 1e9,
+            "covariance_general_frac_fp64_peak": 2.0 * P * K * K / ms_cov_full / 1e9 / pk,
+            "covariance_parity": par_cov,
+            "adjoint_one_value_set_ms": ms_adj1, "adjoint_240_value_sets_ms": ms_adjE,
+            "adjoint_240_tflops": 2.0 * P * K * E / ms_adjE / 1e9, "adjoint_parity_2048_points": par_adj,
+            "cpu_baseline": {"synthesis_one_epoch_s_extrapolated_from_512_points": cpu_syn,
+                             "covariance_s_extrapolated_from_512_points": cpu_cov,
+                             "adjoint_one_value_set_s_extrapolated_from_2048_points": cpu_adj,
+                             "cores": blas_threads(), "kind": "port"}}
+
+
 def main():
     torch.cuda.set_device(0)
     pk = peak()
-    which = sys.argv[1:] or ["c1", "c3", "c4", "c5", "f"]
-    fns = {"c1": config1, "c3": config3, "c4": config4, "c5": config5, "f": widened}
+    which = sys.argv[1:] or ["c1", "c3", "c4", "c5", "f", "pts"]
+    fns = {"c1": config1, "c3": config3, "c4": config4, "c5": config5, "f": widened, "pts": point_sets}
     for name in which:
         line = fns[name](pk)
         line["fp64_peak_tflops_measured_live"] = pk
