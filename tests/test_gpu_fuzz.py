@@ -56,7 +56,10 @@ def test_random_synthesis_analysis_filter(gb, orc, seed):
         nmin = int(rng.integers(0, min(3, N) + 1))
         back = gb.analysis_batch(ref, grid, nmin, N, kernel)
         want = orc.analysis_separable(ref, og, nmin, N, kernel)
-        assert maxnorm_err(back, want) < 1e-10, (dlon, dlat, N, nmin, kernel)
+        # normalised by the size of the input coefficients: a band that holds no signal (only C00 set, nmin = N = 1)
+        # comes back as rounding noise around zero from both sides
+        scale = max(np.abs(want).max(), np.abs(anm).max())
+        assert np.abs(back - want).max() / scale < 1e-10, (dlon, dlat, N, nmin, kernel)
 
 
 @pytest.mark.parametrize("seed", range(max(5, int(__import__("os").environ.get("GB_FUZZ_SEEDS", "10")) // 2)))
