@@ -89,3 +89,34 @@ def test_random_covariance_and_statistics(gb, orc, seed):
         g1.values = vals[e]
         assert abs(st["mean"][e] - g1.mean(masks[0])) < 1e-13
         assert abs(st["std"][e] - g1.std(masks[0])) < 1e-13
+
+
+@pytest.mark.parametrize("seed", range(max(5, int(__import__("os").environ.get("GB_FUZZ_SEEDS", "10")) // 2)))
+def test_random_point_sets(gb, orc, seed):
+    """Point-set kernels at random sizes: synthesis on both sides of the per-point / GEMM switch (16 epochs), the
+    direct diag(F Sigma F'), the adjoint on all three epoch-tile widths (24 / 48 / 120), the dense operator."""
+    rng = np.random.default_rng(500 + seed)
+    P = int(rng.choice((1, 3, 127, 128, 129, int(rng.integers(2, 1500)))))
+    N = int(rng.integers(1, 31))
+    E = int(rng.choice((1, 2, 15, 16, 17, 24, 25, 48, 49, int(rng.integers(1, 60)))))
+    kernel = str(rng.choice(("ewh", "potential", "geoid", "obp")))
+    lon, lat = rng.uniform(-np.pi, np.pi, P), np.arcsin(rng.uniform(-1, 1, P))
+    pts = gb.IrregularGrid(lon, lat)
+    anm = np.stack([orc.synthetic_coefficients(N, 31 * seed + e) for e in range(E)])
+    anm[:, 0, 0] = rng.standard_normal(E) * 1e-6
+    out = gb.to_grid_batch(anm, pts, kernel)
+    pick = sorted(set((0, E // 2, E - 1)))
+    ref = np.stack([orc.synthesis_points(anm[e], lon, lat, kernel) for e in pick])
+    assert out.shape == (E, P) and maxnorm_err(out[pick], ref) < TOL, (P, N, E, kernel)
+    nmin = int(rng.integers(0, min(2, N) + 1))
+    sigma = orc.synthetic_covariance(N, rank=int(rng.integers(4, 20)), seed=seed)[nmin * nmin:, nmin * nmin:]
+    std = pts.covariance_propagation(sigma, nmin, N, kernel)
+    assert maxnorm_err(std, orc.covariance_propagation_points(sigma, lon, lat, nmin, N, kernel)) < TOL, (P, N, nmin, kernel)
+    K = rng.uniform(0.5, 1.5, (N + 1, N + 1))
+    rbf = gb.RadialBasisFunctions(pts, K, 0, N)
+    v = rng.standard_normal((E, P))
+    got = rbf.to_potential_coefficients_batch(v).cpu().numpy()
+    want = np.stack([orc.radial_basis_to_coefficients(K, v[e], lon, lat, N) for e in pick])
+    assert maxnorm_err(got[pick], want) < TOL, (P, N, E)
+    A = pts.synthesis_matrix(nmin, N, kernel)
+    assert maxnorm_err(A, orc.synthesis_matrix_points(lon, lat, nmin, N, kernel)) < TOL
