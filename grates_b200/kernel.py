@@ -380,6 +380,30 @@ class AnisotropicKernel:
                                             colatitude=np.pi * 0.5 - lat)
         return self._plans[key].synthesis(self._source_vectors(source_longitude, source_latitude))
 
+    def modulation_transfer(self, psi, central_longitude=0, central_latitude=0, azimuth=0):
+        """Modulation transfer function of the kernel along a great circle (reference kernel.py:654-711): two kernels
+        are shifted apart by psi[k]; all kernel evaluations of the reference's loop are one batched call here."""
+        psi_array = np.atleast_1d(psi)
+        theta0 = np.pi * 0.5 - (psi_array + central_latitude)
+        x0 = np.vstack((np.sin(theta0) * np.cos(central_longitude), np.sin(theta0) * np.sin(central_longitude),
+                        np.cos(theta0)))
+        ux, uy, uz = x0[0, 0], x0[1, 0], x0[2, 0]
+        ca, sa = np.cos(azimuth), np.sin(azimuth)
+        rotation_matrix = np.array([[ca + ux**2 * (1 - ca), ux * uy * (1 - ca) - uz * sa, ux * uz * (1 - ca) + uy * sa],
+                                    [uy * ux * (1 - ca) + uz * sa, ca + uy**2 * (1 - ca), uy * uz * (1 - ca) - ux * sa],
+                                    [uz * ux * (1 - ca) - uy * sa, uz * uy * (1 - ca) + ux * sa, ca + uz**2 * (1 - ca)]])
+        x = rotation_matrix @ x0
+        lon = -np.arctan2(x[1, :], x[0, :])
+        lat = np.pi * 0.5 - np.arctan2(np.sqrt(x[0, :]**2 + x[1, :]**2), x[2, :])
+        G = self.evaluate_batch(lon, lat, lon, lat).cpu().numpy()        # G[k, j]: kernel of source k at point j
+        kn1 = G[0]
+        mtf = np.zeros(psi_array.size)
+        for k in range(0, psi_array.size):
+            kn = kn1[0:k + 1] + G[k, 0:k + 1]
+            edge_threshold = min(kn[0], kn[-1])
+            mtf[k] = 0 if np.min(kn) >= edge_threshold else 1 - kn[int(kn.size // 2)] / np.max(kn)
+        return mtf
+
     def evaluate(self, source_longitude, source_latitude, eval_longitude, eval_latitude):
         """Kernel of one source point at the evaluation points, ndarray(m,) (reference kernel.py:595-620)."""
         return self.evaluate_batch(source_longitude, source_latitude, eval_longitude, eval_latitude)[0].cpu().numpy()

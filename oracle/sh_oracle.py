@@ -737,6 +737,29 @@ def anisotropic_kernel_evaluate_grid(K, nmin, nmax, source_lon, source_lat, eval
     return grid
 
 
+def anisotropic_kernel_modulation_transfer(K, nmin, nmax, psi, central_longitude=0, central_latitude=0, azimuth=0):
+    """AnisotropicKernel.modulation_transfer (reference kernel.py:654-711)."""
+    psi_array = np.atleast_1d(psi)
+    theta0 = np.pi * 0.5 - (psi_array + central_latitude)
+    x0 = np.vstack((np.sin(theta0) * np.cos(central_longitude), np.sin(theta0) * np.sin(central_longitude), np.cos(theta0)))
+    ux, uy, uz = x0[0, 0], x0[1, 0], x0[2, 0]
+    ca, sa = np.cos(azimuth), np.sin(azimuth)
+    rot = np.array([[ca + ux**2 * (1 - ca), ux * uy * (1 - ca) - uz * sa, ux * uz * (1 - ca) + uy * sa],
+                    [uy * ux * (1 - ca) + uz * sa, ca + uy**2 * (1 - ca), uy * uz * (1 - ca) - ux * sa],
+                    [uz * ux * (1 - ca) - uy * sa, uz * uy * (1 - ca) + ux * sa, ca + uz**2 * (1 - ca)]])
+    x = rot @ x0
+    lon = -np.arctan2(x[1, :], x[0, :])
+    lat = np.pi * 0.5 - np.arctan2(np.sqrt(x[0, :]**2 + x[1, :]**2), x[2, :])
+    kn1 = anisotropic_kernel_evaluate(K, nmin, nmax, lon[0], lat[0], lon, lat).flatten()
+    mtf = np.zeros(psi_array.size)
+    for k in range(psi_array.size):
+        kn2 = anisotropic_kernel_evaluate(K, nmin, nmax, lon[k], lat[k], lon[0:k + 1], lat[0:k + 1]).flatten()
+        kn = kn1[0:k + 1] + kn2
+        edge_threshold = min(kn[0], kn[-1])
+        mtf[k] = 0 if np.min(kn) >= edge_threshold else 1 - kn[int(kn.size // 2)] / np.max(kn)
+    return mtf
+
+
 def filter_kernel_matrix(F, nmin, nmax, kernel='potential'):
     """Matrix of FilterKernel (reference filter.py:588-598) with the reference's broadcasting: both ravelled factor
     arrays have shape [1, K'], so both scale the columns of F."""

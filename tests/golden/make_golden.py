@@ -381,6 +381,8 @@ def space_kernels():
         out["block_%d" % i] = b
     fo = grates.filter.FilterKernel(grates.filter.OrderWiseFilter(blocks), nmin, nmax, "potential")
     out["orderwise_points"] = fo.evaluate(-2.0, -0.4, elon, elat)
+    out["mtf_psi"] = np.linspace(0.0, 0.6, 25)
+    out["mtf"] = fo.modulation_transfer(out["mtf_psi"], 0.2, 0.3, 0.4)
     save("space_kernels", **out)
 
 

@@ -703,6 +703,7 @@ def test_space_kernels_golden_and_batch(gb, orc, golden):
     assert maxnorm_err(fk.evaluate(0.3, 0.7, g["eval_lon"], g["eval_lat"]), g["gauss_points"]) < TOL
     fo = FilterKernel(gb.OrderWiseFilter([g["block_%d" % i] for i in range(25)]), 2, 12, "potential")
     assert maxnorm_err(fo.evaluate(-2.0, -0.4, g["eval_lon"], g["eval_lat"]), g["orderwise_points"]) < TOL
+    np.testing.assert_allclose(fo.modulation_transfer(g["mtf_psi"], 0.2, 0.3, 0.4), g["mtf"], rtol=0, atol=1e-10)
     # footprints of 40 source points on a grid in one call, against the oracle (where the reference's FilterKernel
     # cannot evaluate grids at all)
     rng = np.random.default_rng(12)
