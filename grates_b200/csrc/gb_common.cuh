@@ -122,6 +122,7 @@ struct gb_plan {
     double* d_ana_lat_t = nullptr;
     int* d_ana_lat_m = nullptr;      // [ana_lat_tiles] order of each row tile
     int* d_ana_lat_n = nullptr;      // [ana_lat_tiles] degree of the tile's first row
+    void* cov_layout = nullptr;      // index tables of the last covariance propagation (owned by gb_covprop.cu)
     double* d_ana_gt = nullptr;      // longitude-stage output as B tiles [order][column tile][parallel][GB_S2_LDB]
     size_t ana_gt_elems = 0;
     int ana_gt_epochs = -1;          // epoch count the buffer was last cleared for (its tiling depends on it)
@@ -133,6 +134,7 @@ struct gb_plan {
 };
 
 int gb_plan_ensure_workspace(gb_plan* p, int n_epochs);
+void gb_cov_layout_free(gb_plan* p);
 // keep stream-ordered allocations in the device's default pool between calls
 void gb_retain_pool_memory(int device);
 

@@ -271,14 +271,110 @@ __global__ void gb_cov_finish(double* v, long long n) {
     if (i < n) v[i] = sqrt(v[i]);
 }
 
-template <typename T>
-int to_device(gb_scratch& scratch, T** d, const std::vector<T>& h) {
-    GB_CUDA(scratch.alloc(d, h.size()));
-    GB_CUDA(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, scratch.st));
+// Index tables of one (min_degree, parallel count): order-wise layouts, permutations, tile offsets.  Built on the host
+// and uploaded once, kept with the plan: a repeated propagation launches its kernels without host work or copies.
+struct CovLayout {
+    int nmin = -1, nrows = -1;
+    int Kp8 = 0, Kp4 = 0, Kg = 8, n_atiles = 0, rows_a = 0, nti = 0, n_ct = 0, hmt = 0, n_padrows = 0;
+    int* d_all = nullptr;     // one allocation; the pointers below point into it
+    int *d_perm8 = nullptr, *d_perm4 = nullptr, *d_rowgroup = nullptr, *d_goff8 = nullptr, *d_koff = nullptr,
+        *d_klen = nullptr, *d_goff4 = nullptr, *d_padrows = nullptr, *d_first_nt = nullptr;
+};
+
+int build_layout(gb_plan* p, int nmin, int nrows, CovLayout** out) {
+    CovLayout* c = static_cast<CovLayout*>(p->cov_layout);
+    if (c && c->nmin == nmin && c->nrows == nrows) {
+        *out = c;
+        return GB_OK;
+    }
+    gb_cov_layout_free(p);
+    c = new CovLayout();
+    const int L = p->L, kpad = p->kpad;
+    // order-wise layouts: group k = 2m + cs holds degrees n0(m)..nmax
+    std::vector<int> gcnt(kpad, 0), goff8(kpad, 0), goff4(kpad, 0);
+    int Kp8 = 0, Kp4 = 0, Kg = 8;   // Kg: rows per U tile (covers the 8-padded groups read by the epilogue)
+    for (int k = 0; k < kpad; ++k) {
+        const int m = k >> 1, cs = k & 1;
+        int cnt = 0;
+        if (m < L && !(m == 0 && cs == 1)) cnt = L - (m > nmin ? m : nmin);
+        gcnt[k] = cnt;
+        goff8[k] = Kp8;
+        goff4[k] = Kp4;
+        Kp8 += (cnt + 7) / 8 * 8;
+        Kp4 += (cnt + 3) / 4 * 4;
+        if ((cnt + 7) / 8 * 8 > Kg) Kg = (cnt + 7) / 8 * 8;
+    }
+    const int n_atiles = (Kp8 + GB_TM - 1) / GB_TM;
+    const int rows_a = n_atiles * GB_TM;
+    std::vector<int> perm8(rows_a, -1), perm4(Kp4, -1), rowgroup(rows_a / 8, -1);
+    for (int k = 0; k < kpad; ++k) {
+        const int m = k >> 1, cs = k & 1;
+        const int n0 = (m > nmin ? m : nmin);
+        for (int r = 0; r < gcnt[k]; ++r) {
+            const int n = n0 + r;
+            const long long idx = (long long)n * n + (m == 0 ? 0 : 2 * m - 1 + cs) - (long long)nmin * nmin;
+            perm8[goff8[k] + r] = (int)idx;
+            perm4[goff4[k] + r] = (int)idx;
+        }
+        for (int r = 0; r < (gcnt[k] + 7) / 8; ++r) rowgroup[goff8[k] / 8 + r] = k;
+    }
+    const int nti = (nrows + GB_S2_TN - 1) / GB_S2_TN;          // parallel tiles
+    const int n_ct = kpad * nti;                                // column tiles of the quadratic-form GEMM
+    std::vector<int> nt_koff(n_ct), nt_klen(n_ct);
+    for (int k = 0; k < kpad; ++k)
+        for (int it = 0; it < nti; ++it) {
+            nt_koff[k * nti + it] = goff4[k];
+            nt_klen[k * nti + it] = (gcnt[k] + 3) / 4 * 4;
+        }
+    std::vector<int> padrows;
+    for (int b = 0; b < Kp4; ++b)
+        if (perm4[b] < 0) padrows.push_back(b);
+    // symmetric Sigma: H_i is symmetric, row tile mt needs the column groups k' >= its first group only
+    std::vector<int> first_nt(n_atiles, 0);
+    for (int t = 0; t < n_atiles; ++t) {
+        int kmin = kpad;
+        for (int sl = t * (GB_TM / 8); sl < (t + 1) * (GB_TM / 8); ++sl)
+            if (rowgroup[sl] >= 0 && rowgroup[sl] < kmin) kmin = rowgroup[sl];
+        first_nt[t] = kmin * nti;
+    }
+    c->nmin = nmin; c->nrows = nrows;
+    c->Kp8 = Kp8; c->Kp4 = Kp4; c->Kg = Kg; c->n_atiles = n_atiles; c->rows_a = rows_a; c->nti = nti; c->n_ct = n_ct;
+    c->hmt = (kpad + GB_TM - 1) / GB_TM;
+    c->n_padrows = (int)padrows.size();
+    const std::vector<int>* parts[9] = {&perm8, &perm4, &rowgroup, &goff8, &nt_koff, &nt_klen, &goff4, &padrows, &first_nt};
+    int** slots[9] = {&c->d_perm8, &c->d_perm4, &c->d_rowgroup, &c->d_goff8, &c->d_koff, &c->d_klen, &c->d_goff4,
+                      &c->d_padrows, &c->d_first_nt};
+    std::vector<int> all;
+    size_t offs[9];
+    for (int i = 0; i < 9; ++i) {
+        offs[i] = all.size();
+        all.insert(all.end(), parts[i]->begin(), parts[i]->end());
+        all.resize((all.size() + 3) / 4 * 4);                   // keep every table 16-byte aligned
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&c->d_all), (all.size() ? all.size() : 4) * sizeof(int)) != cudaSuccess) {
+        delete c;
+        return gb_set_error(GB_ERR_CUDA, "gb_covariance_propagation: cannot allocate the index tables");
+    }
+    if (cudaMemcpy(c->d_all, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(c->d_all);
+        delete c;
+        return gb_set_error(GB_ERR_CUDA, "gb_covariance_propagation: cannot upload the index tables");
+    }
+    for (int i = 0; i < 9; ++i) *slots[i] = c->d_all + offs[i];
+    p->cov_layout = c;
+    *out = c;
     return GB_OK;
 }
 
 }  // namespace
+
+void gb_cov_layout_free(gb_plan* p) {
+    CovLayout* c = static_cast<CovLayout*>(p->cov_layout);
+    if (!c) return;
+    cudaFree(c->d_all);
+    delete c;
+    p->cov_layout = nullptr;
+}
 
 extern "C" int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
                                          double* d_out, int flags, void* stream) {
@@ -306,73 +402,23 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
     const int L = p->L, kpad = p->kpad;
     const long long K = (long long)L * L - (long long)nmin * nmin;
 
-    // order-wise layouts: group k = 2m + cs holds degrees n0(m)..nmax
-    std::vector<int> gcnt(kpad, 0), goff8(kpad, 0), goff4(kpad, 0);
-    int Kp8 = 0, Kp4 = 0, Kg = 8;   // Kg: rows per U tile (covers the 8-padded groups read by the epilogue)
-    for (int k = 0; k < kpad; ++k) {
-        const int m = k >> 1, cs = k & 1;
-        int cnt = 0;
-        if (m < L && !(m == 0 && cs == 1)) cnt = L - (m > nmin ? m : nmin);
-        gcnt[k] = cnt;
-        goff8[k] = Kp8;
-        goff4[k] = Kp4;
-        Kp8 += (cnt + 7) / 8 * 8;
-        Kp4 += (cnt + 3) / 4 * 4;
-        if ((cnt + 7) / 8 * 8 > Kg) Kg = (cnt + 7) / 8 * 8;
+    CovLayout* lay = nullptr;
+    {
+        int rc0 = build_layout(p, nmin, nrows, &lay);
+        if (rc0) return rc0;
     }
+    const int Kp4 = lay->Kp4, Kg = lay->Kg, n_atiles = lay->n_atiles, rows_a = lay->rows_a, nti = lay->nti,
+              n_ct = lay->n_ct, hmt = lay->hmt;
     GB_REQUIRE(Kp4 <= 65535, "gb_covariance_propagation: degree %d is too large for this path", p->nmax);
-    const int n_atiles = (Kp8 + GB_TM - 1) / GB_TM;
-    const int rows_a = n_atiles * GB_TM;
-    std::vector<int> perm8(rows_a, -1), perm4(Kp4, -1), rowgroup(rows_a / 8, -1);
-    for (int k = 0; k < kpad; ++k) {
-        const int m = k >> 1, cs = k & 1;
-        const int n0 = (m > nmin ? m : nmin);
-        for (int r = 0; r < gcnt[k]; ++r) {
-            const int n = n0 + r;
-            const long long idx = (long long)n * n + (m == 0 ? 0 : 2 * m - 1 + cs) - (long long)nmin * nmin;
-            perm8[goff8[k] + r] = (int)idx;
-            perm4[goff4[k] + r] = (int)idx;
-        }
-        for (int r = 0; r < (gcnt[k] + 7) / 8; ++r) rowgroup[goff8[k] / 8 + r] = k;
-    }
-    const int nti = (nrows + GB_S2_TN - 1) / GB_S2_TN;          // parallel tiles
-    const int n_ct = kpad * nti;                                // column tiles of the quadratic-form GEMM
-    std::vector<int> nt_koff(n_ct), nt_klen(n_ct);
-    for (int k = 0; k < kpad; ++k)
-        for (int it = 0; it < nti; ++it) {
-            nt_koff[k * nti + it] = goff4[k];
-            nt_klen[k * nti + it] = (gcnt[k] + 3) / 4 * 4;
-        }
-    const int hmt = (kpad + GB_TM - 1) / GB_TM;                 // row tiles of H_i
     GB_REQUIRE((long long)n_ct * Kg * GB_S2_LDB < (1LL << 31),
                "gb_covariance_propagation: %d parallels at degree %d exceed the 32-bit tile index; pass row blocks", nrows, p->nmax);
-
-    std::vector<int> padrows;
-    for (int b = 0; b < Kp4; ++b)
-        if (perm4[b] < 0) padrows.push_back(b);
     const size_t permute_smem = (size_t)CP_ROWS * (2 * p->nmax + 1) * sizeof(double);
     const bool by_degree = permute_smem <= 200 * 1024;
-
-    // symmetric Sigma: H_i is symmetric, row tile mt needs the column groups k' >= its first group only
-    std::vector<int> first_nt(n_atiles, 0);
-    for (int t = 0; t < n_atiles; ++t) {
-        int kmin = kpad;
-        for (int sl = t * (GB_TM / 8); sl < (t + 1) * (GB_TM / 8); ++sl)
-            if (rowgroup[sl] >= 0 && rowgroup[sl] < kmin) kmin = rowgroup[sl];
-        first_nt[t] = kmin * nti;
-    }
-    int* d_first_nt = nullptr;
-
-    int *d_perm8 = nullptr, *d_perm4 = nullptr, *d_rowgroup = nullptr, *d_goff8 = nullptr, *d_koff = nullptr,
-        *d_klen = nullptr, *d_goff4 = nullptr, *d_padrows = nullptr;
+    int *d_perm8 = lay->d_perm8, *d_perm4 = lay->d_perm4, *d_rowgroup = lay->d_rowgroup, *d_goff8 = lay->d_goff8,
+        *d_koff = lay->d_koff, *d_klen = lay->d_klen, *d_goff4 = lay->d_goff4, *d_padrows = lay->d_padrows,
+        *d_first_nt = lay->d_first_nt;
     double *d_st = nullptr, *d_ut = nullptr, *d_ht = nullptr;
     int rc = GB_OK;
-    if ((rc = to_device(scratch, &d_perm8, perm8)) || (rc = to_device(scratch, &d_perm4, perm4)) ||
-        (rc = to_device(scratch, &d_rowgroup, rowgroup)) || (rc = to_device(scratch, &d_goff8, goff8)) ||
-        (rc = to_device(scratch, &d_koff, nt_koff)) || (rc = to_device(scratch, &d_klen, nt_klen)) ||
-        (rc = to_device(scratch, &d_goff4, goff4)) || (rc = to_device(scratch, &d_padrows, padrows)) ||
-        (rc = to_device(scratch, &d_first_nt, first_nt)))
-        return rc;
     const size_t st_elems = (size_t)n_atiles * Kp4 * GB_LDA;
     const size_t ut_elems = (size_t)n_ct * Kg * GB_S2_LDB;
     const size_t ht_elems = (size_t)nrows * hmt * kpad * GB_LDA;
@@ -383,7 +429,6 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
     GB_CUDA(cudaMemsetAsync(d_ut, 0, ut_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_ht, 0, ht_elems * sizeof(double), st));
     GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nrows * p->nlon * sizeof(double), st));
-    GB_CUDA(cudaStreamSynchronize(st));   // the host index vectors go out of scope; their copies are tiny
     if (by_degree) {
         // pad columns 128..131 of the St rows stay unwritten: no DMMA fragment reads them
         if (permute_smem > 48 * 1024)
@@ -392,8 +437,8 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
         dim3 grid(rows_a / CP_ROWS, L - nmin);
         gb_cov_permute_degree<<<grid, 256, permute_smem, st>>>(d_sigma, d_st, d_perm8, d_goff4, Kp4, K, nmin);
         GB_LAUNCH_CHECK();
-        if (!padrows.empty()) {
-            dim3 gz(n_atiles, (unsigned)padrows.size());
+        if (lay->n_padrows > 0) {
+            dim3 gz(n_atiles, (unsigned)lay->n_padrows);
             gb_cov_zero_rows<<<gz, GB_TM, 0, st>>>(d_st, d_padrows, Kp4);
             GB_LAUNCH_CHECK();
         }

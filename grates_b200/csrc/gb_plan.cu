@@ -253,6 +253,7 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     cudaFree(p->d_ana_w_t); cudaFree(p->d_ana_kmap); cudaFree(p->d_ana_vf);
     cudaFree(p->d_ana_lat_t); cudaFree(p->d_ana_lat_m); cudaFree(p->d_ana_lat_n); cudaFree(p->d_ana_gt);
     delete[] p->h_lat_off;
+    gb_cov_layout_free(p);
     if (p->prof_ev) {
         for (int i = 0; i < p->prof_capacity * 4; ++i) cudaEventDestroy(p->prof_ev[i]);
         delete[] p->prof_ev;
