@@ -23,6 +23,7 @@ SIGNATURES = {
     "gb_plan_destroy": (ctypes.c_int, [_vp]),
     "gb_plan_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(ctypes.c_int)] * 4),
     "gb_plan_is_symmetric": (ctypes.c_int, [_vp]),
+    "gb_plan_is_folded": (ctypes.c_int, [_vp]),
     "gb_synthesis": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
     "gb_synthesis_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "gb_legendre_table": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),

@@ -120,6 +120,40 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
         }
     std::vector<double> ct(cos_theta, cos_theta + nlat), knv(kn, kn + (size_t)nlat * L);
 
+    // Equatorial symmetry: parallel nlat-1-i mirrors parallel i (cos(theta) changes sign; sin(theta), and with it the
+    // sectorial seeds, and the radius-dependent degree factors are the same), and the folded stage 1 derives the southern
+    // parallels from the northern recursion, P_nm(pi - theta) = (-1)^(n-m) P_nm(theta).  The reference's own tables are
+    // mirror images only to rounding (arccos next to the poles), so the shortcut is gated on a measurement: the zonal
+    // functions -- the ones that are large at the poles and most sensitive to cos(theta) -- are run for both
+    // hemispheres with the kernels' recursion, and the fold is used only if no degree differs by more than 2e-13 of its
+    // largest value (0.5 deg grid: 5e-14; a 0.25 deg grid: 1e-12, not folded), i.e. ten times below the parity bar.
+    {
+        bool fold = (nlat % 2 == 0) && nlat >= 2 && L >= 2;
+        std::vector<double> diff(L, 0.0), scale(L, 0.0);
+        for (int i = 0; i < nlat / 2 && fold; ++i) {
+            const int j = nlat - 1 - i;
+            double n2 = 1.0, s2 = 1.0, n1 = rc[1] * ct[i], s1 = rc[1] * ct[j];
+            for (int n = 0; n < L; ++n) {
+                double pn, ps;
+                if (n == 0) { pn = 1.0; ps = 1.0; }
+                else if (n == 1) { pn = n1; ps = s1; }
+                else {
+                    pn = ra[(size_t)n * L] * ct[i] * n1 - rb[(size_t)n * L] * n2;
+                    ps = ra[(size_t)n * L] * ct[j] * s1 - rb[(size_t)n * L] * s2;
+                    n2 = n1; n1 = pn; s2 = s1; s1 = ps;
+                }
+                const double vn = pn * knv[(size_t)i * L + n], vs = ((n & 1) ? -ps : ps) * knv[(size_t)j * L + n];
+                diff[n] = std::max(diff[n], std::fabs(vn - vs));
+                scale[n] = std::max(scale[n], std::fabs(vn));
+                const double pa = pmm[(size_t)i * L + n], pb = pmm[(size_t)j * L + n];
+                if (std::fabs(pa - pb) > 2e-13 * (n + 1) * std::fabs(pa) + 1e-200) fold = false;   // seeds (underflow next to the poles)
+            }
+        }
+        for (int n = 0; n < L && fold; ++n)
+            if (diff[n] > 2e-13 * scale[n]) fold = false;
+        p->fold_ns = fold ? 1 : 0;
+    }
+
     // Four-fold longitude symmetry: with h = nlon/2, q = nlon/4 and mu = lon[h + j'] in (0, pi/2),
     //   lon[nlon-1-j'] = pi - mu,  lon[h-1-j'] = -mu,  lon[j'] = mu - pi.
     // Checked on the tables themselves (they are what the kernels multiply with).
@@ -239,6 +273,8 @@ extern "C" int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon
 }
 
 extern "C" int gb_plan_is_symmetric(const gb_plan* plan) { return (plan && plan->sym) ? 1 : 0; }
+
+extern "C" int gb_plan_is_folded(const gb_plan* plan) { return (plan && plan->fold_ns) ? 1 : 0; }
 
 extern "C" int gb_plan_destroy(gb_plan* p) {
     if (!p) return GB_OK;

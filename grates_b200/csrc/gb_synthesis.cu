@@ -119,7 +119,11 @@ struct T1Tables {
     int nlat_pad, lpad;
 };
 
-template <bool PAIRS, int NWN>   // PAIRS: nlat even, rows (e, i), (e, i+1) with i even are 16-byte aligned in AB
+// FOLD (declared shortcut, grids that are symmetric about the equator): P_nm(pi - theta) = (-1)^(n-m) P_nm(theta), so an
+// item covers 32 northern parallels AND their mirror images: the degrees of a chunk are contracted in two parity
+// classes (even / odd n - m: every other shared-memory row), north = even + odd, south = even - odd.  Half the
+// recursion steps and half the DMMAs for the same output; one Legendre warp per item.
+template <bool PAIRS, int NWN, bool FOLD>   // PAIRS: nlat even, rows (e, i), (e, i+1) with i even are 16-byte aligned in AB
 __global__ void __launch_bounds__(t1_threads(NWN), NWN <= 2 ? 2 : 1)
 gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tables tb, int L, int nlat, int E,
                    int ab_rows, int n_lattiles, int n_coltiles, int n_items) {
@@ -135,7 +139,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T1_STAGES; ++s) {
-            gb::mbar_init(&full[s], 3);                      // copy warp (+tx bytes) and two Legendre warps
+            gb::mbar_init(&full[s], FOLD ? 2 : 3);           // copy warp (+tx bytes) and the Legendre warp(s)
             gb::mbar_init(&empty[s], T1_CONSUMER_WARPS);
         }
         gb::fence_mbar_init();
@@ -148,7 +152,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int m_first = item / tiles_per_pair;
         const int rem = item - m_first * tiles_per_pair;
-        const int i0 = (rem / n_coltiles) * T1_TM;
+        const int i0 = (rem / n_coltiles) * (FOLD ? 32 : T1_TM);
         const int c0 = (rem % n_coltiles) * T1_TN;
         const int m_second = L - 1 - m_first;
         const int npass = (m_second == m_first) ? 1 : 2;
@@ -163,7 +167,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
                 const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
                 const double* Xm = X + xo + c0;
                 for (int c = 0; c < n_chunks; ++c) {
-                    const int rows = min(T1_KC, (Kn - c * T1_KC + 3) & ~3);
+                    const int rows = min(T1_KC, FOLD ? ((Kn - c * T1_KC + 7) & ~7) : ((Kn - c * T1_KC + 3) & ~3));
                     gb::mbar_wait(&empty[stage], phase ^ 1u);
                     double* sB = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA;
                     if (lane == 0) gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * width * sizeof(double)));
@@ -178,6 +182,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
             }
         } else if (warp > T1_CONSUMER_WARPS) {
             // ===== Legendre warps: lane = parallel, recursion state lives in registers =====
+            if (FOLD && warp != T1_CONSUMER_WARPS + 1) continue;      // folded items hold 32 parallels: one warp
             const int li = (warp - T1_CONSUMER_WARPS - 1) * 32 + lane;
             const int i = i0 + li;                           // < nlat_pad; padded parallels read zeros
             const double cti = tb.ct_pad[i];
@@ -224,6 +229,72 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
             const int wn = warp % NWN;
             const int g = lane >> 2, q = lane & 3;
             const bool has_columns = wn * 40 < width;      // narrow batches (few epochs): the other warps only keep the ring moving
+            if constexpr (FOLD) {
+                const int nh = nlat >> 1;
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int m = pass ? m_second : m_first;
+                    const int Kn = L - m;
+                    const int n_chunks = (Kn + T1_KC - 1) / T1_KC;
+                    double ev[5][2][2], od[5][2][2];         // even / odd n - m, 40 columns x 16 northern parallels
+#pragma unroll
+                    for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) ev[mi][ni][0] = ev[mi][ni][1] = od[mi][ni][0] = od[mi][ni][1] = 0.0;
+                    for (int c = 0; c < n_chunks; ++c) {
+                        const int rows = Kn - c * T1_KC;
+                        gb::mbar_wait(&full[stage], phase);
+                        const double* sP = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + wm * 16 + g;
+                        const double* sX = s_tiles + (size_t)stage * T1_STAGE_DOUBLES + T1_KC * T1_LDA + wn * 40 + g;
+#pragma unroll
+                        for (int kk = 0; kk < T1_KC; kk += 8) {
+                            if (kk >= rows || !has_columns) break;
+                            double a[5], b[2];
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + 2 * q) * T1_LDB + mi * 8];
+#pragma unroll
+                            for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(kk + 2 * q) * T1_LDA + ni * 8];
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < 2; ++ni) gb::dmma_884(ev[mi][ni][0], ev[mi][ni][1], a[mi], b[ni]);
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + 2 * q + 1) * T1_LDB + mi * 8];
+#pragma unroll
+                            for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(kk + 2 * q + 1) * T1_LDA + ni * 8];
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < 2; ++ni) gb::dmma_884(od[mi][ni][0], od[mi][ni][1], a[mi], b[ni]);
+                        }
+                        __syncwarp();
+                        if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                        if (++stage == T1_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    // epilogue: northern parallels i, i + 1 get even + odd, their mirror images nlat-1-i, nlat-2-i even - odd
+                    const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
+                    const int ib = i0 + wm * 16 + 2 * q;
+#pragma unroll
+                    for (int mi = 0; mi < 5; ++mi) {
+                        const int col = c0 + wn * 40 + mi * 8 + g;
+                        if (col >= cols) continue;
+                        const int cs = col >= E;
+                        const int e = col - cs * E;
+                        const int k = cs ? ks_row : kc_row;
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) {
+                            const int i = ib + ni * 8;
+                            if (i >= nh) continue;               // nlat even: i even, so i + 1 < nh as well
+                            const long long rn = (long long)e * nlat + i;
+                            const long long rs = (long long)e * nlat + (nlat - 2 - i);
+                            gb::st_v2(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][ni][0] + od[mi][ni][0],
+                                      ev[mi][ni][1] + od[mi][ni][1]);
+                            gb::st_v2(AB + gb_ab_offset(rs, k, ab_rows), ev[mi][ni][1] - od[mi][ni][1],
+                                      ev[mi][ni][0] - od[mi][ni][0]);
+                        }
+                    }
+                }
+                continue;
+            }
             for (int pass = 0; pass < npass; ++pass) {
                 const int m = pass ? m_second : m_first;
                 const int Kn = L - m;
@@ -529,25 +600,28 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     } else {
         // narrow batches (at most 80 epochs): 80-column items, two CTAs per SM
         const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
+        const bool fold = p->fold_ns && !env_flag("GB_NO_FOLD");        // equatorial symmetry: 32 northern parallels per item
         const int tn = narrow ? t1_tn(2) : t1_tn(6);
         const int n_coltiles = (2 * E + tn - 1) / tn;
-        const int n_lattiles = (p->nlat + T1_TM - 1) / T1_TM;
+        const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 : (p->nlat + T1_TM - 1) / T1_TM;
         const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
         const int max_ctas = narrow ? 2 * p->sm_count : p->sm_count;
         const int grid = n_items < max_ctas ? n_items : max_ctas;
         T1Tables tb{p->d_ct_pad, p->d_kn_t, p->d_pmm_t, p->d_rec_a, p->d_rec_b, p->d_zero, d_krow, p->nlat_pad, p->lpad};
-#define GB_S1_LAUNCH(PAIRS, NWN)                                                                                     \
+#define GB_S1_LAUNCH(PAIRS, NWN, FOLD)                                                                               \
     do {                                                                                                             \
-        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<PAIRS, NWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                     (int)t1_smem(NWN)));                                                            \
-        gb_legendre_stage1<PAIRS, NWN><<<grid, t1_threads(NWN), t1_smem(NWN), st>>>(                                  \
+        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<PAIRS, NWN, FOLD>,                                           \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem(NWN)));               \
+        gb_legendre_stage1<PAIRS, NWN, FOLD><<<grid, t1_threads(NWN), t1_smem(NWN), st>>>(                            \
             p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows, n_lattiles, n_coltiles, n_items);                        \
     } while (0)
         const bool pairs = p->nlat % 2 == 0;
-        if (narrow) {
-            if (pairs) GB_S1_LAUNCH(true, 2); else GB_S1_LAUNCH(false, 2);
+        if (fold) {                     // implies an even number of parallels
+            if (narrow) GB_S1_LAUNCH(true, 2, true); else GB_S1_LAUNCH(true, 6, true);
+        } else if (narrow) {
+            if (pairs) GB_S1_LAUNCH(true, 2, false); else GB_S1_LAUNCH(false, 2, false);
         } else {
-            if (pairs) GB_S1_LAUNCH(true, 6); else GB_S1_LAUNCH(false, 6);
+            if (pairs) GB_S1_LAUNCH(true, 6, false); else GB_S1_LAUNCH(false, 6, false);
         }
 #undef GB_S1_LAUNCH
         GB_LAUNCH_CHECK();

@@ -121,6 +121,13 @@ class SHPlan:
         forced_off = os.environ.get("GB_NO_SYMMETRY", "") not in ("", "0")
         return bool(self._lib.gb_plan_is_symmetric(self._handle)) and not forced_off
 
+    @property
+    def folded(self):
+        """True if the Legendre stage uses the equatorial symmetry of the parallels (see gb_plan_is_folded)."""
+        import os
+        forced_off = os.environ.get("GB_NO_FOLD", "") not in ("", "0")
+        return bool(self._lib.gb_plan_is_folded(self._handle)) and not forced_off
+
     def _check_anm(self, anm):
         if anm.dim() != 3 or anm.shape[1] != self.L or anm.shape[2] != self.L:
             raise ValueError("coefficients must have shape [epochs, {0}, {0}] (got {1})".format(self.L, tuple(anm.shape)))

@@ -83,6 +83,16 @@ int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon, int* devi
 int gb_plan_is_symmetric(const gb_plan* plan);
 
 /*
+ * 1 if the plan's parallels are mirror images about the equator closely enough for the folded Legendre stage
+ * (GeographicGrid / GaussGrid down to about 0.5 degree spacing): gb_synthesis then runs the recursion for the northern
+ * parallels only and obtains the southern ones from P_nm(pi - theta) = (-1)^(n-m) P_nm(theta) -- half the recursion steps
+ * and multiply-adds of the Legendre stage.  The gate is measured at plan creation: the zonal functions of both
+ * hemispheres, computed with the reference's own (not exactly mirrored) cos(theta) tables, must agree to 2e-13 of their
+ * largest value in every degree.  GB_NO_FOLD=1 forces the unfolded stage.
+ */
+int gb_plan_is_folded(const gb_plan* plan);
+
+/*
  * Spherical-harmonic synthesis of n_epochs coefficient sets onto the plan's grid.
  * Replaces the body of PotentialCoefficients.to_grid, gravityfield.py:358-368, for a batch:
  *   out[e][i][j] = sum_n kn[i][n] sum_m P_nm(theta_i) (C_nm^e cos m lon_j + S_nm^e sin m lon_j)

@@ -146,6 +146,42 @@ def test_synthesis_symmetric_vs_general_path(gb, orc, monkeypatch, nmax, dlon, E
     assert maxnorm_err(sym, ref) < TOL and maxnorm_err(gen, ref) < TOL
 
 
+@pytest.mark.parametrize("nmax,dlat,E", [(1, 30.0, 1), (2, 45.0, 3), (15, 10.0, 2), (16, 6.0, 41), (47, 2.0, 90), (96, 0.5, 2), (120, 1.0, 3)])
+def test_synthesis_equator_fold_vs_unfolded(gb, orc, monkeypatch, nmax, dlat, E):
+    """Grids that mirror about the equator run the Legendre recursion for the northern parallels only (declared
+    shortcut, gb_plan_is_folded).  White spectra, zonal and full, are the worst case for the hemisphere asymmetry of the
+    reference's own cos(theta) table: the folded result must stay within tolerance of the oracle and agree with the
+    unfolded stage (GB_NO_FOLD=1) to rounding."""
+    grid, og = gb.GeographicGrid(4 * dlat if dlat < 20 else dlat, dlat), None
+    og = orc.geographic_grid(4 * dlat if dlat < 20 else dlat, dlat)
+    plan = gb.get_plan(grid, nmax, "potential")
+    assert plan.folded == (nmax >= 1)
+    rng = np.random.default_rng(nmax)
+    anm = rng.standard_normal((E, nmax + 1, nmax + 1))
+    anm[0] = 0.0
+    anm[0, :, 0] = rng.standard_normal(nmax + 1)            # zonal only: largest at the poles
+    folded = gb.to_grid_batch(anm, grid, "potential")
+    monkeypatch.setenv("GB_NO_FOLD", "1")
+    plain = gb.to_grid_batch(anm, grid, "potential")
+    monkeypatch.delenv("GB_NO_FOLD")
+    ref = np.stack([orc.synthesis(a, og, "potential") for a in anm[:2]])
+    assert maxnorm_err(plain[:2], ref) < TOL
+    assert maxnorm_err(folded[:2], ref) < TOL
+    for e in range(E):
+        assert maxnorm_err(folded[e], plain[e]) < 5e-13
+
+
+def test_equator_fold_is_gated_on_measured_asymmetry(gb):
+    """A 0.25 degree grid is not folded (the reference's colatitudes next to the poles differ between the hemispheres
+    by more than the gate allows), grids that are not mirror images are not either."""
+    assert gb.get_plan(gb.GeographicGrid(0.5, 0.5), 96, "ewh").folded
+    assert not gb.get_plan(gb.GeographicGrid(1.0, 0.25), 60, "ewh").folded
+    par = gb.GeographicGrid(10.0, 10.0).parallels.copy()
+    par[3] += 1e-9
+    assert not gb.get_plan(gb.RegularGrid(gb.GeographicGrid(10.0, 10.0).meridians, par), 8, "ewh").folded
+    assert not gb.get_plan(gb.RegularGrid(gb.GeographicGrid(10.0, 10.0).meridians, par[:-1]), 8, "ewh").folded   # odd count
+
+
 @pytest.mark.parametrize("nmax,dlon,dlat,E", [(1, 30.0, 30.0, 1), (2, 90.0, 45.0, 2), (17, 7.5, 4.0, 7),
                                               (33, 3.0, 3.0, 2), (96, 1.0, 0.5, 3)])
 def test_synthesis_ragged_shapes_vs_oracle(gb, orc, nmax, dlon, dlat, E):
