@@ -306,6 +306,9 @@ def main():
         # executed multiply-adds of the dominant kernel: the symmetric path contracts one quadrant of meridians
         sym = plan.symmetric
         f2_exec = f2 / 4.0 if sym else f2
+        # the folded Legendre stage runs the recursion and its multiply-adds for the northern parallels only
+        folded = plan.folded
+        f1_exec = f1 / 2.0 if folded else f1
         step_mean_ms = 1e3 * my_time / args.steps
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "stage2_traffic.json")
@@ -329,12 +332,15 @@ def main():
             "note": ("declared algorithmic shortcut: four-fold longitude symmetry of the grid (meridians symmetric "
                      "about 0 and under a half turn) -> the kernel executes 1/4 of the contract multiply-adds; "
                      "`achieved`/`frac` use the SURVEY 8(d) contract flops (direct contraction, no symmetry credit), "
-                     "`executed_*` what the tensor pipe really did. GB_NO_SYMMETRY=1 runs the direct contraction."
+                     "`executed_*` what the tensor pipe really did. GB_NO_SYMMETRY=1 runs the direct contraction. "
+                     "Second declared shortcut (Legendre stage): parallels mirrored about the equator share one "
+                     "recursion, gated on a measured hemisphere asymmetry of the reference's tables (GB_NO_FOLD=1 disables)."
                      if sym else "direct contraction (no symmetry shortcut active)"),
             "step": {"algorithmic_flops": f1 + f2 + fl, "ms": step_mean_ms,
                      "frac_of_fp64_peak": (f1 + f2 + fl) / (step_mean_ms * 1e-3) / 1e12 / peak,
-                     "executed_flops": f1 + f2_exec + fl,
-                     "executed_frac_of_fp64_peak": (f1 + f2_exec + fl) / (step_mean_ms * 1e-3) / 1e12 / peak,
+                     "executed_flops": f1_exec + f2_exec + fl,
+                     "executed_frac_of_fp64_peak": (f1_exec + f2_exec + fl) / (step_mean_ms * 1e-3) / 1e12 / peak,
+                     "legendre_stage_folded_about_equator": bool(folded),
                      "kernel_ms": {"pack": pk_ms, "legendre_stage1": s1_ms, "fourier_stage2": s2_ms}},
             "hbm": {"algorithmic_bytes_per_step": bytes_step, "peak_gbs": hbm,
                     "achieved_gbs": bytes_step / (step_mean_ms * 1e-3) / 1e9,
