@@ -84,6 +84,7 @@ struct gb_plan {
     // spectral rows regrouped as [even-m cos | odd-m cos | even-m sin | odd-m sin], each padded to 4
     int sym = 0;                // 1 if the meridians allow the symmetric stage 2
     int fold_ns = 0;            // 1 if the parallels are symmetric about the equator (folded stage 1)
+    int fold_cap = 0;           // leading parallels per hemisphere (0, 32 or 64) that stay with the unfolded stage
     int kpad_s = 0;             // rows of AB in the symmetric layout (incl. 4 dummy rows at the end)
     int grp_off[5] = {0, 0, 0, 0, 0};
     int nq = 0, nqp = 0;        // first-quadrant meridians, padded to a multiple of 8

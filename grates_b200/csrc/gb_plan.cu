@@ -129,8 +129,10 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
     // largest value (0.5 deg grid: 5e-14; a 0.25 deg grid: 1e-12, not folded), i.e. ten times below the parity bar.
     {
         bool fold = (nlat % 2 == 0) && nlat >= 2 && L >= 2;
-        std::vector<double> diff(L, 0.0), scale(L, 0.0);
-        for (int i = 0; i < nlat / 2 && fold; ++i) {
+        const int nh = nlat / 2;
+        std::vector<double> diff((size_t)nh * L, 0.0), scale(L, 0.0);
+        std::vector<char> seed_bad(nh, 0);
+        for (int i = 0; i < nh && fold; ++i) {
             const int j = nlat - 1 - i;
             double n2 = 1.0, s2 = 1.0, n1 = rc[1] * ct[i], s1 = rc[1] * ct[j];
             for (int n = 0; n < L; ++n) {
@@ -143,15 +145,25 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
                     n2 = n1; n1 = pn; s2 = s1; s1 = ps;
                 }
                 const double vn = pn * knv[(size_t)i * L + n], vs = ((n & 1) ? -ps : ps) * knv[(size_t)j * L + n];
-                diff[n] = std::max(diff[n], std::fabs(vn - vs));
+                diff[(size_t)i * L + n] = std::fabs(vn - vs);
                 scale[n] = std::max(scale[n], std::fabs(vn));
                 const double pa = pmm[(size_t)i * L + n], pb = pmm[(size_t)j * L + n];
-                if (std::fabs(pa - pb) > 2e-13 * (n + 1) * std::fabs(pa) + 1e-200) fold = false;   // seeds (underflow next to the poles)
+                if (std::fabs(pa - pb) > 2e-13 * (n + 1) * std::fabs(pa) + 1e-200) seed_bad[i] = 1;   // (underflow next to the poles)
             }
         }
-        for (int n = 0; n < L && fold; ++n)
-            if (diff[n] > 2e-13 * scale[n]) fold = false;
+        // Parallels that fail the gate are next to the poles (the reference's arccos): up to two leading tiles of 32
+        // parallels per hemisphere are left to the unfolded stage, everything else is folded.
+        int last_bad = -1;
+        for (int i = 0; i < nh && fold; ++i) {
+            bool bad = seed_bad[i] != 0;
+            for (int n = 0; n < L && !bad; ++n)
+                if (diff[(size_t)i * L + n] > 2e-13 * scale[n]) bad = true;
+            if (bad) last_bad = i;
+        }
+        int cap = last_bad < 0 ? 0 : (last_bad / 32 + 1) * 32;
+        if (cap > 64 || (cap > 0 && (nlat < 128 || nh - cap < 32))) fold = false;
         p->fold_ns = fold ? 1 : 0;
+        p->fold_cap = fold ? cap : 0;
     }
 
     // Four-fold longitude symmetry: with h = nlon/2, q = nlon/4 and mu = lon[h + j'] in (0, pi/2),
@@ -274,7 +286,7 @@ extern "C" int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon
 
 extern "C" int gb_plan_is_symmetric(const gb_plan* plan) { return (plan && plan->sym) ? 1 : 0; }
 
-extern "C" int gb_plan_is_folded(const gb_plan* plan) { return (plan && plan->fold_ns) ? 1 : 0; }
+extern "C" int gb_plan_is_folded(const gb_plan* plan) { return (plan && plan->fold_ns) ? 1 + plan->fold_cap / 32 : 0; }
 
 extern "C" int gb_plan_destroy(gb_plan* p) {
     if (!p) return GB_OK;

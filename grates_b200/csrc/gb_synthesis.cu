@@ -126,7 +126,9 @@ struct T1Tables {
 template <bool PAIRS, int NWN, bool FOLD>   // PAIRS: nlat even, rows (e, i), (e, i+1) with i even are 16-byte aligned in AB
 __global__ void __launch_bounds__(t1_threads(NWN), NWN <= 2 ? 2 : 1)
 gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tables tb, int L, int nlat, int E,
-                   int ab_rows, int n_lattiles, int n_coltiles, int n_items) {
+                   int ab_rows, int n_lattiles, int n_coltiles, int n_items, int polar) {
+    // polar: FOLD -- number of leading 32-parallel tiles left to the unfolded launch; !FOLD -- nonzero selects the
+    // "polar cap" tiling (tile t = northern parallels [32t, 32t+32) and their mirror images), see launch_synthesis
     constexpr int T1_TN = t1_tn(NWN), T1_LDB = T1_TN + 4, T1_CONSUMER_WARPS = 2 * NWN;
     constexpr int T1_STAGE_DOUBLES = T1_KC * (T1_LDA + T1_LDB);
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -152,7 +154,8 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int m_first = item / tiles_per_pair;
         const int rem = item - m_first * tiles_per_pair;
-        const int i0 = (rem / n_coltiles) * (FOLD ? 32 : T1_TM);
+        const int i0 = FOLD ? (polar + rem / n_coltiles) * 32 : (rem / n_coltiles) * (polar ? 32 : T1_TM);
+        const int i_south = nlat - 64 - i0;            // cap tiling: rows 32..63 of the tile are parallels nlat-32-i0 ..
         const int c0 = (rem % n_coltiles) * T1_TN;
         const int m_second = L - 1 - m_first;
         const int npass = (m_second == m_first) ? 1 : 2;
@@ -184,7 +187,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
             // ===== Legendre warps: lane = parallel, recursion state lives in registers =====
             if (FOLD && warp != T1_CONSUMER_WARPS + 1) continue;      // folded items hold 32 parallels: one warp
             const int li = (warp - T1_CONSUMER_WARPS - 1) * 32 + lane;
-            const int i = i0 + li;                           // < nlat_pad; padded parallels read zeros
+            const int i = (!FOLD && polar && li >= 32) ? i_south + li : i0 + li;   // < nlat_pad; padded parallels read zeros
             const double cti = tb.ct_pad[i];
             for (int pass = 0; pass < npass; ++pass) {
                 const int m = pass ? m_second : m_first;
@@ -329,7 +332,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
                 // epilogue: columns [0, E) are the cosine coefficients of epoch col, [E, 2E) the sines.
                 // The 32 parallels of a warp sit in at most two neighbouring 128-row tiles of AB.
                 const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
-                const int ib = i0 + wm * 32 + 2 * q;
+                const int ib = ((polar && wm) ? i_south : i0) + wm * 32 + 2 * q;
                 const int tile_step = ab_rows * GB_LDA - GB_TM;      // to the same k row of the next row tile
 #pragma unroll
                 for (int mi = 0; mi < 5; ++mi) {
@@ -603,7 +606,8 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         const bool fold = p->fold_ns && !env_flag("GB_NO_FOLD");        // equatorial symmetry: 32 northern parallels per item
         const int tn = narrow ? t1_tn(2) : t1_tn(6);
         const int n_coltiles = (2 * E + tn - 1) / tn;
-        const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 : (p->nlat + T1_TM - 1) / T1_TM;
+        const int cap_tiles = fold ? p->fold_cap / 32 : 0;              // polar tiles that stay unfolded
+        const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 - cap_tiles : (p->nlat + T1_TM - 1) / T1_TM;
         const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
         const int max_ctas = narrow ? 2 * p->sm_count : p->sm_count;
         const int grid = n_items < max_ctas ? n_items : max_ctas;
@@ -613,11 +617,26 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<PAIRS, NWN, FOLD>,                                           \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem(NWN)));               \
         gb_legendre_stage1<PAIRS, NWN, FOLD><<<grid, t1_threads(NWN), t1_smem(NWN), st>>>(                            \
-            p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows, n_lattiles, n_coltiles, n_items);                        \
+            p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows, n_lattiles, n_coltiles, n_items, cap_tiles);             \
     } while (0)
         const bool pairs = p->nlat % 2 == 0;
         if (fold) {                     // implies an even number of parallels
             if (narrow) GB_S1_LAUNCH(true, 2, true); else GB_S1_LAUNCH(true, 6, true);
+            if (cap_tiles > 0) {
+                // the polar caps (parallels whose mirror image is not close enough in the reference's tables): the
+                // unfolded kernel on tiles of 32 northern parallels + their 32 mirror images
+                const int cap_items = (L + 1) / 2 * cap_tiles * n_coltiles;
+                const int cap_grid = cap_items < max_ctas ? cap_items : max_ctas;
+#define GB_S1_CAP(NWN)                                                                                               \
+    do {                                                                                                             \
+        GB_CUDA(cudaFuncSetAttribute(gb_legendre_stage1<true, NWN, false>,                                           \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem(NWN)));               \
+        gb_legendre_stage1<true, NWN, false><<<cap_grid, t1_threads(NWN), t1_smem(NWN), st>>>(                        \
+            p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows, cap_tiles, n_coltiles, cap_items, 1);                    \
+    } while (0)
+                if (narrow) GB_S1_CAP(2); else GB_S1_CAP(6);
+#undef GB_S1_CAP
+            }
         } else if (narrow) {
             if (pairs) GB_S1_LAUNCH(true, 2, false); else GB_S1_LAUNCH(false, 2, false);
         } else {

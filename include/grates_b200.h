@@ -88,7 +88,9 @@ int gb_plan_is_symmetric(const gb_plan* plan);
  * parallels only and obtains the southern ones from P_nm(pi - theta) = (-1)^(n-m) P_nm(theta) -- half the recursion steps
  * and multiply-adds of the Legendre stage.  The gate is measured at plan creation: the zonal functions of both
  * hemispheres, computed with the reference's own (not exactly mirrored) cos(theta) tables, must agree to 2e-13 of their
- * largest value in every degree.  GB_NO_FOLD=1 forces the unfolded stage.
+ * largest value in every degree.  Parallels next to the poles that fail (the reference's arccos is ill-conditioned
+ * there; e.g. one parallel of a 0.25 degree grid) keep the unfolded stage in tiles of 32 per hemisphere: the return
+ * value is 0 (not folded) or 1 + the number of such polar tiles (at most two).  GB_NO_FOLD=1 forces the unfolded stage.
  */
 int gb_plan_is_folded(const gb_plan* plan);
 

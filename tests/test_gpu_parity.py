@@ -146,7 +146,7 @@ def test_synthesis_symmetric_vs_general_path(gb, orc, monkeypatch, nmax, dlon, E
     assert maxnorm_err(sym, ref) < TOL and maxnorm_err(gen, ref) < TOL
 
 
-@pytest.mark.parametrize("nmax,dlat,E", [(1, 30.0, 1), (2, 45.0, 3), (15, 10.0, 2), (16, 6.0, 41), (47, 2.0, 90), (96, 0.5, 2), (120, 1.0, 3)])
+@pytest.mark.parametrize("nmax,dlat,E", [(1, 30.0, 1), (2, 45.0, 3), (15, 10.0, 2), (16, 6.0, 41), (47, 2.0, 90), (96, 0.5, 2), (120, 1.0, 3), (120, 0.25, 2), (60, 0.25, 130)])
 def test_synthesis_equator_fold_vs_unfolded(gb, orc, monkeypatch, nmax, dlat, E):
     """Grids that mirror about the equator run the Legendre recursion for the northern parallels only (declared
     shortcut, gb_plan_is_folded).  White spectra, zonal and full, are the worst case for the hemisphere asymmetry of the
@@ -172,10 +172,14 @@ def test_synthesis_equator_fold_vs_unfolded(gb, orc, monkeypatch, nmax, dlat, E)
 
 
 def test_equator_fold_is_gated_on_measured_asymmetry(gb):
-    """A 0.25 degree grid is not folded (the reference's colatitudes next to the poles differ between the hemispheres
-    by more than the gate allows), grids that are not mirror images are not either."""
-    assert gb.get_plan(gb.GeographicGrid(0.5, 0.5), 96, "ewh").folded
-    assert not gb.get_plan(gb.GeographicGrid(1.0, 0.25), 60, "ewh").folded
+    """On a 0.25 degree grid one parallel next to the pole fails the gate (the reference's colatitudes there differ
+    between the hemispheres by more than it allows): its tile of 32 parallels per hemisphere stays with the unfolded
+    stage, the rest is folded.  Grids that are not mirror images are not folded at all."""
+    lib = gb._lib.load()
+    half = gb.get_plan(gb.GeographicGrid(0.5, 0.5), 96, "ewh")
+    assert half.folded and lib.gb_plan_is_folded(half._handle) == 1              # no polar cap needed
+    quarter = gb.get_plan(gb.GeographicGrid(1.0, 0.25), 60, "ewh")
+    assert quarter.folded and lib.gb_plan_is_folded(quarter._handle) == 2         # one 32-parallel cap per pole
     par = gb.GeographicGrid(10.0, 10.0).parallels.copy()
     par[3] += 1e-9
     assert not gb.get_plan(gb.RegularGrid(gb.GeographicGrid(10.0, 10.0).meridians, par), 8, "ewh").folded
