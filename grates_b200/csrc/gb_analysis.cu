@@ -408,6 +408,10 @@ extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_o
 }
 
 static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_anm, cudaStream_t st) {
+    {
+        int rca = gb_plan_acquire(p, st);   // one workspace per plan: order this call behind the previous one
+        if (rca) return rca;
+    }
     const int L = p->L;
     const long long M = (long long)E * p->nlat;
     const long long mpad = p->ws_mpad;

@@ -131,9 +131,26 @@ struct gb_plan {
     // optional per-kernel event timing (gb_plan_set_profiling)
     cudaEvent_t* prof_ev = nullptr;  // [capacity][4]
     int prof_capacity = 0, prof_count = 0;
+    // Legendre tables of stage 1: kn[i,n] * P_nm(theta_i), written once per plan by the bit-exact device recursion
+    // (gb_synthesis.cu) in the tile layout the stage-1 kernel bulk-copies: [lat tile][order m: rows roff[m]..][pitch].
+    // kind 0: folded tiles (32 northern parallels, pitch 36, even/odd degrees grouped), 1: polar-cap tiles
+    // (32 northern + 32 mirrored parallels, pitch 68), 2: plain tiles of 64 parallels (pitch 68)
+    double* d_ptab[3] = {nullptr, nullptr, nullptr};
+    int* d_ptab_roff = nullptr;      // [L + 1] first table row of every order (orders padded to 8 rows)
+    long long ptab_rtot = 0;         // rows per lat tile
+    int ptab_state[3] = {0, 0, 0};   // 0: not built yet, 1: built, -1: over the memory budget (on-the-fly recursion instead)
+    // stream ordering of the shared workspace (d_x, d_ab, analysis / covariance scratch, cached index tables): a call
+    // on another stream than the previous call's first waits for everything that stream holds (gb_plan_acquire)
+    cudaEvent_t ws_free = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    int ws_used = 0;
     // device facts
     int sm_count = 0;
 };
+
+// The plan's workspace is one buffer set: make `st` wait until the previous call that used it (on whatever stream) is
+// done.  Free when consecutive calls share a stream.  Host threads must not call into one plan concurrently.
+int gb_plan_acquire(gb_plan* p, cudaStream_t st);
 
 int gb_plan_ensure_workspace(gb_plan* p, int n_epochs);
 void gb_cov_layout_free(gb_plan* p);
@@ -173,6 +190,31 @@ struct gb_scratch {
         return e;
     }
 };
+
+// Kernel launch with the programmatic-stream-serialization attribute (PDL); GB_NO_PDL=1 launches plainly.
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+inline bool gb_pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("GB_NO_PDL"); return !(v && v[0] && v[0] != '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t gb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gb_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 // Recursion coefficients a_nm, b_nm [L][L], sqrt(2n+1) [L] and sectorial seeds P_mm [npts][L],
 // evaluated in IEEE double in the operation order of reference utilities.py:37-54.
@@ -253,6 +295,11 @@ __device__ __forceinline__ void legendre_column(int m, int L, double ct, double 
         p1 = p;
     }
 }
+
+// Programmatic dependent launch: a kernel launched with gb_launch_pdl may start while its predecessor in the stream
+// drains; everything it reads or writes that the predecessor (or anything before it) touches comes after griddep_wait().
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 __device__ __forceinline__ void st_cs_v2(double* p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(a), "d"(b) : "memory");

@@ -398,6 +398,10 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
                "gb_covariance_propagation_filtered: the order-wise filter (degree %d) does not reach degree %d", nf, p->nmax);
     GB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        int rca = gb_plan_acquire(p, st);   // the cached index tables are rebuilt when the shape changes
+        if (rca) return rca;
+    }
     gb_scratch scratch(st);           // frees every temporary of this call on all return paths
     const int L = p->L, kpad = p->kpad;
     const long long K = (long long)L * L - (long long)nmin * nmin;

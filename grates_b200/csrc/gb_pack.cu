@@ -4,8 +4,8 @@
 //   X               order-wise: the block of order m starts at 2E (m L - m(m-1)/2) and is
 //                   X_m[n - m][cs * E + e], cs = 0 (cos) / 1 (sin), epochs contiguous
 //
-// Row r of anm[e] holds C_{r,0..r} followed by S_{r+1, r+1..nmax}; one CTA moves that row for 32
-// epochs through shared memory, so both sides are touched in full contiguous lines: reads are
+// Row r of anm[e] holds C_{r,0..r} followed by S_{r+1, r+1..nmax}; one CTA moves that row for 32 (8 for small
+// shards) epochs through shared memory, so both sides are touched in full contiguous lines: reads are
 // rows of L doubles, writes are 32 consecutive epochs (256 B).  The sine plane of order 0 does not
 // exist in anm and is kept at zero (stage 1 contracts it like any other column).  Optional per-degree
 // weights w[n] (Gaussian / Butterworth filters, reference filter.py:31-130) are multiplied in while
@@ -14,8 +14,6 @@
 
 namespace {
 
-constexpr int PK_E = 32;          // epochs per CTA
-constexpr int PK_LD = PK_E + 1;   // shared-memory pitch
 constexpr int PK_C = 512;         // columns of anm per CTA (bounds shared memory at high degree)
 
 __device__ __forceinline__ long long x_block_offset(int m, int L, int E) {
@@ -30,16 +28,21 @@ __device__ __forceinline__ long long x_position(int r, int c, int L, int E) {
     return x_block_offset(m, L, E) + (long long)nn * 2 * E + (long long)cs * E;
 }
 
-template <bool PACK>
+// PKE epochs per CTA: 32 for epoch batches (256-byte runs on the X side), 8 for small shards (four times as many
+// CTAs: a 30-epoch shard is latency-, not bandwidth-bound)
+template <bool PACK, int PKE>
 __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int L,
                                                       int E, const double* __restrict__ wn) {
+    constexpr int PK_LD = PKE + 1;    // shared-memory pitch
     extern __shared__ double s_t[];   // [min(L, PK_C)][PK_LD]
     const int r = blockIdx.x;
     const int cb = blockIdx.z * PK_C;                 // first column of this CTA
     const int nc = min(PK_C, L - cb);
-    const int e0 = blockIdx.y * PK_E;
-    const int ne = min(PK_E, E - e0);
+    const int e0 = blockIdx.y * PKE;
+    const int ne = min(PKE, E - e0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    gb::griddep_wait();
+    gb::griddep_launch_dependents();
     if (PACK) {
         for (int e = warp; e < ne; e += nwarps) {
             const double* row = src + ((size_t)(e0 + e) * L + r) * L;
@@ -50,13 +53,17 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
             }
         }
         __syncthreads();
-        for (int c = warp; c < nc; c += nwarps)
-            if (lane < ne) dst[x_position(r, cb + c, L, E) + e0 + lane] = s_t[c * PK_LD + lane];
+        for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
+            const int c = idx / PKE, e = idx % PKE;
+            if (e < ne) dst[x_position(r, cb + c, L, E) + e0 + e] = s_t[c * PK_LD + e];
+        }
         // sine plane of order 0, degree r
-        if (blockIdx.z == 0 && warp == 0 && lane < ne) dst[(long long)r * 2 * E + E + e0 + lane] = 0.0;
+        if (blockIdx.z == 0 && threadIdx.x < ne) dst[(long long)r * 2 * E + E + e0 + threadIdx.x] = 0.0;
     } else {
-        for (int c = warp; c < nc; c += nwarps)
-            if (lane < ne) s_t[c * PK_LD + lane] = src[x_position(r, cb + c, L, E) + e0 + lane];
+        for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
+            const int c = idx / PKE, e = idx % PKE;
+            if (e < ne) s_t[c * PK_LD + e] = src[x_position(r, cb + c, L, E) + e0 + e];
+        }
         __syncthreads();
         for (int e = warp; e < ne; e += nwarps) {
             double* row = dst + ((size_t)(e0 + e) * L + r) * L;
@@ -75,15 +82,20 @@ __global__ void __launch_bounds__(256) gb_scale_degree_kernel(const double* __re
     out[idx] = __dmul_rn(in[idx], wn[max(r, c)]);
 }
 
-template <bool PACK>
-int launch(const double* src, double* dst, int L, int E, const double* wn, cudaStream_t st) {
-    const size_t smem = (size_t)(L < PK_C ? L : PK_C) * PK_LD * sizeof(double);
+template <bool PACK, int PKE>
+int launch_pke(const double* src, double* dst, int L, int E, const double* wn, cudaStream_t st) {
+    const size_t smem = (size_t)(L < PK_C ? L : PK_C) * (PKE + 1) * sizeof(double);
     if (smem > 48 * 1024)
-        GB_CUDA(cudaFuncSetAttribute(gb_pack_kernel<PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(L, (E + PK_E - 1) / PK_E, (L + PK_C - 1) / PK_C);
-    gb_pack_kernel<PACK><<<grid, 256, smem, st>>>(src, dst, L, E, wn);
+        GB_CUDA(cudaFuncSetAttribute(gb_pack_kernel<PACK, PKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(L, (E + PKE - 1) / PKE, (L + PK_C - 1) / PK_C);
+    GB_CUDA(gb_launch_pdl(gb_pack_kernel<PACK, PKE>, grid, dim3(256), smem, st, src, dst, L, E, wn));
     GB_LAUNCH_CHECK();
     return GB_OK;
+}
+
+template <bool PACK>
+int launch(const double* src, double* dst, int L, int E, const double* wn, cudaStream_t st) {
+    return E <= 64 ? launch_pke<PACK, 8>(src, dst, L, E, wn, st) : launch_pke<PACK, 32>(src, dst, L, E, wn, st);
 }
 
 }  // namespace

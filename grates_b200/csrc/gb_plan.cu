@@ -302,6 +302,9 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     cudaFree(p->d_ana_lat_t); cudaFree(p->d_ana_lat_m); cudaFree(p->d_ana_lat_n); cudaFree(p->d_ana_gt);
     delete[] p->h_lat_off;
     gb_cov_layout_free(p);
+    for (auto& t : p->d_ptab) cudaFree(t);
+    cudaFree(p->d_ptab_roff);
+    if (p->ws_free) cudaEventDestroy(p->ws_free);
     if (p->prof_ev) {
         for (int i = 0; i < p->prof_capacity * 4; ++i) cudaEventDestroy(p->prof_ev[i]);
         delete[] p->prof_ev;
@@ -311,6 +314,20 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
     delete p;
+    return GB_OK;
+}
+
+int gb_plan_acquire(gb_plan* p, cudaStream_t st) {
+    if (p->ws_used && p->ws_stream != st) {
+        if (!p->ws_free) GB_CUDA(cudaEventCreateWithFlags(&p->ws_free, cudaEventDisableTiming));
+        // everything queued on the previous call's stream so far includes that call's last kernel
+        if (cudaEventRecord(p->ws_free, p->ws_stream) != cudaSuccess || cudaStreamWaitEvent(st, p->ws_free, 0) != cudaSuccess) {
+            cudaGetLastError();                       // e.g. the other stream no longer exists
+            GB_CUDA(cudaDeviceSynchronize());
+        }
+    }
+    p->ws_stream = st;
+    p->ws_used = 1;
     return GB_OK;
 }
 

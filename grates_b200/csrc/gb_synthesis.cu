@@ -21,6 +21,7 @@
 //   gbgemm::kernel       persistent FP64 tensor-core GEMM  V = AB^T * trig  (DMMA.8x8x4, gb_gemm.cuh),
 //                        operands staged by the TMA unit (cp.async.bulk) through a 3-stage
 //                        mbarrier pipeline fed by a dedicated producer warp
+#include <vector>
 #include "gb_common.cuh"
 #include "gb_gemm.cuh"
 
@@ -363,6 +364,269 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
 }
 
 // ---------------------------------------------------------------------------------------------
+// stage 1 fed from the plan's Legendre table (the default).  kn[i,n] * P_nm(theta_i) does not depend on the epoch, so
+// the plan holds it -- written once by gb_ptab_kernel with the same bit-exact recursion -- in exactly the tile layout a
+// pipeline chunk needs: ONE bulk copy per chunk, no recursion warp, no FP64 instructions that compete with the DMMA
+// stream for the pipe (the on-the-fly recursion warp above was starved by the three DMMA-issuing warps of its
+// sub-partition: 300 cycles per degree, DMMA pipe 45 % active).  Same items, tiles, epilogues and AB layout as
+// gb_legendre_stage1; the degrees of a folded chunk are grouped [even n-m | odd n-m] per 8 rows, so both parity
+// classes read consecutive shared-memory rows (pitch 36 = 4 mod 16: conflict-free fragments).
+// ---------------------------------------------------------------------------------------------
+constexpr int TB_KC = 16;
+__host__ __device__ constexpr int tb_lda(bool fold) { return fold ? 36 : 68; }
+__host__ __device__ constexpr int tb_stages(int nwn, bool fold) { return nwn <= 2 ? 4 : (fold ? 6 : 5); }
+__host__ __device__ constexpr int tb_threads(int nwn) { return 32 * (2 * nwn + 1); }
+__host__ __device__ constexpr size_t tb_smem(int nwn, bool fold) {
+    return (size_t)tb_stages(nwn, fold) * TB_KC * (tb_lda(fold) + t1_tn(nwn) + 4) * sizeof(double) +
+           2 * tb_stages(nwn, fold) * sizeof(uint64_t);
+}
+// row of degree offset nn inside a folded table / chunk: even offsets first
+__host__ __device__ __forceinline__ int tb_fold_row(int nn) { return (nn & ~7) + ((nn & 1) << 2) + ((nn & 7) >> 1); }
+__host__ __device__ __forceinline__ int tb_fold_degree(int row) {
+    const int r = row & 7;
+    return (row & ~7) + (r < 4 ? 2 * r : 2 * (r - 4) + 1);
+}
+
+struct TabArgs {
+    const double* tab;      // [lat tile][rtot][lda]
+    const int* roff;        // [L + 1]
+    long long tile_stride;  // rtot * lda
+    const double* zeros;
+    const int* krow;
+};
+
+template <bool PAIRS, int NWN, bool FOLD>
+__global__ void __launch_bounds__(tb_threads(NWN), NWN <= 2 ? (FOLD ? 3 : 2) : 1)
+gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb, int L, int nlat, int E, int ab_rows,
+              int n_lattiles, int n_coltiles, int n_items, int polar) {
+    constexpr int KC = TB_KC, STAGES = tb_stages(NWN, FOLD);
+    constexpr int TN = t1_tn(NWN), LDA = tb_lda(FOLD), LDB = TN + 4, CONSUMER_WARPS = 2 * NWN;
+    constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tiles = reinterpret_cast<double*>(s_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)STAGES * STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + STAGES;
+    const int cols = 2 * E;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            gb::mbar_init(&full[s], 1);
+            gb::mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        gb::fence_mbar_init();
+    }
+    __syncthreads();
+    gb::griddep_wait();                 // X comes from the pack kernel, AB is still being read by the previous call
+    gb::griddep_launch_dependents();
+
+    int stage = 0;
+    uint32_t phase = 0;
+    const int tiles_per_pair = n_lattiles * n_coltiles;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int m_first = item / tiles_per_pair;
+        const int rem = item - m_first * tiles_per_pair;
+        const int lt = rem / n_coltiles;
+        const int i0 = FOLD ? (polar + lt) * 32 : lt * (polar ? 32 : T1_TM);
+        const int i_south = nlat - 64 - i0;
+        const int c0 = (rem % n_coltiles) * TN;
+        const int m_second = L - 1 - m_first;
+        const int npass = (m_second == m_first) ? 1 : 2;
+        const int width = min(TN, cols - c0);
+
+        if (warp == CONSUMER_WARPS) {
+            // ===== copy warp: one bulk copy for the table chunk, one per row of X_m =====
+            const double* tab_t = tb.tab + (size_t)lt * tb.tile_stride;
+            for (int pass = 0; pass < npass; ++pass) {
+                const int m = pass ? m_second : m_first;
+                const int Kn = L - m;
+                const int n_chunks = (Kn + KC - 1) / KC;
+                const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
+                const double* Xm = X + xo + c0;
+                const double* tab_m = tab_t + (size_t)tb.roff[m] * LDA;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int rows = min(KC, (Kn - c * KC + 7) & ~7);
+                    gb::mbar_wait(&empty[stage], phase ^ 1u);
+                    double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES;
+                    double* sB = sA + KC * LDA;
+                    if (lane == 0) {
+                        gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * (width + LDA) * sizeof(double)));
+                        gb::bulk_g2s(sA, tab_m + (size_t)c * KC * LDA, (uint32_t)(rows * LDA * sizeof(double)), &full[stage]);
+                    }
+                    __syncwarp();
+                    if (lane < rows) {
+                        const int nn = c * KC + (FOLD ? tb_fold_degree(lane) : lane);
+                        const double* src = (nn < Kn) ? Xm + (size_t)nn * cols : tb.zeros;
+                        gb::bulk_g2s(sB + lane * LDB, src, (uint32_t)(width * sizeof(double)), &full[stage]);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        } else {
+            const int wm = warp / NWN;
+            const int wn = warp % NWN;
+            const int g = lane >> 2, q = lane & 3;
+            const bool has_columns = wn * 40 < width;
+            if constexpr (FOLD) {
+                const int nh = nlat >> 1;
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int m = pass ? m_second : m_first;
+                    const int Kn = L - m;
+                    const int n_chunks = (Kn + KC - 1) / KC;
+                    double ev[5][2][2], od[5][2][2];
+#pragma unroll
+                    for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) ev[mi][ni][0] = ev[mi][ni][1] = od[mi][ni][0] = od[mi][ni][1] = 0.0;
+                    for (int c = 0; c < n_chunks; ++c) {
+                        const int rows = Kn - c * KC;
+                        gb::mbar_wait(&full[stage], phase);
+                        const double* sP = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 16 + g;
+                        const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
+#pragma unroll
+                        for (int kk = 0; kk < KC; kk += 8) {
+                            if (kk >= rows || !has_columns) break;
+                            double a[5], b[2];
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + q) * LDB + mi * 8];
+#pragma unroll
+                            for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(kk + q) * LDA + ni * 8];
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < 2; ++ni) gb::dmma_884(ev[mi][ni][0], ev[mi][ni][1], a[mi], b[ni]);
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + 4 + q) * LDB + mi * 8];
+#pragma unroll
+                            for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(kk + 4 + q) * LDA + ni * 8];
+#pragma unroll
+                            for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < 2; ++ni) gb::dmma_884(od[mi][ni][0], od[mi][ni][1], a[mi], b[ni]);
+                        }
+                        __syncwarp();
+                        if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
+                    const int ib = i0 + wm * 16 + 2 * q;
+#pragma unroll
+                    for (int mi = 0; mi < 5; ++mi) {
+                        const int col = c0 + wn * 40 + mi * 8 + g;
+                        if (col >= cols) continue;
+                        const int cs = col >= E;
+                        const int e = col - cs * E;
+                        const int k = cs ? ks_row : kc_row;
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) {
+                            const int i = ib + ni * 8;
+                            if (i >= nh) continue;
+                            const long long rn = (long long)e * nlat + i;
+                            const long long rs = (long long)e * nlat + (nlat - 2 - i);
+                            gb::st_v2(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][ni][0] + od[mi][ni][0],
+                                      ev[mi][ni][1] + od[mi][ni][1]);
+                            gb::st_v2(AB + gb_ab_offset(rs, k, ab_rows), ev[mi][ni][1] - od[mi][ni][1],
+                                      ev[mi][ni][0] - od[mi][ni][0]);
+                        }
+                    }
+                }
+                continue;
+            }
+            for (int pass = 0; pass < npass; ++pass) {
+                const int m = pass ? m_second : m_first;
+                const int Kn = L - m;
+                const int n_chunks = (Kn + KC - 1) / KC;
+                double acc[5][4][2];
+#pragma unroll
+                for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int rows = Kn - c * KC;
+                    gb::mbar_wait(&full[stage], phase);
+                    const double* sP = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 32 + g;
+                    const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        if (kk >= rows || !has_columns) break;
+                        double a[5], b[4];
+#pragma unroll
+                        for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + q) * LDB + mi * 8];
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) b[ni] = sP[(kk + q) * LDA + ni * 8];
+#pragma unroll
+                        for (int mi = 0; mi < 5; ++mi)
+#pragma unroll
+                            for (int ni = 0; ni < 4; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
+                const int ib = ((polar && wm) ? i_south : i0) + wm * 32 + 2 * q;
+                const int tile_step = ab_rows * GB_LDA - GB_TM;
+#pragma unroll
+                for (int mi = 0; mi < 5; ++mi) {
+                    const int col = c0 + wn * 40 + mi * 8 + g;
+                    if (col >= cols) continue;
+                    const int cs = col >= E;
+                    const int e = col - cs * E;
+                    const long long row = (long long)e * nlat + ib;
+                    const int o0 = (int)(row & (GB_TM - 1));
+                    double* base = AB + ((size_t)(row >> 7) * ab_rows + (cs ? ks_row : kc_row)) * GB_LDA + o0;
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int i = ib + ni * 8;
+                        if (PAIRS) {
+                            if (i < nlat)
+                                gb::st_v2(base + ni * 8 + ((o0 + ni * 8 >= GB_TM) ? tile_step : 0), acc[mi][ni][0],
+                                          acc[mi][ni][1]);
+                        } else {
+                            if (i < nlat) base[ni * 8 + ((o0 + ni * 8 >= GB_TM) ? tile_step : 0)] = acc[mi][ni][0];
+                            if (i + 1 < nlat)
+                                base[ni * 8 + 1 + ((o0 + ni * 8 + 1 >= GB_TM) ? tile_step : 0)] = acc[mi][ni][1];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// The table itself: thread = (lat tile, order, parallel of the tile) runs the recursion of utilities.py:37-54 once.
+__global__ void __launch_bounds__(128)
+gb_ptab_kernel(double* __restrict__ tab, const int* __restrict__ roff, long long rtot, int kind, int tile0, int n_tiles,
+               int L, int nlat, const double* __restrict__ ct, const double* __restrict__ kn,
+               const double* __restrict__ pmm, const double* __restrict__ ra, const double* __restrict__ rb,
+               const double* __restrict__ rc) {
+    const int per_tile = kind == 0 ? 32 : 64;
+    const int lda = kind == 0 ? 36 : 68;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_tiles * L * per_tile) return;
+    const int li = (int)(idx % per_tile);
+    const int m = (int)((idx / per_tile) % L);
+    const int t = (int)(idx / ((long long)per_tile * L));
+    int i;
+    if (kind == 0) {
+        i = (tile0 + t) * 32 + li;       // parallels beyond the equator keep their own values: with an odd number of
+                                         // northern parallels the last pair of a thread straddles the equator
+    } else if (kind == 1) {
+        i = li < 32 ? t * 32 + li : nlat - 64 - 32 * t + li;
+    } else {
+        i = t * 64 + li;
+    }
+    if (i < 0 || i >= nlat) return;
+    double* out = tab + ((size_t)t * rtot + roff[m]) * lda + li;
+    const double* kn_i = kn + (size_t)i * L;
+    legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int n, double p) {
+        const int nn = n - m;
+        out[(size_t)(kind == 0 ? tb_fold_row(nn) : nn) * lda] = __dmul_rn(p, kn_i[n]);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
 // stage 2, direct contraction: V[row][j] = sum_k AB[k][row] * trig[k][j]  (M = E*nlat rows, K = kpad,
 // N = nlon) on the shared persistent DMMA GEMM (gb_gemm.cuh) with a streaming row-major epilogue.
 // ---------------------------------------------------------------------------------------------
@@ -426,6 +690,8 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
         gb::fence_mbar_init();
     }
     __syncthreads();
+    gb::griddep_wait();                 // AB comes from stage 1; `out` may still be read by whatever ran before
+    gb::griddep_launch_dependents();
 
     const long long n_tiles = (long long)n_mtiles * n_ntiles;
     int stage = 0;
@@ -578,10 +844,55 @@ bool env_flag(const char* name) {
 
 }  // namespace
 
+// Build (once) the Legendre table of `kind` (gb_common.cuh: 0 folded tiles, 1 polar-cap tiles, 2 plain tiles).
+// Returns 1 if the table exists, 0 if it is over the memory budget (GB_PTAB_MAX_MB, default 2048: the caller then runs
+// the on-the-fly recursion kernel), < 0 on error (-code).
+static int ensure_ptab(gb_plan* p, int kind, int n_tiles, int tile0, cudaStream_t st) {
+    if (p->ptab_state[kind] != 0) return p->ptab_state[kind] > 0 ? 1 : 0;
+    const int L = p->L;
+    if (!p->d_ptab_roff) {
+        std::vector<int> roff(L + 1, 0);
+        for (int m = 0; m < L; ++m) roff[m + 1] = roff[m] + ((L - m + 7) & ~7);
+        p->ptab_rtot = roff[L];
+        if (cudaMalloc(reinterpret_cast<void**>(&p->d_ptab_roff), (L + 1) * sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(p->d_ptab_roff, roff.data(), (L + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+            return -gb_set_error(GB_ERR_CUDA, "Legendre table: offsets upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    const int lda = kind == 0 ? 36 : 68, per_tile = kind == 0 ? 32 : 64;
+    const size_t elems = (size_t)n_tiles * p->ptab_rtot * lda;
+    const char* lim = getenv("GB_PTAB_MAX_MB");
+    const double max_mb = lim ? atof(lim) : 2048.0;
+    if (elems * sizeof(double) > max_mb * 1048576.0) {
+        p->ptab_state[kind] = -1;
+        return 0;
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&p->d_ptab[kind]), elems * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        p->ptab_state[kind] = -1;          // no room: the recursion kernel needs none
+        return 0;
+    }
+    cudaError_t e = cudaMemsetAsync(p->d_ptab[kind], 0, elems * sizeof(double), st);
+    if (e == cudaSuccess) {
+        const long long total = (long long)n_tiles * L * per_tile;
+        gb_ptab_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p->d_ptab[kind], p->d_ptab_roff, p->ptab_rtot, kind,
+                                                                      tile0, n_tiles, L, p->nlat, p->d_ct, p->d_kn, p->d_pmm,
+                                                                      p->d_ra, p->d_rb, p->d_rc);
+        gb_count_launch();
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return -gb_set_error(GB_ERR_CUDA, "Legendre table build failed: %s", cudaGetErrorString(e));
+    p->ptab_state[kind] = 1;
+    return 1;
+}
+
 static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_out, cudaStream_t st,
                             const double* d_wn = nullptr) {
     const int L = p->L;
     const long long M = (long long)E * p->nlat;
+    {
+        int rca = gb_plan_acquire(p, st);   // one workspace (X, AB) per plan: order this call behind the previous one
+        if (rca) return rca;
+    }
     cudaEvent_t* prof = (p->prof_ev && p->prof_count < p->prof_capacity) ? p->prof_ev + (size_t)p->prof_count * 4 : nullptr;
     if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
     {
@@ -601,7 +912,7 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
                                                            p->d_rb, p->d_rc, d_krow, L, p->nlat, E, p->ab_rows);
         GB_LAUNCH_CHECK();
     } else {
-        // narrow batches (at most 80 epochs): 80-column items, two CTAs per SM
+        // narrow batches (at most 80 epochs): 80-column items, several CTAs per SM
         const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
         const bool fold = p->fold_ns && !env_flag("GB_NO_FOLD");        // equatorial symmetry: 32 northern parallels per item
         const int tn = narrow ? t1_tn(2) : t1_tn(6);
@@ -609,6 +920,41 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         const int cap_tiles = fold ? p->fold_cap / 32 : 0;              // polar tiles that stay unfolded
         const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 - cap_tiles : (p->nlat + T1_TM - 1) / T1_TM;
         const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
+        const int cap_items = (L + 1) / 2 * cap_tiles * n_coltiles;
+        const bool pairs = p->nlat % 2 == 0;
+        // the Legendre table(s) of this tiling; 0 = over budget -> on-the-fly recursion
+        int have_tab = env_flag("GB_S1_ONTHEFLY") ? 0 : ensure_ptab(p, fold ? 0 : 2, n_lattiles, cap_tiles, st);
+        if (have_tab > 0 && cap_tiles > 0) have_tab = ensure_ptab(p, 1, cap_tiles, 0, st);
+        if (have_tab < 0) return -have_tab;
+        if (have_tab) {
+            auto launch_tab = [&](auto kernel, int nwn, bool kfold, int kind, int lattiles, int items, int polar) -> int {
+                const int per_sm = nwn <= 2 ? (kfold ? 3 : 2) : 1;
+                const int max_ctas = per_sm * p->sm_count;
+                const int grid = items < max_ctas ? items : max_ctas;
+                const size_t smem = tb_smem(nwn, kfold);
+                TabArgs ta{p->d_ptab[kind], p->d_ptab_roff, p->ptab_rtot * tb_lda(kfold), p->d_zero, d_krow};
+                GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                GB_CUDA(gb_launch_pdl(kernel, dim3(grid), dim3(tb_threads(nwn)), smem, st, p->d_x, p->d_ab, ta, L, p->nlat, E,
+                                      p->ab_rows, lattiles, n_coltiles, items, polar));
+                GB_LAUNCH_CHECK();
+                return GB_OK;
+            };
+            int rc = GB_OK;
+            if (fold) {
+                rc = narrow ? launch_tab(gb_stage1_tab<true, 2, true>, 2, true, 0, n_lattiles, n_items, cap_tiles)
+                            : launch_tab(gb_stage1_tab<true, 6, true>, 6, true, 0, n_lattiles, n_items, cap_tiles);
+                if (!rc && cap_tiles > 0)
+                    rc = narrow ? launch_tab(gb_stage1_tab<true, 2, false>, 2, false, 1, cap_tiles, cap_items, 1)
+                                : launch_tab(gb_stage1_tab<true, 6, false>, 6, false, 1, cap_tiles, cap_items, 1);
+            } else if (narrow) {
+                rc = pairs ? launch_tab(gb_stage1_tab<true, 2, false>, 2, false, 2, n_lattiles, n_items, 0)
+                           : launch_tab(gb_stage1_tab<false, 2, false>, 2, false, 2, n_lattiles, n_items, 0);
+            } else {
+                rc = pairs ? launch_tab(gb_stage1_tab<true, 6, false>, 6, false, 2, n_lattiles, n_items, 0)
+                           : launch_tab(gb_stage1_tab<false, 6, false>, 6, false, 2, n_lattiles, n_items, 0);
+            }
+            if (rc) return rc;
+        } else {
         const int max_ctas = narrow ? 2 * p->sm_count : p->sm_count;
         const int grid = n_items < max_ctas ? n_items : max_ctas;
         T1Tables tb{p->d_ct_pad, p->d_kn_t, p->d_pmm_t, p->d_rec_a, p->d_rec_b, p->d_zero, d_krow, p->nlat_pad, p->lpad};
@@ -619,13 +965,11 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         gb_legendre_stage1<PAIRS, NWN, FOLD><<<grid, t1_threads(NWN), t1_smem(NWN), st>>>(                            \
             p->d_x, p->d_ab, tb, L, p->nlat, E, p->ab_rows, n_lattiles, n_coltiles, n_items, cap_tiles);             \
     } while (0)
-        const bool pairs = p->nlat % 2 == 0;
         if (fold) {                     // implies an even number of parallels
             if (narrow) GB_S1_LAUNCH(true, 2, true); else GB_S1_LAUNCH(true, 6, true);
             if (cap_tiles > 0) {
                 // the polar caps (parallels whose mirror image is not close enough in the reference's tables): the
                 // unfolded kernel on tiles of 32 northern parallels + their 32 mirror images
-                const int cap_items = (L + 1) / 2 * cap_tiles * n_coltiles;
                 const int cap_grid = cap_items < max_ctas ? cap_items : max_ctas;
 #define GB_S1_CAP(NWN)                                                                                               \
     do {                                                                                                             \
@@ -644,6 +988,7 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         }
 #undef GB_S1_LAUNCH
         GB_LAUNCH_CHECK();
+        }
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[2], st));
     if (naive2) {
@@ -661,8 +1006,8 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
         // 32-byte stores need 32-byte aligned rows: nlon is a multiple of 8 here, so only the base pointer matters
         const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 8 == 0 && !env_flag("GB_S2_NARROW_STORES")) ? 1 : 0;
-        gb_fourier_stage2_sym<<<grid, Q_THREADS, Q_SMEM, st>>>(p->d_ab, p->ab_rows, p->d_trig_q_t, p->kpad_s, grp, d_out, M,
-                                                               p->nlon, p->nq, n_mtiles, n_ntiles, wide);
+        GB_CUDA(gb_launch_pdl(gb_fourier_stage2_sym, dim3(grid), dim3(Q_THREADS), Q_SMEM, st, p->d_ab, p->ab_rows,
+                              p->d_trig_q_t, p->kpad_s, grp, d_out, M, p->nlon, p->nq, n_mtiles, n_ntiles, wide));
         GB_LAUNCH_CHECK();
     } else {
         gbgemm::Shape sh;
