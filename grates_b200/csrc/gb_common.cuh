@@ -138,7 +138,9 @@ struct gb_plan {
     double* d_ptab[3] = {nullptr, nullptr, nullptr};
     int* d_ptab_roff = nullptr;      // [L + 1] first table row of every order (orders padded to 8 rows)
     long long ptab_rtot = 0;         // rows per lat tile
-    int ptab_state[3] = {0, 0, 0};   // 0: not built yet, 1: built, -1: over the memory budget (on-the-fly recursion instead)
+    int ptab_state[3] = {0, 0, 0};
+    long long x_layout_key = 0;      // (epochs, tile width) d_x was last cleared for; 0: order-wise layout / unknown
+    size_t x_elems = 0;              // doubles allocated in d_x   // 0: not built yet, 1: built, -1: over the memory budget (on-the-fly recursion instead)
     // stream ordering of the shared workspace (d_x, d_ab, analysis / covariance scratch, cached index tables): a call
     // on another stream than the previous call's first waits for everything that stream holds (gb_plan_acquire)
     cudaEvent_t ws_free = nullptr;
@@ -161,6 +163,10 @@ void gb_retain_pool_memory(int device);
 // X_m[n - m][cs * E + e]
 int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st, const double* d_wn = nullptr);
 int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st);
+// anm -> X in the tiled layout of the table-fed stage 1: [order][column tile of tn][degree row][tn + 4] (gb_pack.cu);
+// d_roff [L + 1] = first row of every order (gb_plan::d_ptab_roff).  The buffer must have been cleared for this layout.
+int gb_launch_pack_tiled(const double* d_anm, double* d_x, int L, int E, const int* d_roff, int tn, int n_ct,
+                         cudaStream_t st, const double* d_wn = nullptr);
 // packed batch -> degree-wise vectors as GEMM B tiles [epoch tile of 120][c][124] (gb_densefilter.cu); K = number of
 // coefficients from degree nmin on, kp4 = K padded to 4, degrees above Lin - 1 read as zero
 int gb_launch_ravel_tiles(const double* d_anm, double* d_bt, int Lin, int nmin, long long K, int kp4, int E, cudaStream_t st);
@@ -294,6 +300,51 @@ __device__ __forceinline__ void legendre_column(int m, int L, double ct, double 
         p2 = p1;
         p1 = p;
     }
+}
+
+// Tensor memory (256 KB per SM, otherwise unused by FP64 kernels) as a thread-private spill area for accumulators:
+// the 32x32b shape gives lane l of warp w its own TMEM lane 32 (w % 4) + l, `x32` = 32 consecutive 32-bit columns
+// = 16 doubles (SASS STTM.x32 / LDTM.x32).  Used to take finished accumulator tiles out of the registers so that
+// their epilogue can be spread over the next tile's K loop.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {   // one whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_result)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {        // the warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const double (&v)[16]) {
+    asm volatile(
+        "{\n.reg .b32 l<16>, h<16>;\n"
+        "mov.b64 {l0,h0}, %1; mov.b64 {l1,h1}, %2; mov.b64 {l2,h2}, %3; mov.b64 {l3,h3}, %4;\n"
+        "mov.b64 {l4,h4}, %5; mov.b64 {l5,h5}, %6; mov.b64 {l6,h6}, %7; mov.b64 {l7,h7}, %8;\n"
+        "mov.b64 {l8,h8}, %9; mov.b64 {l9,h9}, %10; mov.b64 {l10,h10}, %11; mov.b64 {l11,h11}, %12;\n"
+        "mov.b64 {l12,h12}, %13; mov.b64 {l13,h13}, %14; mov.b64 {l14,h14}, %15; mov.b64 {l15,h15}, %16;\n"
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {l0,h0,l1,h1,l2,h2,l3,h3,l4,h4,l5,h5,l6,h6,l7,h7,"
+        "l8,h8,l9,h9,l10,h10,l11,h11,l12,h12,l13,h13,l14,h14,l15,h15};\n}\n" ::"r"(taddr),
+        "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]), "d"(v[8]), "d"(v[9]),
+        "d"(v[10]), "d"(v[11]), "d"(v[12]), "d"(v[13]), "d"(v[14]), "d"(v[15])
+        : "memory");
+}
+// load + wait: the values are valid when this returns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, double (&v)[16]) {
+    asm volatile(
+        "{\n.reg .b32 l<16>, h<16>;\n"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {l0,h0,l1,h1,l2,h2,l3,h3,l4,h4,l5,h5,l6,h6,l7,h7,"
+        "l8,h8,l9,h9,l10,h10,l11,h11,l12,h12,l13,h13,l14,h14,l15,h15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        "mov.b64 %0, {l0,h0}; mov.b64 %1, {l1,h1}; mov.b64 %2, {l2,h2}; mov.b64 %3, {l3,h3};\n"
+        "mov.b64 %4, {l4,h4}; mov.b64 %5, {l5,h5}; mov.b64 %6, {l6,h6}; mov.b64 %7, {l7,h7};\n"
+        "mov.b64 %8, {l8,h8}; mov.b64 %9, {l9,h9}; mov.b64 %10, {l10,h10}; mov.b64 %11, {l11,h11};\n"
+        "mov.b64 %12, {l12,h12}; mov.b64 %13, {l13,h13}; mov.b64 %14, {l14,h14}; mov.b64 %15, {l15,h15};\n}\n"
+        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]), "=d"(v[8]),
+          "=d"(v[9]), "=d"(v[10]), "=d"(v[11]), "=d"(v[12]), "=d"(v[13]), "=d"(v[14]), "=d"(v[15])
+        : "r"(taddr)
+        : "memory");
 }
 
 // Programmatic dependent launch: a kernel launched with gb_launch_pdl may start while its predecessor in the stream

@@ -28,11 +28,28 @@ __device__ __forceinline__ long long x_position(int r, int c, int L, int E) {
     return x_block_offset(m, L, E) + (long long)nn * 2 * E + (long long)cs * E;
 }
 
+// Tiled layout for the table-fed stage 1 (gb_synthesis.cu): [order m][column tile][degree row][tn + 4], the rows of an
+// order padded to a multiple of 8 and, inside every 8, ordered [even n-m | odd n-m] like the Legendre table, so that a
+// pipeline chunk of stage 1 is ONE contiguous bulk copy.  roff[m] = first row of order m, columns (cs * E + e).
+struct XTiling {
+    const int* roff;
+    int tn, n_ct;
+};
+__device__ __forceinline__ long long x_tiled_position(int r, int c, int e, int E, const XTiling& xt) {
+    const int m = (c <= r) ? c : r + 1;
+    const int nn = (c <= r) ? r - c : c - r - 1;
+    const int col = ((c <= r) ? 0 : E) + e;
+    const int ct = col / xt.tn, cc = col - ct * xt.tn;
+    const int r0 = xt.roff[m], kn_pad = xt.roff[m + 1] - r0;
+    const int row = (nn & ~7) + ((nn & 1) << 2) + ((nn & 7) >> 1);
+    return ((long long)r0 * xt.n_ct + (long long)ct * kn_pad + row) * (xt.tn + 4) + cc;
+}
+
 // PKE epochs per CTA: 32 for epoch batches (256-byte runs on the X side), 8 for small shards (four times as many
 // CTAs: a 30-epoch shard is latency-, not bandwidth-bound)
-template <bool PACK, int PKE>
+template <bool PACK, int PKE, bool TILED = false>
 __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int L,
-                                                      int E, const double* __restrict__ wn) {
+                                                      int E, const double* __restrict__ wn, XTiling xt) {
     constexpr int PK_LD = PKE + 1;    // shared-memory pitch
     extern __shared__ double s_t[];   // [min(L, PK_C)][PK_LD]
     const int r = blockIdx.x;
@@ -55,10 +72,13 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
         __syncthreads();
         for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
             const int c = idx / PKE, e = idx % PKE;
-            if (e < ne) dst[x_position(r, cb + c, L, E) + e0 + e] = s_t[c * PK_LD + e];
+            if (e < ne) {
+                if (TILED) dst[x_tiled_position(r, cb + c, e0 + e, E, xt)] = s_t[c * PK_LD + e];
+                else dst[x_position(r, cb + c, L, E) + e0 + e] = s_t[c * PK_LD + e];
+            }
         }
-        // sine plane of order 0, degree r
-        if (blockIdx.z == 0 && threadIdx.x < ne) dst[(long long)r * 2 * E + E + e0 + threadIdx.x] = 0.0;
+        // sine plane of order 0, degree r (the tiled buffer is cleared when its layout changes: nothing to write)
+        if (!TILED && blockIdx.z == 0 && threadIdx.x < ne) dst[(long long)r * 2 * E + E + e0 + threadIdx.x] = 0.0;
     } else {
         for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
             const int c = idx / PKE, e = idx % PKE;
@@ -82,26 +102,34 @@ __global__ void __launch_bounds__(256) gb_scale_degree_kernel(const double* __re
     out[idx] = __dmul_rn(in[idx], wn[max(r, c)]);
 }
 
-template <bool PACK, int PKE>
-int launch_pke(const double* src, double* dst, int L, int E, const double* wn, cudaStream_t st) {
+template <bool PACK, int PKE, bool TILED>
+int launch_pke(const double* src, double* dst, int L, int E, const double* wn, XTiling xt, cudaStream_t st) {
     const size_t smem = (size_t)(L < PK_C ? L : PK_C) * (PKE + 1) * sizeof(double);
     if (smem > 48 * 1024)
-        GB_CUDA(cudaFuncSetAttribute(gb_pack_kernel<PACK, PKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GB_CUDA(cudaFuncSetAttribute(gb_pack_kernel<PACK, PKE, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L, (E + PKE - 1) / PKE, (L + PK_C - 1) / PK_C);
-    GB_CUDA(gb_launch_pdl(gb_pack_kernel<PACK, PKE>, grid, dim3(256), smem, st, src, dst, L, E, wn));
+    GB_CUDA(gb_launch_pdl(gb_pack_kernel<PACK, PKE, TILED>, grid, dim3(256), smem, st, src, dst, L, E, wn, xt));
     GB_LAUNCH_CHECK();
     return GB_OK;
 }
 
 template <bool PACK>
 int launch(const double* src, double* dst, int L, int E, const double* wn, cudaStream_t st) {
-    return E <= 64 ? launch_pke<PACK, 8>(src, dst, L, E, wn, st) : launch_pke<PACK, 32>(src, dst, L, E, wn, st);
+    const XTiling none{nullptr, 0, 0};
+    return E <= 64 ? launch_pke<PACK, 8, false>(src, dst, L, E, wn, none, st)
+                   : launch_pke<PACK, 32, false>(src, dst, L, E, wn, none, st);
 }
 
 }  // namespace
 
 int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st, const double* d_wn) {
     return launch<true>(d_anm, d_x, L, E, d_wn, st);
+}
+int gb_launch_pack_tiled(const double* d_anm, double* d_x, int L, int E, const int* d_roff, int tn, int n_ct,
+                         cudaStream_t st, const double* d_wn) {
+    const XTiling xt{d_roff, tn, n_ct};
+    return E <= 64 ? launch_pke<true, 8, true>(d_anm, d_x, L, E, d_wn, xt, st)
+                   : launch_pke<true, 32, true>(d_anm, d_x, L, E, d_wn, xt, st);
 }
 int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st) {
     return launch<false>(d_x, d_anm, L, E, nullptr, st);

@@ -1,4 +1,5 @@
 // Plan management, error reporting and small utilities of the grates_b200 C ABI.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -259,8 +260,13 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
             rec_b[(size_t)m * p->lpad + (n - m)] = (n == m + 1) ? 0.0 : rb[(size_t)n * L + m];
         }
 
+    // first table row of every order in the tiled Legendre table / tiled X (orders padded to 8 rows)
+    std::vector<int> roff(L + 1, 0);
+    for (int m = 0; m < L; ++m) roff[m + 1] = roff[m] + ((L - m + 7) & ~7);
+    p->ptab_rtot = roff[L];
+
     int rc_ = GB_OK;
-    if ((rc_ = upload(&p->d_ct_pad, ct_pad)) || (rc_ = upload(&p->d_kn_t, kn_t)) || (rc_ = upload(&p->d_pmm_t, pmm_t)) ||
+    if ((rc_ = upload(&p->d_ptab_roff, roff)) || (rc_ = upload(&p->d_ct_pad, ct_pad)) || (rc_ = upload(&p->d_kn_t, kn_t)) || (rc_ = upload(&p->d_pmm_t, pmm_t)) ||
         (rc_ = upload(&p->d_rec_a, rec_a)) || (rc_ = upload(&p->d_rec_b, rec_b)) ||
         (rc_ = upload(&p->d_trig_t, trig_t)) || (p->sym && (rc_ = upload(&p->d_trig_q_t, trig_q_t))) ||
         (rc_ = upload(&p->d_ct, ct)) || (rc_ = upload(&p->d_kn, knv)) || (rc_ = upload(&p->d_pmm, pmm)) ||
@@ -341,8 +347,13 @@ int gb_plan_ensure_workspace(gb_plan* p, int n_epochs) {
     p->ws_epochs = 0;
     const long long m = (long long)n_epochs * p->nlat;
     const long long mpad = (m + 127) / 128 * 128;
-    const size_t x_elems = (size_t)p->L * (p->L + 1) / 2 * 2 * (size_t)n_epochs;
+    // X holds either the order-wise layout or the tiled one (80- or 240-column tiles + 4 pad columns, gb_pack.cu)
+    const size_t cols = 2 * (size_t)n_epochs;
+    const size_t tiled = (size_t)p->ptab_rtot * std::max(((cols + 79) / 80) * 84, ((cols + 239) / 240) * 244);
+    const size_t x_elems = std::max((size_t)p->L * (p->L + 1) / 2 * cols, tiled);
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_x), x_elems * sizeof(double)));
+    p->x_elems = x_elems;
+    p->x_layout_key = 0;
     const size_t ab_elems = (size_t)(mpad / GB_TM) * p->ab_rows * GB_LDA;
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ab), ab_elems * sizeof(double)));
     // padding rows and padded columns must stay finite (they meet zero trig rows / masked stores)

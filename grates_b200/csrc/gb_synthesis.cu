@@ -372,13 +372,20 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
 // gb_legendre_stage1; the degrees of a folded chunk are grouped [even n-m | odd n-m] per 8 rows, so both parity
 // classes read consecutive shared-memory rows (pitch 36 = 4 mod 16: conflict-free fragments).
 // ---------------------------------------------------------------------------------------------
-constexpr int TB_KC = 16;
 __host__ __device__ constexpr int tb_lda(bool fold) { return fold ? 36 : 68; }
-__host__ __device__ constexpr int tb_stages(int nwn, bool fold) { return nwn <= 2 ? 4 : (fold ? 6 : 5); }
+__host__ __device__ constexpr int tb_ctas_per_sm(int nwn, bool fold) { return nwn <= 2 ? (fold ? 3 : 2) : 1; }
+__host__ __device__ constexpr size_t tb_stage_bytes(int nwn, bool fold, int kc) {
+    return (size_t)kc * (tb_lda(fold) + t1_tn(nwn) + 4) * sizeof(double);
+}
+// as many ring stages (at most 6) as the CTA's share of the 227 KB of shared memory holds
+__host__ __device__ constexpr int tb_stages(int nwn, bool fold, int kc) {
+    const size_t budget = (232448 - 1024 * tb_ctas_per_sm(nwn, fold)) / tb_ctas_per_sm(nwn, fold) - 128;
+    const int s = (int)(budget / tb_stage_bytes(nwn, fold, kc));
+    return s > 6 ? 6 : s;
+}
 __host__ __device__ constexpr int tb_threads(int nwn) { return 32 * (2 * nwn + 1); }
-__host__ __device__ constexpr size_t tb_smem(int nwn, bool fold) {
-    return (size_t)tb_stages(nwn, fold) * TB_KC * (tb_lda(fold) + t1_tn(nwn) + 4) * sizeof(double) +
-           2 * tb_stages(nwn, fold) * sizeof(uint64_t);
+__host__ __device__ constexpr size_t tb_smem(int nwn, bool fold, int kc) {
+    return (size_t)tb_stages(nwn, fold, kc) * tb_stage_bytes(nwn, fold, kc) + 2 * tb_stages(nwn, fold, kc) * sizeof(uint64_t);
 }
 // row of degree offset nn inside a folded table / chunk: even offsets first
 __host__ __device__ __forceinline__ int tb_fold_row(int nn) { return (nn & ~7) + ((nn & 1) << 2) + ((nn & 7) >> 1); }
@@ -391,15 +398,17 @@ struct TabArgs {
     const double* tab;      // [lat tile][rtot][lda]
     const int* roff;        // [L + 1]
     long long tile_stride;  // rtot * lda
-    const double* zeros;
     const int* krow;
 };
 
-template <bool PAIRS, int NWN, bool FOLD>
-__global__ void __launch_bounds__(tb_threads(NWN), NWN <= 2 ? (FOLD ? 3 : 2) : 1)
+template <bool PAIRS, int NWN, bool FOLD, int KC>
+__global__ void __launch_bounds__(tb_threads(NWN), tb_ctas_per_sm(NWN, FOLD))
 gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb, int L, int nlat, int E, int ab_rows,
               int n_lattiles, int n_coltiles, int n_items, int polar) {
-    constexpr int KC = TB_KC, STAGES = tb_stages(NWN, FOLD);
+    constexpr int STAGES = tb_stages(NWN, FOLD, KC);
+    static_assert(STAGES >= 2, "the ring needs at least two stages");
+    const bool diag_nostore = (polar & 0x10000) != 0;   // DIAG
+    polar &= 0xffff;
     constexpr int TN = t1_tn(NWN), LDA = tb_lda(FOLD), LDB = TN + 4, CONSUMER_WARPS = 2 * NWN;
     constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -436,31 +445,24 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
         const int width = min(TN, cols - c0);
 
         if (warp == CONSUMER_WARPS) {
-            // ===== copy warp: one bulk copy for the table chunk, one per row of X_m =====
-            const double* tab_t = tb.tab + (size_t)lt * tb.tile_stride;
-            for (int pass = 0; pass < npass; ++pass) {
-                const int m = pass ? m_second : m_first;
-                const int Kn = L - m;
-                const int n_chunks = (Kn + KC - 1) / KC;
-                const long long xo = (long long)cols * ((long long)m * L - (long long)m * (m - 1) / 2);
-                const double* Xm = X + xo + c0;
-                const double* tab_m = tab_t + (size_t)tb.roff[m] * LDA;
-                for (int c = 0; c < n_chunks; ++c) {
-                    const int rows = min(KC, (Kn - c * KC + 7) & ~7);
-                    gb::mbar_wait(&empty[stage], phase ^ 1u);
-                    double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES;
-                    double* sB = sA + KC * LDA;
-                    if (lane == 0) {
-                        gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * (width + LDA) * sizeof(double)));
-                        gb::bulk_g2s(sA, tab_m + (size_t)c * KC * LDA, (uint32_t)(rows * LDA * sizeof(double)), &full[stage]);
+            // ===== copy warp (one elected lane): one bulk copy for the table chunk, one for the chunk of X_m =====
+            if (lane == 0) {
+                const double* tab_t = tb.tab + (size_t)lt * tb.tile_stride;
+                const int ct = rem % n_coltiles;
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int m = pass ? m_second : m_first;
+                    const int r0 = tb.roff[m], kn_pad = tb.roff[m + 1] - r0;       // rows of the order, padded to 8
+                    const double* tab_m = tab_t + (size_t)r0 * LDA;
+                    const double* x_m = X + ((size_t)r0 * n_coltiles + (size_t)ct * kn_pad) * LDB;
+                    for (int r = 0; r < kn_pad; r += KC) {
+                        const int rows = min(KC, kn_pad - r);
+                        gb::mbar_wait(&empty[stage], phase ^ 1u);
+                        double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES;
+                        gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * (LDB + LDA) * sizeof(double)));
+                        gb::bulk_g2s(sA, tab_m + (size_t)r * LDA, (uint32_t)(rows * LDA * sizeof(double)), &full[stage]);
+                        gb::bulk_g2s(sA + KC * LDA, x_m + (size_t)r * LDB, (uint32_t)(rows * LDB * sizeof(double)), &full[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    __syncwarp();
-                    if (lane < rows) {
-                        const int nn = c * KC + (FOLD ? tb_fold_degree(lane) : lane);
-                        const double* src = (nn < Kn) ? Xm + (size_t)nn * cols : tb.zeros;
-                        gb::bulk_g2s(sB + lane * LDB, src, (uint32_t)(width * sizeof(double)), &full[stage]);
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         } else {
@@ -474,6 +476,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     const int m = pass ? m_second : m_first;
                     const int Kn = L - m;
                     const int n_chunks = (Kn + KC - 1) / KC;
+                    const int kc_row = __ldg(tb.krow + 2 * m), ks_row = __ldg(tb.krow + 2 * m + 1);   // latency hides behind the K loop
                     double ev[5][2][2], od[5][2][2];
 #pragma unroll
                     for (int mi = 0; mi < 5; ++mi)
@@ -509,11 +512,14 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                         if (lane == 0) gb::mbar_arrive(&empty[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
+                    // the store addresses are derived here, behind an opaque copy of the item's column offset: hoisted to the
+                    // item prologue they would live (spilled) across the whole K loop
+                    int c0e = c0;
+                    asm volatile("" : "+r"(c0e));
                     const int ib = i0 + wm * 16 + 2 * q;
 #pragma unroll
                     for (int mi = 0; mi < 5; ++mi) {
-                        const int col = c0 + wn * 40 + mi * 8 + g;
+                        const int col = c0e + wn * 40 + mi * 8 + g;
                         if (col >= cols) continue;
                         const int cs = col >= E;
                         const int e = col - cs * E;
@@ -522,6 +528,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                         for (int ni = 0; ni < 2; ++ni) {
                             const int i = ib + ni * 8;
                             if (i >= nh) continue;
+                            if (diag_nostore) continue;   // DIAG
                             const long long rn = (long long)e * nlat + i;
                             const long long rs = (long long)e * nlat + (nlat - 2 - i);
                             gb::st_v2(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][ni][0] + od[mi][ni][0],
@@ -537,13 +544,14 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                 const int m = pass ? m_second : m_first;
                 const int Kn = L - m;
                 const int n_chunks = (Kn + KC - 1) / KC;
+                const int kc_row = __ldg(tb.krow + 2 * m), ks_row = __ldg(tb.krow + 2 * m + 1);
                 double acc[5][4][2];
 #pragma unroll
                 for (int mi = 0; mi < 5; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
                 for (int c = 0; c < n_chunks; ++c) {
-                    const int rows = Kn - c * KC;
+                    const int rows = (Kn - c * KC + 7) & ~7;      // the degrees of an 8-row group are interleaved
                     gb::mbar_wait(&full[stage], phase);
                     const double* sP = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 32 + g;
                     const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
@@ -564,12 +572,13 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     if (lane == 0) gb::mbar_arrive(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                const int kc_row = tb.krow[2 * m], ks_row = tb.krow[2 * m + 1];
+                int c0e = c0;
+                asm volatile("" : "+r"(c0e));
                 const int ib = ((polar && wm) ? i_south : i0) + wm * 32 + 2 * q;
                 const int tile_step = ab_rows * GB_LDA - GB_TM;
 #pragma unroll
                 for (int mi = 0; mi < 5; ++mi) {
-                    const int col = c0 + wn * 40 + mi * 8 + g;
+                    const int col = c0e + wn * 40 + mi * 8 + g;
                     if (col >= cols) continue;
                     const int cs = col >= E;
                     const int e = col - cs * E;
@@ -622,7 +631,7 @@ gb_ptab_kernel(double* __restrict__ tab, const int* __restrict__ roff, long long
     const double* kn_i = kn + (size_t)i * L;
     legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int n, double p) {
         const int nn = n - m;
-        out[(size_t)(kind == 0 ? tb_fold_row(nn) : nn) * lda] = __dmul_rn(p, kn_i[n]);
+        out[(size_t)tb_fold_row(nn) * lda] = __dmul_rn(p, kn_i[n]);   // same row order in every table kind and in X
     });
 }
 
@@ -668,11 +677,22 @@ constexpr int Q_LDB = Q_TN + 4;               // 36
 constexpr int Q_CONSUMER_WARPS = Q_WM * Q_WN;
 constexpr int Q_THREADS = 32 * (Q_CONSUMER_WARPS + 1);
 constexpr int Q_STAGE_DOUBLES = Q_KC * (Q_LDA + Q_LDB);
-constexpr size_t Q_SMEM = (size_t)Q_STAGES * Q_STAGE_DOUBLES * sizeof(double) + 2 * Q_STAGES * sizeof(uint64_t);
+constexpr size_t Q_SMEM = (size_t)Q_STAGES * Q_STAGE_DOUBLES * sizeof(double) + (2 * Q_STAGES + 4) * sizeof(uint64_t) + 16;
 
 struct QGroups { int off[5]; };
 
-__global__ void __launch_bounds__(Q_THREADS, 1)
+// EW ("epilogue warps", the default): 16 warps.  The eight consumer warps never store to global memory: a finished
+// accumulator tile is parked in tensor memory (thread-private columns, gb::tmem_st16; double buffered: 2 x 2 x 128 of
+// the 512 columns per sub-partition) and the warp goes straight back to the next tile's K loop.  Four epilogue warps,
+// one per sub-partition (a warp reaches the tensor-memory lanes 32 (warp % 4) .. only), read the tile back, apply the
+// butterfly and issue the stores, so the store back-pressure of the 128 KB burst per tile (every store waits for the
+// LSU to drain its predecessors: 13 % of the consumers' time in the direct kernel) lands on warps that have a whole
+// tile period to absorb it.  Registers are rebalanced with setmaxnreg: the kernel starts with 128 per thread
+// (512 threads), consumers grow to 168, epilogue warps shrink to 104, the producer's warpgroup to 40.
+// !EW: the direct kernel (nine warps, epilogue in the consumers), kept for comparison (GB_S2_DIRECT_EPILOGUE=1).
+constexpr int QE_THREADS = 512;
+template <bool EW>
+__global__ void __launch_bounds__(EW ? QE_THREADS : Q_THREADS, 1)
 gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig_q_t, int kpad_s,
                       QGroups grp, double* __restrict__ out, long long M, int nlon, int nq, int n_mtiles,
                       int n_ntiles, int wide) {
@@ -680,53 +700,135 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)Q_STAGES * Q_STAGE_DOUBLES * sizeof(double));
     uint64_t* empty = full + Q_STAGES;
+    uint64_t* tfull = empty + Q_STAGES;     // [2] accumulator tile parked in tensor memory
+    uint64_t* tempty = tfull + 2;           // [2] tensor-memory buffer read back
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int PRODUCER_WARP = EW ? 12 : Q_CONSUMER_WARPS;
     if (threadIdx.x == 0) {
         for (int s = 0; s < Q_STAGES; ++s) {
             gb::mbar_init(&full[s], 1);
             gb::mbar_init(&empty[s], Q_CONSUMER_WARPS);
         }
+        for (int b = 0; b < 2; ++b) {
+            gb::mbar_init(&tfull[b], Q_CONSUMER_WARPS);
+            gb::mbar_init(&tempty[b], 4);
+        }
         gb::fence_mbar_init();
     }
+    if (EW && warp == 0) gb::tmem_alloc(s_tmem, 512);
+    if (EW) gb::tmem_fence_before_sync();
     __syncthreads();
+    if (EW) gb::tmem_fence_after_sync();
     gb::griddep_wait();                 // AB comes from stage 1; `out` may still be read by whatever ran before
     gb::griddep_launch_dependents();
 
     const long long n_tiles = (long long)n_mtiles * n_ntiles;
-    int stage = 0;
-    uint32_t phase = 0;
-
-    if (warp == Q_CONSUMER_WARPS) {
-        if (lane == 0) {
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const long long mt = t / n_ntiles;
-                const int nt = (int)(t % n_ntiles);
-                for (int k0 = 0; k0 < grp.off[4];) {
-                    // chunks never straddle a group boundary
-                    int gend = grp.off[1];
+    const int h = nlon >> 1;
+    // butterfly + stores of one 8-row slab (mi) of the 32 x 16 warp tile (wm, wn) of tile (mt, nt);
+    // v[4 s + 2 ni + r] = accumulator set s.  The trig tiles interleave the columns of a warp's slab (gb_plan.cu), so a
+    // lane's two fragments are the four consecutive meridians jq .. jq+3: one 32-byte store per lane and quadrant.
+    auto emit_row = [&](long long mt, int nt, int wm, int wn, int mi, const double (&v)[16]) {
+        const int g = lane >> 2, q = lane & 3;
+        const long long row = mt * Q_TM + wm * 32 + g + mi * 8;
+        const int jq = nt * Q_TN + wn * 16 + 4 * q;
+        if (row >= M || jq >= nq) return;
+        double* orow = out + (size_t)row * nlon;
+        double v1[4], v2[4], v3[4], v4[4];
 #pragma unroll
-                    for (int s = 1; s < 4; ++s)
-                        if (k0 >= grp.off[s]) gend = grp.off[s + 1];
-                    const int kc = min(Q_KC, gend - k0);
-                    gb::mbar_wait(&empty[stage], phase ^ 1u);
-                    double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES;
-                    double* sB = sA + Q_KC * Q_LDA;
-                    const uint32_t bytes_a = (uint32_t)(kc * Q_LDA * sizeof(double));
-                    const uint32_t bytes_b = (uint32_t)(kc * Q_LDB * sizeof(double));
-                    gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
-                    gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * Q_LDA, bytes_a, &full[stage]);
-                    gb::bulk_g2s(sB, trig_q_t + ((size_t)nt * kpad_s + k0) * Q_LDB, bytes_b, &full[stage]);
-                    if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
-                    k0 += kc;
+        for (int c = 0; c < 4; ++c) {
+            const double ce = v[c], co = v[4 + c], se = v[8 + c], so = v[12 + c];
+            const double cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
+            v1[c] = cp + sp;   // mu
+            v2[c] = cm - sm;   // pi - mu
+            v3[c] = cp - sp;   // -mu
+            v4[c] = cm + sm;   // mu - pi
+        }
+        if (wide && jq + 4 <= nq) {
+            gb::st_cs_v4(orow + h + jq, v1[0], v1[1], v1[2], v1[3]);
+            gb::st_cs_v4(orow + nlon - 4 - jq, v2[3], v2[2], v2[1], v2[0]);
+            gb::st_cs_v4(orow + h - 4 - jq, v3[3], v3[2], v3[1], v3[0]);
+            gb::st_cs_v4(orow + jq, v4[0], v4[1], v4[2], v4[3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c += 2) {          // nq is even: pairs are all in or all out
+                const int j = jq + c;
+                if (j >= nq) continue;
+                gb::st_cs_v2(orow + h + j, v1[c], v1[c + 1]);
+                gb::st_cs_v2(orow + nlon - 2 - j, v2[c + 1], v2[c]);
+                gb::st_cs_v2(orow + h - 2 - j, v3[c + 1], v3[c]);
+                gb::st_cs_v2(orow + j, v4[c], v4[c + 1]);
+            }
+        }
+    };
+
+    if (warp >= PRODUCER_WARP) {
+        if (EW) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (warp == PRODUCER_WARP) {
+            if (lane == 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                    const long long mt = t / n_ntiles;
+                    const int nt = (int)(t % n_ntiles);
+                    for (int k0 = 0; k0 < grp.off[4];) {
+                        // chunks never straddle a group boundary
+                        int gend = grp.off[1];
+#pragma unroll
+                        for (int s = 1; s < 4; ++s)
+                            if (k0 >= grp.off[s]) gend = grp.off[s + 1];
+                        const int kc = min(Q_KC, gend - k0);
+                        gb::mbar_wait(&empty[stage], phase ^ 1u);
+                        double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES;
+                        double* sB = sA + Q_KC * Q_LDA;
+                        const uint32_t bytes_a = (uint32_t)(kc * Q_LDA * sizeof(double));
+                        const uint32_t bytes_b = (uint32_t)(kc * Q_LDB * sizeof(double));
+                        gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
+                        gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * Q_LDA, bytes_a, &full[stage]);
+                        gb::bulk_g2s(sB, trig_q_t + ((size_t)nt * kpad_s + k0) * Q_LDB, bytes_b, &full[stage]);
+                        if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+                        k0 += kc;
+                    }
                 }
             }
         }
+    } else if (EW && warp >= Q_CONSUMER_WARPS) {
+        {
+            // ===== epilogue warp of sub-partition sp: the tiles of consumer warps sp and sp + 4 =====
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
+            const int sp = warp & 3;
+            int tb = 0;
+            uint32_t tphase = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const long long mt = t / n_ntiles;
+                const int nt = (int)(t % n_ntiles);
+                gb::mbar_wait(&tfull[tb], tphase);
+                gb::tmem_fence_after_sync();
+#pragma unroll 1
+                for (int cw = 0; cw < 2; ++cw) {
+                    const int w = sp + 4 * cw;                 // consumer warp whose tile this is
+                    const uint32_t taddr = *s_tmem + ((uint32_t)(32 * sp) << 16) + (uint32_t)(tb * 256 + cw * 128);
+#pragma unroll 1
+                    for (int mi = 0; mi < 4; ++mi) {
+                        double v[16];
+                        gb::tmem_ld16(taddr + 32u * mi, v);
+                        emit_row(mt, nt, w / Q_WN, w % Q_WN, mi, v);
+                    }
+                }
+                gb::tmem_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) gb::mbar_arrive(&tempty[tb]);
+                if (++tb == 2) { tb = 0; tphase ^= 1u; }
+            }
+        }
     } else {
+        if (EW) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
         const int wm = warp / Q_WN;
         const int wn = warp % Q_WN;
         const int g = lane >> 2, q = lane & 3;
-        const int h = nlon >> 1;
+        int stage = 0, tb = 0;
+        uint32_t phase = 0, tphase = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const long long mt = t / n_ntiles;
             const int nt = (int)(t % n_ntiles);
@@ -764,46 +866,42 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
                     k0 += kc;
                 }
             }
-            // butterfly epilogue: four output columns per first-quadrant column.  The trig tiles interleave the
-            // columns of a warp's slab (gb_plan.cu), so this lane's two fragments are the four consecutive meridians
-            // jq .. jq+3: every output row gets one 32-byte store per lane, eight full 128-byte lines per warp store.
-            const long long row_base = mt * Q_TM + wm * 32 + g;
-            const int jq = nt * Q_TN + wn * 16 + 4 * q;
+            if (EW) {
+                // park the tile: this warp's 128 columns of buffer tb (lanes 32 (warp % 4) .., columns 256 tb + 128 (warp / 4) ..)
+                gb::mbar_wait(&tempty[tb], tphase ^ 1u);
+                gb::tmem_fence_after_sync();
+                const uint32_t taddr = *s_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(tb * 256 + (warp >> 2) * 128);
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                const long long row = row_base + mi * 8;
-                if (row >= M || jq >= nq) continue;
-                double* orow = out + (size_t)row * nlon;
-                double v1[4], v2[4], v3[4], v4[4];
+                for (int mi = 0; mi < 4; ++mi) {
+                    double v[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int ni = c >> 1, r = c & 1;
-                    const double ce = acc[0][mi][ni][r], co = acc[1][mi][ni][r];
-                    const double se = acc[2][mi][ni][r], so = acc[3][mi][ni][r];
-                    const double cp = ce + co, cm = ce - co, sp = se + so, sm = se - so;
-                    v1[c] = cp + sp;   // mu
-                    v2[c] = cm - sm;   // pi - mu
-                    v3[c] = cp - sp;   // -mu
-                    v4[c] = cm + sm;   // mu - pi
+                    for (int s = 0; s < 4; ++s)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) v[4 * s + c] = acc[s][mi][c >> 1][c & 1];
+                    gb::tmem_st16(taddr + 32u * mi, v);
                 }
-                if (wide && jq + 4 <= nq) {
-                    gb::st_cs_v4(orow + h + jq, v1[0], v1[1], v1[2], v1[3]);
-                    gb::st_cs_v4(orow + nlon - 4 - jq, v2[3], v2[2], v2[1], v2[0]);
-                    gb::st_cs_v4(orow + h - 4 - jq, v3[3], v3[2], v3[1], v3[0]);
-                    gb::st_cs_v4(orow + jq, v4[0], v4[1], v4[2], v4[3]);
-                } else {
+                gb::tmem_wait_st();
+                gb::tmem_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) gb::mbar_arrive(&tfull[tb]);
+                if (++tb == 2) { tb = 0; tphase ^= 1u; }
+            } else {
 #pragma unroll
-                    for (int c = 0; c < 4; c += 2) {          // nq is even: pairs are all in or all out
-                        const int j = jq + c;
-                        if (j >= nq) continue;
-                        gb::st_cs_v2(orow + h + j, v1[c], v1[c + 1]);
-                        gb::st_cs_v2(orow + nlon - 2 - j, v2[c + 1], v2[c]);
-                        gb::st_cs_v2(orow + h - 2 - j, v3[c + 1], v3[c]);
-                        gb::st_cs_v2(orow + j, v4[c], v4[c + 1]);
-                    }
+                for (int mi = 0; mi < 4; ++mi) {
+                    double v[16];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) v[4 * s + c] = acc[s][mi][c >> 1][c & 1];
+                    emit_row(mt, nt, wm, wn, mi, v);
                 }
             }
         }
+    }
+    if (EW) {
+        gb::tmem_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) gb::tmem_dealloc(*s_tmem, 512);
     }
 }
 
@@ -850,14 +948,6 @@ bool env_flag(const char* name) {
 static int ensure_ptab(gb_plan* p, int kind, int n_tiles, int tile0, cudaStream_t st) {
     if (p->ptab_state[kind] != 0) return p->ptab_state[kind] > 0 ? 1 : 0;
     const int L = p->L;
-    if (!p->d_ptab_roff) {
-        std::vector<int> roff(L + 1, 0);
-        for (int m = 0; m < L; ++m) roff[m + 1] = roff[m] + ((L - m + 7) & ~7);
-        p->ptab_rtot = roff[L];
-        if (cudaMalloc(reinterpret_cast<void**>(&p->d_ptab_roff), (L + 1) * sizeof(int)) != cudaSuccess ||
-            cudaMemcpy(p->d_ptab_roff, roff.data(), (L + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
-            return -gb_set_error(GB_ERR_CUDA, "Legendre table: offsets upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
     const int lda = kind == 0 ? 36 : 68, per_tile = kind == 0 ? 32 : 64;
     const size_t elems = (size_t)n_tiles * p->ptab_rtot * lda;
     const char* lim = getenv("GB_PTAB_MAX_MB");
@@ -894,16 +984,42 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         if (rca) return rca;
     }
     cudaEvent_t* prof = (p->prof_ev && p->prof_count < p->prof_capacity) ? p->prof_ev + (size_t)p->prof_count * 4 : nullptr;
-    if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
-    {
-        int rc = gb_launch_pack(d_anm, p->d_x, L, E, st, d_wn);
-        if (rc) return rc;
-    }
-    if (prof) GB_CUDA(cudaEventRecord(prof[1], st));
     const bool naive2 = env_flag("GB_NAIVE_STAGE2");
     const bool use_sym = p->sym && !naive2 && !env_flag("GB_NO_SYMMETRY");
     const int* d_krow = use_sym ? p->d_krow_sym : p->d_krow_id;
-    if (env_flag("GB_SIMPLE_STAGE1")) {
+    // stage-1 tiling: narrow batches (at most 80 epochs) run 80-column items, several CTAs per SM
+    const bool simple1 = env_flag("GB_SIMPLE_STAGE1");
+    const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
+    const bool fold = p->fold_ns && !env_flag("GB_NO_FOLD");        // equatorial symmetry: 32 northern parallels per item
+    const int tn = narrow ? t1_tn(2) : t1_tn(6);
+    const int n_coltiles = (2 * E + tn - 1) / tn;
+    const int cap_tiles = fold ? p->fold_cap / 32 : 0;              // polar tiles that stay unfolded
+    const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 - cap_tiles : (p->nlat + T1_TM - 1) / T1_TM;
+    const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
+    const int cap_items = (L + 1) / 2 * cap_tiles * n_coltiles;
+    const bool pairs = p->nlat % 2 == 0;
+    // the Legendre table(s) of this tiling; 0 = over budget -> on-the-fly recursion
+    int have_tab = (simple1 || env_flag("GB_S1_ONTHEFLY")) ? 0 : ensure_ptab(p, fold ? 0 : 2, n_lattiles, cap_tiles, st);
+    if (have_tab > 0 && cap_tiles > 0) have_tab = ensure_ptab(p, 1, cap_tiles, 0, st);
+    if (have_tab < 0) return -have_tab;
+    if (have_tab) {
+        // tiled X: pad rows, pad columns and the (non-existent) sine plane of order 0 are never written by the pack
+        const long long key = ((long long)E << 16) | tn;
+        if (p->x_layout_key != key) {
+            GB_CUDA(cudaMemsetAsync(p->d_x, 0, p->x_elems * sizeof(double), st));
+            p->x_layout_key = key;
+        }
+    } else {
+        p->x_layout_key = 0;
+    }
+    if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
+    {
+        int rc = have_tab ? gb_launch_pack_tiled(d_anm, p->d_x, L, E, p->d_ptab_roff, tn, n_coltiles, st, d_wn)
+                          : gb_launch_pack(d_anm, p->d_x, L, E, st, d_wn);
+        if (rc) return rc;
+    }
+    if (prof) GB_CUDA(cudaEventRecord(prof[1], st));
+    if (simple1) {
         dim3 grid((p->nlat + S1_TI - 1) / S1_TI, L);
         const size_t smem = (size_t)L * S1_TI * sizeof(double);
         if (smem > 48 * 1024)
@@ -912,46 +1028,33 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
                                                            p->d_rb, p->d_rc, d_krow, L, p->nlat, E, p->ab_rows);
         GB_LAUNCH_CHECK();
     } else {
-        // narrow batches (at most 80 epochs): 80-column items, several CTAs per SM
-        const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
-        const bool fold = p->fold_ns && !env_flag("GB_NO_FOLD");        // equatorial symmetry: 32 northern parallels per item
-        const int tn = narrow ? t1_tn(2) : t1_tn(6);
-        const int n_coltiles = (2 * E + tn - 1) / tn;
-        const int cap_tiles = fold ? p->fold_cap / 32 : 0;              // polar tiles that stay unfolded
-        const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 - cap_tiles : (p->nlat + T1_TM - 1) / T1_TM;
-        const int n_items = (L + 1) / 2 * n_lattiles * n_coltiles;     // order pairs (p, nmax - p) x tiles
-        const int cap_items = (L + 1) / 2 * cap_tiles * n_coltiles;
-        const bool pairs = p->nlat % 2 == 0;
-        // the Legendre table(s) of this tiling; 0 = over budget -> on-the-fly recursion
-        int have_tab = env_flag("GB_S1_ONTHEFLY") ? 0 : ensure_ptab(p, fold ? 0 : 2, n_lattiles, cap_tiles, st);
-        if (have_tab > 0 && cap_tiles > 0) have_tab = ensure_ptab(p, 1, cap_tiles, 0, st);
-        if (have_tab < 0) return -have_tab;
         if (have_tab) {
-            auto launch_tab = [&](auto kernel, int nwn, bool kfold, int kind, int lattiles, int items, int polar) -> int {
-                const int per_sm = nwn <= 2 ? (kfold ? 3 : 2) : 1;
-                const int max_ctas = per_sm * p->sm_count;
+            auto launch_tab = [&](auto kernel, int nwn, bool kfold, int kc, int kind, int lattiles, int items, int polar) -> int {
+                const int max_ctas = tb_ctas_per_sm(nwn, kfold) * p->sm_count;
                 const int grid = items < max_ctas ? items : max_ctas;
-                const size_t smem = tb_smem(nwn, kfold);
-                TabArgs ta{p->d_ptab[kind], p->d_ptab_roff, p->ptab_rtot * tb_lda(kfold), p->d_zero, d_krow};
+                const size_t smem = tb_smem(nwn, kfold, kc);
+                TabArgs ta{p->d_ptab[kind], p->d_ptab_roff, p->ptab_rtot * tb_lda(kfold), d_krow};
                 GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 GB_CUDA(gb_launch_pdl(kernel, dim3(grid), dim3(tb_threads(nwn)), smem, st, p->d_x, p->d_ab, ta, L, p->nlat, E,
                                       p->ab_rows, lattiles, n_coltiles, items, polar));
                 GB_LAUNCH_CHECK();
                 return GB_OK;
             };
+            const bool kc32 = env_flag("GB_S1_KC32");
             int rc = GB_OK;
             if (fold) {
-                rc = narrow ? launch_tab(gb_stage1_tab<true, 2, true>, 2, true, 0, n_lattiles, n_items, cap_tiles)
-                            : launch_tab(gb_stage1_tab<true, 6, true>, 6, true, 0, n_lattiles, n_items, cap_tiles);
+                rc = narrow ? launch_tab(gb_stage1_tab<true, 2, true, 16>, 2, true, 16, 0, n_lattiles, n_items, cap_tiles)
+                     : kc32 ? launch_tab(gb_stage1_tab<true, 6, true, 32>, 6, true, 32, 0, n_lattiles, n_items, cap_tiles)
+                            : launch_tab(gb_stage1_tab<true, 6, true, 16>, 6, true, 16, 0, n_lattiles, n_items, cap_tiles | (env_flag("GB_DIAG_NOSTORE") ? 0x10000 : 0));
                 if (!rc && cap_tiles > 0)
-                    rc = narrow ? launch_tab(gb_stage1_tab<true, 2, false>, 2, false, 1, cap_tiles, cap_items, 1)
-                                : launch_tab(gb_stage1_tab<true, 6, false>, 6, false, 1, cap_tiles, cap_items, 1);
+                    rc = narrow ? launch_tab(gb_stage1_tab<true, 2, false, 16>, 2, false, 16, 1, cap_tiles, cap_items, 1)
+                                : launch_tab(gb_stage1_tab<true, 6, false, 16>, 6, false, 16, 1, cap_tiles, cap_items, 1);
             } else if (narrow) {
-                rc = pairs ? launch_tab(gb_stage1_tab<true, 2, false>, 2, false, 2, n_lattiles, n_items, 0)
-                           : launch_tab(gb_stage1_tab<false, 2, false>, 2, false, 2, n_lattiles, n_items, 0);
+                rc = pairs ? launch_tab(gb_stage1_tab<true, 2, false, 16>, 2, false, 16, 2, n_lattiles, n_items, 0)
+                           : launch_tab(gb_stage1_tab<false, 2, false, 16>, 2, false, 16, 2, n_lattiles, n_items, 0);
             } else {
-                rc = pairs ? launch_tab(gb_stage1_tab<true, 6, false>, 6, false, 2, n_lattiles, n_items, 0)
-                           : launch_tab(gb_stage1_tab<false, 6, false>, 6, false, 2, n_lattiles, n_items, 0);
+                rc = pairs ? launch_tab(gb_stage1_tab<true, 6, false, 16>, 6, false, 16, 2, n_lattiles, n_items, 0)
+                           : launch_tab(gb_stage1_tab<false, 6, false, 16>, 6, false, 16, 2, n_lattiles, n_items, 0);
             }
             if (rc) return rc;
         } else {
@@ -1003,10 +1106,12 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
         QGroups grp;
         for (int g = 0; g < 5; ++g) grp.off[g] = p->grp_off[g];
-        GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+        const bool defer = !env_flag("GB_S2_DIRECT_EPILOGUE");
+        auto s2_kernel = defer ? gb_fourier_stage2_sym<true> : gb_fourier_stage2_sym<false>;
+        GB_CUDA(cudaFuncSetAttribute(s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
         // 32-byte stores need 32-byte aligned rows: nlon is a multiple of 8 here, so only the base pointer matters
         const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 8 == 0 && !env_flag("GB_S2_NARROW_STORES")) ? 1 : 0;
-        GB_CUDA(gb_launch_pdl(gb_fourier_stage2_sym, dim3(grid), dim3(Q_THREADS), Q_SMEM, st, p->d_ab, p->ab_rows,
+        GB_CUDA(gb_launch_pdl(s2_kernel, dim3(grid), dim3(defer ? QE_THREADS : Q_THREADS), Q_SMEM, st, p->d_ab, p->ab_rows,
                               p->d_trig_q_t, p->kpad_s, grp, d_out, M, p->nlon, p->nq, n_mtiles, n_ntiles, wide));
         GB_LAUNCH_CHECK();
     } else {
