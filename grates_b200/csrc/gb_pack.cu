@@ -35,12 +35,12 @@ struct XTiling {
     const int* roff;
     int tn, n_ct;
 };
-__device__ __forceinline__ long long x_tiled_position(int r, int c, int e, int E, const XTiling& xt) {
+__device__ __forceinline__ long long x_tiled_position(int r, int c, int e, int E, const XTiling& xt, const int* roff) {
     const int m = (c <= r) ? c : r + 1;
     const int nn = (c <= r) ? r - c : c - r - 1;
     const int col = ((c <= r) ? 0 : E) + e;
     const int ct = col / xt.tn, cc = col - ct * xt.tn;
-    const int r0 = xt.roff[m], kn_pad = xt.roff[m + 1] - r0;
+    const int r0 = roff[m], kn_pad = roff[m + 1] - r0;
     const int row = (nn & ~7) + ((nn & 1) << 2) + ((nn & 7) >> 1);
     return ((long long)r0 * xt.n_ct + (long long)ct * kn_pad + row) * (xt.tn + 4) + cc;
 }
@@ -51,13 +51,16 @@ template <bool PACK, int PKE, bool TILED = false>
 __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__ src, double* __restrict__ dst, int L,
                                                       int E, const double* __restrict__ wn, XTiling xt) {
     constexpr int PK_LD = PKE + 1;    // shared-memory pitch
-    extern __shared__ double s_t[];   // [min(L, PK_C)][PK_LD]
+    extern __shared__ double s_t[];   // [min(L, PK_C)][PK_LD] (+ the row offsets of the tiled layout)
+    int* s_roff = reinterpret_cast<int*>(s_t + (size_t)min(L, PK_C) * PK_LD);
     const int r = blockIdx.x;
     const int cb = blockIdx.z * PK_C;                 // first column of this CTA
     const int nc = min(PK_C, L - cb);
     const int e0 = blockIdx.y * PKE;
     const int ne = min(PKE, E - e0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (TILED)
+        for (int i = threadIdx.x; i <= L; i += blockDim.x) s_roff[i] = xt.roff[i];    // plan constant: before the wait
     gb::griddep_wait();
     gb::griddep_launch_dependents();
     if (PACK) {
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
         for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
             const int c = idx / PKE, e = idx % PKE;
             if (e < ne) {
-                if (TILED) dst[x_tiled_position(r, cb + c, e0 + e, E, xt)] = s_t[c * PK_LD + e];
+                if (TILED) dst[x_tiled_position(r, cb + c, e0 + e, E, xt, s_roff)] = s_t[c * PK_LD + e];
                 else dst[x_position(r, cb + c, L, E) + e0 + e] = s_t[c * PK_LD + e];
             }
         }
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(256) gb_scale_degree_kernel(const double* __re
 
 template <bool PACK, int PKE, bool TILED>
 int launch_pke(const double* src, double* dst, int L, int E, const double* wn, XTiling xt, cudaStream_t st) {
-    const size_t smem = (size_t)(L < PK_C ? L : PK_C) * (PKE + 1) * sizeof(double);
+    const size_t smem = (size_t)(L < PK_C ? L : PK_C) * (PKE + 1) * sizeof(double) + (TILED ? (L + 2) * sizeof(int) : 0);
     if (smem > 48 * 1024)
         GB_CUDA(cudaFuncSetAttribute(gb_pack_kernel<PACK, PKE, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L, (E + PKE - 1) / PKE, (L + PK_C - 1) / PK_C);

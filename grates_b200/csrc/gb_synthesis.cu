@@ -21,6 +21,7 @@
 //   gbgemm::kernel       persistent FP64 tensor-core GEMM  V = AB^T * trig  (DMMA.8x8x4, gb_gemm.cuh),
 //                        operands staged by the TMA unit (cp.async.bulk) through a 3-stage
 //                        mbarrier pipeline fed by a dedicated producer warp
+#include <type_traits>
 #include <vector>
 #include "gb_common.cuh"
 #include "gb_gemm.cuh"
@@ -690,6 +691,35 @@ struct QGroups { int off[5]; };
 // tile period to absorb it.  Registers are rebalanced with setmaxnreg: the kernel starts with 128 per thread
 // (512 threads), consumers grow to 168, epilogue warps shrink to 104, the producer's warpgroup to 40.
 // !EW: the direct kernel (nine warps, epilogue in the consumers), kept for comparison (GB_S2_DIRECT_EPILOGUE=1).
+// Work list of a CTA: whole tiles t = b, b + grid, ... of the full rounds; when the last, partial round holds at most
+// grid / 2 tiles they are cut into halves of 64 rows, one per CTA, so that the tail costs half a tile period.
+struct QWork {
+    long long n_tiles, n_full;
+    int n_ntiles, split, grid;
+    __device__ QWork(int n_mtiles, int n_nt, int g) : n_tiles((long long)n_mtiles * n_nt), n_ntiles(n_nt), grid(g) {
+        n_full = n_tiles / grid * grid;
+        const long long rest = n_tiles - n_full;
+        split = rest > 0 && 2 * rest <= grid;
+    }
+    // i-th work item of CTA b: returns false when there is none; half = -1 for a whole tile
+    __device__ bool get(int b, long long i, long long& mt, int& nt, int& half) const {
+        long long t = b + i * grid;
+        half = -1;
+        if (split && t >= n_full) {
+            if (t >= n_full + grid) return false;
+            const long long j = t - n_full;
+            if (j >= 2 * (n_tiles - n_full)) return false;
+            t = n_full + (j >> 1);
+            half = (int)(j & 1);
+        } else if (t >= n_tiles) {
+            return false;
+        }
+        mt = t / n_ntiles;
+        nt = (int)(t % n_ntiles);
+        return true;
+    }
+};
+
 constexpr int QE_THREADS = 512;
 template <bool EW>
 __global__ void __launch_bounds__(EW ? QE_THREADS : Q_THREADS, 1)
@@ -724,15 +754,12 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
     gb::griddep_wait();                 // AB comes from stage 1; `out` may still be read by whatever ran before
     gb::griddep_launch_dependents();
 
-    const long long n_tiles = (long long)n_mtiles * n_ntiles;
+    const QWork work(n_mtiles, n_ntiles, (int)gridDim.x);
     const int h = nlon >> 1;
-    // butterfly + stores of one 8-row slab (mi) of the 32 x 16 warp tile (wm, wn) of tile (mt, nt);
+    // butterfly + stores of one 8-row slab of a warp tile: output row `row`, first-quadrant meridians jq .. jq+3;
     // v[4 s + 2 ni + r] = accumulator set s.  The trig tiles interleave the columns of a warp's slab (gb_plan.cu), so a
-    // lane's two fragments are the four consecutive meridians jq .. jq+3: one 32-byte store per lane and quadrant.
-    auto emit_row = [&](long long mt, int nt, int wm, int wn, int mi, const double (&v)[16]) {
-        const int g = lane >> 2, q = lane & 3;
-        const long long row = mt * Q_TM + wm * 32 + g + mi * 8;
-        const int jq = nt * Q_TN + wn * 16 + 4 * q;
+    // lane's two fragments are four consecutive meridians: one 32-byte store per lane and quadrant.
+    auto emit_row = [&](long long row, int jq, const double (&v)[16]) {
         if (row >= M || jq >= nq) return;
         double* orow = out + (size_t)row * nlon;
         double v1[4], v2[4], v3[4], v4[4];
@@ -762,65 +789,66 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
             }
         }
     };
+    // first row (inside the 128-row tile) of consumer warp row wm: whole tiles 32 rows per warp, half tiles 16
+    auto warp_row0 = [](int wm, int half) { return half < 0 ? wm * 32 : half * 64 + wm * 16; };
 
     if (warp >= PRODUCER_WARP) {
         if (EW) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-        if (warp == PRODUCER_WARP) {
-            if (lane == 0) {
-                int stage = 0;
-                uint32_t phase = 0;
-                for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                    const long long mt = t / n_ntiles;
-                    const int nt = (int)(t % n_ntiles);
-                    for (int k0 = 0; k0 < grp.off[4];) {
-                        // chunks never straddle a group boundary
-                        int gend = grp.off[1];
+        if (warp == PRODUCER_WARP && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            long long mt;
+            int nt, half;
+            for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
+                for (int k0 = 0; k0 < grp.off[4];) {
+                    // chunks never straddle a group boundary
+                    int gend = grp.off[1];
 #pragma unroll
-                        for (int s = 1; s < 4; ++s)
-                            if (k0 >= grp.off[s]) gend = grp.off[s + 1];
-                        const int kc = min(Q_KC, gend - k0);
-                        gb::mbar_wait(&empty[stage], phase ^ 1u);
-                        double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES;
-                        double* sB = sA + Q_KC * Q_LDA;
-                        const uint32_t bytes_a = (uint32_t)(kc * Q_LDA * sizeof(double));
-                        const uint32_t bytes_b = (uint32_t)(kc * Q_LDB * sizeof(double));
-                        gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
-                        gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * Q_LDA, bytes_a, &full[stage]);
-                        gb::bulk_g2s(sB, trig_q_t + ((size_t)nt * kpad_s + k0) * Q_LDB, bytes_b, &full[stage]);
-                        if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
-                        k0 += kc;
-                    }
+                    for (int s = 1; s < 4; ++s)
+                        if (k0 >= grp.off[s]) gend = grp.off[s + 1];
+                    const int kc = min(Q_KC, gend - k0);
+                    gb::mbar_wait(&empty[stage], phase ^ 1u);
+                    double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES;
+                    double* sB = sA + Q_KC * Q_LDA;
+                    const uint32_t bytes_a = (uint32_t)(kc * Q_LDA * sizeof(double));
+                    const uint32_t bytes_b = (uint32_t)(kc * Q_LDB * sizeof(double));
+                    gb::mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_b);
+                    gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * Q_LDA, bytes_a, &full[stage]);
+                    gb::bulk_g2s(sB, trig_q_t + ((size_t)nt * kpad_s + k0) * Q_LDB, bytes_b, &full[stage]);
+                    if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+                    k0 += kc;
                 }
             }
         }
     } else if (EW && warp >= Q_CONSUMER_WARPS) {
-        {
-            // ===== epilogue warp of sub-partition sp: the tiles of consumer warps sp and sp + 4 =====
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
-            const int sp = warp & 3;
-            int tb = 0;
-            uint32_t tphase = 0;
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const long long mt = t / n_ntiles;
-                const int nt = (int)(t % n_ntiles);
-                gb::mbar_wait(&tfull[tb], tphase);
-                gb::tmem_fence_after_sync();
+        // ===== epilogue warp of sub-partition sp: the tiles of consumer warps sp and sp + 4 =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
+        const int sp = warp & 3;
+        int tb = 0;
+        uint32_t tphase = 0;
+        long long mt;
+        int nt, half;
+        for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
+            gb::mbar_wait(&tfull[tb], tphase);
+            gb::tmem_fence_after_sync();
+            const int n_slabs = half < 0 ? 4 : 2;
 #pragma unroll 1
-                for (int cw = 0; cw < 2; ++cw) {
-                    const int w = sp + 4 * cw;                 // consumer warp whose tile this is
-                    const uint32_t taddr = *s_tmem + ((uint32_t)(32 * sp) << 16) + (uint32_t)(tb * 256 + cw * 128);
+            for (int cw = 0; cw < 2; ++cw) {
+                const int w = sp + 4 * cw;                 // consumer warp whose tile this is
+                const uint32_t taddr = *s_tmem + ((uint32_t)(32 * sp) << 16) + (uint32_t)(tb * 256 + cw * 128);
+                const long long row0 = mt * Q_TM + warp_row0(w / Q_WN, half) + (lane >> 2);
+                const int jq = nt * Q_TN + (w % Q_WN) * 16 + 4 * (lane & 3);
 #pragma unroll 1
-                    for (int mi = 0; mi < 4; ++mi) {
-                        double v[16];
-                        gb::tmem_ld16(taddr + 32u * mi, v);
-                        emit_row(mt, nt, w / Q_WN, w % Q_WN, mi, v);
-                    }
+                for (int mi = 0; mi < n_slabs; ++mi) {
+                    double v[16];
+                    gb::tmem_ld16(taddr + 32u * mi, v);
+                    emit_row(row0 + mi * 8, jq, v);
                 }
-                gb::tmem_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) gb::mbar_arrive(&tempty[tb]);
-                if (++tb == 2) { tb = 0; tphase ^= 1u; }
             }
+            gb::tmem_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) gb::mbar_arrive(&tempty[tb]);
+            if (++tb == 2) { tb = 0; tphase ^= 1u; }
         }
     } else {
         if (EW) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
@@ -829,14 +857,15 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
         const int g = lane >> 2, q = lane & 3;
         int stage = 0, tb = 0;
         uint32_t phase = 0, tphase = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const long long mt = t / n_ntiles;
-            const int nt = (int)(t % n_ntiles);
-            double acc[4][4][2][2];   // [set][mi][ni][2]
+        // one tile: MI 8-row slabs per warp (4: whole tile, 2: half tile)
+        auto run_tile = [&](auto mi_tag, long long mt, int nt, int half) {
+            constexpr int MI = decltype(mi_tag)::value;
+            const int r0 = warp_row0(wm, half);
+            double acc[4][MI][2][2];   // [set][mi][ni][2]
 #pragma unroll
             for (int s = 0; s < 4; ++s)
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 2; ++ni) acc[s][mi][ni][0] = acc[s][mi][ni][1] = 0.0;
 #pragma unroll
@@ -844,21 +873,29 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
                 for (int k0 = grp.off[s]; k0 < grp.off[s + 1];) {
                     const int kc = min(Q_KC, grp.off[s + 1] - k0);
                     gb::mbar_wait(&full[stage], phase);
-                    const double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES + wm * 32 + g;
+                    const double* sA = s_tiles + (size_t)stage * Q_STAGE_DOUBLES + r0 + g;
                     const double* sB = s_tiles + (size_t)stage * Q_STAGE_DOUBLES + Q_KC * Q_LDA + wn * 16 + g;
+                    auto k_step = [&](int kk) {
+                        double a[MI], b[2];
 #pragma unroll
-                    for (int kk = 0; kk < Q_KC; kk += 4) {
-                        if (kk >= kc) break;
-                        double a[4], b[2];
-#pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(kk + q) * Q_LDA + mi * 8];
+                        for (int mi = 0; mi < MI; ++mi) a[mi] = sA[(kk + q) * Q_LDA + mi * 8];
 #pragma unroll
                         for (int ni = 0; ni < 2; ++ni) b[ni] = sB[(kk + q) * Q_LDB + ni * 8];
 #pragma unroll
-                        for (int mi = 0; mi < 4; ++mi)
+                        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                             for (int ni = 0; ni < 2; ++ni)
                                 gb::dmma_884(acc[s][mi][ni][0], acc[s][mi][ni][1], a[mi], b[ni]);
+                    };
+                    if (kc == Q_KC) {                 // whole chunk: no per-step test in the DMMA stream
+#pragma unroll
+                        for (int kk = 0; kk < Q_KC; kk += 4) k_step(kk);
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < Q_KC; kk += 4) {
+                            if (kk >= kc) break;
+                            k_step(kk);
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) gb::mbar_arrive(&empty[stage]);
@@ -872,7 +909,7 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
                 gb::tmem_fence_after_sync();
                 const uint32_t taddr = *s_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(tb * 256 + (warp >> 2) * 128);
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
+                for (int mi = 0; mi < MI; ++mi) {
                     double v[16];
 #pragma unroll
                     for (int s = 0; s < 4; ++s)
@@ -886,16 +923,24 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
                 if (lane == 0) gb::mbar_arrive(&tfull[tb]);
                 if (++tb == 2) { tb = 0; tphase ^= 1u; }
             } else {
+                const long long row0 = mt * Q_TM + r0 + g;
+                const int jq = nt * Q_TN + wn * 16 + 4 * q;
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
+                for (int mi = 0; mi < MI; ++mi) {
                     double v[16];
 #pragma unroll
                     for (int s = 0; s < 4; ++s)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) v[4 * s + c] = acc[s][mi][c >> 1][c & 1];
-                    emit_row(mt, nt, wm, wn, mi, v);
+                    emit_row(row0 + mi * 8, jq, v);
                 }
             }
+        };
+        long long mt;
+        int nt, half;
+        for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
+            if (half < 0) run_tile(std::integral_constant<int, 4>{}, mt, nt, half);
+            else run_tile(std::integral_constant<int, 2>{}, mt, nt, half);
         }
     }
     if (EW) {
