@@ -47,19 +47,83 @@ def blas_threads():
         return os.cpu_count()
 
 
-def peak():
+def peak(device=0):
     import ctypes
     a, b = ctypes.c_double(0), ctypes.c_double(0)
-    gb._lib.check(gb._lib.load().gb_probe_fp64_peak(0, ctypes.byref(a), ctypes.byref(b)))
+    gb._lib.check(gb._lib.load().gb_probe_fp64_peak(int(device or 0), ctypes.byref(a), ctypes.byref(b)))
     return max(a.value, b.value)
 
 
 def syn_flops(N, nlat, nlon, E):
+    """SURVEY 8(d) contract flops of the direct two-stage synthesis."""
     L = N + 1
     return 2.0 * E * nlat * L * L + 2.0 * (2 * L - 1) * E * nlat * nlon
 
 
-def config1(pk):
+def syn_flops_executed(N, plan, E):
+    """What the kernels execute: the symmetric stage 2 contracts one quadrant of meridians, the folded stage 1 the
+    northern parallels."""
+    L = N + 1
+    s1 = 2.0 * E * plan.nlat * L * L / (2.0 if plan.folded else 1.0)
+    s2 = 2.0 * (2 * L - 1) * E * plan.nlat * plan.nlon / (4.0 if plan.symmetric else 1.0)
+    return s1 + s2
+
+
+class Ctx:
+    """Rank layout and collectives of one run (a single process when dist is None)."""
+
+    def __init__(self, rank=0, world=1, dev=None, dist=None):
+        self.rank, self.world, self.dist = rank, world, dist
+        self.dev = dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x):
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def shard(self, count):
+        return gb.distributed.shard_range(count, self.world, self.rank)
+
+    def time(self, fn, reps=5, warm=3):
+        """Device milliseconds of fn: CUDA events on the launch stream, L2 flushed before every repetition, mean of
+        `reps` after `warm` warm-ups, max over ranks."""
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        total = 0.0
+        for _ in range(reps):
+            self.flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return self.max(total / reps)
+
+
+def _reference():
+    """The unmodified reference package (baseline/_ref) or None; see bench.load_reference."""
+    import bench
+    return bench.load_reference()
+
+
+def _ref_field(grates, anm):
+    pc = grates.gravityfield.PotentialCoefficients(3.9860044150e+14, 6.3781363000e+06)
+    pc.anm = anm
+    return pc
+
+
+def config1(pk, ctx=None, with_cpu=True):
+    """Single coefficient set: no useful sharding, every rank is a replica."""
+    ctx = ctx or Ctx()
     N, d = 60, 1.0
     grid, og = gb.GeographicGrid(d, d), orc.geographic_grid(d, d)
     anm = orc.synthetic_coefficients(N, 0)
@@ -70,140 +134,220 @@ def config1(pk):
     for _ in range(20):
         pc.to_grid(grid, "ewh")
     host_call = (time.perf_counter() - t0) / 20
-    plan = gb.get_plan(grid, N, "ewh")
-    x = torch.as_tensor(anm[None]).cuda()
-    buf = torch.empty((1, 180, 360), dtype=torch.float64, device="cuda")
-    ms = ev_time(lambda: plan.synthesis(x, out=buf))
-    orc.synthesis(anm, og, "ewh")
-    t0 = time.perf_counter()
-    for _ in range(5):
-        ref = orc.synthesis(anm, og, "ewh")
-    cpu = (time.perf_counter() - t0) / 5
-    return {"config": "c1: single degree-60 set -> 1deg grid, ewh", "gpu_kernels_ms": ms,
-            "gpu_to_grid_call_ms": host_call * 1e3, "grid_pts_per_s_device": 64800 / ms * 1e3,
-            "grid_pts_per_s_call": 64800 / host_call, "parity_max_normalised": err(out.value_array, ref),
-            "cpu_baseline": {"s_per_call": cpu, "grid_pts_per_s": 64800 / cpu, "cores": blas_threads(), "kind": "port",
-                             "sample": "5 full calls after warm-up"},
-            "note": "latency bound: 19 MFLOP; the call time is plan lookup + 0.5 MB D2H"}
+    plan = gb.get_plan(grid, N, "ewh", device=ctx.dev.index)
+    x = torch.as_tensor(anm[None]).to(ctx.dev)
+    buf = torch.empty((1, 180, 360), dtype=torch.float64, device=ctx.dev)
+    ms = ctx.time(lambda: plan.synthesis(x, out=buf))
+    ref = orc.synthesis(anm, og, "ewh")
+    res = {"config": "c1: single degree-60 set -> 1deg grid, ewh", "gpu_kernels_ms": ms,
+           "gpu_to_grid_call_ms": host_call * 1e3, "grid_pts_per_s_device": 64800 / ms * 1e3,
+           "grid_pts_per_s_call": 64800 / host_call, "parity_max_normalised": err(out.value_array, ref),
+           "contract_flops": syn_flops(N, 180, 360, 1), "frac_fp64_peak_contract_flops": syn_flops(N, 180, 360, 1) / ms / 1e9 / pk,
+           "sharding": "replicas only (one set)",
+           "note": "latency bound: 19 MFLOP; the call time is plan lookup + 0.5 MB D2H"}
+    if with_cpu and ctx.rank == 0:
+        grates = _reference()
+        if grates is not None:
+            rg, rp = grates.grid.GeographicGrid(d, d), _ref_field(grates, anm)
+            run, kind = (lambda: rp.to_grid(rg, "ewh")), "reference"
+        else:
+            run, kind = (lambda: orc.synthesis(anm, og, "ewh")), "port"
+        run()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            run()
+        cpu = (time.perf_counter() - t0) / 5
+        res["cpu_baseline"] = {"s_per_call": cpu, "grid_pts_per_s": 64800 / cpu, "cores": blas_threads(), "kind": kind,
+                               "sample": "5 full calls after warm-up"}
+    return res
 
 
-def config3(pk):
-    N, d, E = 180, 0.25, 120
+def config3(pk, ctx=None, with_cpu=True):
+    ctx = ctx or Ctx()
+    N, d, E_all = 180, 0.25, 120
+    e0, e1 = ctx.shard(E_all)
+    E = e1 - e0
     grid, og = gb.GeographicGrid(d, d), orc.geographic_grid(d, d)
-    plan = gb.get_plan(grid, N, "ewh")
+    plan = gb.get_plan(grid, N, "ewh", device=ctx.dev.index)
     t0 = time.perf_counter()
     plan.set_analysis(0, grid.area.reshape(plan.nlat, plan.nlon))
     t_ops = time.perf_counter() - t0
-    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
-    x = torch.as_tensor(anm).cuda()
-    v = torch.empty((E, plan.nlat, plan.nlon), dtype=torch.float64, device="cuda")
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(e0, e1)])
+    x = torch.as_tensor(anm).to(ctx.dev)
+    v = torch.empty((E, plan.nlat, plan.nlon), dtype=torch.float64, device=ctx.dev)
     back = torch.empty_like(x)
-    ms_syn = ev_time(lambda: plan.synthesis(x, out=v))
-    ms_ana = ev_time(lambda: plan.analysis(v, out=back))
+    ms_syn = ctx.time(lambda: plan.synthesis(x, out=v))
+    ms_ana = ctx.time(lambda: plan.analysis(v, out=back))
     rt = float((back - x).abs().max() / x.abs().max())
-    # CPU: synthesis on 2 epochs; analysis: per-order operator build + mat-vec for orders 0, 60, 120, 180 of ONE epoch,
-    # integrated over the orders (a full epoch is ~16 min and 6 GB in the reference, grid.py:665-696)
-    t0 = time.perf_counter()
-    ref0 = orc.synthesis(anm[0], og, "ewh")
-    orc.synthesis(anm[1], og, "ewh")
-    cpu_syn = (time.perf_counter() - t0) / 2
-    par_syn = err(v[0].cpu().numpy(), ref0)
-    orders, secs = [0, 90, 180], []
-    vals0 = ref0.ravel()
-    for m in orders:
-        t0 = time.perf_counter()
-        ops = orc.analysis_operator_per_order(og, m, 0, N, "ewh")
-        for op in (ops if isinstance(ops, tuple) else (ops,)):
-            op @ vals0
-        secs.append(time.perf_counter() - t0)
-    cpu_ana = float((np.trapezoid if hasattr(np, "trapezoid") else np.trapz)(secs, orders))          # seconds per epoch, integrated over orders 0..180
-    par_ana = err(back[0].cpu().numpy(), orc.analysis_separable(ref0, og, 0, N, "ewh"))
     P = plan.nlat * plan.nlon
-    return {"config": "c3: degree-180 synthesis to 0.25deg + analysis round trip, 120 epochs",
-            "synthesis_ms": ms_syn, "analysis_ms": ms_ana, "analysis_operator_build_s_host_once": t_ops,
-            "synthesis_grid_pts_epochs_per_s": E * P / ms_syn * 1e3, "analysis_grid_pts_epochs_per_s": E * P / ms_ana * 1e3,
-            "synthesis_frac_fp64_peak_contract_flops": syn_flops(N, plan.nlat, plan.nlon, E) / ms_syn / 1e9 / pk,
-            "analysis_frac_fp64_peak_contract_flops": syn_flops(N, plan.nlat, plan.nlon, E) / ms_ana / 1e9 / pk,
-            "round_trip_max_normalised": rt, "parity_synthesis": par_syn, "parity_analysis_vs_oracle": par_ana,
-            "cpu_baseline": {"synthesis_s_per_epoch": cpu_syn, "analysis_s_per_epoch_extrapolated": cpu_ana,
-                             "synthesis_grid_pts_epochs_per_s": P / cpu_syn, "analysis_grid_pts_epochs_per_s": P / cpu_ana,
-                             "cores": blas_threads(), "kind": "port",
-                             "sample": "synthesis: 2 of 120 epochs; analysis: orders 0/90/180 of one epoch "
-                                       "(%.1f/%.1f/%.1f s) integrated over 181 orders" % tuple(secs)}}
+    res = {"config": "c3: degree-180 synthesis to 0.25deg + analysis round trip, 120 epochs",
+           "epochs_per_gpu": E, "synthesis_ms": ms_syn, "analysis_ms": ms_ana, "analysis_operator_build_s_host_once": t_ops,
+           "synthesis_grid_pts_epochs_per_s": E_all * P / ms_syn * 1e3, "analysis_grid_pts_epochs_per_s": E_all * P / ms_ana * 1e3,
+           "contract_flops": syn_flops(N, plan.nlat, plan.nlon, E_all),
+           "synthesis_contract_multiple_of_fp64_peak": syn_flops(N, plan.nlat, plan.nlon, E_all) / ms_syn / 1e9 / pk / ctx.world,
+           "analysis_contract_multiple_of_fp64_peak": syn_flops(N, plan.nlat, plan.nlon, E_all) / ms_ana / 1e9 / pk / ctx.world,
+           # executed: the four-fold meridian symmetry quarters the longitude stage of both directions, the equator fold
+           # halves the Legendre stage of the synthesis
+           "synthesis_frac_fp64_peak_executed_flops": syn_flops_executed(N, plan, E_all) / ms_syn / 1e9 / pk / ctx.world,
+           "round_trip_max_normalised": rt}
+    if ctx.rank == 0:
+        # parity on a bounded sample: epoch 0 against the oracle (synthesis and analysis)
+        ref0 = orc.synthesis(anm[0], og, "ewh")
+        res["parity_synthesis"] = err(v[0].cpu().numpy(), ref0)
+        res["parity_analysis_vs_oracle"] = err(back[0].cpu().numpy(), orc.analysis_separable(ref0, og, 0, N, "ewh"))
+        if with_cpu:
+            # CPU: synthesis through the reference on 2 epochs; analysis: per-order operator build + mat-vec for orders
+            # 0, 90, 180 of ONE epoch, integrated over the orders (a full epoch is ~16 min and 6 GB in the reference,
+            # grid.py:665-696)
+            grates = _reference()
+            if grates is not None:
+                rg = grates.grid.GeographicGrid(d, d)
+                run, kind = (lambda a: _ref_field(grates, a).to_grid(rg, "ewh")), "reference"
+            else:
+                run, kind = (lambda a: orc.synthesis(a, og, "ewh")), "port"
+            t0 = time.perf_counter()
+            run(anm[0])
+            run(anm[1])
+            cpu_syn = (time.perf_counter() - t0) / 2
+            orders, secs = [0, 90, 180], []
+            vals0 = ref0.ravel()
+            for m in orders:
+                t0 = time.perf_counter()
+                ops = orc.analysis_operator_per_order(og, m, 0, N, "ewh")
+                for op in (ops if isinstance(ops, tuple) else (ops,)):
+                    op @ vals0
+                secs.append(time.perf_counter() - t0)
+            cpu_ana = float((np.trapezoid if hasattr(np, "trapezoid") else np.trapz)(secs, orders))
+            res["cpu_baseline"] = {"synthesis_s_per_epoch": cpu_syn, "analysis_s_per_epoch_extrapolated": cpu_ana,
+                                   "synthesis_grid_pts_epochs_per_s": P / cpu_syn, "analysis_grid_pts_epochs_per_s": P / cpu_ana,
+                                   "cores": blas_threads(), "kind": kind + " (synthesis) / port (analysis)",
+                                   "sample": "synthesis: 2 of 120 epochs; analysis: orders 0/90/180 of one epoch "
+                                             "(%.1f/%.1f/%.1f s) integrated over 181 orders" % tuple(secs)}
+    return res
 
 
-def config4(pk):
+def config4(pk, ctx=None, with_cpu=True, extras=True):
+    ctx = ctx or Ctx()
     N, d = 96, 0.5
     grid, og = gb.GeographicGrid(d, d), orc.geographic_grid(d, d)
-    plan = gb.get_plan(grid, N, "ewh")
-    sig_h = orc.synthetic_covariance(N)
-    sigma = torch.as_tensor(sig_h).cuda()
-    out = torch.empty((plan.nlat, plan.nlon), dtype=torch.float64, device="cuda")
-    ms = ev_time(lambda: plan.covariance_propagation(sigma, 0, out=out), reps=3, warm=1)
-    rows = [0, 123, 359]
-    t0 = time.perf_counter()
-    ref = orc.covariance_propagation(sig_h, og, 0, N, "ewh", rows=rows)
-    cpu_row = (time.perf_counter() - t0) / len(rows)
+    plan = gb.get_plan(grid, N, "ewh", device=ctx.dev.index)
+    sig_h = orc.synthetic_covariance(N)          # the same matrix on every rank: Sigma resident everywhere
+    sigma = torch.as_tensor(sig_h).to(ctx.dev)
+    r0, r1 = ctx.shard(plan.nlat)                # row blocks sharded over the GPUs
+    out = torch.empty((r1 - r0, plan.nlon), dtype=torch.float64, device=ctx.dev)
+    ms = ctx.time(lambda: plan.covariance_propagation(sigma, 0, r0, r1 - r0, out=out), reps=3, warm=1)
+    again = torch.empty_like(out)
+    plan.covariance_propagation(sigma, 0, r0, r1 - r0, out=again)
     K, P = (N + 1) ** 2, plan.nlat * plan.nlon
     contract = 2.0 * P * K * K + 2.0 * P * K
     # symmetric Sigma (detected by the host): only the order-block pairs k <= k' of H_i are formed
     executed = 1.0 * plan.nlat * K * K + 2.0 * P * (2 * N + 2) ** 2
-    ms_full = ev_time(lambda: plan.covariance_propagation(sigma, 0, out=out, symmetric=False), reps=3, warm=1)
-    # the direct point kernel (no grid structure assumed) on a 4-parallel slice, for the contract-flop roofline
-    sl = gb.IrregularGrid(grid.longitude[:4 * plan.nlon], grid.latitude[:4 * plan.nlon])
-    pp = gb.get_points_plan(sl, N, "ewh")
-    ms_direct = ev_time(lambda: pp.covariance_propagation(sigma, 0, symmetric=False), reps=2, warm=1)
-    ms_direct_sym = ev_time(lambda: pp.covariance_propagation(sigma, 0, symmetric=True), reps=2, warm=1)
-    direct_flops = 2.0 * sl.point_count * K * K
-    par_direct = err(pp.covariance_propagation(sigma, 0).cpu().numpy()[:plan.nlon], ref[0])
-    return {"config": "c4: covariance propagation, degree 96 (K=9409) -> 0.5deg grid",
-            "ms": ms, "points_per_s": P / ms * 1e3, "parity_max_normalised_3_parallels": err(out[rows].cpu().numpy(), ref),
-            "contract_flops": contract, "executed_flops": executed,
-            "frac_fp64_peak_contract_flops": contract / ms / 1e9 / pk, "frac_fp64_peak_executed_flops": executed / ms / 1e9 / pk,
-            "declared_restructuring": "regular grid: F = U (x) T factors, H_i = U_i' Sigma U_i per parallel then a "
-                                      "longitude quadratic form; 2 nlat K^2 + 2 P (2L)^2 flops instead of 2 P K^2; "
-                                      "a symmetric Sigma (checked on a sample of entries) halves the first term",
-            "ms_without_symmetry": ms_full,
-            "executed_flops_without_symmetry": 2.0 * plan.nlat * K * K + 2.0 * P * (2 * N + 2) ** 2,
-            "direct_point_kernel": {"points": sl.point_count, "ms": ms_direct, "flops": direct_flops,
-                                    "frac_fp64_peak": direct_flops / ms_direct / 1e9 / pk,
-                                    "parity_first_parallel": par_direct,
-                                    "ms_upper_triangle_of_symmetric_sigma": ms_direct_sym,
-                                    "note": "gb_points_quadform: blocked diag(F Sigma F') on DMMA, no grid structure assumed; "
-                                            "`ms` uses the full matrix, the second figure only the upper triangle of a symmetric Sigma"},
-            "cpu_baseline": {"s_per_parallel": cpu_row, "s_total_extrapolated": cpu_row * plan.nlat,
-                             "points_per_s": plan.nlon / cpu_row, "cores": blas_threads(), "kind": "port",
-                             "sample": "3 of 360 parallels (cost is identical per parallel: two dgemms)"}}
+    res = {"config": "c4: covariance propagation, degree 96 (K=9409) -> 0.5deg grid",
+           "parallels_per_gpu": r1 - r0, "ms": ms, "points_per_s": P / ms * 1e3,
+           "bit_identical_across_two_runs": bool(torch.equal(out, again)),
+           "contract_flops": contract, "executed_flops": executed,
+           "contract_multiple_of_fp64_peak": contract / ms / 1e9 / pk / ctx.world,
+           "frac_fp64_peak_executed_flops": executed / ms / 1e9 / pk / ctx.world,
+           "declared_restructuring": "regular grid: F = U (x) T factors, H_i = U_i' Sigma U_i per parallel then a "
+                                     "longitude quadratic form; 2 nlat K^2 + 2 P (2L)^2 flops instead of 2 P K^2; "
+                                     "a symmetric Sigma (checked on a sample of entries) halves the first term"}
+    if ctx.dist is not None:
+        # the broadcast a caller pays when Sigma originates on one rank (not part of `ms`)
+        buf = torch.empty_like(sigma)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.dist.broadcast(buf if ctx.rank else sigma, src=0)
+        e1.record()
+        e1.synchronize()
+        res["sigma_broadcast_ms_not_in_ms"] = ctx.max(e0.elapsed_time(e1))
+        del buf
+    if ctx.rank == 0:
+        rows = [0, min(123, r1 - 1), r1 - 1]
+        t0 = time.perf_counter()
+        ref = orc.covariance_propagation(sig_h, og, 0, N, "ewh", rows=rows)
+        cpu_row = (time.perf_counter() - t0) / len(rows)
+        res["parity_max_normalised_3_parallels"] = err(out[[r - r0 for r in rows]].cpu().numpy(), ref)
+        if with_cpu:
+            res["cpu_baseline"] = {"s_per_parallel": cpu_row, "s_total_extrapolated": cpu_row * plan.nlat,
+                                   "points_per_s": plan.nlon / cpu_row, "cores": blas_threads(), "kind": "port",
+                                   "sample": "3 of 360 parallels of grid.py:833-835 (cost is identical per parallel: two dgemms)"}
+    if extras and ctx.world == 1:
+        ms_full = ctx.time(lambda: plan.covariance_propagation(sigma, 0, out=out, symmetric=False), reps=3, warm=1)
+        res["ms_without_symmetry"] = ms_full
+        res["executed_flops_without_symmetry"] = 2.0 * plan.nlat * K * K + 2.0 * P * (2 * N + 2) ** 2
+        # the direct point kernel (no grid structure assumed) on a 4-parallel slice, for the contract-flop roofline
+        sl = gb.IrregularGrid(grid.longitude[:4 * plan.nlon], grid.latitude[:4 * plan.nlon])
+        pp = gb.get_points_plan(sl, N, "ewh")
+        ms_direct = ctx.time(lambda: pp.covariance_propagation(sigma, 0, symmetric=False), reps=2, warm=1)
+        ms_direct_sym = ctx.time(lambda: pp.covariance_propagation(sigma, 0, symmetric=True), reps=2, warm=1)
+        direct_flops = 2.0 * sl.point_count * K * K
+        res["direct_point_kernel"] = {"points": sl.point_count, "ms": ms_direct, "flops": direct_flops,
+                                      "frac_fp64_peak": direct_flops / ms_direct / 1e9 / pk,
+                                      "ms_upper_triangle_of_symmetric_sigma": ms_direct_sym,
+                                      "note": "gb_points_quadform: blocked diag(F Sigma F') on DMMA, no grid structure assumed"}
+    return res
 
 
-def config5(pk):
-    N, d, E = 120, 0.25, 500
+def config5(pk, ctx=None, with_cpu=True):
+    ctx = ctx or Ctx()
+    N, d, E_all = 120, 0.25, 500
+    e0, e1 = ctx.shard(E_all)
+    E = e1 - e0
     grid, og = gb.GeographicGrid(d, d), orc.geographic_grid(d, d)
     blocks = orc.synthetic_filter_blocks(N)
     flt = gb.OrderWiseFilter(blocks)
-    plan = gb.get_plan(grid, N, "ewh")
-    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
-    x = torch.as_tensor(anm).cuda()
+    plan = gb.get_plan(grid, N, "ewh", device=ctx.dev.index)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(e0, e1)])
+    x = torch.as_tensor(anm).to(ctx.dev)
     y = torch.empty_like(x)
-    v = torch.empty((E, plan.nlat, plan.nlon), dtype=torch.float64, device="cuda")
-    ms_f = ev_time(lambda: flt.filter_batch(x, out=y))
-    ms_all = ev_time(lambda: plan.synthesis(flt.filter_batch(x, out=y), out=v), reps=3, warm=1)
-    t0 = time.perf_counter()
-    refs = [orc.synthesis(orc.orderwise_filter(blocks, anm[e]), og, "ewh") for e in (0, 499)]
-    cpu = (time.perf_counter() - t0) / 2
-    par = max(err(v[0].cpu().numpy(), refs[0]), err(v[499].cpu().numpy(), refs[1]))
+    v = torch.empty((E, plan.nlat, plan.nlon), dtype=torch.float64, device=ctx.dev)
+    ms_f = ctx.time(lambda: flt.filter_batch(x, out=y))
+    ms_all = ctx.time(lambda: plan.synthesis(flt.filter_batch(x, out=y), out=v), reps=3, warm=1)
     P = plan.nlat * plan.nlon
     fbytes = 2.0 * x.numel() * 8 + sum(b.size for b in blocks) * 8
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
-    return {"config": "c5: order-wise block filter + synthesis, 500 epochs, degree 120 -> 0.25deg grid",
-            "filter_ms": ms_f, "filter_gbs_algorithmic": fbytes / ms_f / 1e6,
-            "filter_frac_hbm_peak": (fbytes / ms_f / 1e6 / hbm) if hbm else None,
-            "filter_plus_synthesis_ms": ms_all, "grid_pts_epochs_per_s": E * P / ms_all * 1e3,
-            "frac_fp64_peak_contract_flops": syn_flops(N, plan.nlat, plan.nlon, E) / ms_all / 1e9 / pk,
-            "parity_max_normalised_2_epochs": par,
-            "cpu_baseline": {"s_per_epoch": cpu, "grid_pts_epochs_per_s": P / cpu, "cores": blas_threads(), "kind": "port",
-                             "sample": "2 of 500 epochs (filter + to_grid, cost linear in epochs)"}}
+    res = {"config": "c5: order-wise block filter + synthesis, 500 epochs, degree 120 -> 0.25deg grid",
+           "epochs_per_gpu": E, "filter_ms": ms_f, "filter_gbs_algorithmic": fbytes / ms_f / 1e6,
+           "filter_frac_hbm_peak": (fbytes / ms_f / 1e6 / hbm) if hbm else None,
+           "filter_plus_synthesis_ms": ms_all, "grid_pts_epochs_per_s": E_all * P / ms_all * 1e3,
+           "contract_flops": syn_flops(N, plan.nlat, plan.nlon, E_all),
+           "contract_multiple_of_fp64_peak": syn_flops(N, plan.nlat, plan.nlon, E_all) / ms_all / 1e9 / pk / ctx.world,
+           "frac_fp64_peak_executed_flops": syn_flops_executed(N, plan, E_all) / ms_all / 1e9 / pk / ctx.world}
+    if ctx.rank == 0:
+        picks = (0, E - 1)
+        refs = [orc.synthesis(orc.orderwise_filter(blocks, anm[e]), og, "ewh") for e in picks]
+        res["parity_max_normalised_2_epochs"] = max(err(v[e].cpu().numpy(), r) for e, r in zip(picks, refs))
+        if with_cpu:
+            grates = _reference()
+            if grates is not None:
+                rg, rf = grates.grid.GeographicGrid(d, d), grates.filter.OrderWiseFilter(blocks)
+                run, kind = (lambda a: rf.filter(_ref_field(grates, a)).to_grid(rg, "ewh")), "reference"
+            else:
+                run, kind = (lambda a: orc.synthesis(orc.orderwise_filter(blocks, a), og, "ewh")), "port"
+            t0 = time.perf_counter()
+            for e in picks:
+                run(anm[e])
+            cpu = (time.perf_counter() - t0) / 2
+            res["cpu_baseline"] = {"s_per_epoch": cpu, "grid_pts_epochs_per_s": P / cpu, "cores": blas_threads(), "kind": kind,
+                                   "sample": "2 of 500 epochs (OrderWiseFilter.filter + to_grid, cost linear in epochs)"}
+    return res
+
+
+def run_all(rank, world, dev, dist, with_cpu=True):
+    """BASELINE configs 1, 3, 4, 5 for bench.py's `configs` block: every rank takes part (epoch shards for c3 / c5, row
+    blocks with Sigma resident on every rank for c4, replicas for c1), times are max over ranks; parity and the CPU
+    arms (N=1 only) on rank 0.  Returns a dict on every rank."""
+    ctx = Ctx(rank, world, dev, dist)
+    pk = peak(dev.index)
+    res = {"fp64_peak_tflops_measured_live": pk, "n_gpus": world,
+           "timing": "CUDA events, L2 flushed before every repetition, mean of 3-5 repetitions, max over ranks"}
+    for name, fn in (("c1", config1), ("c3", config3), ("c4", lambda p, c, w: config4(p, c, w, extras=False)), ("c5", config5)):
+        res[name] = fn(pk, ctx, with_cpu)
+        gb.clear_plan_cache()
+        torch.cuda.empty_cache()
+    return res
 
 
 def widened(pk):

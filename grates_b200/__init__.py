@@ -6,7 +6,7 @@ Host code is Python (numpy for small tables, torch for device memory / streams /
 torch.distributed); all arithmetic on the path runs in hand-written CUDA kernels behind the
 C ABI of ``include/grates_b200.h``.  There is no CPU fallback.
 """
-from . import _lib, utilities, kernel, plan, grid, gravityfield, filter  # noqa: F401
+from . import _lib, utilities, kernel, plan, grid, gravityfield, filter, distributed  # noqa: F401
 from .gravityfield import PotentialCoefficients, RadialBasisFunctions, AnisotropicBasisFunctions, TimeSeries, to_grid_batch, gridded_rms, grid_statistics, ravel_batch  # noqa: F401
 from .grid import (RegularGrid, IrregularGrid, GeographicGrid, GaussGrid, analysis_batch, basin_variances,  # noqa: F401
                    covariance_from_normals)
