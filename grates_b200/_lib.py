@@ -12,12 +12,14 @@ _c_int64_p = ctypes.POINTER(ctypes.c_int64)
 _vp = ctypes.c_void_p
 
 GB_OK, GB_ERR_ARGUMENT, GB_ERR_CUDA, GB_ERR_UNSUPPORTED, GB_ERR_MEMORY = 0, 1, 2, 3, 4
+GB_VERSION = 200        # must equal GB_VERSION of include/grates_b200.h: the argtypes below describe THAT header
 
 # name -> (restype, argtypes); must list every symbol of include/grates_b200.h
 SIGNATURES = {
     "gb_version": (ctypes.c_int, []),
     "gb_last_error": (ctypes.c_char_p, []),
     "gb_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "gb_trim": (ctypes.c_int, [ctypes.c_int]),
     "gb_plan_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
                                       _vp, _vp, ctypes.c_int]),
     "gb_plan_destroy": (ctypes.c_int, [_vp]),
@@ -71,19 +73,31 @@ def library_path():
 
 
 def load():
-    """Load (building first if the sources are newer and nvcc exists) and return the CDLL."""
+    """Load and return the CDLL.  The library is rebuilt first when it is missing, older than its sources or the
+    header, or when GRATES_B200_REBUILD is set; a current library loads without nvcc (the GPU box has the prebuilt
+    file).  A library of another ABI version is refused rather than called with the wrong argument types."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
         path = library_path()
-        if not os.path.exists(path) or os.environ.get("GRATES_B200_REBUILD"):
-            from . import build as _build
-            _build.build()
+        from . import build as _build
+        if os.environ.get("GRATES_B200_REBUILD") or _build.needs_build():
+            try:
+                _build.build(force=True)
+            except RuntimeError:
+                if not os.path.exists(path):
+                    raise
+                import warnings
+                warnings.warn("libgrates_b200.so is older than its sources and could not be rebuilt (no nvcc?)")
         if not os.path.exists(path):
             raise RuntimeError("libgrates_b200.so is missing (%s); run `python -m grates_b200.build`. "
                                "grates_b200 has no CPU fallback." % path)
         lib = ctypes.CDLL(path)
+        lib.gb_version.restype = ctypes.c_int
+        if lib.gb_version() != GB_VERSION:
+            raise RuntimeError("libgrates_b200.so has ABI version %d, this package expects %d; rebuild it with "
+                               "`python -m grates_b200.build`" % (lib.gb_version(), GB_VERSION))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)      # AttributeError here means header and library disagree
             fn.restype = res

@@ -156,8 +156,9 @@ int gb_plan_acquire(gb_plan* p, cudaStream_t st);
 
 int gb_plan_ensure_workspace(gb_plan* p, int n_epochs);
 void gb_cov_layout_free(gb_plan* p);
-// keep stream-ordered allocations in the device's default pool between calls
-void gb_retain_pool_memory(int device);
+// the library's own stream-ordered memory pool of `device` (gb_plan.cu); nullptr if it cannot be created
+cudaMemPool_t gb_scratch_pool(int device);
+void gb_retain_pool_memory(int device);   // makes sure the pool exists
 
 // anm [E][L][L] <-> order-wise packed X (gb_pack.cu): block of order m at 2E (m L - m(m-1)/2),
 // X_m[n - m][cs * E + e]
@@ -188,7 +189,11 @@ struct gb_scratch {
         *out = nullptr;
         if (n >= 24) return cudaErrorMemoryAllocation;
         void* p = nullptr;
-        cudaError_t e = cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool = gb_scratch_pool(dev);
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&p, (count ? count : 1) * sizeof(T), pool, st)
+                             : cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st);
         if (e == cudaSuccess) {
             ptrs[n++] = p;
             *out = static_cast<T*>(p);

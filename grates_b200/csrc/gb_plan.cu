@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "gb_common.cuh"
 
@@ -17,7 +18,7 @@ int gb_set_error(int code, const char* fmt, ...) {
 }
 void gb_count_launch(int n) { g_launches += n; }
 
-extern "C" int gb_version(void) { return 100; }
+extern "C" int gb_version(void) { return GB_VERSION; }
 extern "C" const char* gb_last_error(void) { return g_err; }
 extern "C" int64_t gb_launch_count(int reset) {
     long long v = g_launches;
@@ -25,14 +26,48 @@ extern "C" int64_t gb_launch_count(int reset) {
     return v;
 }
 
-// The default release threshold (0) returns stream-ordered workspace to the driver at every
-// synchronisation: milliseconds per GB on the next call.
-void gb_retain_pool_memory(int device) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+// Stream-ordered scratch memory (gb_scratch) comes from a pool the library owns, one per device: its release threshold
+// keeps the multi-GB temporaries of covariance propagation / filtering between calls (the default threshold of 0 returns
+// them to the driver at every synchronisation: milliseconds per GB on the next call) without touching the attributes of
+// the device's default pool, which belongs to the process (torch, other libraries).  gb_trim() hands the memory back.
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {};
+
+cudaMemPool_t gb_scratch_pool(int device) {
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
         unsigned long long keep = ~0ULL;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        g_pools[device] = pool;
     }
+    return g_pools[device];
+}
+
+void gb_retain_pool_memory(int device) { (void)gb_scratch_pool(device); }
+
+extern "C" int gb_trim(int device) {
+    GB_REQUIRE(device >= 0 && device < 64, "gb_trim: device %d out of range", device);
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        pool = g_pools[device];
+    }
+    if (!pool) return GB_OK;
+    GB_CUDA(cudaSetDevice(device));
+    GB_CUDA(cudaDeviceSynchronize());
+    GB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return GB_OK;
 }
 
 extern "C" int gb_device_count(int* count) {

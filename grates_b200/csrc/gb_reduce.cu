@@ -41,6 +41,7 @@ gb_moments_partial(const double* __restrict__ v, const double* __restrict__ w, c
     double a = 0.0, b = 0.0;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
         const double wp = w[p];
+        if (wp == 0.0) continue;             // outside the mask: the value does not take part, whatever it is (NaN on land)
         const double d = ve[p] - c;
         a = fma(wp, d, a);
         b = fma(wp * d, d, b);

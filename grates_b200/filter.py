@@ -49,7 +49,7 @@ class _DegreeWiseFilter(SpatialFilter):
             raise ValueError("coefficients must be a float64 array of shape [epochs, L, L]")
         nmax = x.shape[-1] - 1
         w = torch.as_tensor(self.degree_weights(nmax)).to(x.device)
-        y = torch.empty_like(x) if out is None else out
+        y = torch.empty_like(x) if out is None else _plan._check_out(out, x.shape, dev)
         lib = _lib.load()
         _lib.check(lib.gb_scale_by_degree(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()), x.shape[0], nmax,
                                           ctypes.c_void_p(y.data_ptr()), dev, _plan._stream_handle(dev)))
@@ -137,7 +137,7 @@ class OrderWiseFilter(SpatialFilter):
         x = torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", dev)) if on_host else anm.contiguous()
         if x.dim() != 3 or x.shape[1] != x.shape[2] or x.dtype != torch.float64:
             raise ValueError("coefficients must be a float64 array of shape [epochs, L, L]")
-        y = torch.empty_like(x) if out is None else out
+        y = torch.empty_like(x) if out is None else _plan._check_out(out, x.shape, dev)
         lib = _lib.load()
         _lib.check(lib.gb_orderwise_filter(ctypes.c_void_p(self._blocks_on(dev).data_ptr()),
                                            self._offsets.ctypes.data_as(ctypes.c_void_p), self._nmax,
@@ -207,9 +207,8 @@ class GeneralMatrix(SpatialFilter):
             raise ValueError("coefficients must be a float64 array of shape [epochs, L, L]")
         nmax_in = x.shape[-1] - 1
         lout = min(nmax_in, self._nmax) + 1
-        y = torch.empty((x.shape[0], lout, lout), dtype=torch.float64, device=x.device) if out is None else out
-        if tuple(y.shape) != (x.shape[0], lout, lout):
-            raise ValueError("out must have shape [{0}, {1}, {1}]".format(x.shape[0], lout))
+        y = (torch.empty((x.shape[0], lout, lout), dtype=torch.float64, device=x.device) if out is None
+             else _plan._check_out(out, (x.shape[0], lout, lout), dev))
         _lib.check(_lib.load().gb_dense_filter(ctypes.c_void_p(self._tiles_on(dev).data_ptr()), self._nmin, self._nmax,
                                                ctypes.c_void_p(x.data_ptr()), x.shape[0], nmax_in,
                                                ctypes.c_void_p(y.data_ptr()), dev, _plan._stream_handle(dev)))

@@ -407,10 +407,17 @@ def gridded_rms(temporal_gravityfield, epochs, kernel='ewh', base_grid=None):
     if not fields:
         raise ValueError("no epochs selected")
     L = max(f.anm.shape[0] for f in fields)
+    GM, R = fields[0].GM, fields[0].R
     packed = np.zeros((len(fields), L, L))
     for k, f in enumerate(fields):
         packed[k, :f.anm.shape[0], :f.anm.shape[1]] = f.anm
-    values = to_grid_batch(packed, base_grid, kernel, fields[0].GM, fields[0].R, device_output=True)
+        if f.GM != GM or f.R != R:
+            # the reference evaluates every epoch with its own constants (gravityfield.py:1165); one batched call has
+            # one (GM, R), so the coefficients of such an epoch are rescaled to it: GM'/R' (R'/r)^(n+1) -> GM/R (R/r)^(n+1)
+            n = np.arange(L, dtype=float)
+            scale = (f.GM / GM) * (f.R / R) ** n
+            packed[k] *= scale[np.maximum(np.arange(L)[:, None], np.arange(L)[None, :])]   # element (r, c) has degree max(r, c)
+    values = to_grid_batch(packed, base_grid, kernel, GM, R, device_output=True)
     values = values.reshape(len(fields), -1)
     rms = torch.empty(values.shape[1], dtype=torch.float64, device=values.device)
     dev = values.device.index

@@ -63,9 +63,8 @@ def install(reference=None):
     def to_grid(self, grid=None, kernel='ewh'):
         grid = ref.grid.GeographicGrid() if grid is None else grid
         values = _mirror_coefficients(self).to_grid(_mirror_grid(grid), kernel).values
-        out = grid.copy()
+        out = grid.copy()                  # keeps the grid's own epoch, as gravityfield.py:367 does
         out.values = np.ascontiguousarray(values).reshape(-1)
-        out.epoch = self.epoch
         return out
 
     def to_potential_coefficients(self, min_degree, max_degree, kernel='potential', GM=3.9860044150e+14,
@@ -75,9 +74,8 @@ def install(reference=None):
         mine = _mirror_grid(self)
         mine.values = np.ascontiguousarray(self.values, dtype=float).reshape(-1)
         res = mine.to_potential_coefficients(min_degree, max_degree, kernel, GM, R)
-        out = ref.gravityfield.PotentialCoefficients(GM, R)
+        out = ref.gravityfield.PotentialCoefficients(GM, R)     # epoch stays None, as in grid.py:752-790
         out.anm = res.anm
-        out.epoch = self.epoch
         return out
 
     def covariance_propagation(self, covariance_matrix, min_degree, max_degree, kernel='potential',

@@ -30,6 +30,25 @@ def _stream_handle(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _check_out(out, shape, device, name="out"):
+    """A caller-supplied result buffer goes to the kernels as a raw pointer: it must be exactly what they write."""
+    if not isinstance(out, torch.Tensor):
+        raise TypeError("{0} must be a torch tensor".format(name))
+    if out.dtype != torch.float64 or not out.is_cuda or out.device.index != device:
+        raise ValueError("{0} must be a float64 CUDA tensor on device {1}".format(name, device))
+    if tuple(out.shape) != tuple(shape) or not out.is_contiguous():
+        raise ValueError("{0} must be a contiguous tensor of shape {1} (got {2})".format(name, tuple(shape), tuple(out.shape)))
+    return out
+
+
+def _check_out_host(out, shape, name="out"):
+    if not isinstance(out, np.ndarray) or out.dtype != np.float64 or not out.flags.c_contiguous or not out.flags.writeable:
+        raise ValueError("{0} must be a writeable C-contiguous float64 array".format(name))
+    if tuple(out.shape) != tuple(shape):
+        raise ValueError("{0} must have shape {1} (got {2})".format(name, tuple(shape), out.shape))
+    return out
+
+
 class PinnedArray:
     """numpy view on page-locked host memory from gb_host_alloc (full PCIe rate for *_host calls)."""
 
@@ -97,6 +116,7 @@ class SHPlan:
         self._handle = handle
         self._analysis_nmin = None
         self._areas_key = None
+        self._lock = threading.RLock()     # one workspace per plan: host threads take turns (grates_b200.h, re-entrancy)
 
     # -- life cycle ---------------------------------------------------------------------
     def close(self):
@@ -144,8 +164,8 @@ class SHPlan:
         E = anm.shape[0]
         if out is None:
             out = torch.empty((E, self.nlat, self.nlon), dtype=torch.float64, device=anm.device)
-        elif tuple(out.shape) != (E, self.nlat, self.nlon) or out.dtype != torch.float64 or not out.is_contiguous():
-            raise ValueError("out must be a contiguous float64 tensor of shape [E, nlat, nlon]")
+        else:
+            _check_out(out, (E, self.nlat, self.nlon), self.device)
         if degree_weights is not None:
             if isinstance(degree_weights, torch.Tensor):        # already on the device: no copy in the call
                 w = degree_weights.to(device=anm.device, dtype=torch.float64).contiguous()
@@ -153,12 +173,14 @@ class SHPlan:
                 w = torch.as_tensor(np.ascontiguousarray(degree_weights, dtype=np.float64)).to(anm.device)
             if w.numel() != self.L:
                 raise ValueError("degree_weights must have {0} entries (got {1})".format(self.L, w.numel()))
-            _lib.check(self._lib.gb_synthesis_weighted(self._handle, ctypes.c_void_p(anm.data_ptr()),
-                                                       ctypes.c_void_p(w.data_ptr()), E,
-                                                       ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+            with self._lock:
+                _lib.check(self._lib.gb_synthesis_weighted(self._handle, ctypes.c_void_p(anm.data_ptr()),
+                                                           ctypes.c_void_p(w.data_ptr()), E,
+                                                           ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
             return out
-        _lib.check(self._lib.gb_synthesis(self._handle, ctypes.c_void_p(anm.data_ptr()), E,
-                                          ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+        with self._lock:
+            _lib.check(self._lib.gb_synthesis(self._handle, ctypes.c_void_p(anm.data_ptr()), E,
+                                              ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
 
     def synthesis_host(self, anm, out=None):
@@ -169,9 +191,10 @@ class SHPlan:
         E = anm.shape[0]
         if out is None:
             out = np.empty((E, self.nlat, self.nlon))
-        elif out.shape != (E, self.nlat, self.nlon) or out.dtype != np.float64 or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous float64 array of shape [E, nlat, nlon]")
-        _lib.check(self._lib.gb_synthesis_host(self._handle, _ptr(anm), E, _ptr(out)))
+        else:
+            _check_out_host(out, (E, self.nlat, self.nlon))
+        with self._lock:
+            _lib.check(self._lib.gb_synthesis_host(self._handle, _ptr(anm), E, _ptr(out)))
         return out
 
     def legendre_table(self, scaled=False):
@@ -206,8 +229,9 @@ class SHPlan:
                              .format(self.max_degree, 2 * self.max_degree, self.nlon))
         w_lat, u_lon = separable_weights(areas)
         lon_ops, lat_ops, offsets = analysis_operators(self, int(min_degree), w_lat, u_lon)
-        _lib.check(self._lib.gb_plan_set_analysis(self._handle, int(min_degree), _ptr(lon_ops), _ptr(lat_ops),
-                                                  _ptr(offsets)))
+        with self._lock:
+            _lib.check(self._lib.gb_plan_set_analysis(self._handle, int(min_degree), _ptr(lon_ops), _ptr(lat_ops),
+                                                      _ptr(offsets)))
         self._analysis_nmin = key
         self.analysis_min_degree = int(min_degree)
 
@@ -220,8 +244,9 @@ class SHPlan:
         if self._analysis_nmin == key:
             return
         lon_ops, lat_ops, offsets = adjoint_operators(self, int(min_degree))
-        _lib.check(self._lib.gb_plan_set_analysis(self._handle, int(min_degree), _ptr(lon_ops), _ptr(lat_ops),
-                                                  _ptr(offsets)))
+        with self._lock:
+            _lib.check(self._lib.gb_plan_set_analysis(self._handle, int(min_degree), _ptr(lon_ops), _ptr(lat_ops),
+                                                      _ptr(offsets)))
         self._analysis_nmin = key
         self.analysis_min_degree = int(min_degree)
 
@@ -237,8 +262,11 @@ class SHPlan:
         E = values.shape[0]
         if out is None:
             out = torch.empty((E, self.L, self.L), dtype=torch.float64, device=values.device)
-        _lib.check(self._lib.gb_analysis(self._handle, ctypes.c_void_p(values.data_ptr()), E,
-                                         ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+        else:
+            _check_out(out, (E, self.L, self.L), self.device)
+        with self._lock:
+            _lib.check(self._lib.gb_analysis(self._handle, ctypes.c_void_p(values.data_ptr()), E,
+                                             ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
 
     def synthesis_matrix(self, min_degree=0):
@@ -268,7 +296,10 @@ class SHPlan:
         E = values.shape[0]
         if out is None:
             out = np.empty((E, self.L, self.L))
-        _lib.check(self._lib.gb_analysis_host(self._handle, _ptr(values), E, _ptr(out)))
+        else:
+            _check_out_host(out, (E, self.L, self.L))
+        with self._lock:
+            _lib.check(self._lib.gb_analysis_host(self._handle, _ptr(values), E, _ptr(out)))
         return out
 
     # -- covariance propagation ---------------------------------------------------------
@@ -289,14 +320,19 @@ class SHPlan:
         sigma = sigma.contiguous()
         if symmetric is None:
             symmetric = _looks_symmetric(sigma)
+        if row0 < 0 or nrows < 0 or row0 + nrows > self.nlat:
+            raise ValueError("row block [{0}, {1}) is outside the grid's {2} parallels".format(row0, row0 + nrows, self.nlat))
         if out is None:
             out = torch.empty((nrows, self.nlon), dtype=torch.float64, device=sigma.device)
+        else:
+            _check_out(out, (nrows, self.nlon), self.device)
         flags = (1 if take_sqrt else 0) | (2 if symmetric else 0)      # GB_COV_SQRT | GB_COV_SYMMETRIC
         if spatial_filter is None:
-            _lib.check(self._lib.gb_covariance_propagation(self._handle, ctypes.c_void_p(sigma.data_ptr()),
-                                                           int(min_degree), int(row0), int(nrows),
-                                                           ctypes.c_void_p(out.data_ptr()), flags,
-                                                           _stream_handle(self.device)))
+            with self._lock:
+                _lib.check(self._lib.gb_covariance_propagation(self._handle, ctypes.c_void_p(sigma.data_ptr()),
+                                                               int(min_degree), int(row0), int(nrows),
+                                                               ctypes.c_void_p(out.data_ptr()), flags,
+                                                               _stream_handle(self.device)))
             return out
         blocks = offsets = wn = None
         nf = 0
@@ -308,12 +344,13 @@ class SHPlan:
             wn = torch.as_tensor(np.ascontiguousarray(spatial_filter._weights(self.max_degree), dtype=np.float64)).to(sigma.device)
         else:
             raise TypeError("spatial_filter must be an OrderWiseFilter, Gaussian or Butterworth instance")
-        _lib.check(self._lib.gb_covariance_propagation_filtered(
-            self._handle, ctypes.c_void_p(sigma.data_ptr()), int(min_degree), int(row0), int(nrows),
-            ctypes.c_void_p(out.data_ptr()), flags,
-            ctypes.c_void_p(blocks.data_ptr()) if blocks is not None else None,
-            offsets.ctypes.data_as(ctypes.c_void_p) if offsets is not None else None, int(nf),
-            ctypes.c_void_p(wn.data_ptr()) if wn is not None else None, _stream_handle(self.device)))
+        with self._lock:
+            _lib.check(self._lib.gb_covariance_propagation_filtered(
+                self._handle, ctypes.c_void_p(sigma.data_ptr()), int(min_degree), int(row0), int(nrows),
+                ctypes.c_void_p(out.data_ptr()), flags,
+                ctypes.c_void_p(blocks.data_ptr()) if blocks is not None else None,
+                offsets.ctypes.data_as(ctypes.c_void_p) if offsets is not None else None, int(nf),
+                ctypes.c_void_p(wn.data_ptr()) if wn is not None else None, _stream_handle(self.device)))
         return out
 
 
@@ -488,6 +525,8 @@ class PointsPlan:
         E = anm.shape[0]
         if out is None:
             out = torch.empty((E, self.npts), dtype=torch.float64, device=anm.device)
+        else:
+            _check_out(out, (E, self.npts), self.device)
         _lib.check(self._lib.gb_points_synthesis(self._handle, ctypes.c_void_p(anm.data_ptr()), E,
                                                  ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
@@ -511,6 +550,8 @@ class PointsPlan:
         E = values.shape[0]
         if out is None:
             out = torch.empty((E, self.L, self.L), dtype=torch.float64, device=values.device)
+        else:
+            _check_out(out, (E, self.L, self.L), self.device)
         _lib.check(self._lib.gb_points_adjoint(self._handle, ctypes.c_void_p(values.data_ptr()), E,
                                                ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
         return out
@@ -578,10 +619,15 @@ def get_plan(grid, max_degree, kernel='ewh', GM=3.9860044150e+14, R=6.3781363000
 
 
 def clear_plan_cache():
+    """Destroy the cached plans and hand the library's pooled scratch memory back to the driver (gb_trim)."""
     with _cache_lock:
+        devices = {plan.device for plan in _cache.values()}
         for plan in _cache.values():
             plan.close()
         _cache.clear()
+    lib = _lib.load()
+    for dev in devices:
+        _lib.check(lib.gb_trim(int(dev)))
 
 
 def legendre_table_for_colatitudes(max_degree, colat, device=None):

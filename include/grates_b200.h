@@ -22,6 +22,11 @@
  *  - The library never frees caller memory and returns no owning pointer except gb_plan*.
  *  - Return value: GB_OK or an error code; gb_last_error() gives the thread-local message.
  *  - There is no CPU fallback anywhere: without a CUDA device every compute call fails.
+ *  - Re-entrancy: a gb_plan owns ONE workspace (packed coefficients, spectral intermediate, analysis and covariance
+ *    scratch).  Calls on one plan may use different streams -- the library orders a call behind the previous call's
+ *    work on whatever stream that ran (an event wait, free when the stream is the same) -- but two host threads must
+ *    not be inside calls on the same plan at the same time (the Python layer holds a per-plan lock).  Different plans
+ *    are independent.
  */
 #ifndef GRATES_B200_H
 #define GRATES_B200_H
@@ -40,7 +45,9 @@ extern "C" {
 
 typedef struct gb_plan gb_plan;
 
-/* Library version (major*10000 + minor*100 + patch). */
+/* Library version (major*10000 + minor*100 + patch); bumped with every change of this header.  The Python binding
+ * refuses a library whose version differs from the one it was written for (grates_b200/_lib.py). */
+#define GB_VERSION 200
 int gb_version(void);
 
 /* Thread-local description of the last error returned on this thread. */
@@ -48,6 +55,11 @@ const char* gb_last_error(void);
 
 /* Number of visible CUDA devices (fails with GB_ERR_CUDA if the driver is unusable). */
 int gb_device_count(int* count);
+
+/* Temporaries of a call (covariance tiles, filter batches; up to a few GB) are stream-ordered allocations from a memory
+ * pool the library owns per device; the pool keeps them between calls.  gb_trim synchronises the device and returns
+ * the pool's unused memory to the driver.  The device's default pool is never touched. */
+int gb_trim(int device);
 
 /*
  * Plan = the epoch-independent tables of one (grid geometry, nmax, kernel, GM, R) combination,

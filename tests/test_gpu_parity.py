@@ -880,6 +880,76 @@ def test_api_errors(gb):
     assert gb.get_plan(gb.GeographicGrid(30.0, 30.0), 3, "ewh") is plan       # cached
 
 
+def test_out_buffers_are_checked(gb):
+    """A caller-supplied result buffer reaches the kernels as a raw pointer: wrong device, dtype, shape or strides
+    must raise before anything is launched."""
+    grid = gb.GeographicGrid(30.0, 30.0)
+    plan = gb.get_plan(grid, 3, "ewh")
+    x = torch.zeros((2, 4, 4), dtype=torch.float64, device="cuda")
+    good = torch.empty((2, 6, 12), dtype=torch.float64, device="cuda")
+    assert plan.synthesis(x, out=good) is good
+    for bad in (torch.empty((2, 6, 12), dtype=torch.float64),                      # host tensor
+                torch.empty((2, 6, 12), dtype=torch.float32, device="cuda"),
+                torch.empty((2, 6, 13), dtype=torch.float64, device="cuda"),
+                torch.empty((2, 12, 6), dtype=torch.float64, device="cuda").transpose(1, 2)):
+        with pytest.raises(ValueError):
+            plan.synthesis(x, out=bad)
+    plan.set_analysis(0, grid.area.reshape(plan.nlat, plan.nlon))
+    with pytest.raises(ValueError):
+        plan.analysis(good, out=torch.empty((2, 4, 5), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        plan.analysis_host(np.zeros((2, 6, 12)), out=np.zeros((2, 4, 4), dtype=np.float32))
+    sigma = torch.eye(16, dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        plan.covariance_propagation(sigma, 0, out=torch.empty((6, 11), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        plan.covariance_propagation(sigma, 0, row0=4, nrows=5)
+    with pytest.raises(ValueError):
+        gb.Gaussian(300.0).filter_batch(x, out=torch.empty((2, 4, 4), dtype=torch.float64))
+    pts = gb.get_points_plan(gb.IrregularGrid(np.linspace(-1, 1, 5), np.linspace(-0.5, 0.5, 5)), 3, "ewh")
+    with pytest.raises(ValueError):
+        pts.synthesis(x, out=torch.empty((2, 6), dtype=torch.float64, device="cuda"))
+
+
+def test_calls_on_different_streams_share_one_plan(gb, orc):
+    """One plan = one workspace: a call on another stream is ordered behind the previous call's kernels
+    (gb_plan_acquire), so back-to-back asynchronous calls from two streams give the serial results."""
+    N, E = 40, 48
+    grid = gb.GeographicGrid(2.0, 2.0)
+    plan = gb.get_plan(grid, N, "ewh")
+    xa = torch.as_tensor(np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])).cuda()
+    xb = torch.as_tensor(np.stack([orc.synthetic_coefficients(N, 100 + e) for e in range(E)])).cuda()
+    want_a, want_b = plan.synthesis(xa).clone(), plan.synthesis(xb).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    got = []
+    for rep in range(6):
+        with torch.cuda.stream(s1):
+            a = plan.synthesis(xa)
+        with torch.cuda.stream(s2):
+            b = plan.synthesis(xb)
+        got.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in got:
+        assert torch.equal(a, want_a) and torch.equal(b, want_b)
+
+
+def test_grid_statistics_ignore_values_outside_the_mask(gb):
+    """Grid.mean / rms / std select the masked points (grid.py:174-260): a NaN outside the mask must not reach the result."""
+    grid = gb.GeographicGrid(10.0, 10.0)
+    rng = np.random.default_rng(3)
+    vals = rng.standard_normal((3, grid.point_count))
+    mask = rng.uniform(size=grid.point_count) < 0.4
+    dirty = vals.copy()
+    dirty[:, ~mask] = np.nan
+    clean, got = gb.grid_statistics(vals, grid, mask), gb.grid_statistics(dirty, grid, mask)
+    for key in ("mean", "rms", "std"):
+        assert np.all(np.isfinite(got[key])) and np.array_equal(got[key], clean[key])
+    g = grid.copy()
+    g.values = vals[1]
+    assert abs(got["mean"][1] - g.mean(mask)) < 1e-14 and abs(got["rms"][1] - g.rms(mask)) < 1e-14
+
+
 # ------------------------------------------------------------------------------ BASELINE full sizes
 def test_config3_full_size_round_trip(gb, orc):
     """BASELINE config 3 geometry (degree 180 -> 0.25 deg, 720 x 1440): synthesis against the oracle
@@ -937,6 +1007,59 @@ def test_config5_filter_then_synthesis_full_degree(gb, orc):
         assert maxnorm_err(vals[e].cpu().numpy(), ref) < TOL
     mix = (2.0 * x[3] - 0.5 * x[9])[None].contiguous()
     lin = 2.0 * vals[3] - 0.5 * vals[9]
+    got = gb.to_grid_batch(flt.filter_batch(mix), grid, "ewh")[0]
+    assert maxnorm_err(got.cpu().numpy(), lin.cpu().numpy()) < 1e-13
+
+
+def test_config3_full_epoch_count(gb, orc):
+    """BASELINE config 3 at its real size (degree 180 -> 0.25 deg, ALL 120 epochs: the tilings of the full batch, not a
+    reduced one): three epochs against the oracle, every other epoch through batch independence (a sub-batch gives
+    bit-identical rows) and linearity; analysis of the 120-epoch batch through the round trip, against the separable
+    oracle on one epoch and bit-identical to a sub-batch."""
+    N, E = 180, 120
+    grid, og = gb.GeographicGrid(0.25, 0.25), orc.geographic_grid(0.25, 0.25)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    x = torch.as_tensor(anm).cuda()
+    vals = gb.to_grid_batch(x, grid, "ewh")
+    assert tuple(vals.shape) == (E, 720, 1440)
+    refs = {e: orc.synthesis(anm[e], og, "ewh") for e in (0, 61, 119)}
+    for e, ref in refs.items():
+        assert maxnorm_err(vals[e].cpu().numpy(), ref) < 1e-10
+    for lo, hi in ((0, 2), (57, 64), (113, 120)):
+        assert torch.equal(gb.to_grid_batch(x[lo:hi].contiguous(), grid, "ewh"), vals[lo:hi])
+    mix = (0.3 * x[5] - 1.7 * x[100])[None].contiguous()
+    lin = 0.3 * vals[5] - 1.7 * vals[100]
+    assert maxnorm_err(gb.to_grid_batch(mix, grid, "ewh")[0].cpu().numpy(), lin.cpu().numpy()) < 1e-13
+    back = gb.analysis_batch(vals, grid, 0, N, "ewh", device_output=True)
+    assert float((back - x).abs().max() / x.abs().max()) < 1e-10
+    assert maxnorm_err(back[61].cpu().numpy(), orc.analysis_separable(refs[61], og, 0, N, "ewh")) < 1e-10
+    sub = gb.analysis_batch(vals[57:64].contiguous(), grid, 0, N, "ewh", device_output=True)
+    assert maxnorm_err(sub.cpu().numpy(), back[57:64].cpu().numpy()) < 1e-14
+
+
+def test_config5_full_epoch_count(gb, orc):
+    """BASELINE config 5 at its real size (degree 120 -> 0.25 deg, ALL 500 epochs: 1000 stage-1 columns = four whole
+    240-column tiles and a ragged fifth): three epochs of filter + synthesis against the oracle, sub-batches
+    bit-identical, linearity."""
+    N, E = 120, 500
+    grid, og = gb.GeographicGrid(0.25, 0.25), orc.geographic_grid(0.25, 0.25)
+    blocks = orc.synthetic_filter_blocks(N)
+    flt = gb.OrderWiseFilter(blocks)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    x = torch.as_tensor(anm).cuda()
+    filt = flt.filter_batch(x)
+    vals = gb.to_grid_batch(filt, grid, "ewh")
+    assert tuple(vals.shape) == (E, 720, 1440)
+    for e in (0, 250, 499):
+        want = orc.orderwise_filter(blocks, anm[e])
+        assert maxnorm_err(filt[e].cpu().numpy(), want) < 1e-13
+        assert maxnorm_err(vals[e].cpu().numpy(), orc.synthesis(want, og, "ewh")) < TOL
+    for lo, hi in ((0, 3), (238, 243), (478, 500)):
+        sub_f = flt.filter_batch(x[lo:hi].contiguous())
+        assert torch.equal(sub_f, filt[lo:hi])
+        assert torch.equal(gb.to_grid_batch(sub_f, grid, "ewh"), vals[lo:hi])
+    mix = (2.0 * x[3] - 0.5 * x[409])[None].contiguous()
+    lin = 2.0 * vals[3] - 0.5 * vals[409]
     got = gb.to_grid_batch(flt.filter_batch(mix), grid, "ewh")[0]
     assert maxnorm_err(got.cpu().numpy(), lin.cpu().numpy()) < 1e-13
 
