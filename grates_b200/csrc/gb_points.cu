@@ -283,15 +283,20 @@ gb_points_quadform(const double* __restrict__ FT, int rows, const double* __rest
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
                 const long long p = mt * C_TM + r;
-                if (q == 0 && p < npts) atomicAdd(var + p, part);
+                // one writer per (point, column tile, warp column): gb_points_finish adds the slots in order
+                if (q == 0 && p < npts) var[(size_t)p * (n_ntiles * C_WN) + (n0 / C_TN) * C_WN + wn] = part;
             }
         }
     }
 }
 
-__global__ void gb_points_sqrt(double* v, int n) {
+// out[p] = (sqrt of) the sum of the point's partial sums, in slot order: bit-identical from run to run
+__global__ void gb_points_finish(const double* __restrict__ part, double* __restrict__ out, int nslots, int n, int take_sqrt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = sqrt(v[i]);
+    if (i >= n) return;
+    double v = 0.0;
+    for (int s = 0; s < nslots; ++s) v += part[(size_t)i * nslots + s];
+    out[i] = take_sqrt ? sqrt(v) : v;
 }
 
 template <typename T>
@@ -551,13 +556,15 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
     int tiles_per_block = 4 * p->sm_count / (n_ntiles > 0 ? n_ntiles : 1);
     if (tiles_per_block < 16) tiles_per_block = 16;
     if (tiles_per_block > n_mtiles_all) tiles_per_block = n_mtiles_all;
-    double *d_ft = nullptr, *d_sig = nullptr;
+    double *d_ft = nullptr, *d_sig = nullptr, *d_part = nullptr;
     const size_t ft_elems = (size_t)tiles_per_block * Kp * C_LDA;
+    const int nslots = n_ntiles * C_WN;
+    gb_retain_pool_memory(p->device);
     gb_scratch scratch(st);
     GB_CUDA(scratch.alloc(&d_ft, ft_elems));
     GB_CUDA(scratch.alloc(&d_sig, (size_t)Kp * lds));
+    GB_CUDA(scratch.alloc(&d_part, (size_t)tiles_per_block * C_TM * nslots));
     GB_CUDA(cudaMemsetAsync(d_sig, 0, (size_t)Kp * lds * sizeof(double), st));
-    GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->npts * sizeof(double), st));
     {   // covariance rows re-pitched to an even leading dimension (16-byte aligned rows for the bulk copies)
         dim3 grid((unsigned)((Kc + 255) / 256), (unsigned)Kc);
         gb_points_sigma_operand<<<grid, 256, 0, st>>>(d_sigma, d_sig, Kc, lds, upper);
@@ -575,12 +582,10 @@ extern "C" int gb_points_covariance(gb_points* p, const double* d_sigma, int nmi
         GB_LAUNCH_CHECK();
         const long long n_tiles = (long long)n_mtiles * n_ntiles;
         const int gridq = (int)(n_tiles < p->sm_count ? n_tiles : p->sm_count);
-        gb_points_quadform<<<gridq, C_THREADS, C_SMEM, st>>>(d_ft, Kp, d_sig, lds, Kp, Kc, d_out + p0, count, n_mtiles,
+        gb_points_quadform<<<gridq, C_THREADS, C_SMEM, st>>>(d_ft, Kp, d_sig, lds, Kp, Kc, d_part, count, n_mtiles,
                                                              n_ntiles, upper);
         GB_LAUNCH_CHECK();
-    }
-    if (take_sqrt) {
-        gb_points_sqrt<<<(p->npts + 255) / 256, 256, 0, st>>>(d_out, p->npts);
+        gb_points_finish<<<(count + 255) / 256, 256, 0, st>>>(d_part, d_out + p0, nslots, count, take_sqrt ? 1 : 0);
         GB_LAUNCH_CHECK();
     }
     return GB_OK;

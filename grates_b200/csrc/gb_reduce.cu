@@ -135,9 +135,10 @@ gb_ravel_kernel(const double* __restrict__ anm, double* __restrict__ vec, int L,
 
 constexpr int QF_B = 8;    // functionals per pass
 
+// partial[(b0 + b) * gridDim.x + blockIdx.x]: one writer per (functional, CTA); gb_quadratic_forms_finish adds them in order
 __global__ void __launch_bounds__(256)
 gb_quadratic_forms_kernel(const double* __restrict__ sigma, const double* __restrict__ vec, long long K, int b0, int nb,
-                          double* __restrict__ out) {
+                          double* __restrict__ partial) {
     __shared__ double s_part[8][QF_B];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double tot[QF_B];
@@ -167,8 +168,16 @@ gb_quadratic_forms_kernel(const double* __restrict__ sigma, const double* __rest
     if (threadIdx.x < nb) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
-        atomicAdd(out + b0 + threadIdx.x, t);
+        partial[(size_t)(b0 + threadIdx.x) * gridDim.x + blockIdx.x] = t;
     }
+}
+
+__global__ void gb_quadratic_forms_finish(const double* __restrict__ partial, int nparts, int n_vec, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_vec) return;
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += partial[(size_t)b * nparts + i];
+    out[b] = t;
 }
 
 }  // namespace
@@ -195,15 +204,23 @@ extern "C" int gb_quadratic_forms(const double* d_sigma, int64_t k, const double
     GB_REQUIRE(d_sigma && d_vec && d_out, "gb_quadratic_forms: NULL pointer");
     GB_CUDA(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_vec * sizeof(double), st));
-    if (k == 0) return GB_OK;
+    if (k == 0) {
+        GB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_vec * sizeof(double), st));
+        return GB_OK;
+    }
     int sm_count = 0;       // cudaGetDeviceProperties would cost milliseconds per call
     GB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     const int grid = (int)((k + 7) / 8 < (long long)sm_count * 8 ? (k + 7) / 8 : sm_count * 8);
+    gb_retain_pool_memory(device);
+    gb_scratch scratch(st);
+    double* d_partial = nullptr;
+    GB_CUDA(scratch.alloc(&d_partial, (size_t)n_vec * grid));
     for (int b0 = 0; b0 < n_vec; b0 += QF_B) {
         const int nb = n_vec - b0 < QF_B ? n_vec - b0 : QF_B;
-        gb_quadratic_forms_kernel<<<grid, 256, 0, st>>>(d_sigma, d_vec, k, b0, nb, d_out);
+        gb_quadratic_forms_kernel<<<grid, 256, 0, st>>>(d_sigma, d_vec, k, b0, nb, d_partial);
         GB_LAUNCH_CHECK();
     }
+    gb_quadratic_forms_finish<<<(n_vec + 127) / 128, 128, 0, st>>>(d_partial, grid, n_vec, d_out);
+    GB_LAUNCH_CHECK();
     return GB_OK;
 }

@@ -992,6 +992,27 @@ def test_config4_full_size_properties(gb, orc):
     assert maxnorm_err(blocks.cpu().numpy(), std.cpu().numpy()) < 1e-13
 
 
+def test_covariance_propagation_is_bit_reproducible(gb, orc):
+    """Every partial sum of the propagation has one writer and the partials are added in a fixed order (no floating-point
+    atomics): two runs give bit-identical standard deviations, for the regular-grid path (symmetric and general matrix,
+    whole grid and a row block) and for the point-set kernel."""
+    N = 60
+    grid = gb.GeographicGrid(1.0, 1.0)
+    plan = gb.get_plan(grid, N, "ewh")
+    sig_h = orc.synthetic_covariance(N)
+    sigma = torch.as_tensor(sig_h).cuda()
+    for kwargs in ({}, {"symmetric": False}, {"row0": 37, "nrows": 45}):
+        first = plan.covariance_propagation(sigma, 0, **kwargs).clone()
+        for _ in range(3):
+            assert torch.equal(plan.covariance_propagation(sigma, 0, **kwargs), first)
+    rng = np.random.default_rng(5)
+    pts = gb.IrregularGrid(rng.uniform(-np.pi, np.pi, 700), np.arcsin(rng.uniform(-1, 1, 700)))
+    pp = gb.get_points_plan(pts, N, "ewh")
+    first = pp.covariance_propagation(sigma, 0).clone()
+    for _ in range(3):
+        assert torch.equal(pp.covariance_propagation(sigma, 0), first)
+
+
 def test_config5_filter_then_synthesis_full_degree(gb, orc):
     """BASELINE config 5 geometry (degree 120 -> 0.25 deg) on a reduced epoch count: two epochs against
     the oracle, linearity of filter + synthesis for the batch."""
