@@ -12,7 +12,7 @@ _c_int64_p = ctypes.POINTER(ctypes.c_int64)
 _vp = ctypes.c_void_p
 
 GB_OK, GB_ERR_ARGUMENT, GB_ERR_CUDA, GB_ERR_UNSUPPORTED, GB_ERR_MEMORY = 0, 1, 2, 3, 4
-GB_VERSION = 200        # must equal GB_VERSION of include/grates_b200.h: the argtypes below describe THAT header
+GB_VERSION = 201        # must equal GB_VERSION of include/grates_b200.h: the argtypes below describe THAT header
 
 # name -> (restype, argtypes); must list every symbol of include/grates_b200.h
 SIGNATURES = {
@@ -62,6 +62,12 @@ SIGNATURES = {
     "gb_plan_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
     "gb_plan_stage_times": (ctypes.c_int, [_vp, _c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "gb_launch_count": (ctypes.c_int64, [ctypes.c_int]),
+    "gb_dgemm": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                _vp, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_double, _vp, ctypes.c_int64, ctypes.c_int,
+                                ctypes.c_int, _vp]),
+    "gb_dpotrf_upper": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int, _vp]),
+    "gb_dtrsm_upper": (ctypes.c_int, [ctypes.c_int, _vp, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_int, _vp]),
 }
 
 _lock = threading.Lock()

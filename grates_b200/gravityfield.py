@@ -135,6 +135,72 @@ class PotentialCoefficients:
         return output_grid
 
 
+class SurfaceMasCons:
+    """Mascon values on a point distribution (reference gravityfield.py:484-570): a container whose analysis runs through
+    the point-set kernels (``IrregularGrid.to_potential_coefficients`` -> gb_points_synthesis_matrix) or, for a regular
+    grid, the separable analysis kernels."""
+
+    def __init__(self, point_distribution, kernel):
+        self.point_distribution = point_distribution
+        if self.point_distribution.values is None:
+            self.point_distribution.values = np.zeros(self.point_distribution.point_count)
+        self.kernel = kernel
+        self.epoch = None
+
+    def copy(self):
+        other = SurfaceMasCons(self.point_distribution.copy(), self.kernel)
+        other.epoch = self.epoch
+        return other
+
+    def is_compatible(self, other):
+        return self.point_distribution.is_compatible(other.point_distribution)
+
+    @property
+    def values(self):
+        return self.point_distribution.values
+
+    @values.setter
+    def values(self, val):
+        self.point_distribution.values = val
+
+    def _checked(self, other, symbol):
+        if not isinstance(other, SurfaceMasCons):
+            raise TypeError("unsupported operand type(s) for " + symbol + ": '" + str(type(self)) + "' and '" + str(type(other)) + "'")
+        if not self.is_compatible(other):
+            raise ValueError("point distributions of '" + str(type(self)) + "' instances are not compatible")
+
+    def __add__(self, other):
+        self._checked(other, '+')
+        result = self.copy()
+        result.values = result.values + other.values
+        return result
+
+    def __sub__(self, other):
+        self._checked(other, '-')
+        result = self.copy()
+        result.values = result.values - other.values
+        return result
+
+    def __mul__(self, other):
+        if not isinstance(other, (int, float)):
+            raise TypeError("unsupported operand type(s) for *: '" + str(type(self)) + "' and '" + str(type(other)) + "'")
+        result = self.copy()
+        result.values = result.values * other
+        return result
+
+    def __truediv__(self, other):
+        if not isinstance(other, (int, float)):
+            raise TypeError("unsupported operand type(s) for /: '" + str(type(self)) + "' and '" + str(type(other)) + "'")
+        return self * (1.0 / other)
+
+    def to_potential_coefficients(self, min_degree, max_degree, GM=GM_DEFAULT, R=R_DEFAULT):
+        """Spherical-harmonic analysis of the mascon values with the instance's kernel.  (The reference passes the builtin
+        ``round`` where R belongs, gravityfield.py:570, and fails; R is passed here.)"""
+        out = self.point_distribution.to_potential_coefficients(min_degree, max_degree, self.kernel, GM, R)
+        out.epoch = self.epoch
+        return out
+
+
 class AnisotropicBasisFunctions:
     """Gravity field represented by anisotropic kernel basis functions (reference gravityfield.py:573-642).
 

@@ -47,7 +47,7 @@ typedef struct gb_plan gb_plan;
 
 /* Library version (major*10000 + minor*100 + patch); bumped with every change of this header.  The Python binding
  * refuses a library whose version differs from the one it was written for (grates_b200/_lib.py). */
-#define GB_VERSION 200
+#define GB_VERSION 201
 int gb_version(void);
 
 /* Thread-local description of the last error returned on this thread. */
@@ -295,6 +295,25 @@ int gb_plan_stage_times(gb_plan* plan, double* ms, int max_calls, int* n_calls);
 
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 int64_t gb_launch_count(int reset);
+
+/*
+ * Covariance producers.  BlockMatrix.cholesky / sparse_inverse / inverse of the reference
+ * (lstsq.py:698-717, 823-846, 848-882; used by NormalEquations.compute_covariance, lstsq.py:1026-1042) are loops over
+ * matrix blocks around four library calls: scipy.linalg.cholesky(lower=False), scipy.linalg.solve_triangular,
+ * scipy.linalg.inv and numpy's `@`.  The three entry points below replace them on device-resident blocks
+ * (row-major FP64, arbitrary leading dimension); the Python mirror (grates_b200/lstsq.py) keeps the block loops.
+ *
+ *   gb_dgemm         C[m][n] = alpha * op(A) * op(B) + beta * C; trans_a: A is stored [k][m], trans_b: B is stored
+ *                    [n][k]; upper_only: tiles strictly below the diagonal are skipped (symmetric updates)
+ *   gb_dpotrf_upper  A = W' W in place, W upper triangular, strict lower triangle zeroed; *d_info (device int) = 0 or
+ *                    the 1-based index of the first non-positive pivot (scipy raises LinAlgError there)
+ *   gb_dtrsm_upper   solves W X = B (trans = 0) or W' X = B (trans = 1) in place of B[n][m], W upper triangular
+ */
+int gb_dgemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double* d_a, int64_t lda,
+             const double* d_b, int64_t ldb, double beta, double* d_c, int64_t ldc, int upper_only, int device, void* stream);
+int gb_dpotrf_upper(double* d_a, int64_t n, int64_t lda, int* d_info, int device, void* stream);
+int gb_dtrsm_upper(int trans, const double* d_w, int64_t n, int64_t ldw, double* d_b, int64_t m, int64_t ldb, int device,
+                   void* stream);
 
 #ifdef __cplusplus
 }

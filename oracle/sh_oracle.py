@@ -807,3 +807,35 @@ def synthetic_filter_blocks(nf, seed=5):
         for _ in range(1 if m == 0 else 2):
             blocks.append(0.5 * np.eye(k) + 0.01 * rng.standard_normal((k, k)))
     return blocks
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# covariance producers: dense restatements of what the reference's block algorithms compute
+# ---------------------------------------------------------------------------------------------------------------------
+def normal_matrix_cholesky(N):
+    """Upper Cholesky factor W, N = W' W: the dense equivalent of BlockMatrix.cholesky (lstsq.py:698-717; block by block
+    la.cholesky(lower=False) + solve_triangular(trans='T') + Schur updates give exactly the dense factor)."""
+    return np.linalg.cholesky(np.asarray(N, dtype=float)).T
+
+
+def normal_matrix_inverse(N):
+    """N^-1 = W^-1 W^-T: what BlockMatrix.inverse leaves in the upper triangle (lstsq.py:848-882) and
+    NormalEquations.compute_covariance(sparse=False) returns (lstsq.py:1026-1042)."""
+    W = normal_matrix_cholesky(N)
+    Wi = np.linalg.solve(W, np.eye(W.shape[0]))
+    return Wi @ Wi.T
+
+
+def normal_matrix_sparse_inverse(N, index):
+    """Sparse inverse (lstsq.py:823-846): the entries of N^-1 on the block sparsity pattern of the Cholesky factor
+    (Takahashi recursion); zero elsewhere, upper block triangle only."""
+    W = normal_matrix_cholesky(N)
+    Z = normal_matrix_inverse(N)
+    out = np.zeros_like(Z)
+    nb = len(index) - 1
+    for i in range(nb):
+        for j in range(i, nb):
+            blk = W[index[i]:index[i + 1], index[j]:index[j + 1]]
+            if np.count_nonzero(blk):
+                out[index[i]:index[i + 1], index[j]:index[j + 1]] = Z[index[i]:index[i + 1], index[j]:index[j + 1]]
+    return out

@@ -386,6 +386,68 @@ def space_kernels():
     save("space_kernels", **out)
 
 
+def normal_equations():
+    """Covariance producers: BlockMatrix.cholesky / sparse_inverse / inverse / solve_triangular /
+    multiply_symmetric and NormalEquations.solve / compute_covariance of the reference on a block-sparse SPD matrix
+    (block arrow + band structure with ragged block sizes), and its SINEX reader on a file written by
+    grates_b200.io.savesinexnormals (committed next to the arrays)."""
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    import copy
+    rng = np.random.default_rng(21)
+    index = np.array([0, 37, 101, 165, 190, 270, 333])          # ragged blocks, 333 parameters
+    nb, n = len(index) - 1, int(index[-1])
+    keep = np.zeros((nb, nb), dtype=bool)
+    for i in range(nb):
+        keep[i, i] = True
+        if i + 1 < nb:
+            keep[i, i + 1] = True          # band
+        keep[i, nb - 1] = True             # arrow
+    keep[0, 3] = True                      # an extra off-band block: fill-in in the factor
+    A = rng.standard_normal((2 * n, n))
+    N = A.T @ A / (2 * n) + np.eye(n)
+    for i in range(nb):
+        for j in range(nb):
+            if not (keep[min(i, j), max(i, j)]):
+                N[index[i]:index[i + 1], index[j]:index[j + 1]] = 0
+    N = N + np.diag(np.abs(N).sum(axis=1))                      # diagonally dominant: SPD with the zero blocks
+    rhs = rng.standard_normal((n, 2))
+    bm = grates.lstsq.BlockMatrix.from_array(N, index, index)
+    out = dict(index=index, N=N, rhs=rhs, keep=keep)
+    out["multiply_symmetric"] = copy.deepcopy(bm).multiply_symmetric(rhs)
+    chol = copy.deepcopy(bm)
+    chol.cholesky()
+    out["cholesky"] = np.triu(chol.to_array())
+    out["solve_t"] = chol.solve_triangular(rhs, transpose=True)
+    out["solve_n"] = chol.solve_triangular(rhs, transpose=False)
+    out["multiply_triangular"] = chol.multiply_triangular(rhs)
+    sp = copy.deepcopy(chol)
+    sp.sparse_inverse()
+    out["sparse_inverse"] = sp.to_array()
+    full = copy.deepcopy(chol)
+    full.inverse()
+    out["inverse"] = full.to_array()
+    ne = grates.lstsq.NormalEquations(copy.deepcopy(bm), rhs[:, 0:1].copy(), 7.5, 4000)
+    ne.compute_covariance(sparse=False)
+    out["covariance_dense"] = ne.matrix.to_array()
+    # SINEX: file written by this repository's writer, read back by the reference's reader
+    from grates_b200 import io as gio
+    pcount = 45
+    cf = []
+    for nn in range(2, 9):
+        for m in range(0, nn + 1):
+            cf.append((0, nn, m))
+            if m > 0:
+                cf.append((1, nn, m))
+    cf = cf[:pcount]
+    B = rng.standard_normal((90, pcount))
+    Ns, ns = B.T @ B, rng.standard_normal((pcount, 1)) * 1e3
+    path = os.path.join(HERE, "normals_small.snx")
+    gio.savesinexnormals(path, Ns, ns, np.array([1234.5678]), 90, cf)
+    rN, rn, rl, rc = grates.io.loadsinexnormals(path)
+    out.update(sinex_N=rN, sinex_n=rn, sinex_lPl=rl, sinex_obs_count=np.array(rc))
+    save("normal_equations", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -403,3 +465,4 @@ if __name__ == "__main__":
     radial_basis()
     irregular_operators()
     space_kernels()
+    normal_equations()

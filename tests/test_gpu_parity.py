@@ -950,6 +950,125 @@ def test_grid_statistics_ignore_values_outside_the_mask(gb):
     assert abs(got["mean"][1] - g.mean(mask)) < 1e-14 and abs(got["rms"][1] - g.rms(mask)) < 1e-14
 
 
+# ------------------------------------------------------------------------------ covariance producers
+def _upper_blocks(index):
+    n = int(index[-1])
+    mask = np.zeros((n, n), dtype=bool)
+    for i in range(len(index) - 1):
+        mask[index[i]:index[i + 1], index[i]:] = True
+    return mask
+
+
+def test_block_matrix_golden(gb, golden):
+    """Device BlockMatrix against the reference's own block algorithms on a block-sparse SPD matrix with ragged blocks
+    (golden vectors of BlockMatrix.cholesky / solve_triangular / multiply_* / sparse_inverse / inverse and
+    NormalEquations.compute_covariance, lstsq.py:698-882, 1026-1042)."""
+    import copy
+    g = golden("normal_equations")
+    N, index, rhs = g["N"], g["index"], g["rhs"]
+    mask = _upper_blocks(index)
+    bm = gb.BlockMatrix.from_array(N, index, index)
+    for i in range(6):
+        for j in range(i, 6):
+            assert bm.is_nonzero(i, j) == bool(g["keep"][i, j])
+    assert np.array_equal(bm.to_array(), N)
+    assert maxnorm_err(bm.multiply_symmetric(rhs), g["multiply_symmetric"]) < 1e-14
+    chol = copy.deepcopy(bm)
+    chol.cholesky()
+    W = chol.to_array()
+    assert maxnorm_err(np.triu(W), g["cholesky"]) < 1e-14 and np.array_equal(np.tril(W[:37, :37], -1), np.zeros((37, 37)))
+    assert chol.is_nonzero(1, 3)                                       # fill-in below the extra block, as in the reference
+    assert maxnorm_err(chol.solve_triangular(rhs, transpose=True), g["solve_t"]) < 1e-13
+    assert maxnorm_err(chol.solve_triangular(rhs, transpose=False), g["solve_n"]) < 1e-13
+    assert maxnorm_err(chol.multiply_triangular(rhs), g["multiply_triangular"]) < 1e-14
+    sp = copy.deepcopy(chol)
+    sp.sparse_inverse()
+    assert maxnorm_err(sp.to_array()[mask], g["sparse_inverse"][mask]) < 1e-13
+    full = copy.deepcopy(chol)
+    full.inverse()
+    assert maxnorm_err(full.to_array()[mask], g["inverse"][mask]) < 1e-13
+    ne = gb.NormalEquations(copy.deepcopy(bm), rhs[:, 0:1].copy(), 7.5, 4000)
+    x = ne.solve()
+    assert maxnorm_err(x, np.linalg.solve(N, rhs[:, 0:1])) < 1e-13
+    ne = gb.NormalEquations(copy.deepcopy(bm), rhs[:, 0:1].copy(), 7.5, 4000)
+    ne.compute_covariance(sparse=False)
+    assert ne.status == 'covariance_matrix'
+    assert maxnorm_err(ne.matrix.to_array()[mask], g["covariance_dense"][mask]) < 1e-13
+    bad = gb.BlockMatrix.from_array(-np.eye(10), np.array([0, 4, 10]), np.array([0, 4, 10]))
+    with pytest.raises(np.linalg.LinAlgError):
+        bad.cholesky()
+    with pytest.raises(ValueError):
+        gb.BlockMatrix.from_array(N, index[:-1], index)
+    with pytest.raises(ValueError):
+        bm[0, 1] = np.zeros((3, 3))
+
+
+def test_dense_kernels_ragged_shapes(gb):
+    """gb_dgemm / gb_dpotrf_upper / gb_dtrsm_upper on shapes that are not multiples of the 64-tile, all transpose
+    combinations, strided views (leading dimension > width)."""
+    from grates_b200.lstsq import _Ops
+    ops = _Ops(None)
+    rng = np.random.default_rng(8)
+    for (m, n, k) in ((1, 1, 1), (65, 130, 17), (200, 63, 129), (7, 300, 64)):
+        for ta in (False, True):
+            for tb in (False, True):
+                a = rng.standard_normal((k, m) if ta else (m, k))
+                b = rng.standard_normal((n, k) if tb else (k, n))
+                c = rng.standard_normal((m, n + 5))
+                ad, bd, cd = (torch.as_tensor(z).cuda() for z in (a, b, c))
+                ops.gemm(ad, bd, cd[:, 2:2 + n], alpha=-0.5, beta=2.0, trans_a=ta, trans_b=tb)
+                want = c.copy()
+                want[:, 2:2 + n] = -0.5 * (a.T if ta else a) @ (b.T if tb else b) + 2.0 * c[:, 2:2 + n]
+                assert maxnorm_err(cd.cpu().numpy(), want) < 1e-14
+    for n in (1, 64, 65, 200, 333):
+        a = rng.standard_normal((n + 20, n))
+        spd = a.T @ a + n * np.eye(n)
+        w = ops.cholesky_upper(torch.as_tensor(spd).cuda()).cpu().numpy()
+        assert maxnorm_err(w, np.linalg.cholesky(spd).T) < 1e-13
+        b = rng.standard_normal((n, 37))
+        wd = torch.as_tensor(w).cuda()
+        for trans in (False, True):
+            x = ops.solve_triangular(wd, torch.as_tensor(b).cuda(), trans=trans).cpu().numpy()
+            assert maxnorm_err((w.T if trans else w) @ x, b) < 1e-12
+        assert maxnorm_err(ops.inv_gram(wd).cpu().numpy(), np.linalg.inv(spd)) < 1e-12
+
+
+def test_normals_to_variances_on_the_device(gb, orc):
+    """End of the f4 row: normal equations (block matrix on the device) -> compute_covariance -> dense tensor ->
+    covariance_propagation, nothing leaves the GPU in between; against the oracle's numpy path."""
+    N = 24
+    K = (N + 1) ** 2
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((3 * K, K)) * (1.0 / (1.0 + np.arange(K)) ** 0.25)[None, :]
+    normals = A.T @ A + 1e-3 * np.eye(K)
+    ri, ci = gb.BlockMatrix.compute_block_index(normals.shape, 200)
+    ne = gb.NormalEquations(gb.BlockMatrix.from_array(normals, ri, ci), rng.standard_normal((K, 1)), 1.0, 3 * K)
+    ne.compute_covariance(sparse=False)
+    sigma = ne.matrix.symmetrize().to_tensor()
+    assert sigma.is_cuda
+    want = orc.normal_matrix_inverse(normals)
+    assert maxnorm_err(sigma.cpu().numpy(), want) < 1e-10
+    grid, og = gb.GeographicGrid(5.0, 5.0), orc.geographic_grid(5.0, 5.0)
+    std = gb.get_plan(grid, N, "ewh").covariance_propagation(sigma, 0).cpu().numpy()
+    assert maxnorm_err(std, orc.covariance_propagation(want, og, 0, N, "ewh").reshape(std.shape)) < 1e-9
+
+
+def test_surface_mascons(gb, orc):
+    """SurfaceMasCons (gravityfield.py:484-570): container arithmetic and analysis through the grid kernels."""
+    grid = gb.GeographicGrid(6.0, 6.0)
+    anm = orc.synthetic_coefficients(12, 4)
+    field = gb.PotentialCoefficients()
+    field.anm = anm
+    grid.values = field.to_grid(grid, "ewh").values
+    mc = gb.SurfaceMasCons(grid, "ewh")
+    back = mc.to_potential_coefficients(0, 12)
+    assert maxnorm_err(back.anm, anm) < 1e-12
+    twice = (mc + mc) / 2 - mc * 0.5
+    assert maxnorm_err(twice.values, 0.5 * mc.values) < 1e-15
+    with pytest.raises(TypeError):
+        mc + 1.0
+
+
 # ------------------------------------------------------------------------------ BASELINE full sizes
 def test_config3_full_size_round_trip(gb, orc):
     """BASELINE config 3 geometry (degree 180 -> 0.25 deg, 720 x 1440): synthesis against the oracle
