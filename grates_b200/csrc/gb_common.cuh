@@ -363,6 +363,10 @@ __device__ __forceinline__ void st_cs_v2(double* p, double a, double b) {
 __device__ __forceinline__ void st_v2(double* p, double a, double b) {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
+// 32-byte store; p must be 32-byte aligned
+__device__ __forceinline__ void st_v4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 // 32-byte streaming store (SASS STG.E.EF.256, sm_100); p must be 32-byte aligned
 __device__ __forceinline__ void st_cs_v4(double* p, double a, double b, double c, double d) {
     asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");

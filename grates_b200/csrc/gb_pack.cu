@@ -73,11 +73,27 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
             }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
-            const int c = idx / PKE, e = idx % PKE;
-            if (e < ne) {
-                if (TILED) dst[x_tiled_position(r, cb + c, e0 + e, E, xt, s_roff)] = s_t[c * PK_LD + e];
-                else dst[x_position(r, cb + c, L, E) + e0 + e] = s_t[c * PK_LD + e];
+        if (TILED) {
+            // PKE lanes share one column c of anm: its order / degree / plane and the row of the tiled layout are
+            // computed once per column, the epoch only moves the position inside (at most two) column tiles
+            constexpr int CPW = 32 / PKE;                      // columns per warp pass
+            const int sub = lane / PKE, e = lane % PKE;
+            for (int c = warp * CPW + sub; c < nc; c += nwarps * CPW) {
+                const int cc_anm = cb + c;
+                const int m = (cc_anm <= r) ? cc_anm : r + 1;
+                const int nn = (cc_anm <= r) ? r - cc_anm : cc_anm - r - 1;
+                const int r0 = s_roff[m], kn_pad = s_roff[m + 1] - r0;
+                const int row = (nn & ~7) + ((nn & 1) << 2) + ((nn & 7) >> 1);
+                const int col = ((cc_anm <= r) ? 0 : E) + e0 + e;
+                const int ct = col / xt.tn;
+                if (e < ne)
+                    dst[((long long)r0 * xt.n_ct + (long long)ct * kn_pad + row) * (xt.tn + 4) + (col - ct * xt.tn)] =
+                        s_t[c * PK_LD + e];
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
+                const int c = idx / PKE, e = idx % PKE;
+                if (e < ne) dst[x_position(r, cb + c, L, E) + e0 + e] = s_t[c * PK_LD + e];
             }
         }
         // sine plane of order 0, degree r (the tiled buffer is cleared when its layout changes: nothing to write)

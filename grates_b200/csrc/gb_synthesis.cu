@@ -517,7 +517,10 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     // item prologue they would live (spilled) across the whole K loop
                     int c0e = c0;
                     asm volatile("" : "+r"(c0e));
-                    const int ib = i0 + wm * 16 + 2 * q;
+                    // the table interleaves the parallels of a slab: this lane holds the four consecutive parallels
+                    // ib .. ib+3 (fragment ni = parallels ib + 2 ni, ib + 2 ni + 1)
+                    const int ib = i0 + wm * 16 + 4 * q;
+                    const bool quads = (nh & 3) == 0;            // 32-byte stores: whole quads on either side of the equator
 #pragma unroll
                     for (int mi = 0; mi < 5; ++mi) {
                         const int col = c0e + wn * 40 + mi * 8 + g;
@@ -525,17 +528,31 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                         const int cs = col >= E;
                         const int e = col - cs * E;
                         const int k = cs ? ks_row : kc_row;
+                        if (quads) {
+                            if (ib >= nh) continue;
+                            const long long rn = (long long)e * nlat + ib;
+                            const long long rs = (long long)e * nlat + (nlat - 4 - ib);
+                            gb::st_v4(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][0][0] + od[mi][0][0], ev[mi][0][1] + od[mi][0][1],
+                                      ev[mi][1][0] + od[mi][1][0], ev[mi][1][1] + od[mi][1][1]);
+                            gb::st_v4(AB + gb_ab_offset(rs, k, ab_rows), ev[mi][1][1] - od[mi][1][1], ev[mi][1][0] - od[mi][1][0],
+                                      ev[mi][0][1] - od[mi][0][1], ev[mi][0][0] - od[mi][0][0]);
+                            continue;
+                        }
 #pragma unroll
                         for (int ni = 0; ni < 2; ++ni) {
-                            const int i = ib + ni * 8;
-                            if (i >= nh) continue;
-                            if (diag_nostore) continue;   // DIAG
-                            const long long rn = (long long)e * nlat + i;
-                            const long long rs = (long long)e * nlat + (nlat - 2 - i);
-                            gb::st_v2(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][ni][0] + od[mi][ni][0],
-                                      ev[mi][ni][1] + od[mi][ni][1]);
-                            gb::st_v2(AB + gb_ab_offset(rs, k, ab_rows), ev[mi][ni][1] - od[mi][ni][1],
-                                      ev[mi][ni][0] - od[mi][ni][0]);
+                            // pairs: the northern store may straddle the equator (the table holds the southern parallel's
+                            // own values there), the mirrored store only covers what no northern store wrote
+                            const int i = ib + ni * 2;
+                            if (i < nh) {
+                                const long long rn = (long long)e * nlat + i;
+                                gb::st_v2(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][ni][0] + od[mi][ni][0],
+                                          ev[mi][ni][1] + od[mi][ni][1]);
+                            }
+                            if (i + 2 <= nh) {
+                                const long long rs = (long long)e * nlat + (nlat - 2 - i);
+                                gb::st_v2(AB + gb_ab_offset(rs, k, ab_rows), ev[mi][ni][1] - od[mi][ni][1],
+                                          ev[mi][ni][0] - od[mi][ni][0]);
+                            }
                         }
                     }
                 }
@@ -620,8 +637,11 @@ gb_ptab_kernel(double* __restrict__ tab, const int* __restrict__ roff, long long
     const int t = (int)(idx / ((long long)per_tile * L));
     int i;
     if (kind == 0) {
-        i = (tile0 + t) * 32 + li;       // parallels beyond the equator keep their own values: with an odd number of
-                                         // northern parallels the last pair of a thread straddles the equator
+        // inside every 16-column slab of a warp the columns are interleaved so that a lane's two DMMA fragments (tile
+        // columns 2q, 2q+1 and 8+2q, 9+2q) are FOUR CONSECUTIVE parallels 4q .. 4q+3: one 32-byte store per lane
+        const int cc = li & 15;
+        i = (tile0 + t) * 32 + (li & 16) + 4 * ((cc & 7) >> 1) + 2 * (cc >> 3) + (cc & 1);
+        // (parallels beyond the equator keep their own values: a lane's parallels may straddle it)
     } else if (kind == 1) {
         i = li < 32 ? t * 32 + li : nlat - 64 - 32 * t + li;
     } else {
