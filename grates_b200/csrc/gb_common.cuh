@@ -352,6 +352,76 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, double (&v)[16]) {
         : "memory");
 }
 
+// The same thread-private tensor-memory access for 2 / 4 / 8 doubles (.x4 / .x8 / .x16); loads wait.
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, double a, double b) {
+    asm volatile(
+        "{\n.reg .b32 l<2>, h<2>;\nmov.b64 {l0,h0}, %1; mov.b64 {l1,h1}, %2;\n"
+        "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {l0,h0,l1,h1};\n}\n" ::"r"(taddr), "d"(a), "d"(b)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const double* v) {
+    asm volatile(
+        "{\n.reg .b32 l<4>, h<4>;\nmov.b64 {l0,h0}, %1; mov.b64 {l1,h1}, %2; mov.b64 {l2,h2}, %3; mov.b64 {l3,h3}, %4;\n"
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {l0,h0,l1,h1,l2,h2,l3,h3};\n}\n" ::"r"(taddr), "d"(v[0]), "d"(v[1]),
+        "d"(v[2]), "d"(v[3])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const double* v) {
+    asm volatile(
+        "{\n.reg .b32 l<8>, h<8>;\n"
+        "mov.b64 {l0,h0}, %1; mov.b64 {l1,h1}, %2; mov.b64 {l2,h2}, %3; mov.b64 {l3,h3}, %4;\n"
+        "mov.b64 {l4,h4}, %5; mov.b64 {l5,h5}, %6; mov.b64 {l6,h6}, %7; mov.b64 {l7,h7}, %8;\n"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {l0,h0,l1,h1,l2,h2,l3,h3,l4,h4,l5,h5,l6,h6,l7,h7};\n}\n" ::"r"(taddr),
+        "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, double* v) {
+    asm volatile(
+        "{\n.reg .b32 l<2>, h<2>;\n"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {l0,h0,l1,h1}, [%2];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        "mov.b64 %0, {l0,h0}; mov.b64 %1, {l1,h1};\n}\n"
+        : "=d"(v[0]), "=d"(v[1])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, double* v) {
+    asm volatile(
+        "{\n.reg .b32 l<4>, h<4>;\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {l0,h0,l1,h1,l2,h2,l3,h3}, [%4];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        "mov.b64 %0, {l0,h0}; mov.b64 %1, {l1,h1}; mov.b64 %2, {l2,h2}; mov.b64 %3, {l3,h3};\n}\n"
+        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, double* v) {
+    asm volatile(
+        "{\n.reg .b32 l<8>, h<8>;\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {l0,h0,l1,h1,l2,h2,l3,h3,l4,h4,l5,h5,l6,h6,l7,h7}, [%8];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        "mov.b64 %0, {l0,h0}; mov.b64 %1, {l1,h1}; mov.b64 %2, {l2,h2}; mov.b64 %3, {l3,h3};\n"
+        "mov.b64 %4, {l4,h4}; mov.b64 %5, {l5,h5}; mov.b64 %6, {l6,h6}; mov.b64 %7, {l7,h7};\n}\n"
+        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
+// N doubles (N even, <= 10) at 32-bit column `taddr`
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const double* v) {
+    static_assert(N == 6 || N == 8 || N == 10, "unsupported row-factor width");
+    if constexpr (N == 6) { tmem_st4(taddr, v); tmem_st2(taddr + 8, v[4], v[5]); }
+    if constexpr (N == 8) tmem_st8(taddr, v);
+    if constexpr (N == 10) { tmem_st8(taddr, v); tmem_st2(taddr + 16, v[8], v[9]); }
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, double* v) {
+    static_assert(N == 6 || N == 8 || N == 10, "unsupported row-factor width");
+    if constexpr (N == 6) { tmem_ld4(taddr, v); tmem_ld2(taddr + 8, v + 4); }
+    if constexpr (N == 8) tmem_ld8(taddr, v);
+    if constexpr (N == 10) { tmem_ld8(taddr, v); tmem_ld2(taddr + 16, v + 8); }
+}
+
 // Programmatic dependent launch: a kernel launched with gb_launch_pdl may start while its predecessor in the stream
 // drains; everything it reads or writes that the predecessor (or anything before it) touches comes after griddep_wait().
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }

@@ -89,8 +89,38 @@ def covariance_propagation_sharded(covariance_matrix, grid, min_degree, max_degr
         sigma = torch.empty((kp, kp), dtype=torch.float64, device=dev)
     if world > 1:
         dist.broadcast(sigma, src=src, group=group)
-    start, stop = shard_range(p.nlat, world, rank)
-    local = p.covariance_propagation(sigma, min_degree, start, stop - start)
+    rows = covariance_row_blocks(p.nlat, world, rank)
+    parts = []
+    for kind, start, count in rows:
+        if count:
+            parts.append(p.covariance_propagation(sigma, min_degree, start, count, mirrored=(kind == "mirrored")))
+    local = torch.cat(parts) if parts else torch.empty((0, p.nlon), dtype=torch.float64, device=dev)
     if not gather:
         return local
-    return gather_shards(local, shard_counts(p.nlat, world), group).reshape(-1)
+    counts = [sum((2 * c if k == "mirrored" else c) for k, _, c in covariance_row_blocks(p.nlat, world, r))
+              for r in range(world)]
+    gathered = gather_shards(local, counts, group)
+    # back to the order of the parallels
+    out = torch.empty_like(gathered)
+    at = 0
+    for r in range(world):
+        for kind, start, count in covariance_row_blocks(p.nlat, world, r):
+            out[start:start + count] = gathered[at:at + count]
+            at += count
+            if kind == "mirrored":
+                out[p.nlat - start - count:p.nlat - start] = gathered[at:at + count]
+                at += count
+    return out.reshape(-1)
+
+
+def covariance_row_blocks(nlat, world, rank):
+    """Row blocks of rank `rank`: the northern parallels are cut into contiguous shards and every rank takes its shard
+    together with the mirror images (GB_COV_MIRRORED: both halves share the first contraction on equator-symmetric
+    grids); with an odd number of parallels the equator goes to the last rank as a plain block.
+    Returns [(kind, first parallel, count)], kind "mirrored" or "plain"."""
+    half = nlat // 2
+    start, stop = shard_range(half, world, rank)
+    blocks = [("mirrored", start, stop - start)]
+    if nlat % 2 and rank == world - 1:
+        blocks.append(("plain", half, 1))
+    return blocks

@@ -304,9 +304,12 @@ class SHPlan:
 
     # -- covariance propagation ---------------------------------------------------------
     def covariance_propagation(self, sigma, min_degree, row0=0, nrows=None, take_sqrt=True, out=None, symmetric=None,
-                               spatial_filter=None):
+                               spatial_filter=None, mirrored=False):
         """sigma: CUDA tensor [K', K'] (degree-wise order, offset min_degree^2) ->
         [nrows, nlon] standard deviations (or variances) for parallels row0..row0+nrows.
+        mirrored: the block is the nrows NORTHERN parallels row0.. together with their mirror images about the equator;
+        the result is [2 nrows, nlon]: the northern rows, then parallels nlat-row0-nrows..nlat-row0 (GB_COV_MIRRORED: on
+        equator-symmetric grids both halves share the first contraction; the way to cut row blocks for several GPUs).
         symmetric: True lets the kernels contract the order-block pairs k <= k' only (half the work);
         None (default) decides by comparing sigma with its transpose on a sample of entries.
         spatial_filter: an OrderWiseFilter, Gaussian or Butterworth instance F; the result then is the propagation
@@ -322,11 +325,15 @@ class SHPlan:
             symmetric = _looks_symmetric(sigma)
         if row0 < 0 or nrows < 0 or row0 + nrows > self.nlat:
             raise ValueError("row block [{0}, {1}) is outside the grid's {2} parallels".format(row0, row0 + nrows, self.nlat))
+        if mirrored and 2 * (row0 + nrows) > self.nlat:
+            raise ValueError("a mirrored row block must lie north of the equator (got [{0}, {1}) of {2} parallels)".format(
+                row0, row0 + nrows, self.nlat))
+        nout = 2 * nrows if mirrored else nrows
         if out is None:
-            out = torch.empty((nrows, self.nlon), dtype=torch.float64, device=sigma.device)
+            out = torch.empty((nout, self.nlon), dtype=torch.float64, device=sigma.device)
         else:
-            _check_out(out, (nrows, self.nlon), self.device)
-        flags = (1 if take_sqrt else 0) | (2 if symmetric else 0)      # GB_COV_SQRT | GB_COV_SYMMETRIC
+            _check_out(out, (nout, self.nlon), self.device)
+        flags = (1 if take_sqrt else 0) | (2 if symmetric else 0) | (4 if mirrored else 0)   # GB_COV_SQRT | _SYMMETRIC | _MIRRORED
         if spatial_filter is None:
             with self._lock:
                 _lib.check(self._lib.gb_covariance_propagation(self._handle, ctypes.c_void_p(sigma.data_ptr()),

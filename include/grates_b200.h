@@ -160,13 +160,19 @@ int gb_analysis_matrix(gb_plan* plan, double* d_out, void* stream);
  * [row0, row0 + nrows) of the plan's grid.  Replaces grid.py:833-835 (the reference then takes
  * the square root, grid.py:837-839; pass GB_COV_SQRT for that).
  *   d_sigma [K'][K'] row-major, K' = (nmax+1)^2 - nmin^2, degree-wise order
- *   d_out   [nrows][nlon]
+ *   d_out   [nrows][nlon]  ([2 nrows][nlon] with GB_COV_MIRRORED)
  *   flags   GB_COV_SQRT: return standard deviations.  GB_COV_SYMMETRIC: the caller states that
  *           Sigma is symmetric (a covariance matrix is); only its order-block pairs k <= k' are
  *           contracted, which halves the work.  Without the flag the full matrix is used.
  */
 #define GB_COV_SQRT 1
 #define GB_COV_SYMMETRIC 2
+/* GB_COV_MIRRORED: the block is the `nrows` NORTHERN parallels [row0, row0 + nrows) (2 (row0 + nrows) <= nlat) together
+ * with their mirror images about the equator; d_out is [2 nrows][nlon]: the northern rows, then the parallels
+ * [nlat - row0 - nrows, nlat - row0) in increasing order.  On grids that are symmetric about the equator the Legendre
+ * factors of a parallel and its mirror image differ by the sign (-1)^(n-m) only, so the first contraction runs once for
+ * both (half its flops); this is how row blocks should be cut for several GPUs.  A full-grid call folds by itself. */
+#define GB_COV_MIRRORED 4
 int gb_covariance_propagation(gb_plan* plan, const double* d_sigma, int nmin, int row0, int nrows,
                               double* d_out, int flags, void* stream);
 /*
