@@ -97,20 +97,28 @@ def covariance_propagation_sharded(covariance_matrix, grid, min_degree, max_degr
     local = torch.cat(parts) if parts else torch.empty((0, p.nlon), dtype=torch.float64, device=dev)
     if not gather:
         return local
-    counts = [sum((2 * c if k == "mirrored" else c) for k, _, c in covariance_row_blocks(p.nlat, world, r))
-              for r in range(world)]
-    gathered = gather_shards(local, counts, group)
-    # back to the order of the parallels
+    gathered = gather_shards(local, covariance_row_counts(p.nlat, world), group)
+    return reorder_row_blocks(gathered, p.nlat, world).reshape(-1)
+
+
+def covariance_row_counts(nlat, world):
+    """Output rows every rank contributes under covariance_row_blocks."""
+    return [sum((2 * c if k == "mirrored" else c) for k, _, c in covariance_row_blocks(nlat, world, r)) for r in range(world)]
+
+
+def reorder_row_blocks(gathered, nlat, world):
+    """Rank-major concatenation of the ranks' (northern block, mirrored block[, equator]) outputs -> rows in the order
+    of the parallels."""
     out = torch.empty_like(gathered)
     at = 0
     for r in range(world):
-        for kind, start, count in covariance_row_blocks(p.nlat, world, r):
+        for kind, start, count in covariance_row_blocks(nlat, world, r):
             out[start:start + count] = gathered[at:at + count]
             at += count
             if kind == "mirrored":
-                out[p.nlat - start - count:p.nlat - start] = gathered[at:at + count]
+                out[nlat - start - count:nlat - start] = gathered[at:at + count]
                 at += count
-    return out.reshape(-1)
+    return out
 
 
 def covariance_row_blocks(nlat, world, rank):

@@ -57,6 +57,18 @@ def _worker(rank, world, port, out_dir):
     block = torch.full((b - a, 4), float(rank), dtype=torch.float64)
     std = gather_shards(block, shard_counts(rows, world)).reshape(-1)
     ok = ok and std.shape[0] == rows * 4 and float(std[0]) == 0.0 and float(std[-1]) == float(world - 1)
+    # covariance row blocks: northern shard + mirror image per rank (+ the equator on the last rank), gathered rank-major
+    # and put back into the order of the parallels
+    from grates_b200.distributed import covariance_row_blocks, covariance_row_counts, reorder_row_blocks
+    for nlat in (9, 12):
+        mine = []
+        for kind, start, count in covariance_row_blocks(nlat, world, rank):
+            mine += list(range(start, start + count))
+            if kind == "mirrored":
+                mine += list(range(nlat - start - count, nlat - start))
+        block = torch.tensor(mine, dtype=torch.float64).reshape(-1, 1).repeat(1, 3)
+        rows_back = reorder_row_blocks(gather_shards(block, covariance_row_counts(nlat, world)), nlat, world)
+        ok = ok and torch.equal(rows_back[:, 0], torch.arange(nlat, dtype=torch.float64))
     # max-over-ranks timing reduction as used by bench.py
     t = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -375,6 +375,35 @@ def test_covariance_vs_oracle_and_row_blocks(gb, orc):
     assert maxnorm_err(full, ref) < TOL and maxnorm_err(half, ref) < TOL
 
 
+def test_covariance_equator_fold_and_mirrored_blocks(gb, orc, monkeypatch):
+    """The first contraction runs for the northern parallels only (parity classes of n - m, S +- D): folded against
+    unfolded against the oracle, GB_COV_MIRRORED row blocks bit-identical to the full grid, odd parallel counts, a
+    min_degree that shifts the parity of the first row of the low orders."""
+    for (N, dlon, dlat, nmin) in ((24, 5.0, 5.0, 0), (30, 6.0, 4.0, 3), (17, 9.0, 9.0, 2)):
+        grid, og = gb.GeographicGrid(dlon, dlat), orc.geographic_grid(dlon, dlat)
+        sigma = orc.synthetic_covariance(N, rank=20)[nmin * nmin:, nmin * nmin:]
+        ref = orc.covariance_propagation(sigma, og, nmin, N, "ewh") ** 2
+        plan = gb.get_plan(grid, N, "ewh")
+        s = torch.as_tensor(np.ascontiguousarray(sigma)).cuda()
+        for sym in (True, False):
+            monkeypatch.delenv("GB_COV_NO_FOLD", raising=False)
+            folded = plan.covariance_propagation(s, nmin, take_sqrt=False, symmetric=sym).cpu().numpy()
+            monkeypatch.setenv("GB_COV_NO_FOLD", "1")
+            unfolded = plan.covariance_propagation(s, nmin, take_sqrt=False, symmetric=sym).cpu().numpy()
+            monkeypatch.delenv("GB_COV_NO_FOLD", raising=False)
+            assert maxnorm_err(folded.ravel(), ref) < TOL and maxnorm_err(unfolded.ravel(), ref) < TOL
+            nl, a, b = plan.nlat, 1, max(2, plan.nlat // 2 - 1)
+            both = plan.covariance_propagation(s, nmin, a, b - a, take_sqrt=False, symmetric=sym, mirrored=True).cpu().numpy()
+            np.testing.assert_array_equal(both[:b - a], folded[a:b])
+            np.testing.assert_array_equal(both[b - a:], folded[nl - b:nl - a])
+        with pytest.raises(ValueError):
+            plan.covariance_propagation(s, nmin, plan.nlat // 2, 2, mirrored=True)     # reaches across the equator
+    for nl in (10, 11):                  # Gauss grids; 11: the equator is its own mirror image
+        sigma = orc.synthetic_covariance(8, rank=8)
+        std = gb.GaussGrid(nl).covariance_propagation(sigma, 0, 8, "geoid")
+        assert maxnorm_err(std, orc.covariance_propagation(sigma, orc.gauss_grid(nl), 0, 8, "geoid")) < TOL
+
+
 def test_ravel_batch_matches_reference_ordering(gb, orc, golden):
     """Device ravel (utilities.py:310-360) against the reference's TimeSeries.to_array ordering."""
     g = golden("filters")
