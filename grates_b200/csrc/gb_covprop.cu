@@ -51,8 +51,8 @@ using gb::legendre_column;
 // row of degree offset r (n = n0 + r) inside its group: class (r + po) & 1, po = (n0 - m) & 1; class 1 starts at ne4
 __host__ __device__ __forceinline__ int cov_cls_pos(int r, int po, int ne4) { return (((r + po) & 1) ? ne4 : 0) + (r >> 1); }
 
-// St[gb_ab_offset(a', b, Kp4)] = Sigma[perm8[a']][perm4[b]]  (0 where either index is padding); fallback for degrees
-// whose row block does not fit shared memory
+// St[gb_ab_offset(a', b, Kp4)] = Sigma[perm8[a']][perm4[b]]  (0 where either index is padding); cross-check of the
+// kernel below (GB_COV_PERMUTE_GATHER=1)
 __global__ void __launch_bounds__(256)
 gb_cov_permute(const double* __restrict__ sigma, double* __restrict__ St, const int* __restrict__ perm8,
                const int* __restrict__ perm4, int rows_a, int Kp4, long long K) {
@@ -63,51 +63,55 @@ gb_cov_permute(const double* __restrict__ sigma, double* __restrict__ St, const 
     St[gb_ab_offset(a, b, Kp4)] = (pa < 0 || pb < 0) ? 0.0 : sigma[(size_t)pa * K + pb];
 }
 
-// The same permutation, one CTA per (32 rows a', degree n of the columns): the 2n+1 columns of a degree
-// are contiguous in the degree-wise order, so Sigma is read in row segments and St written in 256-byte
-// runs (the element-wise gather above fetches a 32-byte sector per double).
+// The same permutation, one CTA per (32 rows a', 64 columns of degree n): the 2n+1 columns of a degree
+// are contiguous in the degree-wise order, so Sigma is read in row segments of up to 512 bytes and St written in
+// 256-byte runs (the element-wise gather above fetches a 32-byte sector per double); 16 KB of shared memory per CTA
+// keeps a dozen CTAs resident per SM.
 // Symmetric Sigma (first_group != nullptr): a row tile only meets column groups k' >= its own first group kmin,
 // i.e. the columns j >= jmin of every degree: the rest of the row block is neither read nor written (the quadratic-form
 // kernel never touches it).
-constexpr int CP_ROWS = 32;
+constexpr int CP_ROWS = 32, CP_COLS = 64, CP_PITCH = CP_COLS + 1;     // odd pitch: conflict-free column reads
 __global__ void __launch_bounds__(256)
 gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St, const int* __restrict__ perm8,
                       const int* __restrict__ goff4, const int* __restrict__ ne4, int Kp4, long long K, int nmin,
                       const int* __restrict__ first_group) {
-    extern __shared__ double s_p[];   // [CP_ROWS][2n+1]
+    __shared__ double s_p[CP_ROWS * CP_PITCH];
     const int a0 = blockIdx.x * CP_ROWS;
     const int n = nmin + blockIdx.y;
-    const int width = 2 * n + 1;      // odd pitch: conflict-free column reads
+    const int width = 2 * n + 1;
     int jmin = 0;
     if (first_group) {
         const int kmin = first_group[a0 >> 7];                        // first group of the 128-row tile
         jmin = kmin <= 1 ? 0 : kmin - 1;                              // group 2m (cos) is column 2m-1, group 2m+1 (sin) column 2m
     }
-    if (jmin >= width) return;
+    const int j0 = blockIdx.z * CP_COLS;                              // this CTA: columns [j0, j1) of the degree
+    const int j1 = min(width, j0 + CP_COLS);
+    const int jlo = max(jmin, j0);
+    if (jlo >= j1) return;
     const long long col0 = (long long)n * n - (long long)nmin * nmin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = warp; r < CP_ROWS; r += 8) {
         const int pa = perm8[a0 + r];
         const double* src = sigma + (size_t)(pa < 0 ? 0 : pa) * K + col0;
         // Sigma is read once: streaming loads keep the re-tiled operand (and U) in L2 instead
-        for (int j = jmin + lane; j < width; j += 32) s_p[r * width + j] = pa < 0 ? 0.0 : __ldcs(src + j);
+        for (int j = jlo + lane; j < j1; j += 32) s_p[r * CP_PITCH + j - j0] = pa < 0 ? 0.0 : __ldcs(src + j);
     }
     __syncthreads();
-    for (int j = jmin + warp; j < width; j += 8) {
+    for (int j = jlo + warp; j < j1; j += 8) {
         const int m = (j + 1) >> 1;
         const int k = (j == 0) ? 0 : 2 * m + ((j & 1) ? 0 : 1);          // j = 2m-1: cos, j = 2m: sin
         const int n0 = max(m, nmin);
         const int b = goff4[k] + cov_cls_pos(n - n0, (n0 - m) & 1, ne4[k]);
         double* dst = St + ((size_t)(a0 >> 7) * Kp4 + b) * GB_LDA + (a0 & (GB_TM - 1));
-#pragma unroll
-        for (int r = lane; r < CP_ROWS; r += 32) dst[r] = s_p[r * width + j];
+        dst[lane] = s_p[lane * CP_PITCH + j - j0];
     }
 }
 
 // rows b of St that pad a class to a multiple of four
 __global__ void __launch_bounds__(128)
-gb_cov_zero_rows(double* __restrict__ St, const int* __restrict__ padrows, int Kp4) {
-    St[((size_t)blockIdx.x * Kp4 + padrows[blockIdx.y]) * GB_LDA + threadIdx.x] = 0.0;
+gb_cov_zero_rows(double* __restrict__ St, const int* __restrict__ padrows, int n_padrows, int Kp4) {
+    for (int r = blockIdx.y * 16; r < min(n_padrows, blockIdx.y * 16 + 16); ++r)
+        St[((size_t)blockIdx.x * Kp4 + padrows[r]) * GB_LDA + threadIdx.x] = 0.0;
 }
 
 // U as B tiles: Ut[((k * nti + r / tn) * Kg + row(n)) * ldb + r % tn] = kn[i][n] * P_nm(theta_i), i = rep[r]
@@ -727,8 +731,7 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
     GB_REQUIRE(Kp4 <= 65535, "gb_covariance_propagation: degree %d is too large for this path", p->nmax);
     GB_REQUIRE((long long)n_ct * Kg * ldb < (1LL << 31),
                "gb_covariance_propagation: %d parallels at degree %d exceed the 32-bit tile index; pass row blocks", nrows, p->nmax);
-    const size_t permute_smem = (size_t)CP_ROWS * (2 * p->nmax + 1) * sizeof(double);
-    const bool by_degree = permute_smem <= 200 * 1024;
+    const bool by_degree = getenv("GB_COV_PERMUTE_GATHER") == nullptr;      // the element-wise gather is a cross-check only
     const int n_pieces = lay->n_pieces, nslots = 4 * hmt;
     double *d_st = nullptr, *d_ut = nullptr, *d_ht = nullptr, *d_hpart = nullptr, *d_vpart = nullptr;
     int rc = GB_OK;
@@ -743,11 +746,9 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
     GB_CUDA(scratch.alloc(&d_hpart, hp_elems));
     GB_CUDA(scratch.alloc(&d_vpart, vp_elems));
     GB_CUDA(cudaMemsetAsync(d_ut, 0, ut_elems * sizeof(double), st));
-    if (permute_smem > 48 * 1024 && by_degree)
-        GB_CUDA(cudaFuncSetAttribute(gb_cov_permute_degree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)permute_smem));
     {
-        dim3 grid((nrep + 127) / 128, L);
-        gb_cov_legendre<<<grid, 128, 0, st>>>(d_ut, p->d_ct, p->d_kn, p->d_pmm, p->d_ra, p->d_rb, p->d_rc, L, nmin,
+        dim3 grid((nrep + 31) / 32, L);      // thread = (parallel, order): a serial recursion each, so many small CTAs
+        gb_cov_legendre<<<grid, 32, 0, st>>>(d_ut, p->d_ct, p->d_kn, p->d_pmm, p->d_ra, p->d_rb, p->d_rc, L, nmin,
                                               lay->d_rep, nrep, nti, Kg, tn, ldb, d_wn, lay->d_ne4);
         GB_LAUNCH_CHECK();
     }
@@ -768,11 +769,11 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
     if (by_degree) {
         // the padding rows of the classes are the only part of St the permutation does not write
         if (lay->n_padrows > 0) {
-            gb_cov_zero_rows<<<dim3(n_atiles, lay->n_padrows), 128, 0, st>>>(d_st, lay->d_padrows, Kp4);
+            gb_cov_zero_rows<<<dim3(n_atiles, (lay->n_padrows + 15) / 16), 128, 0, st>>>(d_st, lay->d_padrows, lay->n_padrows, Kp4);
             GB_LAUNCH_CHECK();
         }
-        dim3 grid(rows_a / CP_ROWS, L - nmin);
-        gb_cov_permute_degree<<<grid, 256, permute_smem, st>>>(d_sigma, d_st, lay->d_perm8, lay->d_goff4, lay->d_ne4, Kp4, K,
+        dim3 grid(rows_a / CP_ROWS, L - nmin, (2 * p->nmax + 1 + CP_COLS - 1) / CP_COLS);
+        gb_cov_permute_degree<<<grid, 256, 0, st>>>(d_sigma, d_st, lay->d_perm8, lay->d_goff4, lay->d_ne4, Kp4, K,
                                                                nmin, symmetric ? lay->d_first_group : nullptr);
         GB_LAUNCH_CHECK();
     } else {
