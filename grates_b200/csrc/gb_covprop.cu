@@ -204,16 +204,19 @@ struct QuadArgs {
     int n_segs, Kp4, Kg, nti, kpad, n_pieces, nrep, nmin, symmetric;
 };
 
-constexpr int CQ_KC = 28, CQ_STAGES = 3, CQ_WM = 4, CQ_WN = 3;
-constexpr int CQ_CONSUMER_WARPS = CQ_WM * CQ_WN, CQ_THREADS = 32 * (CQ_CONSUMER_WARPS + 1);
-__host__ __device__ constexpr int cq_tn(int ni) { return 8 * ni * CQ_WN; }
-__host__ __device__ constexpr size_t cq_smem(int ni) {
-    return (size_t)CQ_STAGES * CQ_KC * (GB_LDA + cq_tn(ni) + 4) * sizeof(double) + 2 * CQ_STAGES * sizeof(uint64_t) + 16;
+constexpr int CQ_KC = 28, CQ_STAGES = 3, CQ_WM = 4;
+// WN warps along the parallels, NI 8-column fragments each: 3 x 5 (120 parallels per tile), 3 x 3 (72) or 4 x 3 (96: sixteen
+// consumer warps, four per scheduler -- a warp that is busy with its epilogue leaves three, not two, to feed the DMMA pipe)
+__host__ __device__ constexpr int cq_threads(int wn) { return 32 * (CQ_WM * wn + 1); }
+__host__ __device__ constexpr int cq_tn(int ni, int wn) { return 8 * ni * wn; }
+__host__ __device__ constexpr size_t cq_smem(int ni, int wn) {
+    return (size_t)CQ_STAGES * CQ_KC * (GB_LDA + cq_tn(ni, wn) + 4) * sizeof(double) + 2 * CQ_STAGES * sizeof(uint64_t) + 16;
 }
 
-template <int NI>
-__global__ void __launch_bounds__(CQ_THREADS, 1) gb_cov_quad_kernel(QuadArgs qa) {
-    constexpr int TN = cq_tn(NI), LDB = TN + 4, STAGE_DOUBLES = CQ_KC * (GB_LDA + LDB);
+template <int NI, int CQ_WN>
+__global__ void __launch_bounds__(cq_threads(CQ_WN), 1) gb_cov_quad_kernel(QuadArgs qa) {
+    constexpr int CQ_CONSUMER_WARPS = CQ_WM * CQ_WN;
+    constexpr int TN = cq_tn(NI, CQ_WN), LDB = TN + 4, STAGE_DOUBLES = CQ_KC * (GB_LDA + LDB);
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)CQ_STAGES * STAGE_DOUBLES * sizeof(double));
@@ -661,13 +664,13 @@ int build_layout(gb_plan* p, int nmin, int row0, int nrows, int key_flags, CovLa
     return GB_OK;
 }
 
-template <int NI>
+template <int NI, int WN>
 int launch_quad(const QuadArgs& qa, int sm_count, cudaStream_t st) {
     if (qa.n_segs == 0) return GB_OK;
     const int grid = qa.n_segs < sm_count ? qa.n_segs : sm_count;
-    constexpr size_t SMEM = cq_smem(NI);
-    GB_CUDA(cudaFuncSetAttribute(gb_cov_quad_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    gb_cov_quad_kernel<NI><<<grid, CQ_THREADS, SMEM, st>>>(qa);
+    constexpr size_t SMEM = cq_smem(NI, WN);
+    GB_CUDA(cudaFuncSetAttribute(gb_cov_quad_kernel<NI, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    gb_cov_quad_kernel<NI, WN><<<grid, cq_threads(WN), SMEM, st>>>(qa);
     GB_LAUNCH_CHECK();
     return GB_OK;
 }
@@ -789,8 +792,8 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
         qa.goff4 = lay->d_goff4; qa.ne4 = lay->d_ne4; qa.no4 = lay->d_no4;
         qa.n_segs = lay->n_segs; qa.Kp4 = Kp4; qa.Kg = Kg; qa.nti = nti; qa.kpad = kpad; qa.n_pieces = n_pieces;
         qa.nrep = nrep; qa.nmin = nmin; qa.symmetric = symmetric;
-        rc = lay->ni == 5 ? launch_quad<5>(qa, p->sm_count, st) : lay->ni == 4 ? launch_quad<4>(qa, p->sm_count, st)
-                                                                               : launch_quad<3>(qa, p->sm_count, st);
+        rc = lay->ni == 5 ? launch_quad<5, 3>(qa, p->sm_count, st) : lay->ni == 4 ? launch_quad<3, 4>(qa, p->sm_count, st)
+                                                                                  : launch_quad<3, 3>(qa, p->sm_count, st);
         if (rc) return rc;
     }
     {
