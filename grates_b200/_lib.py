@@ -40,6 +40,7 @@ SIGNATURES = {
                                                           ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp]),
     "gb_scale_by_degree": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     "gb_synthesis_weighted": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, _vp]),
+    "gb_synthesis_orderwise_filtered": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp]),
     "gb_dense_filter_tile_elements": (ctypes.c_int64, [ctypes.c_int64]),
     "gb_dense_filter_prepare": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int, _vp]),
     "gb_dense_filter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp]),

@@ -168,6 +168,10 @@ int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_
 // d_roff [L + 1] = first row of every order (gb_plan::d_ptab_roff).  The buffer must have been cleared for this layout.
 int gb_launch_pack_tiled(const double* d_anm, double* d_x, int L, int E, const int* d_roff, int tn, int n_ct,
                          cudaStream_t st, const double* d_wn = nullptr);
+// order-wise block filter of a batch, written straight into a synthesis workspace X (gb_filter.cu): order-wise packed
+// (d_roff == nullptr) or the tiled layout of gb_launch_pack_tiled (the buffer must have been cleared for it)
+int gb_filter_into_x(const double* d_blocks, const int64_t* block_offsets, int nf, const double* d_anm, int E, int nmax,
+                     double* d_x, const int* d_roff, int tn, int n_ct, cudaStream_t st);
 // packed batch -> degree-wise vectors as GEMM B tiles [epoch tile of 120][c][124] (gb_densefilter.cu); K = number of
 // coefficients from degree nmin on, kp4 = K padded to 4, degrees above Lin - 1 read as zero
 int gb_launch_ravel_tiles(const double* d_anm, double* d_bt, int Lin, int nmin, long long K, int kp4, int E, cudaStream_t st);

@@ -25,9 +25,17 @@ constexpr int FT_KC = 16;           // columns of W per chunk
 constexpr int FT_LDX = FT_E + 4;    // pitch of the X tile
 constexpr int FT_LDW = FT_R + 4;    // pitch of a (transposed) W chunk
 
+// TILED: Y is written in the layout of the table-fed Legendre stage of the synthesis (gb_pack.cu, x_tiled_position):
+// [order][column tile of tn][degree row, even | odd n - m per 8][tn + 4] -- filter + synthesis then needs neither the
+// unpack nor a second pack.  The buffer was cleared for this layout (the sine plane of order 0 stays zero).
+struct FilterTiling {
+    const int* roff;        // [L + 1] first row of every order
+    int tn, n_ct;
+};
+template <bool TILED>
 __global__ void __launch_bounds__(256, 3)
 gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __restrict__ offsets, int nf,
-                        const double* __restrict__ X, double* __restrict__ Y, int E, int nmax) {
+                        const double* __restrict__ X, double* __restrict__ Y, int E, int nmax, FilterTiling ft) {
     extern __shared__ __align__(16) double s_f[];
     const int L = nmax + 1;
     const int g = blockIdx.x;                 // 0 .. 2*nmax
@@ -111,18 +119,32 @@ gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __re
                 const int r = r0 + 16 * warp + mi * 8 + fg;
                 if (r >= k) continue;
                 const bool pass = (m + r) < 2;         // degrees 0 and 1 pass through unchanged (filter.py:189)
+                long long trow = 0;
+                int kn_pad = 0;
+                if (TILED) {
+                    const int t0 = ft.roff[m];
+                    kn_pad = ft.roff[m + 1] - t0;
+                    trow = (long long)t0 * ft.n_ct + ((r & ~7) + ((r & 1) << 2) + ((r & 7) >> 1));
+                }
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const int e = ni * 8 + 2 * q + j;
-                        if (e < ne) Yg[(size_t)r * 2 * E + e] = pass ? s_x[r * FT_LDX + e] : acc[mi][ni][j];
+                        if (e >= ne) continue;
+                        const double v = pass ? s_x[r * FT_LDX + e] : acc[mi][ni][j];
+                        if (TILED) {
+                            const int col = cs * E + e0 + e, ct = col / ft.tn;
+                            Y[(trow + (long long)ct * kn_pad) * (ft.tn + 4) + (col - ct * ft.tn)] = v;
+                        } else {
+                            Yg[(size_t)r * 2 * E + e] = v;
+                        }
                     }
             }
         }
     }
     // order 0 has no sine coefficients: keep that plane of Y defined (zero)
-    if (g == 0) {
+    if (!TILED && g == 0) {
         for (int idx = tid; idx < k * FT_E; idx += 256) {
             const int c = idx / FT_E, e = idx % FT_E;
             if (e < ne) Y[(size_t)c * 2 * E + E + e0 + e] = 0.0;
@@ -131,6 +153,45 @@ gb_filter_blocks_kernel(const double* __restrict__ blocks, const long long* __re
 }
 
 }  // namespace
+
+// pack -> filter; the filtered coefficients land in d_y, order-wise packed (roff == nullptr) or in the tiled layout
+static int filter_packed(const double* d_blocks, const int64_t* block_offsets, int nf, const double* d_anm_in, int E, int nmax,
+                         double* d_y, const int* d_roff, int tn, int n_ct, gb_scratch& scratch, cudaStream_t st) {
+    const int nblocks = 2 * nf + 1;
+    const int L = nmax + 1;
+    const size_t x_elems = (size_t)L * (L + 1) * (size_t)E;      // 2E doubles per (order, degree) pair
+    const int kp_max = (L + FT_KC - 1) / FT_KC * FT_KC;
+    const size_t smem = ((size_t)kp_max * FT_LDX + 2 * FT_KC * FT_LDW) * sizeof(double);
+    GB_REQUIRE(smem <= 227 * 1024, "gb_orderwise_filter: max_degree=%d exceeds the shared-memory tile of the filter kernel", nmax);
+    long long* d_off = nullptr;
+    double* d_x = nullptr;
+    GB_CUDA(scratch.alloc(&d_off, (size_t)nblocks + 1));
+    GB_CUDA(scratch.alloc(&d_x, x_elems));
+    GB_CUDA(cudaMemcpyAsync(d_off, block_offsets, (nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    int rc = gb_launch_pack(d_anm_in, d_x, L, E, st);
+    if (rc) return rc;
+    const FilterTiling ft{d_roff, tn, n_ct};
+    dim3 grid(2 * nmax + 1, (E + FT_E - 1) / FT_E);
+    if (d_roff) {
+        if (smem > 48 * 1024)
+            GB_CUDA(cudaFuncSetAttribute(gb_filter_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gb_filter_blocks_kernel<true><<<grid, 256, smem, st>>>(d_blocks, d_off, nf, d_x, d_y, E, nmax, ft);
+    } else {
+        if (smem > 48 * 1024)
+            GB_CUDA(cudaFuncSetAttribute(gb_filter_blocks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gb_filter_blocks_kernel<false><<<grid, 256, smem, st>>>(d_blocks, d_off, nf, d_x, d_y, E, nmax, ft);
+    }
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}
+
+// Filtered coefficients straight into the synthesis workspace X of a plan (gb_synthesis.cu: launch_synthesis).
+int gb_filter_into_x(const double* d_blocks, const int64_t* block_offsets, int nf, const double* d_anm, int E, int nmax,
+                     double* d_x, const int* d_roff, int tn, int n_ct, cudaStream_t st) {
+    GB_REQUIRE(nmax <= nf, "gb_synthesis_orderwise_filtered: max_degree=%d exceeds the filter's maximum degree %d", nmax, nf);
+    gb_scratch scratch(st);
+    return filter_packed(d_blocks, block_offsets, nf, d_anm, E, nmax, d_x, d_roff, tn, n_ct, scratch, st);
+}
 
 extern "C" int gb_orderwise_filter(const double* d_blocks, const int64_t* block_offsets, int nf, const double* d_anm_in,
                                    int n_epochs, int nmax, double* d_anm_out, int device, void* stream) {
@@ -143,33 +204,13 @@ extern "C" int gb_orderwise_filter(const double* d_blocks, const int64_t* block_
     GB_CUDA(cudaSetDevice(device));
     gb_retain_pool_memory(device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int nblocks = 2 * nf + 1;
     const int L = nmax + 1;
     const int E = n_epochs;
-    const size_t x_elems = (size_t)L * (L + 1) * (size_t)E;      // 2E doubles per (order, degree) pair
-    const int kp_max = (L + FT_KC - 1) / FT_KC * FT_KC;
-    const size_t smem = ((size_t)kp_max * FT_LDX + 2 * FT_KC * FT_LDW) * sizeof(double);
-    GB_REQUIRE(smem <= 227 * 1024, "gb_orderwise_filter: max_degree=%d exceeds the shared-memory tile of the filter kernel", nmax);
-    long long* d_off = nullptr;
-    double* d_xy = nullptr;
+    const size_t x_elems = (size_t)L * (L + 1) * (size_t)E;
+    double* d_y = nullptr;
     gb_scratch scratch(st);
-    GB_CUDA(scratch.alloc(&d_off, (size_t)nblocks + 1));
-    GB_CUDA(scratch.alloc(&d_xy, 2 * x_elems));
-    GB_CUDA(cudaMemcpyAsync(d_off, block_offsets, (nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-    int rc = gb_launch_pack(d_anm_in, d_xy, L, E, st);
-    if (!rc) {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(gb_filter_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) rc = gb_set_error(GB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-        }
-    }
-    if (!rc) {
-        dim3 grid(2 * nmax + 1, (E + FT_E - 1) / FT_E);
-        gb_filter_blocks_kernel<<<grid, 256, smem, st>>>(d_blocks, d_off, nf, d_xy, d_xy + x_elems, E, nmax);
-        gb_count_launch();
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = gb_set_error(GB_ERR_CUDA, "gb_filter_blocks_kernel launch failed: %s", cudaGetErrorString(e));
-    }
-    if (!rc) rc = gb_launch_unpack(d_xy + x_elems, d_anm_out, L, E, st);
+    GB_CUDA(scratch.alloc(&d_y, x_elems));
+    int rc = filter_packed(d_blocks, block_offsets, nf, d_anm_in, E, nmax, d_y, nullptr, 0, 0, scratch, st);
+    if (!rc) rc = gb_launch_unpack(d_y, d_anm_out, L, E, st);
     return rc;
 }

@@ -1040,8 +1040,15 @@ static int ensure_ptab(gb_plan* p, int kind, int n_tiles, int tile0, cudaStream_
     return 1;
 }
 
+// order-wise block filter applied between the pack and the Legendre stage (gb_synthesis_orderwise_filtered)
+struct SynthesisFilter {
+    const double* d_blocks;
+    const int64_t* block_offsets;
+    int nf;
+};
+
 static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_out, cudaStream_t st,
-                            const double* d_wn = nullptr) {
+                            const double* d_wn = nullptr, const SynthesisFilter* flt = nullptr) {
     const int L = p->L;
     const long long M = (long long)E * p->nlat;
     {
@@ -1078,7 +1085,12 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         p->x_layout_key = 0;
     }
     if (prof) GB_CUDA(cudaEventRecord(prof[0], st));
-    {
+    if (flt) {
+        // pack -> filter, whose epilogue writes X in the layout the Legendre stage reads (no unpack / second pack)
+        int rc = gb_filter_into_x(flt->d_blocks, flt->block_offsets, flt->nf, d_anm, E, p->nmax, p->d_x,
+                                  have_tab ? p->d_ptab_roff : nullptr, tn, n_coltiles, st);
+        if (rc) return rc;
+    } else {
         int rc = have_tab ? gb_launch_pack_tiled(d_anm, p->d_x, L, E, p->d_ptab_roff, tn, n_coltiles, st, d_wn)
                           : gb_launch_pack(d_anm, p->d_x, L, E, st, d_wn);
         if (rc) return rc;
@@ -1221,6 +1233,21 @@ extern "C" int gb_synthesis_weighted(gb_plan* plan, const double* d_anm, const d
     int rc = gb_plan_ensure_workspace(plan, n_epochs);
     if (rc) return rc;
     return launch_synthesis(plan, d_anm, n_epochs, d_out, static_cast<cudaStream_t>(stream), d_wn);
+}
+
+extern "C" int gb_synthesis_orderwise_filtered(gb_plan* plan, const double* d_blocks, const int64_t* block_offsets, int nf,
+                                               const double* d_anm, int n_epochs, double* d_out, void* stream) {
+    GB_REQUIRE(plan != nullptr, "gb_synthesis_orderwise_filtered: plan is NULL");
+    GB_REQUIRE(n_epochs >= 0, "gb_synthesis_orderwise_filtered: n_epochs=%d is negative", n_epochs);
+    GB_REQUIRE(nf >= plan->nmax, "gb_synthesis_orderwise_filtered: the filter (degree %d) does not reach degree %d", nf,
+               plan->nmax);
+    if (n_epochs == 0) return GB_OK;
+    GB_REQUIRE(d_anm && d_out && d_blocks && block_offsets, "gb_synthesis_orderwise_filtered: NULL pointer");
+    GB_CUDA(cudaSetDevice(plan->device));
+    int rc = gb_plan_ensure_workspace(plan, n_epochs);
+    if (rc) return rc;
+    const SynthesisFilter flt{d_blocks, block_offsets, nf};
+    return launch_synthesis(plan, d_anm, n_epochs, d_out, static_cast<cudaStream_t>(stream), nullptr, &flt);
 }
 
 static int ensure_pipeline(gb_plan* p) {

@@ -433,7 +433,7 @@ def ravel_batch(anm, min_degree=0):
 
 
 def to_grid_batch(anm, grid=None, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT, device_output=False, out=None,
-                  degree_weights=None):
+                  degree_weights=None, orderwise_filter=None):
     """Batched synthesis.  anm: [E, L, L] packed coefficients (numpy array or CUDA float64
     tensor).  Returns [E, nlat, nlon]; with a CUDA tensor input (or device_output=True) the
     result stays on the device, otherwise it is copied to the host inside the call.
@@ -441,13 +441,15 @@ def to_grid_batch(anm, grid=None, kernel='ewh', GM=GM_DEFAULT, R=R_DEFAULT, devi
     the synthesis on regular grids."""
     grid = GeographicGrid() if grid is None else grid
     L = anm.shape[-1]
-    if degree_weights is not None:
+    if degree_weights is not None or orderwise_filter is not None:
+        # orderwise_filter: an OrderWiseFilter applied first, its result written straight into the synthesis workspace
         if not _plan.is_regular(grid):
-            raise ValueError("degree_weights are fused into the regular-grid synthesis only; filter the coefficients first")
+            raise ValueError("filters are fused into the regular-grid synthesis only; filter the coefficients first")
         p = _plan.get_plan(grid, L - 1, kernel, GM, R)
         on_device = isinstance(anm, torch.Tensor)
         x = anm if on_device else torch.as_tensor(np.ascontiguousarray(anm, dtype=float)).to(torch.device("cuda", p.device))
-        vals = p.synthesis(x, out=out if (on_device or device_output) else None, degree_weights=degree_weights)
+        vals = p.synthesis(x, out=out if (on_device or device_output) else None, degree_weights=degree_weights,
+                           orderwise_filter=orderwise_filter)
         return vals if (on_device or device_output) else vals.cpu().numpy()
     if not _plan.is_regular(grid):
         p = _plan.get_points_plan(grid, L - 1, kernel, GM, R)      # -> [E, points]

@@ -155,10 +155,12 @@ class SHPlan:
             raise ValueError("coefficients must be a float64 CUDA tensor on device {0}".format(self.device))
 
     # -- synthesis ----------------------------------------------------------------------
-    def synthesis(self, anm, out=None, degree_weights=None):
+    def synthesis(self, anm, out=None, degree_weights=None, orderwise_filter=None):
         """anm: CUDA float64 tensor [E, L, L] (packed) -> CUDA tensor [E, nlat, nlon].
         degree_weights: optional [L] weights w_n of an isotropic filter (Gaussian, Butterworth),
-        multiplied into the coefficients while they are packed (gb_synthesis_weighted)."""
+        multiplied into the coefficients while they are packed (gb_synthesis_weighted).
+        orderwise_filter: an OrderWiseFilter applied to the batch first (gb_synthesis_orderwise_filtered: its result goes
+        straight into the layout the Legendre stage reads; bit-identical to filter_batch followed by synthesis)."""
         self._check_anm(anm)
         anm = anm.contiguous()
         E = anm.shape[0]
@@ -166,6 +168,18 @@ class SHPlan:
             out = torch.empty((E, self.nlat, self.nlon), dtype=torch.float64, device=anm.device)
         else:
             _check_out(out, (E, self.nlat, self.nlon), self.device)
+        if orderwise_filter is not None:
+            if degree_weights is not None:
+                raise ValueError("pass either degree_weights or orderwise_filter")
+            if orderwise_filter.max_degree < self.max_degree:
+                raise ValueError("filter of degree {0} does not reach degree {1}".format(orderwise_filter.max_degree, self.max_degree))
+            blocks = orderwise_filter._blocks_on(self.device)
+            with self._lock:
+                _lib.check(self._lib.gb_synthesis_orderwise_filtered(
+                    self._handle, ctypes.c_void_p(blocks.data_ptr()),
+                    orderwise_filter._offsets.ctypes.data_as(ctypes.c_void_p), int(orderwise_filter.max_degree),
+                    ctypes.c_void_p(anm.data_ptr()), E, ctypes.c_void_p(out.data_ptr()), _stream_handle(self.device)))
+            return out
         if degree_weights is not None:
             if isinstance(degree_weights, torch.Tensor):        # already on the device: no copy in the call
                 w = degree_weights.to(device=anm.device, dtype=torch.float64).contiguous()

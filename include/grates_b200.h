@@ -202,6 +202,15 @@ int gb_synthesis_weighted(gb_plan* plan, const double* d_anm, const double* d_wn
                           double* d_out, void* stream);
 
 /*
+ * Order-wise block filter (gb_orderwise_filter) followed by gb_synthesis of the filtered batch, without materialising
+ * it: the filter writes its result in the layout the Legendre stage of the synthesis reads.  Replaces
+ * OrderWiseFilter.filter (filter.py:180-189) + PotentialCoefficients.to_grid (gravityfield.py:331-368) per epoch;
+ * bit-identical to the two calls in sequence.  nf >= the plan's nmax.
+ */
+int gb_synthesis_orderwise_filtered(gb_plan* plan, const double* d_blocks, const int64_t* block_offsets, int nf,
+                                    const double* d_anm, int n_epochs, double* d_out, void* stream);
+
+/*
  * Dense filter matrices (GeneralMatrix / VDK, filter.py:430-572), batched over epochs: x_e = ravel(anm_e, nmin,
  * nmax_filter), y_e = W x_e, unravel up to min(nmax_in, nmax_filter), degrees below nmin copied through.
  *   gb_dense_filter_tile_elements   doubles needed for the operand tiles of a k x k matrix

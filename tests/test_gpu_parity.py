@@ -889,6 +889,23 @@ def test_orderwise_filter_batch_then_synthesis(gb, orc):
     vals = gb.to_grid_batch(dev, grid, "ewh").cpu().numpy()
     og = orc.geographic_grid(3.0, 3.0)
     assert maxnorm_err(vals, np.stack([orc.synthesis(a, og, "ewh") for a in ref])) < TOL
+    # fused: the filter writes into the synthesis workspace (tiled layout of the table-fed Legendre stage, or the
+    # order-wise layout of the on-the-fly stage); bit-identical to the two calls, on folded and unfolded grids,
+    # batches above and below the narrow-tile limit, a filter of higher degree than the data
+    x = torch.as_tensor(anm).cuda()
+    for g2 in (grid, gb.GeographicGrid(7.0, 5.0), gb.GaussGrid(19)):
+        for xe in (x, x[:3], torch.cat([x] * 9)):
+            two = gb.to_grid_batch(flt.filter_batch(xe), g2, "ewh")
+            one = gb.to_grid_batch(xe, g2, "ewh", orderwise_filter=flt)
+            assert torch.equal(one, two)
+    import os
+    os.environ["GB_S1_ONTHEFLY"] = "1"
+    try:
+        assert torch.equal(gb.to_grid_batch(x, grid, "ewh", orderwise_filter=flt), gb.to_grid_batch(dev, grid, "ewh"))
+    finally:
+        del os.environ["GB_S1_ONTHEFLY"]
+    with pytest.raises(ValueError):
+        gb.to_grid_batch(x, grid, "ewh", orderwise_filter=gb.OrderWiseFilter(orc.synthetic_filter_blocks(20)))
 
 
 # ------------------------------------------------------------------------------ API behaviour
