@@ -168,6 +168,8 @@ int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_
 // d_roff [L + 1] = first row of every order (gb_plan::d_ptab_roff).  The buffer must have been cleared for this layout.
 int gb_launch_pack_tiled(const double* d_anm, double* d_x, int L, int E, const int* d_roff, int tn, int n_ct,
                          cudaStream_t st, const double* d_wn = nullptr);
+// symmetric Fourier stage of the synthesis on rows [0, M) of an AB-layout operand (gb_synthesis.cu); needs p->sym
+int gb_launch_stage2_sym(gb_plan* p, const double* d_ab, long long M, double* d_out, cudaStream_t st);
 // order-wise block filter of a batch, written straight into a synthesis workspace X (gb_filter.cu): order-wise packed
 // (d_roff == nullptr) or the tiled layout of gb_launch_pack_tiled (the buffer must have been cleared for it)
 int gb_filter_into_x(const double* d_blocks, const int64_t* block_offsets, int nf, const double* d_anm, int E, int nmax,

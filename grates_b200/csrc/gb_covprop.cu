@@ -389,14 +389,43 @@ __global__ void __launch_bounds__(cq_threads(CQ_WN), 1) gb_cov_quad_kernel(QuadA
 // the A-tile layout of stage 4: Ht[((row * hmt + k / 128) * kpad + k') * 132 + k % 128] (every element is written,
 // padding with zero).  Symmetric: pairs k > k' are zero, pairs k < k' count twice.  CTA = (representative r, column
 // group k'), thread = row group k.
+// krow != nullptr: H goes out in the AB layout of the synthesis' Fourier stage instead (rows (output row, k), spectral
+// index k' at row krow[k'] of the symmetric order): the plain values S +- D, both triangles when Sigma is symmetric; the
+// buffer was cleared (padding rows of the spectral groups stay zero).
 __global__ void __launch_bounds__(256)
 gb_cov_reduce_h(const double* __restrict__ Hpart, double* __restrict__ Ht, const int* __restrict__ pstart,
                 const int* __restrict__ ne4, const int* __restrict__ no4, const int* __restrict__ out_n,
-                const int* __restrict__ out_s, int kpad, int n_pieces, int hmt, int symmetric, int nmin) {
+                const int* __restrict__ out_s, int kpad, int n_pieces, int hmt, int symmetric, int nmin,
+                const int* __restrict__ krow, int ab_rows, int L) {
     const int r = blockIdx.x, kp = blockIdx.y;
     const double* src = Hpart + ((size_t)r * kpad + kp) * n_pieces * 4;
     const bool has0 = ne4[kp] > 0, has1 = no4[kp] > 0;
     const int on = out_n[r], os = out_s[r];
+    if (krow) {
+        if ((kp >> 1) >= L || kp == 1) return;                    // not a spectral row
+        const int colp = krow[kp];
+        for (int kg = threadIdx.x; kg < kpad; kg += blockDim.x) {
+            if ((kg >> 1) >= L || kg == 1 || (symmetric && kg > kp)) continue;
+            const int m = kg >> 1;
+            const int po = (max(m, nmin) - m) & 1;
+            double S = 0.0, D = 0.0;
+            for (int pc = pstart[kg]; pc < pstart[kg + 1]; ++pc) {
+                const double* v = src + (size_t)pc * 4;
+                if (has0) { S += po ? v[1] : v[0]; D += po ? v[0] : v[1]; }
+                if (has1) { S += po ? v[2] : v[3]; D += po ? v[3] : v[2]; }
+            }
+            const int colk = krow[kg];
+            if (on >= 0) {
+                Ht[gb_ab_offset((long long)on * kpad + kg, colp, ab_rows)] = S + D;
+                if (symmetric && kg != kp) Ht[gb_ab_offset((long long)on * kpad + kp, colk, ab_rows)] = S + D;
+            }
+            if (os >= 0) {
+                Ht[gb_ab_offset((long long)os * kpad + kg, colp, ab_rows)] = S - D;
+                if (symmetric && kg != kp) Ht[gb_ab_offset((long long)os * kpad + kp, colk, ab_rows)] = S - D;
+            }
+        }
+        return;
+    }
     for (int k = threadIdx.x; k < hmt * GB_LDA; k += blockDim.x) {
         const int kt = k / GB_LDA, kk = k - kt * GB_LDA;
         const int kg = kt * GB_TM + kk;
@@ -472,6 +501,30 @@ struct LonEpilogue {
         }
     }
 };
+
+// var[i][j] = sum_k T[k][j] W[(i, k)][j]: the second half of the longitude quadratic form when W = H T came from the
+// synthesis' Fourier stage; four partial sums in a fixed order (deterministic), optional sqrt.
+__global__ void __launch_bounds__(256)
+gb_cov_lon_reduce(const double* __restrict__ W, const double* __restrict__ trig, double* __restrict__ out, int kpad, int nlp,
+                  int nlon, long long n, int take_sqrt) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const long long i = idx / nlon;
+    const int j = (int)(idx - i * nlon);
+    const double* w = W + (size_t)i * kpad * nlon + j;
+    const double* t = trig + j;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 3 < kpad; k += 4) {
+        a0 = fma(t[(size_t)k * nlp], __ldcs(w + (size_t)k * nlon), a0);
+        a1 = fma(t[(size_t)(k + 1) * nlp], __ldcs(w + (size_t)(k + 1) * nlon), a1);
+        a2 = fma(t[(size_t)(k + 2) * nlp], __ldcs(w + (size_t)(k + 2) * nlon), a2);
+        a3 = fma(t[(size_t)(k + 3) * nlp], __ldcs(w + (size_t)(k + 3) * nlon), a3);
+    }
+    for (; k < kpad; ++k) a0 = fma(t[(size_t)k * nlp], __ldcs(w + (size_t)k * nlon), a0);
+    const double v = (a0 + a1) + (a2 + a3);
+    out[idx] = take_sqrt ? sqrt(v) : v;
+}
 
 __global__ void gb_cov_finish(const double* __restrict__ part, double* __restrict__ out, int nslots, int nlon, long long n,
                               int take_sqrt) {
@@ -745,9 +798,7 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
     const size_t vp_elems = (size_t)nout * nslots * p->nlon;
     GB_CUDA(scratch.alloc(&d_st, st_elems));
     GB_CUDA(scratch.alloc(&d_ut, ut_elems));
-    GB_CUDA(scratch.alloc(&d_ht, ht_elems));
     GB_CUDA(scratch.alloc(&d_hpart, hp_elems));
-    GB_CUDA(scratch.alloc(&d_vpart, vp_elems));
     GB_CUDA(cudaMemsetAsync(d_ut, 0, ut_elems * sizeof(double), st));
     {
         dim3 grid((nrep + 31) / 32, L);      // thread = (parallel, order): a serial recursion each, so many small CTAs
@@ -796,10 +847,35 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
                                                                                   : launch_quad<3, 3>(qa, p->sm_count, st);
         if (rc) return rc;
     }
+    // longitude quadratic form.  Four-fold symmetric meridians (every grid the reference builds): W = H T is exactly the
+    // Fourier stage of the synthesis on the rows (parallel, k) -- one quarter of the multiply-adds of a plain GEMM, no padded
+    // spectral rows -- followed by a streaming reduction over k.  Otherwise: the GEMM with the fused reduction below.
+    const char* lon_env = getenv("GB_COV_LON_GEMM");
+    if (p->sym && !(lon_env && lon_env[0] && lon_env[0] != '0')) {
+        const long long Mrows = (long long)nout * kpad;
+        const size_t h2_elems = (size_t)((Mrows + GB_TM - 1) / GB_TM) * p->ab_rows * GB_LDA;
+        const size_t w_elems = (size_t)Mrows * p->nlon;
+        double *d_h2 = nullptr, *d_w = nullptr;
+        GB_CUDA(scratch.alloc(&d_h2, h2_elems));
+        GB_CUDA(scratch.alloc(&d_w, w_elems));
+        GB_CUDA(cudaMemsetAsync(d_h2, 0, h2_elems * sizeof(double), st));
+        gb_cov_reduce_h<<<dim3(nrep, kpad), 256, 0, st>>>(d_hpart, d_h2, lay->d_pstart, lay->d_ne4, lay->d_no4, lay->d_out_n,
+                                                          lay->d_out_s, kpad, n_pieces, hmt, symmetric, nmin, p->d_krow_sym,
+                                                          p->ab_rows, L);
+        GB_LAUNCH_CHECK();
+        if ((rc = gb_launch_stage2_sym(p, d_h2, Mrows, d_w, st))) return rc;
+        const long long n = (long long)nout * p->nlon;
+        gb_cov_lon_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_w, p->d_trig, d_out, kpad, p->nlp, p->nlon, n,
+                                                                      take_sqrt ? 1 : 0);
+        GB_LAUNCH_CHECK();
+        return GB_OK;
+    }
+    GB_CUDA(scratch.alloc(&d_ht, ht_elems));
+    GB_CUDA(scratch.alloc(&d_vpart, vp_elems));
     {
         dim3 grid(nrep, kpad);
         gb_cov_reduce_h<<<grid, 256, 0, st>>>(d_hpart, d_ht, lay->d_pstart, lay->d_ne4, lay->d_no4, lay->d_out_n, lay->d_out_s,
-                                              kpad, n_pieces, hmt, symmetric, nmin);
+                                              kpad, n_pieces, hmt, symmetric, nmin, nullptr, 0, L);
         GB_LAUNCH_CHECK();
     }
     {

@@ -402,7 +402,9 @@ struct TabArgs {
     const int* krow;
 };
 
-template <bool PAIRS, int NWN, bool FOLD, int KC>
+// MI: 8-column fragments per consumer warp (5: 40 columns; 4: shards of at most 32 epochs, whose 64 columns then carry
+// no padding fragment)
+template <bool PAIRS, int NWN, bool FOLD, int KC, int MI = 5>
 __global__ void __launch_bounds__(tb_threads(NWN), tb_ctas_per_sm(NWN, FOLD))
 gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb, int L, int nlat, int E, int ab_rows,
               int n_lattiles, int n_coltiles, int n_items, int polar) {
@@ -410,7 +412,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
     static_assert(STAGES >= 2, "the ring needs at least two stages");
     const bool diag_nostore = (polar & 0x10000) != 0;   // DIAG
     polar &= 0xffff;
-    constexpr int TN = t1_tn(NWN), LDA = tb_lda(FOLD), LDB = TN + 4, CONSUMER_WARPS = 2 * NWN;
+    constexpr int TN = 8 * MI * NWN, LDA = tb_lda(FOLD), LDB = TN + 4, CONSUMER_WARPS = 2 * NWN;
     constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
     extern __shared__ __align__(128) unsigned char s_raw[];
     double* s_tiles = reinterpret_cast<double*>(s_raw);
@@ -470,7 +472,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
             const int wm = warp / NWN;
             const int wn = warp % NWN;
             const int g = lane >> 2, q = lane & 3;
-            const bool has_columns = wn * 40 < width;
+            const bool has_columns = wn * (8 * MI) < width;
             if constexpr (FOLD) {
                 const int nh = nlat >> 1;
                 for (int pass = 0; pass < npass; ++pass) {
@@ -478,34 +480,34 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     const int Kn = L - m;
                     const int n_chunks = (Kn + KC - 1) / KC;
                     const int kc_row = __ldg(tb.krow + 2 * m), ks_row = __ldg(tb.krow + 2 * m + 1);   // latency hides behind the K loop
-                    double ev[5][2][2], od[5][2][2];
+                    double ev[MI][2][2], od[MI][2][2];
 #pragma unroll
-                    for (int mi = 0; mi < 5; ++mi)
+                    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                         for (int ni = 0; ni < 2; ++ni) ev[mi][ni][0] = ev[mi][ni][1] = od[mi][ni][0] = od[mi][ni][1] = 0.0;
                     for (int c = 0; c < n_chunks; ++c) {
                         const int rows = Kn - c * KC;
                         gb::mbar_wait(&full[stage], phase);
                         const double* sP = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 16 + g;
-                        const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
+                        const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * (8 * MI) + g;
 #pragma unroll
                         for (int kk = 0; kk < KC; kk += 8) {
                             if (kk >= rows || !has_columns) break;
-                            double a[5], b[2];
+                            double a[MI], b[2];
 #pragma unroll
-                            for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + q) * LDB + mi * 8];
+                            for (int mi = 0; mi < MI; ++mi) a[mi] = sX[(kk + q) * LDB + mi * 8];
 #pragma unroll
                             for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(kk + q) * LDA + ni * 8];
 #pragma unroll
-                            for (int mi = 0; mi < 5; ++mi)
+                            for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                                 for (int ni = 0; ni < 2; ++ni) gb::dmma_884(ev[mi][ni][0], ev[mi][ni][1], a[mi], b[ni]);
 #pragma unroll
-                            for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + 4 + q) * LDB + mi * 8];
+                            for (int mi = 0; mi < MI; ++mi) a[mi] = sX[(kk + 4 + q) * LDB + mi * 8];
 #pragma unroll
                             for (int ni = 0; ni < 2; ++ni) b[ni] = sP[(kk + 4 + q) * LDA + ni * 8];
 #pragma unroll
-                            for (int mi = 0; mi < 5; ++mi)
+                            for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                                 for (int ni = 0; ni < 2; ++ni) gb::dmma_884(od[mi][ni][0], od[mi][ni][1], a[mi], b[ni]);
                         }
@@ -522,8 +524,8 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     const int ib = i0 + wm * 16 + 4 * q;
                     const bool quads = (nh & 3) == 0;            // 32-byte stores: whole quads on either side of the equator
 #pragma unroll
-                    for (int mi = 0; mi < 5; ++mi) {
-                        const int col = c0e + wn * 40 + mi * 8 + g;
+                    for (int mi = 0; mi < MI; ++mi) {
+                        const int col = c0e + wn * (8 * MI) + mi * 8 + g;
                         if (col >= cols) continue;
                         const int cs = col >= E;
                         const int e = col - cs * E;
@@ -563,26 +565,26 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                 const int Kn = L - m;
                 const int n_chunks = (Kn + KC - 1) / KC;
                 const int kc_row = __ldg(tb.krow + 2 * m), ks_row = __ldg(tb.krow + 2 * m + 1);
-                double acc[5][4][2];
+                double acc[MI][4][2];
 #pragma unroll
-                for (int mi = 0; mi < 5; ++mi)
+                for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
                 for (int c = 0; c < n_chunks; ++c) {
                     const int rows = (Kn - c * KC + 7) & ~7;      // the degrees of an 8-row group are interleaved
                     gb::mbar_wait(&full[stage], phase);
                     const double* sP = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 32 + g;
-                    const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * 40 + g;
+                    const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * (8 * MI) + g;
 #pragma unroll
                     for (int kk = 0; kk < KC; kk += 4) {
                         if (kk >= rows || !has_columns) break;
-                        double a[5], b[4];
+                        double a[MI], b[4];
 #pragma unroll
-                        for (int mi = 0; mi < 5; ++mi) a[mi] = sX[(kk + q) * LDB + mi * 8];
+                        for (int mi = 0; mi < MI; ++mi) a[mi] = sX[(kk + q) * LDB + mi * 8];
 #pragma unroll
                         for (int ni = 0; ni < 4; ++ni) b[ni] = sP[(kk + q) * LDA + ni * 8];
 #pragma unroll
-                        for (int mi = 0; mi < 5; ++mi)
+                        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                             for (int ni = 0; ni < 4; ++ni) gb::dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
                     }
@@ -595,8 +597,8 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                 const int ib = ((polar && wm) ? i_south : i0) + wm * 32 + 2 * q;
                 const int tile_step = ab_rows * GB_LDA - GB_TM;
 #pragma unroll
-                for (int mi = 0; mi < 5; ++mi) {
-                    const int col = c0e + wn * 40 + mi * 8 + g;
+                for (int mi = 0; mi < MI; ++mi) {
+                    const int col = c0e + wn * (8 * MI) + mi * 8 + g;
                     if (col >= cols) continue;
                     const int cs = col >= E;
                     const int e = col - cs * E;
@@ -1063,7 +1065,10 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     const bool simple1 = env_flag("GB_SIMPLE_STAGE1");
     const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
     const bool fold = p->fold_ns && !env_flag("GB_NO_FOLD");        // equatorial symmetry: 32 northern parallels per item
-    const int tn = narrow ? t1_tn(2) : t1_tn(6);
+    // shards of at most 32 epochs on folded grids without polar caps: 64-column items (no padding fragment)
+    const bool narrow32 = narrow && fold && p->fold_cap == 0 && 2 * E <= 64 && !simple1 && !env_flag("GB_S1_ONTHEFLY") &&
+                          !env_flag("GB_S1_MI5");
+    const int tn = narrow32 ? 64 : narrow ? t1_tn(2) : t1_tn(6);
     const int n_coltiles = (2 * E + tn - 1) / tn;
     const int cap_tiles = fold ? p->fold_cap / 32 : 0;              // polar tiles that stay unfolded
     const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 - cap_tiles : (p->nlat + T1_TM - 1) / T1_TM;
@@ -1120,7 +1125,8 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
             const bool kc32 = env_flag("GB_S1_KC32");
             int rc = GB_OK;
             if (fold) {
-                rc = narrow ? launch_tab(gb_stage1_tab<true, 2, true, 16>, 2, true, 16, 0, n_lattiles, n_items, cap_tiles)
+                rc = narrow32 ? launch_tab(gb_stage1_tab<true, 2, true, 16, 4>, 2, true, 16, 0, n_lattiles, n_items, cap_tiles)
+                     : narrow ? launch_tab(gb_stage1_tab<true, 2, true, 16>, 2, true, 16, 0, n_lattiles, n_items, cap_tiles)
                      : kc32 ? launch_tab(gb_stage1_tab<true, 6, true, 32>, 6, true, 32, 0, n_lattiles, n_items, cap_tiles)
                             : launch_tab(gb_stage1_tab<true, 6, true, 16>, 6, true, 16, 0, n_lattiles, n_items, cap_tiles | (env_flag("GB_DIAG_NOSTORE") ? 0x10000 : 0));
                 if (!rc && cap_tiles > 0)
@@ -1209,6 +1215,25 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         GB_CUDA(cudaEventRecord(prof[3], st));
         p->prof_count++;
     }
+    return GB_OK;
+}
+
+// The symmetric Fourier stage on any row set in the AB layout (used by the covariance propagation, whose longitude
+// quadratic form starts with the same contraction): d_out[row][j] = sum_k d_ab[row][k] trig[k][j], rows [0, M).
+int gb_launch_stage2_sym(gb_plan* p, const double* d_ab, long long M, double* d_out, cudaStream_t st) {
+    GB_REQUIRE(p->sym, "gb_launch_stage2_sym: the plan's meridians are not four-fold symmetric");
+    const int n_mtiles = (int)((M + Q_TM - 1) / Q_TM);
+    const int n_ntiles = p->n_qtiles;
+    const long long n_tiles = (long long)n_mtiles * n_ntiles;
+    if (n_tiles == 0) return GB_OK;
+    const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
+    QGroups grp;
+    for (int g = 0; g < 5; ++g) grp.off[g] = p->grp_off[g];
+    GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_sym<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
+    const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 8 == 0) ? 1 : 0;
+    gb_fourier_stage2_sym<true><<<grid, QE_THREADS, Q_SMEM, st>>>(d_ab, p->ab_rows, p->d_trig_q_t, p->kpad_s, grp, d_out, M,
+                                                                 p->nlon, p->nq, n_mtiles, n_ntiles, wide);
+    GB_LAUNCH_CHECK();
     return GB_OK;
 }
 
