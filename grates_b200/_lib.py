@@ -30,6 +30,7 @@ SIGNATURES = {
     "gb_synthesis_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "gb_legendre_table": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "gb_plan_set_analysis": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),
+    "gb_plan_set_analysis_weights": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
     "gb_analysis": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
     "gb_analysis_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "gb_synthesis_matrix": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),

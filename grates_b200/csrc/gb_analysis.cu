@@ -263,11 +263,105 @@ gb_analysis_lat_kernel(const double* __restrict__ G, const double* __restrict__ 
 
 }  // namespace
 
-extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_ops, const double* lat_ops,
-                                    const int64_t* lat_op_offsets) {
+// ---------------------------------------------------------------------------------------------
+// The latitude-side least-squares operators on the device (reference grid.py:690-696 per order:
+// op_m = solve(P' W P, P' W), P[i][n] = kn[i,n] P_nm(theta_i), W = diag(w_lat)): P and (W P)' by the bit-exact recursion,
+// then per order the normal matrix (gb_dgemm, FP64 tensor cores), its Cholesky factor (gb_dpotrf_upper) and two
+// triangular solves (gb_dtrsm_upper) in place of (W P)'.  The host variant (plan.py: analysis_operators, numpy LU) costs
+// 0.5-0.8 s at degree 180; the normal matrices of a quadrature-like grid are well conditioned, the two agree to 1e-14.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+gb_ana_design_kernel(double* __restrict__ P, double* __restrict__ PW, const long long* __restrict__ off,
+                     const double* __restrict__ ct, const double* __restrict__ kn, const double* __restrict__ pmm,
+                     const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc, int L,
+                     int nlat, int nmin, const double* __restrict__ w) {
+    const int i = blockIdx.x * 32 + threadIdx.x, m = blockIdx.y;
+    if (i >= nlat) return;
+    const int n0 = max(m, nmin), cnt = L - n0;
+    if (cnt <= 0) return;
+    double* Pm = P + off[m] + (size_t)i * cnt;           // [nlat][cnt]
+    double* PWm = PW + off[m] + i;                       // [cnt][nlat]
+    const double* kn_i = kn + (size_t)i * L;
+    const double wi = w[i];
+    gb::legendre_column(m, L, ct[i], pmm[(size_t)i * L + m], ra, rb, rc, [&](int n, double p) {
+        if (n < n0) return;
+        const double v = __dmul_rn(p, kn_i[n]);
+        Pm[n - n0] = v;
+        PWm[(size_t)(n - n0) * nlat] = v * wi;
+    });
+}
+
+// lt[(tile * nlat_p4 + i) * GB_LDA + r] = op_m[r0 + r][i]   (the A operand of the latitude GEMM)
+__global__ void __launch_bounds__(GB_TM)
+gb_ana_tile_lat_kernel(const double* __restrict__ lat_ops, const long long* __restrict__ off, double* __restrict__ lt,
+                       const int* __restrict__ tile_m, const int* __restrict__ tile_n, int nlat, int nlat_p4, int L, int nmin) {
+    __shared__ double s_t[32][GB_TM + 1];
+    const int t = blockIdx.x, m = tile_m[t];
+    const int n0 = max(m, nmin), r0 = tile_n[t] - n0;
+    const int rows = min(GB_TM, L - tile_n[t]);
+    const int i0 = blockIdx.y * 32;
+    const double* op = lat_ops + off[m] + (size_t)r0 * nlat;
+    // coalesced along the parallels on the way in, along the rows on the way out
+    for (int idx = threadIdx.x; idx < rows * 32; idx += GB_TM) {
+        const int r = idx >> 5, ii = idx & 31;
+        s_t[ii][r] = (i0 + ii < nlat) ? op[(size_t)r * nlat + i0 + ii] : 0.0;
+    }
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < rows)
+        for (int ii = 0; ii < 32 && i0 + ii < nlat; ++ii) lt[((size_t)t * nlat_p4 + i0 + ii) * GB_LDA + r] = s_t[ii][r];
+}
+
+static int build_lat_operators(gb_plan* p, int nmin, const double* w_lat) {
+    const int L = p->L, nlat = p->nlat, dev = p->device;
+    const size_t total = (size_t)p->h_lat_off[L];
+    if (total == 0) return GB_OK;
+    double *d_p = nullptr, *d_n = nullptr, *d_w = nullptr;
+    int* d_info = nullptr;
+    auto cleanup = [&] { cudaFree(d_p); cudaFree(d_n); cudaFree(d_w); cudaFree(d_info); };
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_p), total * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_n), (size_t)L * L * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_w), (size_t)nlat * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_info), (size_t)L * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(d_w, w_lat, (size_t)nlat * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cleanup();
+        return gb_set_error(GB_ERR_CUDA, "gb_plan_set_analysis_weights: %s", cudaGetErrorString(e));
+    }
+    gb_ana_design_kernel<<<dim3((nlat + 31) / 32, L), 32>>>(d_p, p->d_lat_ops, p->d_lat_off, p->d_ct, p->d_kn, p->d_pmm, p->d_ra,
+                                                          p->d_rb, p->d_rc, L, nlat, nmin, d_w);
+    gb_count_launch();
+    int rc = GB_OK;
+    for (int m = 0; m < L && !rc; ++m) {
+        const long long cnt = L - (m > nmin ? m : nmin);
+        if (cnt <= 0) continue;
+        double* pw = p->d_lat_ops + p->h_lat_off[m];      // (W P)' [cnt][nlat] -> the operator, in place
+        const double* pm = d_p + p->h_lat_off[m];         // P [nlat][cnt]
+        rc = gb_dgemm(0, 0, cnt, cnt, nlat, 1.0, pw, nlat, pm, cnt, 0.0, d_n, cnt, 1, dev, nullptr);
+        if (!rc) rc = gb_dpotrf_upper(d_n, cnt, cnt, d_info + m, dev, nullptr);
+        if (!rc) rc = gb_dtrsm_upper(1, d_n, cnt, cnt, pw, nlat, nlat, dev, nullptr);
+        if (!rc) rc = gb_dtrsm_upper(0, d_n, cnt, cnt, pw, nlat, nlat, dev, nullptr);
+    }
+    if (!rc) {
+        std::vector<int> info(L, 0);
+        e = cudaMemcpy(info.data(), d_info, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost);   // also waits for the stream
+        if (e != cudaSuccess) rc = gb_set_error(GB_ERR_CUDA, "gb_plan_set_analysis_weights: %s", cudaGetErrorString(e));
+        for (int m = 0; m < L && !rc; ++m)
+            if (L - (m > nmin ? m : nmin) > 0 && info[m] != 0)
+                rc = gb_set_error(GB_ERR_ARGUMENT, "gb_plan_set_analysis_weights: the normal matrix of order %d is not positive "
+                                  "definite (pivot %d): the grid does not resolve degree %d", m, info[m], p->nmax);
+    }
+    cleanup();
+    return rc;
+}
+
+// lat_ops != nullptr: host operators (gb_plan_set_analysis); else they are built on the device from the latitude
+// weights w_lat (gb_plan_set_analysis_weights)
+static int set_analysis(gb_plan* plan, int nmin, const double* lon_ops, const double* lat_ops, const int64_t* lat_op_offsets,
+                        const double* w_lat) {
     GB_REQUIRE(plan != nullptr, "gb_plan_set_analysis: plan is NULL");
     GB_REQUIRE(nmin >= 0 && nmin <= plan->nmax, "gb_plan_set_analysis: min_degree=%d outside [0, %d]", nmin, plan->nmax);
-    GB_REQUIRE(lon_ops && lat_ops && lat_op_offsets, "gb_plan_set_analysis: NULL pointer");
+    GB_REQUIRE(lon_ops && ((lat_ops && lat_op_offsets) || w_lat), "gb_plan_set_analysis: NULL pointer");
     gb_plan* p = plan;
     GB_CUDA(cudaSetDevice(p->device));
     GB_CUDA(cudaDeviceSynchronize());
@@ -284,18 +378,26 @@ extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_o
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_lon_ops), lonT.size() * sizeof(double)));
     GB_CUDA(cudaMemcpy(p->d_lon_ops, lonT.data(), lonT.size() * sizeof(double), cudaMemcpyHostToDevice));
     p->h_lat_off = new long long[L + 1];
-    for (int m = 0; m <= L; ++m) p->h_lat_off[m] = lat_op_offsets[m];
+    p->h_lat_off[0] = 0;
     for (int m = 0; m < L; ++m) {
         const long long expect = (long long)(L - (m > nmin ? m : nmin)) * p->nlat;
-        GB_REQUIRE(p->h_lat_off[m + 1] - p->h_lat_off[m] == (expect > 0 ? expect : 0),
-                   "gb_plan_set_analysis: operator of order %d has %lld elements, expected %lld", m,
-                   p->h_lat_off[m + 1] - p->h_lat_off[m], expect);
+        if (lat_ops) {
+            GB_REQUIRE(lat_op_offsets[m + 1] - lat_op_offsets[m] == (expect > 0 ? expect : 0),
+                       "gb_plan_set_analysis: operator of order %d has %lld elements, expected %lld", m,
+                       (long long)(lat_op_offsets[m + 1] - lat_op_offsets[m]), expect);
+        }
+        p->h_lat_off[m + 1] = p->h_lat_off[m] + (expect > 0 ? expect : 0);
     }
     const size_t total = (size_t)p->h_lat_off[L];
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_lat_ops), (total ? total : 1) * sizeof(double)));
-    GB_CUDA(cudaMemcpy(p->d_lat_ops, lat_ops, total * sizeof(double), cudaMemcpyHostToDevice));
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_lat_off), (L + 1) * sizeof(long long)));
     GB_CUDA(cudaMemcpy(p->d_lat_off, p->h_lat_off, (L + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    if (lat_ops) {
+        GB_CUDA(cudaMemcpy(p->d_lat_ops, lat_ops, total * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        int rcb = build_lat_operators(p, nmin, w_lat);
+        if (rcb) return rcb;
+    }
 
     // ---- operator tiles for the tensor-core longitude stage ----
     cudaFree(p->d_ana_w_t); p->d_ana_w_t = nullptr;
@@ -386,25 +488,34 @@ extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_o
             }
         }
         p->ana_lat_tiles = (int)tile_m.size();
-        std::vector<double> lt((size_t)p->ana_lat_tiles * p->ana_nlat_p4 * GB_LDA, 0.0);
-        for (int t = 0; t < p->ana_lat_tiles; ++t) {
-            const int m = tile_m[t], n0 = m > nmin ? m : nmin;
-            const int r0 = tile_n[t] - n0;
-            const int rows = (L - tile_n[t]) < GB_TM ? (L - tile_n[t]) : GB_TM;
-            const double* op = lat_ops + p->h_lat_off[m];
-            for (int r = 0; r < rows; ++r)
-                for (int i = 0; i < nlat; ++i)
-                    lt[((size_t)t * p->ana_nlat_p4 + i) * GB_LDA + r] = op[(size_t)(r0 + r) * nlat + i];
-        }
-        GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_lat_t), (lt.size() ? lt.size() : 1) * sizeof(double)));
-        GB_CUDA(cudaMemcpy(p->d_ana_lat_t, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice));
+        const size_t lt_elems = (size_t)p->ana_lat_tiles * p->ana_nlat_p4 * GB_LDA;
+        GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_lat_t), (lt_elems ? lt_elems : 1) * sizeof(double)));
+        GB_CUDA(cudaMemset(p->d_ana_lat_t, 0, (lt_elems ? lt_elems : 1) * sizeof(double)));
         GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_lat_m), (tile_m.size() + 1) * sizeof(int)));
         GB_CUDA(cudaMemcpy(p->d_ana_lat_m, tile_m.data(), tile_m.size() * sizeof(int), cudaMemcpyHostToDevice));
         GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_ana_lat_n), (tile_n.size() + 1) * sizeof(int)));
         GB_CUDA(cudaMemcpy(p->d_ana_lat_n, tile_n.data(), tile_n.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (p->ana_lat_tiles > 0) {
+            // A[i][r] = lat_op_m[r][i]: the operators (host-built and uploaded, or built on the device) re-tiled on the device
+            gb_ana_tile_lat_kernel<<<dim3(p->ana_lat_tiles, (nlat + 31) / 32), GB_TM>>>(
+                p->d_lat_ops, p->d_lat_off, p->d_ana_lat_t, p->d_ana_lat_m, p->d_ana_lat_n, nlat, p->ana_nlat_p4, L, nmin);
+            GB_LAUNCH_CHECK();
+            GB_CUDA(cudaDeviceSynchronize());
+        }
     }
     p->ana_nmin = nmin;
     return GB_OK;
+}
+
+extern "C" int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_ops, const double* lat_ops,
+                                    const int64_t* lat_op_offsets) {
+    GB_REQUIRE(lat_ops && lat_op_offsets, "gb_plan_set_analysis: NULL pointer");
+    return set_analysis(plan, nmin, lon_ops, lat_ops, lat_op_offsets, nullptr);
+}
+
+extern "C" int gb_plan_set_analysis_weights(gb_plan* plan, int nmin, const double* lon_ops, const double* w_lat) {
+    GB_REQUIRE(w_lat, "gb_plan_set_analysis_weights: NULL pointer");
+    return set_analysis(plan, nmin, lon_ops, nullptr, nullptr, w_lat);
 }
 
 static int launch_analysis(gb_plan* p, const double* d_grid, int E, double* d_anm, cudaStream_t st) {

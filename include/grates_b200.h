@@ -142,6 +142,11 @@ int gb_legendre_table(gb_plan* plan, double* d_out, int scaled, void* stream);
  */
 int gb_plan_set_analysis(gb_plan* plan, int nmin, const double* lon_ops, const double* lat_ops,
                          const int64_t* lat_op_offsets);
+/* The same with the latitude-side operators built ON THE DEVICE from the latitude factor w_lat [nlat] (host) of the
+ * separable area weights: P by the bit-exact recursion, per order the normal matrix, its Cholesky factor and two
+ * triangular solves (gb_dgemm / gb_dpotrf_upper / gb_dtrsm_upper).  Fails with GB_ERR_ARGUMENT if a normal matrix is
+ * not positive definite (the grid does not resolve the degree). */
+int gb_plan_set_analysis_weights(gb_plan* plan, int nmin, const double* lon_ops, const double* w_lat);
 /*   d_grid [n_epochs][nlat][nlon] -> d_anm [n_epochs][L][L] packed (degrees < nmin zero). */
 int gb_analysis(gb_plan* plan, const double* d_grid, int n_epochs, double* d_anm, void* stream);
 int gb_analysis_host(gb_plan* plan, const double* h_grid, int n_epochs, double* h_anm);

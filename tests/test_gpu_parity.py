@@ -292,7 +292,9 @@ def test_analysis_paths_agree(gb, orc, monkeypatch, nmax, dlon, dlat):
     vals = rng.standard_normal((3,) + og.shape)
     ref = orc.analysis_separable(vals, og, 1, nmax, "potential")
     results = {}
-    for tag, env in (("default", {}), ("nosym", {"GB_NO_SYMMETRY": "1"}), ("simple", {"GB_SIMPLE_ANALYSIS": "1"})):
+    # "hostops": the latitude operators solved with numpy on the host instead of the device Cholesky path
+    for tag, env in (("default", {}), ("nosym", {"GB_NO_SYMMETRY": "1"}), ("simple", {"GB_SIMPLE_ANALYSIS": "1"}),
+                     ("hostops", {"GB_ANALYSIS_HOST_OPERATORS": "1"})):
         gb.clear_plan_cache()
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -302,6 +304,7 @@ def test_analysis_paths_agree(gb, orc, monkeypatch, nmax, dlon, dlat):
     gb.clear_plan_cache()
     for tag, out in results.items():
         assert maxnorm_err(out, ref) < TOL, tag
+    assert maxnorm_err(results["default"], results["hostops"]) < 1e-13
 
 
 def test_dense_operators_golden(gb, golden):
