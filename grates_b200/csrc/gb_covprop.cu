@@ -276,14 +276,23 @@ __global__ void __launch_bounds__(cq_threads(CQ_WN), 1) gb_cov_quad_kernel(QuadA
             const int mt = sg.x, it = sg.y;
             const int cc = wn * (8 * NI) + 2 * q;                       // first column of the thread inside the tile (even)
             const int i0 = it * TN + cc;                                // its first representative parallel
-            int kslab[4], piece[4];
+            int kslab[4];
+            // runs of slabs with one group (warp-uniform): bit mi of head_mask = slab mi starts a run, of valid_mask = it
+            // belongs to a group; hb[mi] = where this lane stores the piece of the run starting at slab mi (see below)
+            int head_mask = 0, valid_mask = 0;
+            double* hb[4];
             // ---- segment head: row-side factors -> tensor memory ----
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const int row = mt * GB_TM + wm * 32 + mi * 8 + g;
                 const int k = qa.rowgroup[row >> 3];
                 kslab[mi] = k;
-                piece[mi] = qa.piece_of[row >> 3];
+                if (k >= 0) {
+                    valid_mask |= 1 << mi;
+                    if (mi == 0 || k != kslab[mi > 0 ? mi - 1 : 0]) head_mask |= 1 << mi;
+                }
+                // lanes 0..15 store: value r = bit 3 of the lane (parallel i0 + r), row parity = bit 2
+                hb[mi] = qa.Hpart + ((size_t)(i0 + ((lane >> 3) & 1)) * qa.kpad * qa.n_pieces + qa.piece_of[row >> 3]) * 4 + (g & 1);
                 double u[2 * NI];
 #pragma unroll
                 for (int j = 0; j < 2 * NI; ++j) u[j] = 0.0;
@@ -348,31 +357,37 @@ __global__ void __launch_bounds__(cq_threads(CQ_WN), 1) gb_cov_quad_kernel(QuadA
                             acc[mi][ni][1] *= u[2 * ni + 1];
                         }
                     }
+                    const size_t toff = ((size_t)kp * qa.n_pieces) * 4 + c * 2;
 #pragma unroll
                     for (int head = 0; head < 4; ++head) {
-                        const int k = kslab[head];
-                        if (k < 0 || (head > 0 && k == kslab[head - 1])) continue;     // padding, or not the first slab of its run
-                        if (qa.symmetric && k > kp) continue;
-                        double* h = qa.Hpart + (((size_t)i0 * qa.kpad + kp) * qa.n_pieces + piece[head]) * 4 + c * 2 + (g & 1);
+                        if (!((head_mask >> head) & 1)) continue;                       // warp-uniform
+                        if (qa.symmetric && kslab[head] > kp) continue;
+                        double s0[NI], s1[NI];
 #pragma unroll
                         for (int ni = 0; ni < NI; ++ni) {
-                            double s0 = 0.0, s1 = 0.0;
+                            s0[ni] = acc[head][ni][0];
+                            s1[ni] = acc[head][ni][1];
+                        }
 #pragma unroll
-                            for (int mi = head; mi < 4; ++mi)
-                                if (kslab[mi] == k) {
-                                    s0 += acc[mi][ni][0];
-                                    s1 += acc[mi][ni][1];
-                                }
-                            // rows g, g + 2, g + 4, g + 6 of the slab: the degrees of one parity
-                            s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
-                            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-                            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                            if (lane < 8) {
-                                const int i = i0 + ni * 8;
-                                if (i < qa.nrep) h[(size_t)(ni * 8) * hstep] = s0;
-                                if (i + 1 < qa.nrep) h[(size_t)(ni * 8 + 1) * hstep] = s1;
+                        for (int mi = head + 1; mi < 4; ++mi) {
+                            if (((head_mask >> mi) & 1) || !((valid_mask >> mi) & 1)) break;
+#pragma unroll
+                            for (int ni = 0; ni < NI; ++ni) {
+                                s0[ni] += acc[mi][ni][0];
+                                s1[ni] += acc[mi][ni][1];
                             }
+                        }
+                        // rows g, g + 2, g + 4, g + 6 of the slab are the degrees of one parity.  Two shuffles per pair of
+                        // values: the lanes with bit 3 clear collect the first value, those with bit 3 set the second
+                        double* h = hb[head] + toff;
+#pragma unroll
+                        for (int ni = 0; ni < NI; ++ni) {
+                            const bool second = (lane & 8) != 0;
+                            double mine = second ? s1[ni] : s0[ni];
+                            const double theirs = second ? s0[ni] : s1[ni];
+                            mine += __shfl_xor_sync(0xffffffffu, theirs, 8);
+                            mine += __shfl_xor_sync(0xffffffffu, mine, 16);
+                            if (lane < 16 && i0 + ((lane >> 3) & 1) + ni * 8 < qa.nrep) h[(size_t)(ni * 8) * hstep] = mine;
                         }
                     }
                 }
