@@ -12,7 +12,7 @@ _c_int64_p = ctypes.POINTER(ctypes.c_int64)
 _vp = ctypes.c_void_p
 
 GB_OK, GB_ERR_ARGUMENT, GB_ERR_CUDA, GB_ERR_UNSUPPORTED, GB_ERR_MEMORY = 0, 1, 2, 3, 4
-GB_VERSION = 201        # must equal GB_VERSION of include/grates_b200.h: the argtypes below describe THAT header
+GB_VERSION = 202        # must equal GB_VERSION of include/grates_b200.h: the argtypes below describe THAT header
 
 # name -> (restype, argtypes); must list every symbol of include/grates_b200.h
 SIGNATURES = {

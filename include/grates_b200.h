@@ -47,7 +47,7 @@ typedef struct gb_plan gb_plan;
 
 /* Library version (major*10000 + minor*100 + patch); bumped with every change of this header.  The Python binding
  * refuses a library whose version differs from the one it was written for (grates_b200/_lib.py). */
-#define GB_VERSION 201
+#define GB_VERSION 202
 int gb_version(void);
 
 /* Thread-local description of the last error returned on this thread. */
