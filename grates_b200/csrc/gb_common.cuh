@@ -94,7 +94,16 @@ struct gb_plan {
     double* d_trig_t = nullptr;   // tiled copy of d_trig:   [n_ntiles][kpad][GB_S2_LDB]
     double* d_trig_q_t = nullptr; // tiled copy of d_trig_q: [n_qtiles][kpad_s][GB_Q_LDB]
     int n_ntiles = 0, n_qtiles = 0;
-    int ab_rows = 0;            // spectral rows allocated per AB tile = max(kpad, kpad_s)
+    // eight-fold longitude symmetry (the first-quadrant meridians are also symmetric about pi/4): spectral rows grouped by
+    // order mod 4 as [CE0 | CE2 | SE0 | SE2 | CO | SO], each padded to 4; two first-OCTANT tables (gb_synthesis.cu)
+    int oct = 0;                // 1 if the octant stage 2 is usable
+    int no = 0;                 // first-octant meridians (nlon / 8)
+    int kpad_o = 0;             // rows of AB in the octant layout (incl. 4 dummy rows at the end)
+    int ogrp_off[7] = {0, 0, 0, 0, 0, 0, 0};
+    int* d_krow_oct = nullptr;  // [kpad] k = 2m+cs -> AB row, octant layout
+    double* d_trig_o_t = nullptr; // [n_otiles][2 tables][kpad_o][GB_Q_LDB]
+    int n_otiles = 0;
+    int ab_rows = 0;            // spectral rows allocated per AB tile = max(kpad, kpad_s, kpad_o)
     // synthesis workspace, grown on demand (epochs)
     int ws_epochs = 0;
     long long ws_mpad = 0;

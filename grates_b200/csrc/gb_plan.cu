@@ -251,8 +251,98 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
         }
     }
 
+    // Eight-fold symmetry: the first-quadrant meridians mirror about pi/4, mu' = pi/2 - mu = lon[h + q - 1 - j], where
+    //   m = 0 (4): cos(m mu') =  cos(m mu), sin(m mu') = -sin(m mu)      m = 1 (4): cos(m mu') =  sin(m mu), sin(m mu') =  cos(m mu)
+    //   m = 2 (4): cos(m mu') = -cos(m mu), sin(m mu') =  sin(m mu)      m = 3 (4): cos(m mu') = -sin(m mu), sin(m mu') = -cos(m mu)
+    // so the even orders split once more (half their multiply-adds) and the odd orders are contracted with the octant's
+    // cosine AND sine row (same multiply-adds, shared coefficient fragments).  Checked on the tables, as above.
+    std::vector<int> krow_oct(p->kpad, 0);
+    std::vector<double> trig_o_t;
+    if (p->sym && nlon % 16 == 0) {
+        const int h = nlon / 2, q = nlon / 4, no = nlon / 8;
+        bool oct = true;
+        for (int m = 0; m < L && oct; ++m) {
+            const double tol = 4.0 * (m + 1) * 2.220446049250313e-16 * 3.141592653589793;
+            const double* c = cos_mlon + (size_t)m * nlon;
+            const double* s = sin_mlon + (size_t)m * nlon;
+            for (int j = 0; j < no; ++j) {
+                const double cm = c[h + j], sm = s[h + j], cp = c[h + q - 1 - j], sp = s[h + q - 1 - j];
+                double ec, es;
+                switch (m & 3) {
+                    case 0: ec = cm; es = -sm; break;
+                    case 1: ec = sm; es = cm; break;
+                    case 2: ec = -cm; es = sm; break;
+                    default: ec = -sm; es = -cm; break;
+                }
+                if (std::fabs(cp - ec) > tol || std::fabs(sp - es) > tol) {
+                    oct = false;
+                    break;
+                }
+            }
+        }
+        const char* env = getenv("GB_NO_OCTANT");
+        if (env && env[0] && env[0] != '0') oct = false;
+        p->oct = oct ? 1 : 0;
+        if (oct) {
+            p->no = no;
+            // group sizes: orders 0, 4, .. | 2, 6, .. (cosine coefficients); 4, 8, .. | 2, 6, .. (sine); odd orders (cos), (sin)
+            int cnt[6] = {0, 0, 0, 0, 0, 0};
+            for (int m = 0; m < L; ++m) {
+                if ((m & 3) == 0) { ++cnt[0]; if (m > 0) ++cnt[2]; }
+                else if ((m & 3) == 2) { ++cnt[1]; ++cnt[3]; }
+                else { ++cnt[4]; ++cnt[5]; }
+            }
+            for (int g = 0; g < 6; ++g) p->ogrp_off[g + 1] = p->ogrp_off[g] + (cnt[g] + 3) / 4 * 4;
+            p->kpad_o = p->ogrp_off[6] + 4;
+            const int nop = (no + GB_Q_TN - 1) / GB_Q_TN * GB_Q_TN;
+            std::vector<double> t1((size_t)p->kpad_o * nop, 0.0), t2((size_t)p->kpad_o * nop, 0.0);
+            int fill[6] = {0, 0, 0, 0, 0, 0};
+            for (int m = 0; m < L; ++m) {
+                const double* c = cos_mlon + (size_t)m * nlon + h;
+                const double* s = sin_mlon + (size_t)m * nlon + h;
+                int rc_row, rs_row = p->kpad_o - 1;           // (m = 0, sin) does not exist: dummy row
+                if ((m & 1) == 0) {
+                    const int gc = (m & 3) == 0 ? 0 : 1, gs = gc + 2;
+                    rc_row = p->ogrp_off[gc] + fill[gc]++;
+                    if (m > 0) rs_row = p->ogrp_off[gs] + fill[gs]++;
+                    for (int j = 0; j < no; ++j) {
+                        t1[(size_t)rc_row * nop + j] = c[j];
+                        if (m > 0) t1[(size_t)rs_row * nop + j] = s[j];
+                    }
+                } else {
+                    const double sg = (m & 3) == 1 ? 1.0 : -1.0;
+                    rc_row = p->ogrp_off[4] + fill[4]++;
+                    rs_row = p->ogrp_off[5] + fill[5]++;
+                    for (int j = 0; j < no; ++j) {
+                        t1[(size_t)rc_row * nop + j] = c[j];          // A_m cos(m mu)           -> CO(mu)
+                        t2[(size_t)rc_row * nop + j] = sg * s[j];     // A_m (+-) sin(m mu)      -> CO(pi/2 - mu)
+                        t1[(size_t)rs_row * nop + j] = s[j];          // B_m sin(m mu)           -> SO(mu)
+                        t2[(size_t)rs_row * nop + j] = sg * c[j];     // B_m (+-) cos(m mu)      -> SO(pi/2 - mu)
+                    }
+                }
+                krow_oct[2 * m] = rc_row;
+                krow_oct[2 * m + 1] = rs_row;
+            }
+            for (int k = 2 * L; k < p->kpad; ++k) krow_oct[k] = p->kpad_o - 1;
+            // tiles of 32 octant meridians, both tables side by side; the columns of a warp's 16-column slab interleaved as
+            // in the quadrant tiles (a lane's two fragments are four consecutive meridians)
+            p->n_otiles = nop / GB_Q_TN;
+            trig_o_t.assign((size_t)p->n_otiles * 2 * p->kpad_o * GB_Q_LDB, 0.0);
+            for (int t = 0; t < p->n_otiles; ++t)
+                for (int tb = 0; tb < 2; ++tb)
+                    for (int k = 0; k < p->kpad_o; ++k)
+                        for (int cc = 0; cc < GB_Q_TN; ++cc) {
+                            const int slab = cc / 16, tc = cc % 16;
+                            const int src = t * GB_Q_TN + slab * 16 + 4 * ((tc % 8) / 2) + 2 * (tc / 8) + (tc % 2);
+                            trig_o_t[(((size_t)t * 2 + tb) * p->kpad_o + k) * GB_Q_LDB + cc] =
+                                (tb ? t2 : t1)[(size_t)k * nop + src];
+                        }
+        }
+    }
+
     // tiled + padded copies of the longitude tables (one bulk copy per pipeline stage)
     p->ab_rows = p->kpad > p->kpad_s ? p->kpad : p->kpad_s;
+    if (p->kpad_o > p->ab_rows) p->ab_rows = p->kpad_o;
     p->n_ntiles = (p->nlp + GB_S2_TN - 1) / GB_S2_TN;
     std::vector<double> trig_t((size_t)p->n_ntiles * p->kpad * GB_S2_LDB, 0.0);
     for (int t = 0; t < p->n_ntiles; ++t)
@@ -308,6 +398,7 @@ extern "C" int gb_plan_create(gb_plan** plan, int nmax, int nlat, int nlon, cons
         (rc_ = upload(&p->d_ra, ra)) || (rc_ = upload(&p->d_rb, rb)) || (rc_ = upload(&p->d_rc, rc)) ||
         (rc_ = upload(&p->d_trig, trig)) || (rc_ = upload(&p->d_zero, std::vector<double>(512, 0.0))) ||
         (rc_ = upload(&p->d_krow_id, krow_id)) || (rc_ = upload(&p->d_krow_sym, krow_sym)) ||
+        (p->oct && ((rc_ = upload(&p->d_krow_oct, krow_oct)) || (rc_ = upload(&p->d_trig_o_t, trig_o_t)))) ||
         (p->sym && (rc_ = upload(&p->d_trig_q, trig_q)))) {
         gb_plan_destroy(p);
         return rc_;
@@ -336,6 +427,7 @@ extern "C" int gb_plan_destroy(gb_plan* p) {
     cudaFree(p->d_rc); cudaFree(p->d_trig); cudaFree(p->d_zero);
     cudaFree(p->d_ct_pad); cudaFree(p->d_kn_t); cudaFree(p->d_pmm_t); cudaFree(p->d_rec_a); cudaFree(p->d_rec_b);
     cudaFree(p->d_krow_id); cudaFree(p->d_krow_sym); cudaFree(p->d_trig_q);
+    cudaFree(p->d_krow_oct); cudaFree(p->d_trig_o_t);
     cudaFree(p->d_trig_t); cudaFree(p->d_trig_q_t); cudaFree(p->d_x); cudaFree(p->d_ab);
     cudaFree(p->d_io_in); cudaFree(p->d_io_out[0]); cudaFree(p->d_io_out[1]);
     cudaFree(p->d_lon_ops); cudaFree(p->d_lat_ops); cudaFree(p->d_lat_off);

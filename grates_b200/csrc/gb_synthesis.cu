@@ -972,6 +972,290 @@ gb_fourier_stage2_sym(const double* __restrict__ AB, int ab_rows, const double* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// stage 2 with EIGHT-fold longitude symmetry -- third declared shortcut of the synthesis (gb_plan::oct, gated on the
+// trig tables like the four-fold one).  The first-quadrant meridians mirror about pi/4: with nu = lon[h + j] in the first
+// octant and mu' = pi/2 - nu, the orders m = 0, 2 (mod 4) only change the SIGN of their cosine / sine rows, the odd
+// orders swap them (gb_plan.cu).  Per octant meridian eight sums
+//   E0, E2 = sum_{m = 0, 2 (4)} A_m cos(m nu)     F0, F2 = sum_{m = 0, 2 (4)} B_m sin(m nu)         (even orders: K / 2 each)
+//   CO = sum_odd A_m cos(m nu),  AS = sum_odd A_m (+-) sin(m nu)      SO = sum_odd B_m sin(m nu),  BC = sum_odd B_m (+-) cos(m nu)
+// give the quadrant sums at nu (CE = E0 + E2, SE = F0 + F2, CO, SO) and at pi/2 - nu (CE = E0 - E2, SE = F2 - F0,
+// CO = AS, SO = BC), hence eight meridians: the even orders cost half the multiply-adds of the quadrant kernel, the odd
+// ones the same -- 3/4 in total -- and an odd k-step feeds two accumulator sets from ONE coefficient fragment (8 LDS per
+// 16 DMMA instead of 6 per 8).
+// Same structure as gb_fourier_stage2_sym<EW>: persistent, 8 consumer warps (4 x 2, 32 rows x 16 octant columns), 4
+// epilogue warps, 1 producer lane, 4-stage ring (coefficient chunk + one or two table chunks).  CTA tile 128 rows x 32 octant
+// columns = 128 x 256 outputs.  A tile is parked in tensor memory in two halves (the four even sets after the even groups,
+// the four odd sets at the end: 2 x 128 columns per consumer warp, single buffered -- the epilogue warp of the lane quarter
+// hands each consumer's buffers back as soon as it has read them).
+// ---------------------------------------------------------------------------------------------
+constexpr int O_KC = 28, O_STAGES = 4;
+constexpr int O_STAGE_DOUBLES = O_KC * (Q_LDA + 2 * Q_LDB);
+constexpr size_t O_SMEM = (size_t)O_STAGES * O_STAGE_DOUBLES * sizeof(double) + (2 * O_STAGES + 4 * Q_CONSUMER_WARPS) * sizeof(uint64_t) + 16;
+
+struct OGroups { int off[7]; };
+
+__global__ void __launch_bounds__(QE_THREADS, 1)
+gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig_o_t, int kpad_o, OGroups grp,
+                      double* __restrict__ out, long long M, int nlon, int no, int n_mtiles, int n_ntiles, int wide) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tiles = reinterpret_cast<double*>(s_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + (size_t)O_STAGES * O_STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + O_STAGES;
+    uint64_t* tfull = empty + O_STAGES;                 // [2 halves][8 consumer warps]
+    uint64_t* tempty = tfull + 2 * Q_CONSUMER_WARPS;    // [2 halves][8 consumer warps]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2 * Q_CONSUMER_WARPS);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr int PRODUCER_WARP = 12;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < O_STAGES; ++s) {
+            gb::mbar_init(&full[s], 1);
+            gb::mbar_init(&empty[s], Q_CONSUMER_WARPS);
+        }
+        for (int b = 0; b < 2 * Q_CONSUMER_WARPS; ++b) {
+            gb::mbar_init(&tfull[b], 1);
+            gb::mbar_init(&tempty[b], 1);
+        }
+        gb::fence_mbar_init();
+    }
+    if (warp == 0) gb::tmem_alloc(s_tmem, 512);
+    gb::tmem_fence_before_sync();
+    __syncthreads();
+    gb::tmem_fence_after_sync();
+    gb::griddep_wait();                 // AB comes from stage 1; `out` may still be read by whatever ran before
+    gb::griddep_launch_dependents();
+
+    const QWork work(n_mtiles, n_ntiles, (int)gridDim.x);
+    const int h = nlon >> 1, nq = nlon >> 2;
+    auto warp_row0 = [](int wm, int half) { return half < 0 ? wm * 32 : half * 64 + wm * 16; };
+
+    if (warp >= PRODUCER_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (warp == PRODUCER_WARP && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            long long mt;
+            int nt, half;
+            for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
+                const double* t1 = trig_o_t + (size_t)nt * 2 * kpad_o * Q_LDB;
+                const double* t2 = t1 + (size_t)kpad_o * Q_LDB;
+                for (int gi = 0; gi < 6; ++gi) {
+                    for (int k0 = grp.off[gi]; k0 < grp.off[gi + 1];) {
+                        const int kc = min(O_KC, grp.off[gi + 1] - k0);
+                        gb::mbar_wait(&empty[stage], phase ^ 1u);
+                        double* sA = s_tiles + (size_t)stage * O_STAGE_DOUBLES;
+                        double* sB = sA + O_KC * Q_LDA;
+                        const uint32_t bytes_a = (uint32_t)(kc * Q_LDA * sizeof(double));
+                        const uint32_t bytes_b = (uint32_t)(kc * Q_LDB * sizeof(double));
+                        gb::mbar_arrive_expect_tx(&full[stage], bytes_a + (gi >= 4 ? 2 : 1) * bytes_b);
+                        gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * Q_LDA, bytes_a, &full[stage]);
+                        gb::bulk_g2s(sB, t1 + (size_t)k0 * Q_LDB, bytes_b, &full[stage]);
+                        if (gi >= 4) gb::bulk_g2s(sB + O_KC * Q_LDB, t2 + (size_t)k0 * Q_LDB, bytes_b, &full[stage]);
+                        if (++stage == O_STAGES) { stage = 0; phase ^= 1u; }
+                        k0 += kc;
+                    }
+                }
+            }
+        }
+    } else if (warp >= Q_CONSUMER_WARPS) {
+        // ===== epilogue warp of lane quarter sp: the tiles of consumer warps sp and sp + 4 =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;\n");
+        const int sp = warp & 3;
+        uint32_t tphase = 0;
+        long long mt;
+        int nt, half;
+        for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
+            const int n_slabs = half < 0 ? 4 : 2;
+#pragma unroll 1
+            for (int cw = 0; cw < 2; ++cw) {
+                const int w = sp + 4 * cw;                 // consumer warp whose tile this is
+                const uint32_t taddr = *s_tmem + ((uint32_t)(32 * sp) << 16) + (uint32_t)(cw * 256);
+                const long long row0 = mt * Q_TM + warp_row0(w / Q_WN, half) + (lane >> 2);
+                const int jo = nt * Q_TN + (w % Q_WN) * 16 + 4 * (lane & 3);      // first of this lane's four octant meridians
+                gb::mbar_wait(&tfull[w], tphase);
+                gb::mbar_wait(&tfull[Q_CONSUMER_WARPS + w], tphase);
+                gb::tmem_fence_after_sync();
+#pragma unroll 1
+                for (int mi = 0; mi < n_slabs; ++mi) {
+                    double ve[16], vo[16];
+                    gb::tmem_ld16(taddr + 32u * mi, ve);             // [E0 | E2 | F0 | F2] x 4 meridians
+                    gb::tmem_ld16(taddr + 128u + 32u * mi, vo);      // [CO | AS | SO | BC] x 4 meridians
+                    if (mi == n_slabs - 1) {
+                        // both halves of this consumer's tile have been read: hand its buffers back
+                        gb::tmem_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) {
+                            gb::mbar_arrive(&tempty[w]);
+                            gb::mbar_arrive(&tempty[Q_CONSUMER_WARPS + w]);
+                        }
+                    }
+                    const long long row = row0 + mi * 8;
+                    if (row >= M || jo >= no) continue;
+                    double* orow = out + (size_t)row * nlon;
+                    // the quadrant sums at nu (p = 0) and at pi/2 - nu (p = 1), then the four mirrored meridians of each
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        double v1[4], v2[4], v3[4], v4[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const double ce = p ? ve[c] - ve[4 + c] : ve[c] + ve[4 + c];
+                            const double se = p ? ve[12 + c] - ve[8 + c] : ve[8 + c] + ve[12 + c];
+                            const double co = p ? vo[4 + c] : vo[c];
+                            const double so = p ? vo[12 + c] : vo[8 + c];
+                            const double cp = ce + co, cm = ce - co, sp_ = se + so, sm = se - so;
+                            v1[c] = cp + sp_;   // mu
+                            v2[c] = cm - sm;    // pi - mu
+                            v3[c] = cp - sp_;   // -mu
+                            v4[c] = cm + sm;    // mu - pi
+                        }
+                        // quadrant index of meridian c: jo + c (p = 0, ascending) or nq - 1 - jo - c (p = 1, descending)
+                        if (wide && jo + 4 <= no) {
+                            if (p == 0) {
+                                gb::st_cs_v4(orow + h + jo, v1[0], v1[1], v1[2], v1[3]);
+                                gb::st_cs_v4(orow + nlon - 4 - jo, v2[3], v2[2], v2[1], v2[0]);
+                                gb::st_cs_v4(orow + h - 4 - jo, v3[3], v3[2], v3[1], v3[0]);
+                                gb::st_cs_v4(orow + jo, v4[0], v4[1], v4[2], v4[3]);
+                            } else {
+                                const int jb = nq - 4 - jo;       // quadrant index of c = 3
+                                gb::st_cs_v4(orow + h + jb, v1[3], v1[2], v1[1], v1[0]);
+                                gb::st_cs_v4(orow + nlon - 4 - jb, v2[0], v2[1], v2[2], v2[3]);
+                                gb::st_cs_v4(orow + h - 4 - jb, v3[0], v3[1], v3[2], v3[3]);
+                                gb::st_cs_v4(orow + jb, v4[3], v4[2], v4[1], v4[0]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; c += 2) {          // no is even: pairs are all in or all out
+                                if (jo + c >= no) continue;
+                                if (p == 0) {
+                                    const int j = jo + c;
+                                    gb::st_cs_v2(orow + h + j, v1[c], v1[c + 1]);
+                                    gb::st_cs_v2(orow + nlon - 2 - j, v2[c + 1], v2[c]);
+                                    gb::st_cs_v2(orow + h - 2 - j, v3[c + 1], v3[c]);
+                                    gb::st_cs_v2(orow + j, v4[c], v4[c + 1]);
+                                } else {
+                                    const int j = nq - 2 - jo - c;    // quadrant index of c + 1
+                                    gb::st_cs_v2(orow + h + j, v1[c + 1], v1[c]);
+                                    gb::st_cs_v2(orow + nlon - 2 - j, v2[c], v2[c + 1]);
+                                    gb::st_cs_v2(orow + h - 2 - j, v3[c], v3[c + 1]);
+                                    gb::st_cs_v2(orow + j, v4[c + 1], v4[c]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tphase ^= 1u;
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
+        const int wm = warp / Q_WN;
+        const int wn = warp % Q_WN;
+        const int g = lane >> 2, q = lane & 3;
+        int stage = 0;
+        uint32_t phase = 0, tphase = 0;
+        const uint32_t taddr = *s_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 256);
+        auto run_tile = [&](auto mi_tag, int half) {
+            constexpr int MI = decltype(mi_tag)::value;
+            const int r0 = warp_row0(wm, half);
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                double acc[4][MI][2][2];   // [set][mi][ni][2]: even part E0 E2 F0 F2, odd part CO AS SO BC
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) acc[s][mi][ni][0] = acc[s][mi][ni][1] = 0.0;
+                auto chunks = [&](int gi, auto&& k_step) {
+                    for (int k0 = grp.off[gi]; k0 < grp.off[gi + 1];) {
+                        const int kc = min(O_KC, grp.off[gi + 1] - k0);
+                        gb::mbar_wait(&full[stage], phase);
+                        const double* sA = s_tiles + (size_t)stage * O_STAGE_DOUBLES + r0 + g;
+                        const double* sB = s_tiles + (size_t)stage * O_STAGE_DOUBLES + O_KC * Q_LDA + wn * 16 + g;
+                        if (kc == O_KC) {
+#pragma unroll
+                            for (int kk = 0; kk < O_KC; kk += 4) k_step(sA, sB, kk);
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < O_KC; kk += 4) {
+                                if (kk >= kc) break;
+                                k_step(sA, sB, kk);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) gb::mbar_arrive(&empty[stage]);
+                        if (++stage == O_STAGES) { stage = 0; phase ^= 1u; }
+                        k0 += kc;
+                    }
+                };
+                if (part == 0) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+                        chunks(s, [&](const double* sA, const double* sB, int kk) {
+                            double a[MI], b[2];
+#pragma unroll
+                            for (int mi = 0; mi < MI; ++mi) a[mi] = sA[(kk + q) * Q_LDA + mi * 8];
+#pragma unroll
+                            for (int ni = 0; ni < 2; ++ni) b[ni] = sB[(kk + q) * Q_LDB + ni * 8];
+#pragma unroll
+                            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < 2; ++ni) gb::dmma_884(acc[s][mi][ni][0], acc[s][mi][ni][1], a[mi], b[ni]);
+                        });
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s)
+                        chunks(4 + s, [&](const double* sA, const double* sB, int kk) {
+                            // one coefficient fragment, two table rows: cos and (+-) sin of the octant meridian
+                            double a[MI], b1[2], b2[2];
+#pragma unroll
+                            for (int mi = 0; mi < MI; ++mi) a[mi] = sA[(kk + q) * Q_LDA + mi * 8];
+#pragma unroll
+                            for (int ni = 0; ni < 2; ++ni) {
+                                b1[ni] = sB[(kk + q) * Q_LDB + ni * 8];
+                                b2[ni] = sB[(O_KC + kk + q) * Q_LDB + ni * 8];
+                            }
+#pragma unroll
+                            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < 2; ++ni) {
+                                    gb::dmma_884(acc[2 * s][mi][ni][0], acc[2 * s][mi][ni][1], a[mi], b1[ni]);
+                                    gb::dmma_884(acc[2 * s + 1][mi][ni][0], acc[2 * s + 1][mi][ni][1], a[mi], b2[ni]);
+                                }
+                        });
+                }
+                // park this half of the tile: columns 256 (warp / 4) + 128 part + 32 mi of this warp's lanes
+                gb::mbar_wait(&tempty[part * Q_CONSUMER_WARPS + warp], tphase ^ 1u);
+                gb::tmem_fence_after_sync();
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                    double v[16];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) v[4 * s + c] = acc[s][mi][c >> 1][c & 1];
+                    gb::tmem_st16(taddr + 128u * part + 32u * mi, v);
+                }
+                gb::tmem_wait_st();
+                gb::tmem_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) gb::mbar_arrive(&tfull[part * Q_CONSUMER_WARPS + warp]);
+            }
+            tphase ^= 1u;
+        };
+        long long mt;
+        int nt, half;
+        for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
+            if (half < 0) run_tile(std::integral_constant<int, 4>{}, half);
+            else run_tile(std::integral_constant<int, 2>{}, half);
+        }
+    }
+    gb::tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) gb::tmem_dealloc(*s_tmem, 512);
+}
+
 // Plain one-thread-per-output stage 2 (debug cross-check of the tensor-core kernel, GB_NAIVE_STAGE2=1).
 __global__ void __launch_bounds__(256)
 gb_fourier_stage2_naive(const double* __restrict__ AB, int ab_rows, const double* __restrict__ trig, int nlp,
@@ -1060,7 +1344,8 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     cudaEvent_t* prof = (p->prof_ev && p->prof_count < p->prof_capacity) ? p->prof_ev + (size_t)p->prof_count * 4 : nullptr;
     const bool naive2 = env_flag("GB_NAIVE_STAGE2");
     const bool use_sym = p->sym && !naive2 && !env_flag("GB_NO_SYMMETRY");
-    const int* d_krow = use_sym ? p->d_krow_sym : p->d_krow_id;
+    const bool use_oct = use_sym && p->oct && !env_flag("GB_S2_QUADRANT");      // eight-fold symmetry (plan gate + override)
+    const int* d_krow = use_oct ? p->d_krow_oct : use_sym ? p->d_krow_sym : p->d_krow_id;
     // stage-1 tiling: narrow batches (at most 80 epochs) run 80-column items, several CTAs per SM
     const bool simple1 = env_flag("GB_SIMPLE_STAGE1");
     const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
@@ -1181,6 +1466,18 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
         const long long total = M * p->nlon;
         gb_fourier_stage2_naive<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p->d_ab, p->ab_rows, p->d_trig, p->nlp,
                                                                                 p->kpad, d_out, M, p->nlon);
+        GB_LAUNCH_CHECK();
+    } else if (use_oct) {
+        const int n_mtiles = (int)((M + Q_TM - 1) / Q_TM);
+        const int n_ntiles = p->n_otiles;
+        const long long n_tiles = (long long)n_mtiles * n_ntiles;
+        const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
+        OGroups grp;
+        for (int g = 0; g < 7; ++g) grp.off[g] = p->ogrp_off[g];
+        GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_oct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O_SMEM));
+        const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 16 == 0 && !env_flag("GB_S2_NARROW_STORES")) ? 1 : 0;
+        GB_CUDA(gb_launch_pdl(gb_fourier_stage2_oct, dim3(grid), dim3(QE_THREADS), O_SMEM, st, p->d_ab, p->ab_rows, p->d_trig_o_t,
+                              p->kpad_o, grp, d_out, M, p->nlon, p->no, n_mtiles, n_ntiles, wide));
         GB_LAUNCH_CHECK();
     } else if (use_sym) {
         const int n_mtiles = (int)((M + Q_TM - 1) / Q_TM);
