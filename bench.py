@@ -320,7 +320,7 @@ def main():
     units_per_step = epochs * nlat * nlon
     lib = gb._lib.load()
     warmup = max(args.warmup, 3)
-    sym, folded = plan.symmetric, plan.folded     # (the configs block below clears the plan cache)
+    sym, folded, octant = plan.symmetric, plan.folded, plan.octant     # (the configs block below clears the plan cache)
 
     def timed_steps(x, y, steps):
         """K steps, device resident, L2 flushed between steps; returns the per-step CUDA-event times (ms)."""
@@ -437,7 +437,8 @@ def main():
         s1_ms = float(np.mean(stages[:, 1])) if len(stages) else float("nan")
         pk_ms = float(np.mean(stages[:, 0])) if len(stages) else float("nan")
         # executed multiply-adds of the dominant kernel: the symmetric path contracts one quadrant of meridians
-        f2_exec = f2 / 4.0 if sym else f2
+        # (the octant kernel: the even orders split once more under mu -> pi/2 - mu, 3/4 of the quadrant kernel's work)
+        f2_exec = f2 / 4.0 * (0.75 if octant else 1.0) if sym else f2
         # the folded Legendre stage contracts the northern parallels only
         f1_exec = f1 / 2.0 if folded else f1
         step_mean_ms = 1e3 * my_time / args.steps
@@ -456,7 +457,8 @@ def main():
         executed_tf = f2_exec / (s2_ms * 1e-3) / 1e12
         roofline = {
             "bound": "tensor",
-            "kernel": ("gb_fourier_stage2_sym" if sym else "gbgemm::kernel<RowMajorStore>") + " (FP64 DMMA.8x8x4)",
+            "kernel": ("gb_fourier_stage2_oct" if octant else "gb_fourier_stage2_sym" if sym else "gbgemm::kernel<RowMajorStore>")
+                      + " (FP64 DMMA.8x8x4)",
             "achieved": executed_tf, "peak": peak, "unit": "TFLOP/s", "frac": executed_tf / peak,
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "live gb_probe_fp64_peak on this GPU (DMMA %.2f / DFMA %.2f TFLOP/s); MEASURED_PEAKS.json "
@@ -468,7 +470,9 @@ def main():
             "note": ("`achieved` / `frac` count the multiply-adds the tensor pipe executes. Declared algorithmic shortcut: "
                      "four-fold longitude symmetry of the grid (meridians symmetric about 0 and under a half turn) -> the "
                      "kernel executes 1/4 of the SURVEY 8(d) contract multiply-adds (direct contraction, no symmetry "
-                     "credit); `contract_*` divide the contract flops by the same time, so `contract_multiple` is not a "
+                     "credit)" + ("; eight-fold here (the first quadrant mirrors about pi/4: the even orders split by order mod 4, "
+                                  "the odd orders are contracted with two table rows per coefficient fragment) -> 3/16"
+                                  if octant else "") + "; `contract_*` divide the contract flops by the same time, so `contract_multiple` is not a "
                      "utilisation. GB_NO_SYMMETRY=1 runs the direct contraction. Second declared shortcut (Legendre stage): "
                      "parallels mirrored about the equator share one table row, gated on a measured hemisphere asymmetry "
                      "of the reference's tables (GB_NO_FOLD=1 disables)."

@@ -61,11 +61,11 @@ def syn_flops(N, nlat, nlon, E):
 
 
 def syn_flops_executed(N, plan, E):
-    """What the kernels execute: the symmetric stage 2 contracts one quadrant of meridians, the folded stage 1 the
-    northern parallels."""
+    """What the kernels execute: the symmetric stage 2 contracts one quadrant of meridians (one octant with the even
+    orders split once more: 3/4 of that), the folded stage 1 the northern parallels."""
     L = N + 1
     s1 = 2.0 * E * plan.nlat * L * L / (2.0 if plan.folded else 1.0)
-    s2 = 2.0 * (2 * L - 1) * E * plan.nlat * plan.nlon / (4.0 if plan.symmetric else 1.0)
+    s2 = 2.0 * (2 * L - 1) * E * plan.nlat * plan.nlon / (4.0 if plan.symmetric else 1.0) * (0.75 if plan.octant else 1.0)
     return s1 + s2
 
 

@@ -416,7 +416,7 @@ extern "C" int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon
     return GB_OK;
 }
 
-extern "C" int gb_plan_is_symmetric(const gb_plan* plan) { return (plan && plan->sym) ? 1 : 0; }
+extern "C" int gb_plan_is_symmetric(const gb_plan* plan) { return (plan && plan->sym) ? (plan->oct ? 2 : 1) : 0; }
 
 extern "C" int gb_plan_is_folded(const gb_plan* plan) { return (plan && plan->fold_ns) ? 1 + plan->fold_cap / 32 : 0; }
 

@@ -1040,7 +1040,8 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
             for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
                 const double* t1 = trig_o_t + (size_t)nt * 2 * kpad_o * Q_LDB;
                 const double* t2 = t1 + (size_t)kpad_o * Q_LDB;
-                for (int gi = 0; gi < 6; ++gi) {
+                for (int go = 0; go < 6; ++go) {
+                    const int gi = go < 2 ? 4 + go : go - 2;        // the odd groups first (see the consumers)
                     for (int k0 = grp.off[gi]; k0 < grp.off[gi + 1];) {
                         const int kc = min(O_KC, grp.off[gi + 1] - k0);
                         gb::mbar_wait(&empty[stage], phase ^ 1u);
@@ -1158,8 +1159,10 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
         auto run_tile = [&](auto mi_tag, int half) {
             constexpr int MI = decltype(mi_tag)::value;
             const int r0 = warp_row0(wm, half);
+            // the odd part (two thirds of the tile's DMMAs) first: its half is parked two thirds into the tile period, by
+            // when the epilogue warp has long read the previous tile (the tensor-memory buffers are single)
 #pragma unroll 1
-            for (int part = 0; part < 2; ++part) {
+            for (int part = 1; part >= 0; --part) {
                 double acc[4][MI][2][2];   // [set][mi][ni][2]: even part E0 E2 F0 F2, odd part CO AS SO BC
 #pragma unroll
                 for (int s = 0; s < 4; ++s)

@@ -143,6 +143,13 @@ class SHPlan:
         return bool(self._lib.gb_plan_is_symmetric(self._handle)) and not forced_off
 
     @property
+    def octant(self):
+        """True if synthesis uses the eight-fold longitude symmetry (gb_plan_is_symmetric returns 2)."""
+        import os
+        forced_off = any(os.environ.get(v, "") not in ("", "0") for v in ("GB_NO_SYMMETRY", "GB_S2_QUADRANT"))
+        return self._lib.gb_plan_is_symmetric(self._handle) == 2 and not forced_off
+
+    @property
     def folded(self):
         """True if the Legendre stage uses the equatorial symmetry of the parallels (see gb_plan_is_folded)."""
         import os

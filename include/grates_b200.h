@@ -91,6 +91,11 @@ int gb_plan_info(const gb_plan* plan, int* nmax, int* nlat, int* nlon, int* devi
  * gb_synthesis then evaluates only the first quadrant of meridians and obtains the other three by
  * sign changes (one quarter of the multiply-adds of the direct longitude contraction); set the
  * environment variable GB_NO_SYMMETRY=1 to force the direct contraction.
+ * Returns 2 if in addition the first-quadrant meridians mirror about pi/4 (meridian count divisible by 16, e.g. the
+ * 0.5 and 0.25 degree GeographicGrid): gb_synthesis then evaluates the first OCTANT only -- the orders 0, 2 (mod 4) change
+ * the sign of their cosine / sine rows under mu -> pi/2 - mu, the odd orders swap them -- for three quarters of the
+ * four-fold kernel's multiply-adds.  Both gates are measured on the plan's own tables.  GB_NO_OCTANT=1 at plan creation
+ * or GB_S2_QUADRANT=1 at call time keep the four-fold kernel.
  */
 int gb_plan_is_symmetric(const gb_plan* plan);
 

@@ -407,6 +407,32 @@ def test_covariance_equator_fold_and_mirrored_blocks(gb, orc, monkeypatch):
         assert maxnorm_err(std, orc.covariance_propagation(sigma, orc.gauss_grid(nl), 0, 8, "geoid")) < TOL
 
 
+def test_octant_stage2_matches_quadrant_and_oracle(gb, orc, monkeypatch):
+    """Eight-fold longitude symmetry (meridian count divisible by 16): the octant kernel against the four-fold kernel
+    (GB_S2_QUADRANT=1), the direct contraction (GB_NO_SYMMETRY=1) and the oracle; whole and half tiles, ragged last
+    column tile (90 and 18 octant meridians), grids whose meridian count keeps the four-fold kernel."""
+    for (N, dlon, dlat, E, octant) in ((96, 0.5, 1.5, 5, True), (40, 2.5, 2.0, 40, True), (20, 7.5, 5.0, 2, True),
+                                       (31, 2.5, 6.0, 130, True), (60, 1.0, 3.0, 4, False)):
+        grid, og = gb.GeographicGrid(dlon, dlat), orc.geographic_grid(dlon, dlat)
+        plan = gb.get_plan(grid, N, "ewh")
+        assert plan.octant == octant and plan.symmetric
+        anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(min(E, 3))] * ((E + 2) // 3))[:E]
+        x = torch.as_tensor(anm).cuda()
+        v8 = plan.synthesis(x)
+        monkeypatch.setenv("GB_S2_QUADRANT", "1")
+        v4 = plan.synthesis(x)
+        monkeypatch.delenv("GB_S2_QUADRANT")
+        monkeypatch.setenv("GB_NO_SYMMETRY", "1")
+        v1 = plan.synthesis(x)
+        monkeypatch.delenv("GB_NO_SYMMETRY")
+        ref = np.stack([orc.synthesis(a, og, "ewh") for a in anm[:3]]).reshape(-1, plan.nlat, plan.nlon)
+        for v in (v8, v4, v1):
+            assert maxnorm_err(v[:ref.shape[0]].cpu().numpy(), ref) < TOL
+        assert maxnorm_err(v8.cpu().numpy(), v4.cpu().numpy()) < 1e-13
+        if E > 3:
+            assert torch.equal(v8[3], v8[0])          # repeated epochs: every row tile gives the same bits
+
+
 def test_ravel_batch_matches_reference_ordering(gb, orc, golden):
     """Device ravel (utilities.py:310-360) against the reference's TimeSeries.to_array ordering."""
     g = golden("filters")
