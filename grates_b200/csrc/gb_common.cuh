@@ -179,6 +179,7 @@ int gb_launch_pack_tiled(const double* d_anm, double* d_x, int L, int E, const i
                          cudaStream_t st, const double* d_wn = nullptr);
 // symmetric Fourier stage of the synthesis on rows [0, M) of an AB-layout operand (gb_synthesis.cu); needs p->sym
 int gb_launch_stage2_sym(gb_plan* p, const double* d_ab, long long M, double* d_out, cudaStream_t st);
+const int* gb_stage2_krow(const gb_plan* p);    // spectral row 2m + cs -> row of that stage's AB layout
 // order-wise block filter of a batch, written straight into a synthesis workspace X (gb_filter.cu): order-wise packed
 // (d_roff == nullptr) or the tiled layout of gb_launch_pack_tiled (the buffer must have been cleared for it)
 int gb_filter_into_x(const double* d_blocks, const int64_t* block_offsets, int nf, const double* d_anm, int E, int nmax,

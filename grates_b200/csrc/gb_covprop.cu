@@ -875,7 +875,7 @@ extern "C" int gb_covariance_propagation_filtered(gb_plan* plan, const double* d
         GB_CUDA(scratch.alloc(&d_w, w_elems));
         GB_CUDA(cudaMemsetAsync(d_h2, 0, h2_elems * sizeof(double), st));
         gb_cov_reduce_h<<<dim3(nrep, kpad), 256, 0, st>>>(d_hpart, d_h2, lay->d_pstart, lay->d_ne4, lay->d_no4, lay->d_out_n,
-                                                          lay->d_out_s, kpad, n_pieces, hmt, symmetric, nmin, p->d_krow_sym,
+                                                          lay->d_out_s, kpad, n_pieces, hmt, symmetric, nmin, gb_stage2_krow(p),
                                                           p->ab_rows, L);
         GB_LAUNCH_CHECK();
         if ((rc = gb_launch_stage2_sym(p, d_h2, Mrows, d_w, st))) return rc;

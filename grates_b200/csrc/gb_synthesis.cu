@@ -1348,6 +1348,7 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     const bool naive2 = env_flag("GB_NAIVE_STAGE2");
     const bool use_sym = p->sym && !naive2 && !env_flag("GB_NO_SYMMETRY");
     const bool use_oct = use_sym && p->oct && !env_flag("GB_S2_QUADRANT");      // eight-fold symmetry (plan gate + override)
+    // (gb_launch_stage2_sym / gb_stage2_krow below apply the same rule for the covariance propagation)
     const int* d_krow = use_oct ? p->d_krow_oct : use_sym ? p->d_krow_sym : p->d_krow_id;
     // stage-1 tiling: narrow batches (at most 80 epochs) run 80-column items, several CTAs per SM
     const bool simple1 = env_flag("GB_SIMPLE_STAGE1");
@@ -1520,8 +1521,28 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
 
 // The symmetric Fourier stage on any row set in the AB layout (used by the covariance propagation, whose longitude
 // quadratic form starts with the same contraction): d_out[row][j] = sum_k d_ab[row][k] trig[k][j], rows [0, M).
+static bool stage2_octant(const gb_plan* p) { return p->sym && p->oct && !env_flag("GB_S2_QUADRANT"); }
+
+// spectral row k = 2m + cs -> row of the AB layout the symmetric Fourier stage of this plan reads (octant or quadrant order)
+const int* gb_stage2_krow(const gb_plan* p) { return stage2_octant(p) ? p->d_krow_oct : p->d_krow_sym; }
+
 int gb_launch_stage2_sym(gb_plan* p, const double* d_ab, long long M, double* d_out, cudaStream_t st) {
     GB_REQUIRE(p->sym, "gb_launch_stage2_sym: the plan's meridians are not four-fold symmetric");
+    if (stage2_octant(p)) {
+        const int n_mtiles = (int)((M + Q_TM - 1) / Q_TM);
+        const int n_ntiles = p->n_otiles;
+        const long long n_tiles = (long long)n_mtiles * n_ntiles;
+        if (n_tiles == 0) return GB_OK;
+        const int grid = (int)((n_tiles < p->sm_count) ? n_tiles : p->sm_count);
+        OGroups grp;
+        for (int g = 0; g < 7; ++g) grp.off[g] = p->ogrp_off[g];
+        GB_CUDA(cudaFuncSetAttribute(gb_fourier_stage2_oct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O_SMEM));
+        const int wide = (reinterpret_cast<uintptr_t>(d_out) % 32 == 0 && p->nlon % 16 == 0) ? 1 : 0;
+        gb_fourier_stage2_oct<<<grid, QE_THREADS, O_SMEM, st>>>(d_ab, p->ab_rows, p->d_trig_o_t, p->kpad_o, grp, d_out, M,
+                                                                 p->nlon, p->no, n_mtiles, n_ntiles, wide);
+        GB_LAUNCH_CHECK();
+        return GB_OK;
+    }
     const int n_mtiles = (int)((M + Q_TM - 1) / Q_TM);
     const int n_ntiles = p->n_qtiles;
     const long long n_tiles = (long long)n_mtiles * n_ntiles;
