@@ -77,7 +77,9 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgrates_b200.so")
+    # GRATES_B200_LIBRARY: a development build of the same ABI (e.g. one compiled with -DGB_TRACE)
+    return os.environ.get("GRATES_B200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                                 "libgrates_b200.so")
 
 
 def load():

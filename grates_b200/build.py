@@ -34,7 +34,8 @@ def needs_build():
 
 
 def _compile(nvcc, src, obj, verbose):
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    extra = os.environ.get("GB_NVCC_EXTRA", "").split()       # development builds only (e.g. -DGB_TRACE)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     return res.returncode, res.stdout + res.stderr
 
@@ -46,7 +47,8 @@ def build(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     nvcc = find_nvcc()
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(PKG, "..", "build", "obj")
+    extra = os.environ.get("GB_NVCC_EXTRA", "").strip()
+    objdir = os.path.join(PKG, "..", "build", "obj" + ("_" + "".join(c if c.isalnum() else "_" for c in extra) if extra else ""))
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers += [os.path.join(PKG, "..", "include", "grates_b200.h"), os.path.abspath(__file__)]

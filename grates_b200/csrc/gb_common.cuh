@@ -443,6 +443,14 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, double* v) {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
+// Read-only load that stays where it is written (volatile asm keeps its place among the barrier waits): issued at the top
+// of a K loop, its latency is over by the epilogue.  A plain __ldg is sunk by the compiler to its first use.
+__device__ __forceinline__ int ld_nc_early(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];\n" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ void st_cs_v2(double* p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(a), "d"(b) : "memory");
 }

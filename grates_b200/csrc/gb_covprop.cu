@@ -70,7 +70,11 @@ gb_cov_permute(const double* __restrict__ sigma, double* __restrict__ St, const 
 // Symmetric Sigma (first_group != nullptr): a row tile only meets column groups k' >= its own first group kmin,
 // i.e. the columns j >= jmin of every degree: the rest of the row block is neither read nor written (the quadratic-form
 // kernel never touches it).
-constexpr int CP_ROWS = 32, CP_COLS = 64, CP_PITCH = CP_COLS + 1;     // odd pitch: conflict-free column reads
+#ifndef GB_CP_ROWS
+#define GB_CP_ROWS 32
+#define GB_CP_COLS 64
+#endif
+constexpr int CP_ROWS = GB_CP_ROWS, CP_COLS = GB_CP_COLS, CP_PITCH = CP_COLS + 1;     // odd pitch: conflict-free column reads
 __global__ void __launch_bounds__(256)
 gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St, const int* __restrict__ perm8,
                       const int* __restrict__ goff4, const int* __restrict__ ne4, int Kp4, long long K, int nmin,
@@ -103,7 +107,8 @@ gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St,
         const int n0 = max(m, nmin);
         const int b = goff4[k] + cov_cls_pos(n - n0, (n0 - m) & 1, ne4[k]);
         double* dst = St + ((size_t)(a0 >> 7) * Kp4 + b) * GB_LDA + (a0 & (GB_TM - 1));
-        dst[lane] = s_p[lane * CP_PITCH + j - j0];
+#pragma unroll
+        for (int r = lane; r < CP_ROWS; r += 32) dst[r] = s_p[r * CP_PITCH + j - j0];
     }
 }
 

@@ -12,6 +12,22 @@
 // packing: element (r, c) of anm has degree max(r, c).
 #include "gb_common.cuh"
 
+#ifdef GB_TRACE
+// development aid (-DGB_TRACE): timeline of the pack kernel, read back with gb_debug_trace_pack
+__device__ unsigned long long gb_trace_pack[512][4];
+#define GB_PACK_MARK(slot)                                                                          \
+    do {                                                                                            \
+        const unsigned cta_ = blockIdx.x + gridDim.x * blockIdx.y;                                  \
+        if (threadIdx.x == 0 && cta_ < 512) {                                                       \
+            unsigned long long gt_;                                                                 \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                  \
+            gb_trace_pack[cta_][slot] = gt_;                                                        \
+        }                                                                                           \
+    } while (0)
+#else
+#define GB_PACK_MARK(slot) ((void)0)
+#endif
+
 namespace {
 
 constexpr int PK_C = 512;         // columns of anm per CTA (bounds shared memory at high degree)
@@ -59,10 +75,12 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
     const int e0 = blockIdx.y * PKE;
     const int ne = min(PKE, E - e0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    GB_PACK_MARK(0);
     if (TILED)
         for (int i = threadIdx.x; i <= L; i += blockDim.x) s_roff[i] = xt.roff[i];    // plan constant: before the wait
     gb::griddep_wait();
     gb::griddep_launch_dependents();
+    GB_PACK_MARK(1);
     if (PACK) {
         for (int e = warp; e < ne; e += nwarps) {
             const double* row = src + ((size_t)(e0 + e) * L + r) * L;
@@ -73,6 +91,7 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
             }
         }
         __syncthreads();
+        GB_PACK_MARK(2);
         if (TILED) {
             // PKE lanes share one column c of anm: its order / degree / plane and the row of the tiled layout are
             // computed once per column, the epoch only moves the position inside (at most two) column tiles
@@ -98,6 +117,7 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
         }
         // sine plane of order 0, degree r (the tiled buffer is cleared when its layout changes: nothing to write)
         if (!TILED && blockIdx.z == 0 && threadIdx.x < ne) dst[(long long)r * 2 * E + E + e0 + threadIdx.x] = 0.0;
+        GB_PACK_MARK(3);
     } else {
         for (int idx = threadIdx.x; idx < nc * PKE; idx += blockDim.x) {
             const int c = idx / PKE, e = idx % PKE;
@@ -109,6 +129,73 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const double* __restrict__
             for (int c = lane; c < nc; c += 32) row[cb + c] = s_t[c * PK_LD + e];
         }
     }
+}
+
+// The tiled pack with its rows fetched by the TMA unit.  One CTA = row r of anm for PKE epochs, as above, but every row is
+// ONE bulk copy (cp.async.bulk) issued by its own lane, so all of the CTA's bytes are in flight at once instead of a few
+// 8-byte loads per lane (the scalar-load kernel needed 7 us to read the 18 MB of a 240-epoch batch).  Bulk copies move
+// whole 16-byte units: a row that starts on an odd double is fetched from the double before it (`off` = 1) and rows are
+// an even number of doubles long in shared memory; a row whose widened range would leave the array (the very first or
+// last one) is read with plain loads by its lane.  The write side is the one of gb_pack_kernel<true, PKE, true>.
+template <int PKE>
+__global__ void __launch_bounds__(256) gb_pack_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int L,
+                                                            int E, const double* __restrict__ wn, XTiling xt) {
+    extern __shared__ __align__(16) double s_rows[];       // [PKE][lp], lp = L + 3 rounded up to even + 2 (bank spread)
+    const int lp = ((L + 3) & ~1) + 2;
+    int* s_roff = reinterpret_cast<int*>(s_rows + (size_t)PKE * lp);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_roff + ((L + 2 + 1) & ~1));
+    const int r = blockIdx.x;
+    const int e0 = blockIdx.y * PKE;
+    const int ne = min(PKE, E - e0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    GB_PACK_MARK(0);
+    for (int i = threadIdx.x; i <= L; i += blockDim.x) s_roff[i] = xt.roff[i];    // plan constant: before the wait
+    if (threadIdx.x == 0) {
+        gb::mbar_init(bar, (uint32_t)ne);
+        gb::fence_mbar_init();
+    }
+    __syncthreads();
+    gb::griddep_wait();
+    gb::griddep_launch_dependents();
+    GB_PACK_MARK(1);
+    const long long a0 = (long long)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
+    const long long total = (long long)E * L * L;
+    if (threadIdx.x < ne) {
+        const int e = threadIdx.x;
+        const long long start = ((long long)(e0 + e) * L + r) * L;
+        const int off = (int)((a0 + start) & 1);
+        const int cnt = (L + off + 1) & ~1;
+        double* row = s_rows + (size_t)e * lp;
+        if (start - off >= 0 && start - off + cnt <= total) {
+            gb::mbar_arrive_expect_tx(bar, (uint32_t)(cnt * sizeof(double)));
+            gb::bulk_g2s(row, src + (start - off), (uint32_t)(cnt * sizeof(double)), bar);
+        } else {
+            for (int c = 0; c < L; ++c) row[off + c] = src[start + c];
+            gb::mbar_arrive(bar);
+        }
+    }
+    gb::mbar_wait(bar, 0);
+    GB_PACK_MARK(2);
+    // PKE lanes share one column c of anm: its order / degree / plane and the row of the tiled layout are computed once
+    // per column, the epoch only moves the position inside (at most two) column tiles
+    constexpr int CPW = 32 / PKE;                      // columns per warp pass
+    const int sub = lane / PKE, e = lane % PKE;
+    const int off_e = (int)((a0 + ((long long)(e0 + e) * L + r) * L) & 1);
+    const double* my_row = s_rows + (size_t)e * lp + off_e;
+    for (int c = warp * CPW + sub; c < L; c += nwarps * CPW) {
+        const int m = (c <= r) ? c : r + 1;
+        const int nn = (c <= r) ? r - c : c - r - 1;
+        const int r0 = s_roff[m], kn_pad = s_roff[m + 1] - r0;
+        const int row = (nn & ~7) + ((nn & 1) << 2) + ((nn & 7) >> 1);
+        const int col = ((c <= r) ? 0 : E) + e0 + e;
+        const int ct = col / xt.tn;
+        if (e < ne) {
+            double v = my_row[c];
+            if (wn) v = __dmul_rn(v, wn[max(r, c)]);
+            dst[((long long)r0 * xt.n_ct + (long long)ct * kn_pad + row) * (xt.tn + 4) + (col - ct * xt.tn)] = v;
+        }
+    }
+    GB_PACK_MARK(3);
 }
 
 // out[e][r][c] = in[e][r][c] * w[max(r, c)]
@@ -144,15 +231,44 @@ int launch(const double* src, double* dst, int L, int E, const double* wn, cudaS
 int gb_launch_pack(const double* d_anm, double* d_x, int L, int E, cudaStream_t st, const double* d_wn) {
     return launch<true>(d_anm, d_x, L, E, d_wn, st);
 }
+template <int PKE>
+static int launch_rows(const double* src, double* dst, int L, int E, const double* wn, XTiling xt, cudaStream_t st) {
+    const int lp = ((L + 3) & ~1) + 2;
+    const size_t smem = (size_t)PKE * lp * sizeof(double) + (size_t)((L + 3) & ~1) * sizeof(int) + sizeof(uint64_t);
+    if (smem > 48 * 1024)
+        GB_CUDA(cudaFuncSetAttribute(gb_pack_rows_kernel<PKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(L, (E + PKE - 1) / PKE, 1);
+    GB_CUDA(gb_launch_pdl(gb_pack_rows_kernel<PKE>, grid, dim3(256), smem, st, src, dst, L, E, wn, xt));
+    GB_LAUNCH_CHECK();
+    return GB_OK;
+}
+
 int gb_launch_pack_tiled(const double* d_anm, double* d_x, int L, int E, const int* d_roff, int tn, int n_ct,
                          cudaStream_t st, const double* d_wn) {
     const XTiling xt{d_roff, tn, n_ct};
+    static const bool scalar_loads = getenv("GB_PACK_SCALAR") && getenv("GB_PACK_SCALAR")[0] == '1';
+    if (L <= PK_C && !scalar_loads)          // rows fetched by the TMA unit
+        return E <= 64 ? launch_rows<8>(d_anm, d_x, L, E, d_wn, xt, st) : launch_rows<32>(d_anm, d_x, L, E, d_wn, xt, st);
     return E <= 64 ? launch_pke<true, 8, true>(d_anm, d_x, L, E, d_wn, xt, st)
                    : launch_pke<true, 32, true>(d_anm, d_x, L, E, d_wn, xt, st);
 }
 int gb_launch_unpack(const double* d_x, double* d_anm, int L, int E, cudaStream_t st) {
     return launch<false>(d_x, d_anm, L, E, nullptr, st);
 }
+
+#ifdef GB_TRACE
+extern "C" int gb_debug_trace_pack(unsigned long long* h_out, int reset) {
+    if (reset) {
+        void* sym = nullptr;
+        GB_CUDA(cudaGetSymbolAddress(&sym, gb_trace_pack));
+        GB_CUDA(cudaMemset(sym, 0, sizeof(gb_trace_pack)));
+        return GB_OK;
+    }
+    GB_CUDA(cudaDeviceSynchronize());
+    GB_CUDA(cudaMemcpyFromSymbol(h_out, gb_trace_pack, sizeof(gb_trace_pack)));
+    return GB_OK;
+}
+#endif
 
 extern "C" int gb_scale_by_degree(const double* d_anm_in, const double* d_wn, int n_epochs, int nmax, double* d_anm_out,
                                   int device, void* stream) {

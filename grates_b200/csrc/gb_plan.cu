@@ -476,7 +476,7 @@ int gb_plan_ensure_workspace(gb_plan* p, int n_epochs) {
     const long long mpad = (m + 127) / 128 * 128;
     // X holds either the order-wise layout or the tiled one (80- or 240-column tiles + 4 pad columns, gb_pack.cu)
     const size_t cols = 2 * (size_t)n_epochs;
-    const size_t tiled = (size_t)p->ptab_rtot * std::max(((cols + 79) / 80) * 84, ((cols + 239) / 240) * 244);
+    const size_t tiled = (size_t)p->ptab_rtot * std::max({((cols + 79) / 80) * 84, ((cols + 119) / 120) * 124, ((cols + 239) / 240) * 244});
     const size_t x_elems = std::max((size_t)p->L * (p->L + 1) / 2 * cols, tiled);
     GB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_x), x_elems * sizeof(double)));
     p->x_elems = x_elems;

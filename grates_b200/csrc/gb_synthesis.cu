@@ -26,6 +26,22 @@
 #include "gb_common.cuh"
 #include "gb_gemm.cuh"
 
+#ifdef GB_TRACE
+// development aid (-DGB_TRACE): in-kernel timeline of the stage-1 / stage-2 kernels, read back with gb_debug_trace
+__device__ unsigned long long gb_trace_buf[2][160][24][2];      // [kernel][CTA][slot][globaltimer ns, clock64]
+#define GB_TRACE_MARK(k, slot)                                                                      \
+    do {                                                                                            \
+        unsigned long long gt_;                                                                     \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                      \
+        if (blockIdx.x < 160 && (slot) < 24) {                                                      \
+            gb_trace_buf[k][blockIdx.x][slot][0] = gt_;                                             \
+            gb_trace_buf[k][blockIdx.x][slot][1] = (unsigned long long)clock64();                   \
+        }                                                                                           \
+    } while (0)
+#else
+#define GB_TRACE_MARK(k, slot) ((void)0)
+#endif
+
 namespace {
 
 using gb::legendre_column;   // f(n, P_nm), n = m..L-1 (gb_common.cuh)
@@ -374,7 +390,7 @@ gb_legendre_stage1(const double* __restrict__ X, double* __restrict__ AB, T1Tabl
 // classes read consecutive shared-memory rows (pitch 36 = 4 mod 16: conflict-free fragments).
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int tb_lda(bool fold) { return fold ? 36 : 68; }
-__host__ __device__ constexpr int tb_ctas_per_sm(int nwn, bool fold) { return nwn <= 2 ? (fold ? 3 : 2) : 1; }
+__host__ __device__ constexpr int tb_ctas_per_sm(int nwn, bool fold) { return nwn <= 2 ? (fold ? 3 : 2) : nwn == 3 ? 2 : 1; }
 __host__ __device__ constexpr size_t tb_stage_bytes(int nwn, bool fold, int kc) {
     return (size_t)kc * (tb_lda(fold) + t1_tn(nwn) + 4) * sizeof(double);
 }
@@ -410,7 +426,8 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
               int n_lattiles, int n_coltiles, int n_items, int polar) {
     constexpr int STAGES = tb_stages(NWN, FOLD, KC);
     static_assert(STAGES >= 2, "the ring needs at least two stages");
-    const bool diag_nostore = (polar & 0x10000) != 0;   // DIAG
+    const bool diag_nostore = (polar & 0x10000) != 0;   // DIAG (GB_DIAG_NOSTORE): the epilogue without its stores
+    const bool diag_v2 = (polar & 0x20000) != 0;        // DIAG (GB_DIAG_V2): 16-byte instead of 32-byte stores
     polar &= 0xffff;
     constexpr int TN = 8 * MI * NWN, LDA = tb_lda(FOLD), LDB = TN + 4, CONSUMER_WARPS = 2 * NWN;
     constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
@@ -423,6 +440,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        GB_TRACE_MARK(0, 0);
         for (int s = 0; s < STAGES; ++s) {
             gb::mbar_init(&full[s], 1);
             gb::mbar_init(&empty[s], CONSUMER_WARPS);
@@ -430,12 +448,38 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
         gb::fence_mbar_init();
     }
     __syncthreads();
-    gb::griddep_wait();                 // X comes from the pack kernel, AB is still being read by the previous call
     gb::griddep_launch_dependents();
+    // griddepcontrol.wait (X comes from the pack kernel, AB is still being read by the previous call) is executed by the
+    // copy lane alone: the Legendre table is a plan constant, so the table halves of the first ring stages are already in
+    // flight (a cold DRAM round trip after an L2 flush) when the wait returns; the consumers touch global memory only
+    // after they have seen chunks of X, which the copy lane requests after the wait.
+    const int tiles_per_pair = n_lattiles * n_coltiles;
+    int n_pre = 0;                      // chunks whose table half (and byte count) went out before the wait
+    if (warp == CONSUMER_WARPS && lane == 0) {
+        for (int item = blockIdx.x; item < n_items && n_pre < STAGES; item += gridDim.x) {
+            const int m_first = item / tiles_per_pair;
+            const int lt = (item - m_first * tiles_per_pair) / n_coltiles;
+            const int m_second = L - 1 - m_first;
+            const int npass = (m_second == m_first) ? 1 : 2;
+            const double* tab_t = tb.tab + (size_t)lt * tb.tile_stride;
+            for (int pass = 0; pass < npass && n_pre < STAGES; ++pass) {
+                const int m = pass ? m_second : m_first;
+                const int r0 = tb.roff[m], kn_pad = tb.roff[m + 1] - r0;
+                for (int r = 0; r < kn_pad && n_pre < STAGES; r += KC, ++n_pre) {
+                    const int rows = min(KC, kn_pad - r);
+                    gb::mbar_arrive_expect_tx(&full[n_pre], (uint32_t)(rows * (LDB + LDA) * sizeof(double)));
+                    gb::bulk_g2s(s_tiles + (size_t)n_pre * STAGE_DOUBLES, tab_t + ((size_t)r0 + r) * LDA,
+                                 (uint32_t)(rows * LDA * sizeof(double)), &full[n_pre]);
+                }
+            }
+        }
+        gb::griddep_wait();
+        GB_TRACE_MARK(0, 1);
+    }
 
     int stage = 0;
     uint32_t phase = 0;
-    const int tiles_per_pair = n_lattiles * n_coltiles;
+    int chunk_idx = 0;                  // copy lane: chunks handed to the ring so far
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int m_first = item / tiles_per_pair;
         const int rem = item - m_first * tiles_per_pair;
@@ -459,10 +503,12 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     const double* x_m = X + ((size_t)r0 * n_coltiles + (size_t)ct * kn_pad) * LDB;
                     for (int r = 0; r < kn_pad; r += KC) {
                         const int rows = min(KC, kn_pad - r);
-                        gb::mbar_wait(&empty[stage], phase ^ 1u);
                         double* sA = s_tiles + (size_t)stage * STAGE_DOUBLES;
-                        gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * (LDB + LDA) * sizeof(double)));
-                        gb::bulk_g2s(sA, tab_m + (size_t)r * LDA, (uint32_t)(rows * LDA * sizeof(double)), &full[stage]);
+                        if (chunk_idx++ >= n_pre) {
+                            gb::mbar_wait(&empty[stage], phase ^ 1u);
+                            gb::mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows * (LDB + LDA) * sizeof(double)));
+                            gb::bulk_g2s(sA, tab_m + (size_t)r * LDA, (uint32_t)(rows * LDA * sizeof(double)), &full[stage]);
+                        }
                         gb::bulk_g2s(sA + KC * LDA, x_m + (size_t)r * LDB, (uint32_t)(rows * LDB * sizeof(double)), &full[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
@@ -479,7 +525,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     const int m = pass ? m_second : m_first;
                     const int Kn = L - m;
                     const int n_chunks = (Kn + KC - 1) / KC;
-                    const int kc_row = __ldg(tb.krow + 2 * m), ks_row = __ldg(tb.krow + 2 * m + 1);   // latency hides behind the K loop
+                    const int kc_row = gb::ld_nc_early(tb.krow + 2 * m), ks_row = gb::ld_nc_early(tb.krow + 2 * m + 1);   // latency hides behind the K loop
                     double ev[MI][2][2], od[MI][2][2];
 #pragma unroll
                     for (int mi = 0; mi < MI; ++mi)
@@ -488,6 +534,9 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                     for (int c = 0; c < n_chunks; ++c) {
                         const int rows = Kn - c * KC;
                         gb::mbar_wait(&full[stage], phase);
+#ifdef GB_TRACE
+                        if (warp == 0 && lane == 0 && item == (int)blockIdx.x && pass == 0 && c == 0) GB_TRACE_MARK(0, 3);
+#endif
                         const double* sP = s_tiles + (size_t)stage * STAGE_DOUBLES + wm * 16 + g;
                         const double* sX = s_tiles + (size_t)stage * STAGE_DOUBLES + KC * LDA + wn * (8 * MI) + g;
 #pragma unroll
@@ -515,6 +564,9 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                         if (lane == 0) gb::mbar_arrive(&empty[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
+#ifdef GB_TRACE
+                    if (warp == 0 && lane == 0 && item == (int)blockIdx.x) GB_TRACE_MARK(0, 4 + 2 * pass);
+#endif
                     // the store addresses are derived here, behind an opaque copy of the item's column offset: hoisted to the
                     // item prologue they would live (spilled) across the whole K loop
                     int c0e = c0;
@@ -534,6 +586,19 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                             if (ib >= nh) continue;
                             const long long rn = (long long)e * nlat + ib;
                             const long long rs = (long long)e * nlat + (nlat - 4 - ib);
+                            if (diag_nostore) {
+                                if (ev[mi][0][0] + od[mi][0][0] + ev[mi][1][1] - od[mi][1][1] == 1.2345e300) AB[0] = 0.0;
+                                continue;
+                            }
+                            if (diag_v2) {
+                                double* pn = AB + gb_ab_offset(rn, k, ab_rows);
+                                double* ps = AB + gb_ab_offset(rs, k, ab_rows);
+                                gb::st_v2(pn, ev[mi][0][0] + od[mi][0][0], ev[mi][0][1] + od[mi][0][1]);
+                                gb::st_v2(pn + 2, ev[mi][1][0] + od[mi][1][0], ev[mi][1][1] + od[mi][1][1]);
+                                gb::st_v2(ps, ev[mi][1][1] - od[mi][1][1], ev[mi][1][0] - od[mi][1][0]);
+                                gb::st_v2(ps + 2, ev[mi][0][1] - od[mi][0][1], ev[mi][0][0] - od[mi][0][0]);
+                                continue;
+                            }
                             gb::st_v4(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][0][0] + od[mi][0][0], ev[mi][0][1] + od[mi][0][1],
                                       ev[mi][1][0] + od[mi][1][0], ev[mi][1][1] + od[mi][1][1]);
                             gb::st_v4(AB + gb_ab_offset(rs, k, ab_rows), ev[mi][1][1] - od[mi][1][1], ev[mi][1][0] - od[mi][1][0],
@@ -557,6 +622,9 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                             }
                         }
                     }
+#ifdef GB_TRACE
+                    if (warp == 0 && lane == 0 && item == (int)blockIdx.x) GB_TRACE_MARK(0, 5 + 2 * pass);
+#endif
                 }
                 continue;
             }
@@ -564,7 +632,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                 const int m = pass ? m_second : m_first;
                 const int Kn = L - m;
                 const int n_chunks = (Kn + KC - 1) / KC;
-                const int kc_row = __ldg(tb.krow + 2 * m), ks_row = __ldg(tb.krow + 2 * m + 1);
+                const int kc_row = gb::ld_nc_early(tb.krow + 2 * m), ks_row = gb::ld_nc_early(tb.krow + 2 * m + 1);
                 double acc[MI][4][2];
 #pragma unroll
                 for (int mi = 0; mi < MI; ++mi)
@@ -622,6 +690,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
             }
         }
     }
+    if (threadIdx.x == 0) GB_TRACE_MARK(0, 10);
 }
 
 // The table itself: thread = (lat tile, order, parallel of the tile) runs the recursion of utilities.py:37-54 once.
@@ -1009,6 +1078,7 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
     const int lane = threadIdx.x & 31;
     constexpr int PRODUCER_WARP = 12;
     if (threadIdx.x == 0) {
+        GB_TRACE_MARK(1, 0);
         for (int s = 0; s < O_STAGES; ++s) {
             gb::mbar_init(&full[s], 1);
             gb::mbar_init(&empty[s], Q_CONSUMER_WARPS);
@@ -1023,12 +1093,74 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
     gb::tmem_fence_before_sync();
     __syncthreads();
     gb::tmem_fence_after_sync();
-    gb::griddep_wait();                 // AB comes from stage 1; `out` may still be read by whatever ran before
     gb::griddep_launch_dependents();
+    // griddepcontrol.wait (AB comes from stage 1; `out` may still be read by whatever ran before) is executed by the
+    // producer lane alone, right before its first copy: everything else -- the work list, the register hand-over, the
+    // first fetch of the kernel parameters (a DRAM round trip after an L2 flush) -- overlaps the predecessor's tail.
+    // No other thread touches global memory before it has seen data those copies delivered.
 
     const QWork work(n_mtiles, n_ntiles, (int)gridDim.x);
     const int h = nlon >> 1, nq = nlon >> 2;
     auto warp_row0 = [](int wm, int half) { return half < 0 ? wm * 32 : half * 64 + wm * 16; };
+    // butterfly + stores of one 8-row slab of a warp tile (output row `row`, octant meridians jo .. jo+3):
+    // ve = [E0 | E2 | F0 | F2] x 4 meridians, vo = [CO | AS | SO | BC] x 4 meridians
+    auto emit_slab = [&](long long row, int jo, const double (&ve)[16], const double (&vo)[16]) {
+        if (row >= M || jo >= no) return;
+        double* orow = out + (size_t)row * nlon;
+        // the quadrant sums at nu (p = 0) and at pi/2 - nu (p = 1), then the four mirrored meridians of each
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            double v1[4], v2[4], v3[4], v4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double ce = p ? ve[c] - ve[4 + c] : ve[c] + ve[4 + c];
+                const double se = p ? ve[12 + c] - ve[8 + c] : ve[8 + c] + ve[12 + c];
+                const double co = p ? vo[4 + c] : vo[c];
+                const double so = p ? vo[12 + c] : vo[8 + c];
+                const double cp = ce + co, cm = ce - co, sp_ = se + so, sm = se - so;
+                v1[c] = cp + sp_;   // mu
+                v2[c] = cm - sm;    // pi - mu
+                v3[c] = cp - sp_;   // -mu
+                v4[c] = cm + sm;    // mu - pi
+            }
+            // quadrant index of meridian c: jo + c (p = 0, ascending) or nq - 1 - jo - c (p = 1, descending)
+            if (wide && jo + 4 <= no) {
+                if (p == 0) {
+                    gb::st_cs_v4(orow + h + jo, v1[0], v1[1], v1[2], v1[3]);
+                    gb::st_cs_v4(orow + nlon - 4 - jo, v2[3], v2[2], v2[1], v2[0]);
+                    gb::st_cs_v4(orow + h - 4 - jo, v3[3], v3[2], v3[1], v3[0]);
+                    gb::st_cs_v4(orow + jo, v4[0], v4[1], v4[2], v4[3]);
+                } else {
+                    const int jb = nq - 4 - jo;       // quadrant index of c = 3
+                    gb::st_cs_v4(orow + h + jb, v1[3], v1[2], v1[1], v1[0]);
+                    gb::st_cs_v4(orow + nlon - 4 - jb, v2[0], v2[1], v2[2], v2[3]);
+                    gb::st_cs_v4(orow + h - 4 - jb, v3[0], v3[1], v3[2], v3[3]);
+                    gb::st_cs_v4(orow + jb, v4[3], v4[2], v4[1], v4[0]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c += 2) {          // no is even: pairs are all in or all out
+                    if (jo + c >= no) continue;
+                    if (p == 0) {
+                        const int j = jo + c;
+                        gb::st_cs_v2(orow + h + j, v1[c], v1[c + 1]);
+                        gb::st_cs_v2(orow + nlon - 2 - j, v2[c + 1], v2[c]);
+                        gb::st_cs_v2(orow + h - 2 - j, v3[c + 1], v3[c]);
+                        gb::st_cs_v2(orow + j, v4[c], v4[c + 1]);
+                    } else {
+                        const int j = nq - 2 - jo - c;    // quadrant index of c + 1
+                        gb::st_cs_v2(orow + h + j, v1[c + 1], v1[c]);
+                        gb::st_cs_v2(orow + nlon - 2 - j, v2[c], v2[c + 1]);
+                        gb::st_cs_v2(orow + h - 2 - j, v3[c], v3[c + 1]);
+                        gb::st_cs_v2(orow + j, v4[c + 1], v4[c]);
+                    }
+                }
+            }
+        }
+    };
+    // The LAST tile of a CTA has no K loop behind it to hide its epilogue: the epilogue warps take only the first
+    // S_TAIL_EPI slab(s) of every consumer's tile, each consumer warp reads the rest of its own tile back and stores it.
+    constexpr int S_TAIL_EPI = 1;
 
     if (warp >= PRODUCER_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
@@ -1037,6 +1169,16 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
             uint32_t phase = 0;
             long long mt;
             int nt, half;
+            {
+                // the parameters and the first work item are in registers before the wait
+                const bool any = work.get(blockIdx.x, 0, mt, nt, half);
+                const double* a0 = AB + ((size_t)mt * ab_rows + grp.off[4]) * Q_LDA;
+                const double* b0 = trig_o_t + ((size_t)nt * 2 * kpad_o + grp.off[4]) * Q_LDB;
+                asm volatile("" ::"r"((int)any), "l"(a0), "l"(b0), "r"(grp.off[5]), "r"(grp.off[6]), "r"(grp.off[0]), "r"(grp.off[1]),
+                             "r"(grp.off[2]), "r"(grp.off[3]));
+            }
+            gb::griddep_wait();
+            GB_TRACE_MARK(1, 1);
             for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
                 const double* t1 = trig_o_t + (size_t)nt * 2 * kpad_o * Q_LDB;
                 const double* t2 = t1 + (size_t)kpad_o * Q_LDB;
@@ -1053,6 +1195,9 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
                         gb::bulk_g2s(sA, AB + ((size_t)mt * ab_rows + k0) * Q_LDA, bytes_a, &full[stage]);
                         gb::bulk_g2s(sB, t1 + (size_t)k0 * Q_LDB, bytes_b, &full[stage]);
                         if (gi >= 4) gb::bulk_g2s(sB + O_KC * Q_LDB, t2 + (size_t)k0 * Q_LDB, bytes_b, &full[stage]);
+#ifdef GB_TRACE
+                        if (i == 0 && go == 0 && k0 == grp.off[gi]) GB_TRACE_MARK(1, 2);
+#endif
                         if (++stage == O_STAGES) { stage = 0; phase ^= 1u; }
                         k0 += kc;
                     }
@@ -1064,10 +1209,13 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
         asm volatile("setmaxnreg.inc.sync.aligned.u32 136;\n");
         const int sp = warp & 3;
         uint32_t tphase = 0;
-        long long mt;
-        int nt, half;
-        for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
+        long long mt, mt_next = 0;
+        int nt, half, nt_next = 0, half_next = 0;
+        bool more = work.get(blockIdx.x, 0, mt, nt, half);
+        for (long long i = 0; more; ++i) {
+            more = work.get(blockIdx.x, i + 1, mt_next, nt_next, half_next);
             const int n_slabs = half < 0 ? 4 : 2;
+            const int n_mine = more ? n_slabs : S_TAIL_EPI;      // last tile: the consumers store the other slabs themselves
 #pragma unroll 1
             for (int cw = 0; cw < 2; ++cw) {
                 const int w = sp + 4 * cw;                 // consumer warp whose tile this is
@@ -1077,12 +1225,15 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
                 gb::mbar_wait(&tfull[w], tphase);
                 gb::mbar_wait(&tfull[Q_CONSUMER_WARPS + w], tphase);
                 gb::tmem_fence_after_sync();
+#ifdef GB_TRACE
+                if (warp == 8 && lane == 0 && cw == 0 && i < 3) GB_TRACE_MARK(1, 16 + 2 * (int)i);
+#endif
 #pragma unroll 1
-                for (int mi = 0; mi < n_slabs; ++mi) {
+                for (int mi = 0; mi < n_mine; ++mi) {
                     double ve[16], vo[16];
                     gb::tmem_ld16(taddr + 32u * mi, ve);             // [E0 | E2 | F0 | F2] x 4 meridians
                     gb::tmem_ld16(taddr + 128u + 32u * mi, vo);      // [CO | AS | SO | BC] x 4 meridians
-                    if (mi == n_slabs - 1) {
+                    if (mi == n_mine - 1 && more) {
                         // both halves of this consumer's tile have been read: hand its buffers back
                         gb::tmem_fence_before_sync();
                         __syncwarp();
@@ -1091,62 +1242,14 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
                             gb::mbar_arrive(&tempty[Q_CONSUMER_WARPS + w]);
                         }
                     }
-                    const long long row = row0 + mi * 8;
-                    if (row >= M || jo >= no) continue;
-                    double* orow = out + (size_t)row * nlon;
-                    // the quadrant sums at nu (p = 0) and at pi/2 - nu (p = 1), then the four mirrored meridians of each
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        double v1[4], v2[4], v3[4], v4[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const double ce = p ? ve[c] - ve[4 + c] : ve[c] + ve[4 + c];
-                            const double se = p ? ve[12 + c] - ve[8 + c] : ve[8 + c] + ve[12 + c];
-                            const double co = p ? vo[4 + c] : vo[c];
-                            const double so = p ? vo[12 + c] : vo[8 + c];
-                            const double cp = ce + co, cm = ce - co, sp_ = se + so, sm = se - so;
-                            v1[c] = cp + sp_;   // mu
-                            v2[c] = cm - sm;    // pi - mu
-                            v3[c] = cp - sp_;   // -mu
-                            v4[c] = cm + sm;    // mu - pi
-                        }
-                        // quadrant index of meridian c: jo + c (p = 0, ascending) or nq - 1 - jo - c (p = 1, descending)
-                        if (wide && jo + 4 <= no) {
-                            if (p == 0) {
-                                gb::st_cs_v4(orow + h + jo, v1[0], v1[1], v1[2], v1[3]);
-                                gb::st_cs_v4(orow + nlon - 4 - jo, v2[3], v2[2], v2[1], v2[0]);
-                                gb::st_cs_v4(orow + h - 4 - jo, v3[3], v3[2], v3[1], v3[0]);
-                                gb::st_cs_v4(orow + jo, v4[0], v4[1], v4[2], v4[3]);
-                            } else {
-                                const int jb = nq - 4 - jo;       // quadrant index of c = 3
-                                gb::st_cs_v4(orow + h + jb, v1[3], v1[2], v1[1], v1[0]);
-                                gb::st_cs_v4(orow + nlon - 4 - jb, v2[0], v2[1], v2[2], v2[3]);
-                                gb::st_cs_v4(orow + h - 4 - jb, v3[0], v3[1], v3[2], v3[3]);
-                                gb::st_cs_v4(orow + jb, v4[3], v4[2], v4[1], v4[0]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 4; c += 2) {          // no is even: pairs are all in or all out
-                                if (jo + c >= no) continue;
-                                if (p == 0) {
-                                    const int j = jo + c;
-                                    gb::st_cs_v2(orow + h + j, v1[c], v1[c + 1]);
-                                    gb::st_cs_v2(orow + nlon - 2 - j, v2[c + 1], v2[c]);
-                                    gb::st_cs_v2(orow + h - 2 - j, v3[c + 1], v3[c]);
-                                    gb::st_cs_v2(orow + j, v4[c], v4[c + 1]);
-                                } else {
-                                    const int j = nq - 2 - jo - c;    // quadrant index of c + 1
-                                    gb::st_cs_v2(orow + h + j, v1[c + 1], v1[c]);
-                                    gb::st_cs_v2(orow + nlon - 2 - j, v2[c], v2[c + 1]);
-                                    gb::st_cs_v2(orow + h - 2 - j, v3[c], v3[c + 1]);
-                                    gb::st_cs_v2(orow + j, v4[c + 1], v4[c]);
-                                }
-                            }
-                        }
-                    }
+                    emit_slab(row0 + mi * 8, jo, ve, vo);
                 }
             }
+#ifdef GB_TRACE
+            if (warp == 8 && lane == 0 && i < 3) GB_TRACE_MARK(1, 17 + 2 * (int)i);
+#endif
             tphase ^= 1u;
+            mt = mt_next; nt = nt_next; half = half_next;
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
@@ -1156,7 +1259,8 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
         int stage = 0;
         uint32_t phase = 0, tphase = 0;
         const uint32_t taddr = *s_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 256);
-        auto run_tile = [&](auto mi_tag, int half) {
+        long long trace_item = 0;
+        auto run_tile = [&](auto mi_tag, long long mt, int nt, int half, bool last) {
             constexpr int MI = decltype(mi_tag)::value;
             const int r0 = warp_row0(wm, half);
             // the odd part (two thirds of the tile's DMMAs) first: its half is parked two thirds into the tile period, by
@@ -1174,6 +1278,9 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
                     for (int k0 = grp.off[gi]; k0 < grp.off[gi + 1];) {
                         const int kc = min(O_KC, grp.off[gi + 1] - k0);
                         gb::mbar_wait(&full[stage], phase);
+#ifdef GB_TRACE
+                        if (warp == 0 && lane == 0 && trace_item == 0 && part == 1 && gi == 4 && k0 == grp.off[4]) GB_TRACE_MARK(1, 3);
+#endif
                         const double* sA = s_tiles + (size_t)stage * O_STAGE_DOUBLES + r0 + g;
                         const double* sB = s_tiles + (size_t)stage * O_STAGE_DOUBLES + O_KC * Q_LDA + wn * 16 + g;
                         if (kc == O_KC) {
@@ -1228,6 +1335,9 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
                                 }
                         });
                 }
+#ifdef GB_TRACE
+                if (warp == 0 && lane == 0 && trace_item < 3) GB_TRACE_MARK(1, 4 + 4 * (int)trace_item + 2 * (1 - part));
+#endif
                 // park this half of the tile: columns 256 (warp / 4) + 128 part + 32 mi of this warp's lanes
                 gb::mbar_wait(&tempty[part * Q_CONSUMER_WARPS + warp], tphase ^ 1u);
                 gb::tmem_fence_after_sync();
@@ -1244,18 +1354,39 @@ gb_fourier_stage2_oct(const double* __restrict__ AB, int ab_rows, const double* 
                 gb::tmem_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) gb::mbar_arrive(&tfull[part * Q_CONSUMER_WARPS + warp]);
+#ifdef GB_TRACE
+                if (warp == 0 && lane == 0 && trace_item < 3) GB_TRACE_MARK(1, 5 + 4 * (int)trace_item + 2 * (1 - part));
+#endif
+            }
+            if (last) {
+                // no K loop follows: this warp stores the slabs the epilogue warp leaves to it (its own parked values)
+                const long long row0 = mt * Q_TM + r0 + g;
+                const int jo = nt * Q_TN + wn * 16 + 4 * q;
+#pragma unroll 1
+                for (int mi = S_TAIL_EPI; mi < MI; ++mi) {
+                    double ve[16], vo[16];
+                    gb::tmem_ld16(taddr + 32u * mi, ve);
+                    gb::tmem_ld16(taddr + 128u + 32u * mi, vo);
+                    emit_slab(row0 + mi * 8, jo, ve, vo);
+                }
             }
             tphase ^= 1u;
+            ++trace_item;
         };
-        long long mt;
-        int nt, half;
-        for (long long i = 0; work.get(blockIdx.x, i, mt, nt, half); ++i) {
-            if (half < 0) run_tile(std::integral_constant<int, 4>{}, half);
-            else run_tile(std::integral_constant<int, 2>{}, half);
+        long long mt, mt_next = 0;
+        int nt, half, nt_next = 0, half_next = 0;
+        bool more = work.get(blockIdx.x, 0, mt, nt, half);
+        for (long long i = 0; more; ++i) {
+            more = work.get(blockIdx.x, i + 1, mt_next, nt_next, half_next);
+            if (half < 0) run_tile(std::integral_constant<int, 4>{}, mt, nt, half, !more);
+            else run_tile(std::integral_constant<int, 2>{}, mt, nt, half, !more);
+            mt = mt_next; nt = nt_next; half = half_next;
         }
     }
+    if (threadIdx.x == 0) GB_TRACE_MARK(1, 22);
     gb::tmem_fence_before_sync();
     __syncthreads();
+    if (threadIdx.x == 0) GB_TRACE_MARK(1, 23);
     if (warp == 0) gb::tmem_dealloc(*s_tmem, 512);
 }
 
@@ -1352,12 +1483,18 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
     const int* d_krow = use_oct ? p->d_krow_oct : use_sym ? p->d_krow_sym : p->d_krow_id;
     // stage-1 tiling: narrow batches (at most 80 epochs) run 80-column items, several CTAs per SM
     const bool simple1 = env_flag("GB_SIMPLE_STAGE1");
-    const bool narrow = 2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE");
+    const char* s1_nwn = getenv("GB_S1_NWN");                       // experiment: column warps of the wide items (2, 3, 6)
+    const int nwn_wide = s1_nwn ? atoi(s1_nwn) : 6;
     const bool fold = p->fold_ns && !env_flag("GB_NO_FOLD");        // equatorial symmetry: 32 northern parallels per item
+    const bool tab_fold = fold && p->fold_cap == 0 && !simple1 && !env_flag("GB_S1_ONTHEFLY");
+    // 41 .. 60 epochs on folded grids without polar caps: ONE 120-column tile per order pair and latitude tile, two CTAs
+    // per SM (80-column tiles would leave a second, mostly empty round of items)
+    const bool mid = tab_fold && !env_flag("GB_S1_WIDE") &&
+                     (nwn_wide == 3 || (!s1_nwn && 2 * E > t1_tn(2) && 2 * E <= t1_tn(3)));
+    const bool narrow = ((2 * E <= 2 * t1_tn(2) && !env_flag("GB_S1_WIDE")) || nwn_wide == 2) && !mid;
     // shards of at most 32 epochs on folded grids without polar caps: 64-column items (no padding fragment)
-    const bool narrow32 = narrow && fold && p->fold_cap == 0 && 2 * E <= 64 && !simple1 && !env_flag("GB_S1_ONTHEFLY") &&
-                          !env_flag("GB_S1_MI5");
-    const int tn = narrow32 ? 64 : narrow ? t1_tn(2) : t1_tn(6);
+    const bool narrow32 = narrow && tab_fold && 2 * E <= 64 && !env_flag("GB_S1_MI5");
+    const int tn = narrow32 ? 64 : narrow ? t1_tn(2) : mid ? t1_tn(3) : t1_tn(6);
     const int n_coltiles = (2 * E + tn - 1) / tn;
     const int cap_tiles = fold ? p->fold_cap / 32 : 0;              // polar tiles that stay unfolded
     const int n_lattiles = fold ? (p->nlat / 2 + 31) / 32 - cap_tiles : (p->nlat + T1_TM - 1) / T1_TM;
@@ -1403,7 +1540,17 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
             auto launch_tab = [&](auto kernel, int nwn, bool kfold, int kc, int kind, int lattiles, int items, int polar) -> int {
                 const int max_ctas = tb_ctas_per_sm(nwn, kfold) * p->sm_count;
                 const int grid = items < max_ctas ? items : max_ctas;
-                const size_t smem = tb_smem(nwn, kfold, kc);
+                size_t smem = tb_smem(nwn, kfold, kc);
+                // Fewer items than CTA slots (a narrow shard): the CTAs are launched while the pack kernel still holds part
+                // of every SM (programmatic dependent launch) and the block scheduler fills whatever is free first -- three
+                // CTAs on some SMs, one on others, and the crowded SMs finish last.  Asking for more shared memory than a
+                // CTA needs caps the CTAs per SM at the even share.
+                const int per_sm = (grid + p->sm_count - 1) / p->sm_count;
+                if (per_sm < tb_ctas_per_sm(nwn, kfold) && !env_flag("GB_S1_NO_SPREAD")) {
+                    const size_t forbid = 233472 / (size_t)(per_sm + 1) - 1024 + 256;      // per_sm + 1 CTAs no longer fit
+                    const size_t allow = 233472 / (size_t)per_sm - 1024;                    // per_sm CTAs still do
+                    if (forbid > smem && forbid <= allow && forbid <= 232448) smem = forbid;
+                }
                 TabArgs ta{p->d_ptab[kind], p->d_ptab_roff, p->ptab_rtot * tb_lda(kfold), d_krow};
                 GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 GB_CUDA(gb_launch_pdl(kernel, dim3(grid), dim3(tb_threads(nwn)), smem, st, p->d_x, p->d_ab, ta, L, p->nlat, E,
@@ -1416,8 +1563,9 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
             if (fold) {
                 rc = narrow32 ? launch_tab(gb_stage1_tab<true, 2, true, 16, 4>, 2, true, 16, 0, n_lattiles, n_items, cap_tiles)
                      : narrow ? launch_tab(gb_stage1_tab<true, 2, true, 16>, 2, true, 16, 0, n_lattiles, n_items, cap_tiles)
+                     : mid ? launch_tab(gb_stage1_tab<true, 3, true, 16>, 3, true, 16, 0, n_lattiles, n_items, cap_tiles)
                      : kc32 ? launch_tab(gb_stage1_tab<true, 6, true, 32>, 6, true, 32, 0, n_lattiles, n_items, cap_tiles)
-                            : launch_tab(gb_stage1_tab<true, 6, true, 16>, 6, true, 16, 0, n_lattiles, n_items, cap_tiles | (env_flag("GB_DIAG_NOSTORE") ? 0x10000 : 0));
+                            : launch_tab(gb_stage1_tab<true, 6, true, 16>, 6, true, 16, 0, n_lattiles, n_items, cap_tiles | (env_flag("GB_DIAG_NOSTORE") ? 0x10000 : 0) | (env_flag("GB_DIAG_V2") ? 0x20000 : 0));
                 if (!rc && cap_tiles > 0)
                     rc = narrow ? launch_tab(gb_stage1_tab<true, 2, false, 16>, 2, false, 16, 1, cap_tiles, cap_items, 1)
                                 : launch_tab(gb_stage1_tab<true, 6, false, 16>, 6, false, 16, 1, cap_tiles, cap_items, 1);
@@ -1661,6 +1809,20 @@ extern "C" int gb_synthesis_host(gb_plan* plan, const double* h_anm, int n_epoch
     GB_CUDA(cudaStreamSynchronize(p->s_compute));
     return GB_OK;
 }
+
+#ifdef GB_TRACE
+extern "C" int gb_debug_trace(unsigned long long* h_out, int reset) {
+    if (reset) {
+        void* sym = nullptr;
+        GB_CUDA(cudaGetSymbolAddress(&sym, gb_trace_buf));
+        GB_CUDA(cudaMemset(sym, 0, sizeof(gb_trace_buf)));
+        return GB_OK;
+    }
+    GB_CUDA(cudaDeviceSynchronize());
+    GB_CUDA(cudaMemcpyFromSymbol(h_out, gb_trace_buf, sizeof(gb_trace_buf)));
+    return GB_OK;
+}
+#endif
 
 extern "C" int gb_legendre_table(gb_plan* plan, double* d_out, int scaled, void* stream) {
     GB_REQUIRE(plan != nullptr && d_out != nullptr, "gb_legendre_table: NULL argument");
