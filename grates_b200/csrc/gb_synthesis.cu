@@ -427,7 +427,6 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
     constexpr int STAGES = tb_stages(NWN, FOLD, KC);
     static_assert(STAGES >= 2, "the ring needs at least two stages");
     const bool diag_nostore = (polar & 0x10000) != 0;   // DIAG (GB_DIAG_NOSTORE): the epilogue without its stores
-    const bool diag_v2 = (polar & 0x20000) != 0;        // DIAG (GB_DIAG_V2): 16-byte instead of 32-byte stores
     polar &= 0xffff;
     constexpr int TN = 8 * MI * NWN, LDA = tb_lda(FOLD), LDB = TN + 4, CONSUMER_WARPS = 2 * NWN;
     constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
@@ -590,15 +589,6 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
                                 if (ev[mi][0][0] + od[mi][0][0] + ev[mi][1][1] - od[mi][1][1] == 1.2345e300) AB[0] = 0.0;
                                 continue;
                             }
-                            if (diag_v2) {
-                                double* pn = AB + gb_ab_offset(rn, k, ab_rows);
-                                double* ps = AB + gb_ab_offset(rs, k, ab_rows);
-                                gb::st_v2(pn, ev[mi][0][0] + od[mi][0][0], ev[mi][0][1] + od[mi][0][1]);
-                                gb::st_v2(pn + 2, ev[mi][1][0] + od[mi][1][0], ev[mi][1][1] + od[mi][1][1]);
-                                gb::st_v2(ps, ev[mi][1][1] - od[mi][1][1], ev[mi][1][0] - od[mi][1][0]);
-                                gb::st_v2(ps + 2, ev[mi][0][1] - od[mi][0][1], ev[mi][0][0] - od[mi][0][0]);
-                                continue;
-                            }
                             gb::st_v4(AB + gb_ab_offset(rn, k, ab_rows), ev[mi][0][0] + od[mi][0][0], ev[mi][0][1] + od[mi][0][1],
                                       ev[mi][1][0] + od[mi][1][0], ev[mi][1][1] + od[mi][1][1]);
                             gb::st_v4(AB + gb_ab_offset(rs, k, ab_rows), ev[mi][1][1] - od[mi][1][1], ev[mi][1][0] - od[mi][1][0],
@@ -692,6 +682,7 @@ gb_stage1_tab(const double* __restrict__ X, double* __restrict__ AB, TabArgs tb,
     }
     if (threadIdx.x == 0) GB_TRACE_MARK(0, 10);
 }
+
 
 // The table itself: thread = (lat tile, order, parallel of the tile) runs the recursion of utilities.py:37-54 once.
 __global__ void __launch_bounds__(128)
@@ -1565,7 +1556,7 @@ static int launch_synthesis(gb_plan* p, const double* d_anm, int E, double* d_ou
                      : narrow ? launch_tab(gb_stage1_tab<true, 2, true, 16>, 2, true, 16, 0, n_lattiles, n_items, cap_tiles)
                      : mid ? launch_tab(gb_stage1_tab<true, 3, true, 16>, 3, true, 16, 0, n_lattiles, n_items, cap_tiles)
                      : kc32 ? launch_tab(gb_stage1_tab<true, 6, true, 32>, 6, true, 32, 0, n_lattiles, n_items, cap_tiles)
-                            : launch_tab(gb_stage1_tab<true, 6, true, 16>, 6, true, 16, 0, n_lattiles, n_items, cap_tiles | (env_flag("GB_DIAG_NOSTORE") ? 0x10000 : 0) | (env_flag("GB_DIAG_V2") ? 0x20000 : 0));
+                            : launch_tab(gb_stage1_tab<true, 6, true, 16>, 6, true, 16, 0, n_lattiles, n_items, cap_tiles | (env_flag("GB_DIAG_NOSTORE") ? 0x10000 : 0));
                 if (!rc && cap_tiles > 0)
                     rc = narrow ? launch_tab(gb_stage1_tab<true, 2, false, 16>, 2, false, 16, 1, cap_tiles, cap_items, 1)
                                 : launch_tab(gb_stage1_tab<true, 6, false, 16>, 6, false, 16, 1, cap_tiles, cap_items, 1);

@@ -232,6 +232,29 @@ def test_synthesis_headline_shape_properties(gb, orc):
     assert isinstance(host, np.ndarray) and np.array_equal(host, out[:40].cpu().numpy())
 
 
+def test_synthesis_shard_sizes_are_bit_identical(gb, orc):
+    """The strong-scaling shards of config 2 (240 / G epochs per GPU) run other tilings than the full batch: 64-column
+    items with the CTAs spread over the SMs (30 epochs), one 120-column tile (45 and 60 epochs), 240-column tiles (120),
+    and a pack kernel that fetches whole rows with bulk copies.  Every shard must reproduce the rows of the full batch
+    bit for bit -- also when the coefficient buffer starts on an odd double, where the bulk copies start one double
+    early and the first / last row of the buffer fall back to plain loads."""
+    E, N = 240, 96
+    grid = gb.GeographicGrid(0.5, 0.5)
+    anm = np.stack([orc.synthetic_coefficients(N, e) for e in range(E)])
+    x = torch.as_tensor(anm).cuda()
+    full = gb.to_grid_batch(x, grid, "ewh")
+    for n, e0 in ((30, 0), (30, 210), (45, 17), (60, 180), (120, 120), (1, 239), (33, 5), (41, 100)):
+        sub = gb.to_grid_batch(x[e0:e0 + n].contiguous(), grid, "ewh")
+        assert torch.equal(sub, full[e0:e0 + n]), (n, e0)
+    L = N + 1
+    for n in (30, 60):
+        flat = torch.zeros(n * L * L + 1, dtype=torch.float64, device="cuda")
+        odd = flat[1:].view(n, L, L)
+        assert odd.data_ptr() % 16 == 8
+        odd.copy_(x[7:7 + n])
+        assert torch.equal(gb.to_grid_batch(odd, grid, "ewh"), full[7:7 + n]), n
+
+
 def test_time_series_and_rms(gb, orc):
     data = []
     for e in range(6):
