@@ -225,13 +225,20 @@ class IrregularGrid:
 
     def _analysis_operator(self, min_degree, max_degree, kernel, GM, R):
         """Area-weighted least-squares operator solve(A'WA, A'W) on the device (reference grid.py:993-1017).  The design
-        matrix comes from the point-set kernels; the dense normal-equation product and solve are cuBLAS / cuSOLVER through
-        torch, where the reference calls BLAS / LAPACK through numpy."""
+        matrix comes from the point-set kernels; the normal matrix A'WA, its Cholesky factor W'W and the two triangular
+        solves run on this library's own FP64 tensor-core kernels (gb_dgemm / gb_dpotrf_upper / gb_dtrsm_upper, gb_linalg.cu)
+        where the reference calls BLAS / LAPACK through numpy."""
+        from .lstsq import _Ops
         p = _plan.get_points_plan(self, max_degree, kernel, GM, R)
         A = p.synthesis_matrix(min_degree)
         sw = torch.as_tensor(np.sqrt(np.asarray(self.area, dtype=float))).to(A.device)
-        A = A * sw[:, None]
-        return torch.linalg.solve(A.T @ A, A.T * sw)
+        A = (A * sw[:, None]).contiguous()
+        ops = _Ops(A.device.index)
+        normals = ops.matmul(A, A, trans_a=True)
+        ops.cholesky_upper(normals)
+        rhs = (A * sw[:, None]).T.contiguous()                  # A'W (A already carries sqrt(w))
+        ops.solve_triangular(normals, rhs, trans=True)
+        return ops.solve_triangular(normals, rhs, trans=False)
 
     def analysis_matrix(self, min_degree, max_degree, kernel='potential', GM=GM_DEFAULT, R=R_DEFAULT):
         """Dense analysis operator [K', points] (reference grid.py:993-1017)."""
@@ -243,7 +250,9 @@ class IrregularGrid:
         if self.values is None:
             raise ValueError('grid has no values to propagate to potential coefficients')
         F = self._analysis_operator(min_degree, max_degree, kernel, GM, R)
-        x = F @ torch.as_tensor(np.ascontiguousarray(self.values, dtype=float)).to(F.device)
+        from .lstsq import _Ops
+        v = torch.as_tensor(np.ascontiguousarray(self.values, dtype=float)).to(F.device).reshape(-1, 1)
+        x = _Ops(F.device.index).matmul(F.contiguous(), v.contiguous()).reshape(-1)
         coeffs = PotentialCoefficients(GM, R)
         coeffs.anm = utilities.unravel_coefficients(x.cpu().numpy(), min_degree, max_degree)
         return coeffs
@@ -309,12 +318,18 @@ def _device_matrix(matrix, device):
 def covariance_from_normals(normal_equation_matrix, device_output=True):
     """Covariance matrix Sigma = N^-1 of a dense, symmetric positive definite normal-equation matrix, kept on the device
     for ``covariance_propagation`` / ``basin_variances`` (the dense case of NormalEquations.compute_covariance, reference
-    lstsq.py:1026-1043: Cholesky factor, then W^-1 W^-T).  The factorisation is cuSOLVER through torch -- where the
-    reference calls LAPACK -- and is not part of the measured path."""
+    lstsq.py:1026-1043: Cholesky factor W'W, then W^-1 W^-T) on this library's own dense kernels (gb_linalg.cu); the
+    blocked / sparse case is ``lstsq.NormalEquations.compute_covariance``."""
+    from .lstsq import _Ops
     dev = torch.device("cuda", _plan._current_device(None))
     n = normal_equation_matrix if isinstance(normal_equation_matrix, torch.Tensor) else \
         torch.as_tensor(np.ascontiguousarray(normal_equation_matrix, dtype=np.float64))
-    sigma = torch.cholesky_inverse(torch.linalg.cholesky(n.to(device=dev, dtype=torch.float64), upper=True), upper=True)
+    w = n.to(device=dev, dtype=torch.float64).clone().contiguous()
+    if w.dim() != 2 or w.shape[0] != w.shape[1]:
+        raise ValueError("expected a square normal-equation matrix")
+    ops = _Ops(dev.index)
+    ops.cholesky_upper(w)
+    sigma = ops.inv_gram(torch.triu(w))
     return sigma if device_output else sigma.cpu().numpy()
 
 
