@@ -946,7 +946,7 @@ def test_orderwise_filter_batch_then_synthesis(gb, orc):
     # batches above and below the narrow-tile limit, a filter of higher degree than the data
     x = torch.as_tensor(anm).cuda()
     for g2 in (grid, gb.GeographicGrid(7.0, 5.0), gb.GaussGrid(19)):
-        for xe in (x, x[:3], torch.cat([x] * 9)):
+        for xe in (x, x[:3], torch.cat([x] * 5), torch.cat([x] * 9)):      # 64-, 120- (55 epochs) and 240-column items
             two = gb.to_grid_batch(flt.filter_batch(xe), g2, "ewh")
             one = gb.to_grid_batch(xe, g2, "ewh", orderwise_filter=flt)
             assert torch.equal(one, two)
