@@ -80,6 +80,7 @@ gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St,
                       const int* __restrict__ goff4, const int* __restrict__ ne4, int Kp4, long long K, int nmin,
                       const int* __restrict__ first_group) {
     __shared__ double s_p[CP_ROWS * CP_PITCH];
+    __shared__ int s_b[CP_COLS];                                      // row of St of every column of this CTA
     const int a0 = blockIdx.x * CP_ROWS;
     const int n = nmin + blockIdx.y;
     const int width = 2 * n + 1;
@@ -94,6 +95,14 @@ gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St,
     if (jlo >= j1) return;
     const long long col0 = (long long)n * n - (long long)nmin * nmin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the two dependent table look-ups per column run here, beside the loads of Sigma, not in front of every store
+    if (threadIdx.x < CP_COLS && jlo + (int)threadIdx.x < j1) {
+        const int j = jlo + threadIdx.x;
+        const int m = (j + 1) >> 1;
+        const int k = (j == 0) ? 0 : 2 * m + ((j & 1) ? 0 : 1);          // j = 2m-1: cos, j = 2m: sin
+        const int n0 = max(m, nmin);
+        s_b[j - j0] = goff4[k] + cov_cls_pos(n - n0, (n0 - m) & 1, ne4[k]);
+    }
     for (int r = warp; r < CP_ROWS; r += 8) {
         const int pa = perm8[a0 + r];
         const double* src = sigma + (size_t)(pa < 0 ? 0 : pa) * K + col0;
@@ -102,10 +111,7 @@ gb_cov_permute_degree(const double* __restrict__ sigma, double* __restrict__ St,
     }
     __syncthreads();
     for (int j = jlo + warp; j < j1; j += 8) {
-        const int m = (j + 1) >> 1;
-        const int k = (j == 0) ? 0 : 2 * m + ((j & 1) ? 0 : 1);          // j = 2m-1: cos, j = 2m: sin
-        const int n0 = max(m, nmin);
-        const int b = goff4[k] + cov_cls_pos(n - n0, (n0 - m) & 1, ne4[k]);
+        const int b = s_b[j - j0];
         double* dst = St + ((size_t)(a0 >> 7) * Kp4 + b) * GB_LDA + (a0 & (GB_TM - 1));
 #pragma unroll
         for (int r = lane; r < CP_ROWS; r += 32) dst[r] = s_p[r * CP_PITCH + j - j0];
