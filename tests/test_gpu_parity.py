@@ -255,6 +255,34 @@ def test_synthesis_shard_sizes_are_bit_identical(gb, orc):
         assert torch.equal(gb.to_grid_batch(odd, grid, "ewh"), full[7:7 + n]), n
 
 
+def test_synthesis_more_than_two_giga_outputs(gb, orc):
+    """2 100 epochs on a 0.25 degree grid are 2.18e9 output values (17 GB) and 1.5e6 rows of the spectral intermediate:
+    every index that could overflow 32 bits does.  Rows from the start, the middle and the very end of the batch must be
+    bit-identical to the same epochs synthesised as a small batch."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 40 GB of free device memory")
+    E, N = 2100, 60
+    grid = gb.GeographicGrid(0.25, 0.25)
+    base = np.stack([orc.synthetic_coefficients(N, e) for e in range(7)])
+    x = torch.as_tensor(base).cuda().repeat(E // 7, 1, 1) * torch.linspace(0.5, 1.5, E, dtype=torch.float64, device="cuda")[:, None, None]
+    out = gb.to_grid_batch(x, grid, "ewh")
+    assert out.numel() > 2**31 and tuple(out.shape) == (E, 720, 1440)
+    for e0 in (0, 1047, E - 3):
+        sub = gb.to_grid_batch(x[e0:e0 + 3].contiguous(), grid, "ewh")
+        assert torch.equal(sub, out[e0:e0 + 3]), e0
+    og = orc.geographic_grid(0.25, 0.25)
+    assert maxnorm_err(out[E - 1].cpu().numpy(), orc.synthesis(x[E - 1].cpu().numpy(), og, "ewh")) < TOL
+    # the analysis of the same 2.18e9 values: the round trip returns the coefficients, the last epochs as a small batch agree
+    back = gb.analysis_batch(out, grid, 0, N, "ewh", device_output=True)
+    assert float((back - x).abs().max() / x.abs().max()) < 1e-11
+    sub = gb.analysis_batch(out[E - 3:].contiguous(), grid, 0, N, "ewh", device_output=True)
+    assert maxnorm_err(sub.cpu().numpy(), back[E - 3:].cpu().numpy()) < 1e-14
+    del out, back
+    gb.clear_plan_cache()               # the 17 GB analysis workspace goes with the plan
+    torch.cuda.empty_cache()
+
+
 def test_time_series_and_rms(gb, orc):
     data = []
     for e in range(6):
