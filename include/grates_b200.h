@@ -27,6 +27,12 @@
  *    work on whatever stream that ran (an event wait, free when the stream is the same) -- but two host threads must
  *    not be inside calls on the same plan at the same time (the Python layer holds a per-plan lock).  Different plans
  *    are independent.
+ *  - Stream order: the kernels of a synthesis call are chained with programmatic dependent launch and signal
+ *    `launch_dependents` early.  Work the caller enqueues behind a call with an ordinary launch (or a copy) starts
+ *    after the call's last kernel has completed, as usual; only a kernel the CALLER launches with
+ *    cudaLaunchAttributeProgrammaticStreamSerialization directly behind a call must execute griddepcontrol.wait
+ *    (cudaGridDependencySynchronize) before it touches the call's output.  The first kernel of every call waits
+ *    for all prior work of the stream before it reads the caller's input.
  */
 #ifndef GRATES_B200_H
 #define GRATES_B200_H
