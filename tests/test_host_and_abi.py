@@ -28,6 +28,39 @@ def test_library_exports_every_header_symbol():
         getattr(raw, name)
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI, not a C++ or Python one: a C99 translation unit includes the header, takes the address of
+    every declared entry point, links against the shared library and runs -- what a cgo / JNI / FFI binding would do.
+    No compute call is made (there is no GPU here): gb_version answers, a NULL plan is refused with an error message."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    header = open(os.path.join(ROOT, "include", "grates_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", header)) - {"gb_plan"})
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "grates_b200.h"\n'
+        "typedef void (*fn)(void);\n"
+        "static fn table[] = {" + ", ".join("(fn)%s" % n for n in declared) + "};\n"
+        "int main(void) {\n"
+        "  unsigned i, n = 0;\n"
+        "  for (i = 0; i < sizeof table / sizeof table[0]; ++i) n += table[i] != 0;\n"
+        "  int rc = gb_synthesis(0, 0, 1, 0, 0);\n"
+        '  printf("%d %u %d %s\\n", gb_version(), n, rc, gb_last_error());\n'
+        "  return rc == GB_OK;\n"
+        "}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(gb._lib.library_path())
+    gb._lib.load()                                                         # builds the library when it is missing
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lgrates_b200", "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 3)
+    assert int(out[0]) == gb._lib.GB_VERSION and int(out[1]) == len(declared)
+    assert int(out[2]) != 0 and "plan is NULL" in out[3]
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
