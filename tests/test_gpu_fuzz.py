@@ -62,6 +62,32 @@ def test_random_synthesis_analysis_filter(gb, orc, seed):
         assert np.abs(back - want).max() / scale < 1e-10, (dlon, dlat, N, nmin, kernel)
 
 
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("GB_FUZZ_SEEDS", "10"))))
+def test_random_epoch_counts_are_batch_independent(gb, orc, seed):
+    """The Legendre stage picks its tiling from the batch width (64-, 80-, 120- and 240-column items, CTAs spread over
+    the SMs for narrow launches), the Fourier stage cuts its last round of tiles by the batch height: epoch counts from
+    11 to 130 on random grids (folded and not, with and without the longitude symmetries) must give, bit for bit, the
+    rows that any sub-batch gives, and agree with the oracle."""
+    rng = np.random.default_rng(700 + seed)
+    dlon, dlat = float(rng.choice(STEPS)), float(rng.choice(STEPS))
+    nlat = int(180 / dlat)
+    N = int(rng.integers(1, min(40, nlat - 1)))
+    E = int(rng.choice((11, 20, 32, 33, 40, 41, 48, 60, 61, 80, 81, int(rng.integers(11, 131)))))
+    kernel = str(rng.choice(KERNELS))
+    grid, og = gb.GeographicGrid(dlon, dlat), orc.geographic_grid(dlon, dlat)
+    base = np.stack([orc.synthetic_coefficients(N, 7 * seed + e) for e in range(5)])
+    scale = rng.uniform(0.5, 1.5, E)
+    anm = base[np.arange(E) % 5] * scale[:, None, None]
+    x = torch.as_tensor(anm).cuda()
+    out = gb.to_grid_batch(x, grid, kernel)
+    for _ in range(3):
+        lo = int(rng.integers(0, E))
+        hi = int(rng.integers(lo + 1, E + 1))
+        assert torch.equal(gb.to_grid_batch(x[lo:hi].contiguous(), grid, kernel), out[lo:hi]), (dlon, dlat, N, E, lo, hi)
+    e = int(rng.integers(0, E))
+    assert maxnorm_err(out[e].cpu().numpy(), orc.synthesis(anm[e], og, kernel)) < TOL, (dlon, dlat, N, E, kernel)
+
+
 @pytest.mark.parametrize("seed", range(max(5, int(__import__("os").environ.get("GB_FUZZ_SEEDS", "10")) // 2)))
 def test_random_covariance_and_statistics(gb, orc, seed):
     rng = np.random.default_rng(300 + seed)
